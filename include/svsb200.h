@@ -1,0 +1,156 @@
+/*
+ * svsb200.h -- C ABI of the B200-native retrieve engine behind svs.KB.retrieve / svs.AsyncKB.retrieve.
+ *
+ * The reference (Rhobota/svs 0.7.4) is pure Python and has no FFI for this path; the seam is the
+ * private class `_EmbeddingsMatrix` (src/svs/kb.py:856-893) and the `superheavy()` closures
+ * (src/svs/kb.py:1184-1189 async, 1622-1627 sync).  Every entry point below names the reference
+ * code it replaces.  INTEGRATION.md shows the ctypes binding and the ~20-line patch to kb.py.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative SVSB_E_* code; nothing throws or aborts;
+ *     svsb_last_error() returns a thread-local message for the last failing call on this thread;
+ *   - there is NO CPU fallback: without a usable CUDA device svsb_create fails;
+ *   - host pointers are plain caller-owned buffers; the library copies before returning;
+ *   - svsb_query* may be called concurrently from several OS threads (AsyncKB runs the compute in
+ *     the default thread pool without holding the KB lock, src/svs/kb.py:1180,1190);
+ *     svsb_invalidate / svsb_load_* may race with in-flight queries: a query keeps the generation
+ *     it started on alive until it returns (the reference relies on NumPy refcounts for the same).
+ *   - result order: score descending, ties by ascending row (== ascending embeddings.id for a rowid
+ *     scan, src/svs/kb.py:603-609).  The reference's get_top_k orders exact ties by DEscending index
+ *     (src/svs/util.py:203); BASELINE.json's north star prescribes ascending id.
+ */
+#ifndef SVSB200_H
+#define SVSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svsb_engine svsb_t;
+
+enum {
+    SVSB_OK            = 0,
+    SVSB_E_INVALID     = -1,   /* bad argument */
+    SVSB_E_CUDA        = -2,   /* CUDA runtime error (message has the detail) */
+    SVSB_E_NOT_LOADED  = -3,   /* query with no matrix resident (Python re-loads, as kb.py:866-877) */
+    SVSB_E_SHAPE       = -4,   /* query d != matrix d, or empty matrix: Python raises ValueError, as np.dot does */
+    SVSB_E_STATE       = -5,   /* load_rows/load_end without load_begin, too many rows, ... */
+    SVSB_E_NOMEM       = -6,
+    SVSB_E_NO_DEVICE   = -7    /* no CUDA device: there is no CPU path */
+};
+
+/* Normalisation policy of the load path (hazard H1). */
+enum {
+    SVSB_NORM_CHECK     = 0,   /* compute row norms on the device, keep rows verbatim (default: the
+                                  reference scores raw dot products, src/svs/kb.py:1623) */
+    SVSB_NORM_NORMALIZE = 1    /* divide every row by its L2 norm on the device */
+};
+
+/* ---- lifetime: KB.__init__ ... KB.close()  (src/svs/kb.py:1420, 1455) -------------------------- */
+
+/* device_ids == NULL / n_dev <= 0: use device 0.  With n_dev > 1 the matrix is row-sharded over the
+ * devices in scan order and every query gathers the per-device top-k lists. */
+int  svsb_create(const int* device_ids, int n_dev, svsb_t** out);
+void svsb_destroy(svsb_t* e);
+
+/* ---- load path: replaces _Querier.build_embeddings_matrix (src/svs/kb.py:573-618) and the cache
+ *      fill of _EmbeddingsMatrix.get_sync / get (src/svs/kb.py:866-893) ------------------------ */
+
+/* Start building a new generation of n rows x d float32.  n == 0 is legal (empty table, kb.py:595-601). */
+int svsb_load_begin(svsb_t* e, int64_t n, int32_t d, int32_t norm_mode);
+/* Append `count` rows (row-major, d floats each, little-endian f32 exactly as the SQLite blobs hold
+ * them, src/svs/embeddings/util.py:15-23) and their embeddings.id values, in scan order.  Data is
+ * staged through the engine's pinned ring and copied to the device asynchronously. */
+int svsb_load_rows(svsb_t* e, const float* rows, const int64_t* emb_ids, int64_t count);
+/* Zero-copy variant: borrow a pinned staging slab, fill rows/ids in place, commit `count` rows. */
+int svsb_load_acquire_slab(svsb_t* e, float** rows, int64_t** emb_ids, int64_t* capacity_rows);
+int svsb_load_commit_slab(svsb_t* e, int64_t count);
+/* Finish: wait for the copies, run the row-norm kernel, publish atomically.  Fails with
+ * SVSB_E_STATE if fewer/more than n rows were supplied (the reference asserts, kb.py:616). */
+int svsb_load_end(svsb_t* e, uint64_t* generation);
+/* Abandon a load in progress (the resident generation, if any, is untouched). */
+int svsb_load_abort(svsb_t* e);
+/* Bench/test support: fill n x d on the device(s) from the counter-based generator
+ * (oracle/svs_oracle.py: counter_uniform_rows), emb_id of row r = id0 + r * id_step, then normalise. */
+int svsb_load_synthetic(svsb_t* e, int64_t n, int32_t d, uint64_t seed, int64_t id0, int64_t id_step,
+                        uint64_t* generation);
+
+/* _EmbeddingsMatrix.invalidate (src/svs/kb.py:861-864; call sites kb.py:984,1062,1086,1455,1523,1541). */
+int svsb_invalidate(svsb_t* e);
+/* Cache-hit test of get_sync / get (src/svs/kb.py:867, 880).  Returns 1 / 0. */
+int svsb_is_loaded(svsb_t* e);
+/* Shape of the resident matrix (embeddings_matrix.shape, used at kb.py:1191, 1629). */
+int svsb_shape(svsb_t* e, int64_t* n, int32_t* d);
+/* Row-norm statistics computed by the load path's norm kernel: max | ||row|| - 1 | and the number of
+ * rows outside the reference's tolerance 1e-3 (src/svs/kb.py:58, src/svs/embeddings/util.py:35-38). */
+int svsb_norm_stats(svsb_t* e, float* max_abs_dev, int64_t* n_out_of_tolerance);
+/* Verification accessor: copy rows [row0, row0+count) of the resident matrix (and ids) back to the host. */
+int svsb_read_rows(svsb_t* e, int64_t row0, int64_t count, float* rows, int64_t* emb_ids);
+
+/* ---- the hot path: replaces superheavy() = np.dot + get_top_k + emb_id_lookup
+ *      (src/svs/kb.py:1622-1627, 1184-1189; src/svs/util.py:190-203) --------------------------- */
+
+/* q: d floats (the provider's vector as float32, NOT re-normalised, kb.py:1620).  Outputs have
+ * capacity k.  *out_count = min(k, N); k <= 0 gives 0 results (util.py:198-201). */
+int svsb_query(svsb_t* e, const float* q, int32_t d, int32_t k,
+               float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
+/* Snapshots.  The reference's retrieve keeps Python references to the (matrix, ids) pair it fetched
+ * while the lock is released (src/svs/kb.py:1178-1190), so a concurrent bulk_add/bulk_del that
+ * invalidates the cache (kb.py:1062, 1086) does not disturb it.  A snapshot is that pair of
+ * references: it pins the generation resident at acquire time until released. */
+typedef struct svsb_snapshot svsb_snap_t;
+int  svsb_snapshot_acquire(svsb_t* e, svsb_snap_t** out);
+void svsb_snapshot_release(svsb_snap_t* s);
+int  svsb_snapshot_shape(svsb_snap_t* s, int64_t* n, int32_t* d, uint64_t* generation);
+int  svsb_snapshot_query(svsb_t* e, svsb_snap_t* s, const float* q, int32_t d, int32_t k,
+                         float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
+/* Batched queries (new; the reference has no batched API): Q is row-major (b, d); outputs (b, k). */
+int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
+                     float* out_scores, int64_t* out_emb_ids, int32_t* out_counts);
+/* Selection only: get_top_k (src/svs/util.py:190-203) on a host score vector, run by the same
+ * selection kernels.  out_index receives row indices. */
+int svsb_topk_scores(svsb_t* e, const float* scores, int64_t n, int32_t k,
+                     float* out_scores, int64_t* out_index, int32_t* out_count);
+
+/* ---- measurement support (device-resident inputs; used by bench.py and the parity tests) ------ */
+
+/* Upload nq query vectors (row-major (nq, d)) to every device once. */
+int svsb_bench_set_queries(svsb_t* e, const float* Q, int32_t nq, int32_t d);
+/* Run `iters` single-query retrieves back to back, cycling through the uploaded queries, everything
+ * device-resident, timed with CUDA events on the launching stream(s).  Returns total milliseconds
+ * (max over devices) and, optionally, the milliseconds spent in the similarity kernel alone and the
+ * number of kernel launches issued. */
+int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* gemv_ms, int64_t* launches);
+/* Same through the batched kernel: one launch set per batch of the uploaded queries. */
+int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, int64_t* launches);
+/* Result of the last bench query (for checking that the timed path computes the right thing). */
+int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
+
+/* ---- stateless launchers on raw device pointers (one process per GPU; pointers may come from
+ *      torch tensors' data_ptr(), stream from torch.cuda.current_stream().cuda_stream) ---------- */
+
+typedef struct svsb_workspace svsb_ws_t;
+int  svsb_ws_create(int device, int64_t n_rows, int32_t k_max, svsb_ws_t** out);
+void svsb_ws_destroy(svsb_ws_t* ws);
+/* Local top-k of one shard: keys (64-bit, order-preserving score in the high word, ~global_row in the
+ * low word) and embeddings.ids of the min(k, n) best rows, sorted.  All pointers are device pointers. */
+int svsb_launch_local_topk(svsb_ws_t* ws, void* stream, const float* d_matrix, int64_t n, int32_t d,
+                           int32_t ld, const int64_t* d_emb_ids, int64_t global_row0, const float* d_query,
+                           int32_t k, uint64_t* d_out_keys, int64_t* d_out_ids, int32_t* d_out_count);
+/* Merge G gathered candidate lists (each `stride` entries long, counts[g] valid) into the global
+ * top-k: scores, ids.  Used after the NCCL all-gather of the per-rank lists. */
+int svsb_launch_merge(svsb_ws_t* ws, void* stream, const uint64_t* d_keys, const int64_t* d_ids,
+                      const int32_t* d_counts, int32_t n_lists, int32_t stride, int32_t k,
+                      float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_count);
+
+const char* svsb_last_error(void);
+const char* svsb_version(void);
+/* Number of kernel launches this process has issued through the library (for bench.py's gpu_launches). */
+int64_t svsb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVSB200_H */

@@ -1,0 +1,1047 @@
+// The engine object and the C ABI (include/svsb200.h).
+//
+// Host-side responsibilities, all replacing pieces of the reference's `_EmbeddingsMatrix`
+// (src/svs/kb.py:856-893) and `superheavy()` (src/svs/kb.py:1184-1189, 1622-1627):
+//   * generations: the device-resident matrix + embeddings.id table is an immutable, ref-counted
+//     snapshot; load builds a new one off to the side and publishes it atomically; invalidate drops
+//     the engine's reference; in-flight queries keep theirs (what NumPy refcounts give the reference);
+//   * load path: caller rows -> pinned ring slabs -> cudaMemcpyAsync -> row-sharded device matrix with a
+//     16-byte-aligned leading dimension -> row-norm kernel;
+//   * query contexts: a small pool of {stream, workspace, pinned in/out buffers} per device so that
+//     svsb_query is re-entrant from several OS threads;
+//   * multi-device: contiguous row shards, per-device GEMV + exact local top-k, candidate lists copied
+//     peer-to-peer to device 0 and merged there by one kernel.
+#include "../../include/svsb200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace svsb;
+
+// ------------------------------------------------------------------------------------------------
+// errors, launch counter
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+namespace svsb { void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); } }
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError();                                                              \
+            return fail(_e == cudaErrorMemoryAllocation ? SVSB_E_NOMEM : SVSB_E_CUDA,              \
+                        std::string(#call) + ": " + cudaGetErrorString(_e));                       \
+        }                                                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// data structures
+// ------------------------------------------------------------------------------------------------
+struct Shard {
+    int dev = 0;
+    int64_t row0 = 0, n = 0;
+    float* M = nullptr;          // n x ld floats
+    int64_t* ids = nullptr;      // n
+};
+
+struct Generation {
+    uint64_t id = 0;
+    int64_t n = 0;
+    int d = 0, ld = 0;
+    std::vector<Shard> shards;
+    float max_dev = 0.f;
+    int64_t n_out_of_tol = 0;
+    ~Generation() {
+        for (auto& s : shards) {
+            if (s.M || s.ids) cudaSetDevice(s.dev);
+            if (s.M) cudaFree(s.M);
+            if (s.ids) cudaFree(s.ids);
+        }
+    }
+};
+
+// per-device scratch for one in-flight query
+struct svsb_workspace {
+    int dev = 0;
+    cudaStream_t st = nullptr;       // owned when created by the engine; null for the stateless API
+    bool own_stream = false;
+    float* d_q = nullptr;   int q_cap = 0;
+    float* scores = nullptr; int64_t n_cap = 0;
+    u64* gmax = nullptr;     int64_t g_cap = 0;
+    u64* cand = nullptr;     int64_t cand_cap = 0;
+    u64* sortbuf = nullptr;  int64_t sort_cap = 0;
+    u64* out_keys = nullptr; float* out_scores = nullptr; int64_t* out_ids = nullptr; int64_t out_cap = 0;
+    int32_t* out_count = nullptr;
+    u64* mscr_keys = nullptr; int64_t* mscr_ids = nullptr; int64_t mscr_cap = 0;   // merge scratch
+    cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr;
+
+    int ensure_rows(int64_t n) {
+        cudaSetDevice(dev);
+        if (n > n_cap) {
+            if (scores) cudaFree(scores); if (gmax) cudaFree(gmax); if (cand) cudaFree(cand);
+            scores = nullptr; gmax = nullptr; cand = nullptr; n_cap = 0;
+            const int shift = group_shift_for(n);
+            const int64_t G = (n + ((int64_t)1 << shift) - 1) >> shift;
+            int64_t cc = (int64_t)K_FAST_MAX << shift; if (cc > n) cc = n;
+            CU(cudaMalloc(&scores, (size_t)n * 4));
+            CU(cudaMalloc(&gmax, (size_t)G * 8));
+            CU(cudaMemset(gmax, 0, (size_t)G * 8));
+            CU(cudaMalloc(&cand, (size_t)cc * 8));
+            n_cap = n; g_cap = G; cand_cap = cc;
+        }
+        return SVSB_OK;
+    }
+    int ensure_q(int ld) {
+        cudaSetDevice(dev);
+        if (ld > q_cap) { if (d_q) cudaFree(d_q); d_q = nullptr; CU(cudaMalloc(&d_q, (size_t)ld * 4)); q_cap = ld; }
+        return SVSB_OK;
+    }
+    int ensure_out(int64_t k) {
+        cudaSetDevice(dev);
+        if (!out_count) CU(cudaMalloc(&out_count, 64));
+        if (k > out_cap) {
+            if (out_keys) cudaFree(out_keys); if (out_scores) cudaFree(out_scores); if (out_ids) cudaFree(out_ids);
+            out_keys = nullptr; out_scores = nullptr; out_ids = nullptr; out_cap = 0;
+            CU(cudaMalloc(&out_keys, (size_t)k * 8));
+            CU(cudaMalloc(&out_scores, (size_t)k * 4));
+            CU(cudaMalloc(&out_ids, (size_t)k * 8));
+            out_cap = k;
+        }
+        return SVSB_OK;
+    }
+    int ensure_sort(int64_t n) {
+        cudaSetDevice(dev);
+        int64_t need = next_pow2(n); if (need < 2048) need = 2048;
+        if (need > sort_cap) { if (sortbuf) cudaFree(sortbuf); sortbuf = nullptr; CU(cudaMalloc(&sortbuf, (size_t)need * 8)); sort_cap = need; }
+        return SVSB_OK;
+    }
+    int ensure_merge_scratch(int64_t entries) {
+        cudaSetDevice(dev);
+        if (entries > mscr_cap) {
+            if (mscr_keys) cudaFree(mscr_keys); if (mscr_ids) cudaFree(mscr_ids);
+            mscr_keys = nullptr; mscr_ids = nullptr; mscr_cap = 0;
+            CU(cudaMalloc(&mscr_keys, (size_t)entries * 8));
+            CU(cudaMalloc(&mscr_ids, (size_t)entries * 8));
+            mscr_cap = entries;
+        }
+        return SVSB_OK;
+    }
+    void release() {
+        cudaSetDevice(dev);
+        void* ptrs[] = {d_q, scores, gmax, cand, sortbuf, out_keys, out_scores, out_ids, out_count, mscr_keys, mscr_ids};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        if (ev) cudaEventDestroy(ev); if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
+        if (own_stream && st) cudaStreamDestroy(st);
+    }
+};
+typedef svsb_workspace DevWs;
+
+struct QueryCtx {
+    std::vector<DevWs> ws;                 // one per engine device
+    // pinned host staging
+    float* h_q = nullptr; int h_q_cap = 0;
+    float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_count = nullptr; int64_t h_out_cap = 0;
+    // device-0 gather + merge outputs (multi-device)
+    u64* g_keys = nullptr; int64_t* g_ids = nullptr; int32_t* g_counts = nullptr; int64_t g_stride = 0;
+    float* m_scores = nullptr; int64_t* m_ids = nullptr; int32_t* m_count = nullptr; int64_t m_cap = 0;
+    cudaEvent_t ev_merge = nullptr; bool merge_recorded = false;   // last merge that read g_keys / g_ids
+};
+
+struct Slab {
+    float* rows = nullptr; int64_t* ids = nullptr;
+    std::vector<cudaEvent_t> ev;           // per device: last copy out of this slab
+    std::vector<char> pending;
+};
+
+struct Loading {
+    std::shared_ptr<Generation> gen;
+    int norm_mode = SVSB_NORM_CHECK;
+    int64_t loaded = 0;
+    int64_t slab_rows = 0;
+    int cur = 0;
+    bool borrowed = false;
+};
+
+struct svsb_engine {
+    std::vector<int> devs;
+    std::mutex mu;                          // guards current, loading, pool bookkeeping
+    std::condition_variable cv;
+    std::shared_ptr<Generation> current;
+    uint64_t next_gen = 1;
+    std::unique_ptr<Loading> loading;
+    std::vector<Slab> slabs; int64_t slab_bytes_rows = 0, slab_ids_cap = 0;
+    std::vector<cudaStream_t> copy_st;      // per device
+    std::vector<std::unique_ptr<QueryCtx>> pool_free;
+    int ctx_total = 0, ctx_max = 4;
+    // bench state
+    std::vector<float*> bench_q; int bench_nq = 0, bench_d = 0, bench_ld = 0;
+    std::unique_ptr<QueryCtx> bench_ctx;
+};
+
+static inline int round_up4(int d) { return (d + 3) & ~3; }
+
+// ------------------------------------------------------------------------------------------------
+// context pool
+// ------------------------------------------------------------------------------------------------
+static int ctx_create(svsb_engine* e, std::unique_ptr<QueryCtx>& out) {
+    std::unique_ptr<QueryCtx> c(new QueryCtx());
+    c->ws.resize(e->devs.size());
+    for (size_t i = 0; i < e->devs.size(); ++i) {
+        DevWs& w = c->ws[i];
+        w.dev = e->devs[i];
+        CU(cudaSetDevice(w.dev));
+        CU(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
+        w.own_stream = true;
+        CU(cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming));
+        CU(cudaEventCreate(&w.ev0));
+        CU(cudaEventCreate(&w.ev1));
+    }
+    out = std::move(c);
+    return SVSB_OK;
+}
+static void ctx_destroy(svsb_engine* e, QueryCtx* c) {
+    if (!c) return;
+    for (auto& w : c->ws) w.release();
+    if (!e->devs.empty()) cudaSetDevice(e->devs[0]);
+    if (c->h_q) cudaFreeHost(c->h_q);
+    if (c->h_scores) cudaFreeHost(c->h_scores);
+    if (c->h_ids) cudaFreeHost(c->h_ids);
+    if (c->h_count) cudaFreeHost(c->h_count);
+    void* ptrs[] = {c->g_keys, c->g_ids, c->g_counts, c->m_scores, c->m_ids, c->m_count};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->ev_merge) cudaEventDestroy(c->ev_merge);
+}
+static int ctx_acquire(svsb_engine* e, std::unique_ptr<QueryCtx>& out) {
+    std::unique_lock<std::mutex> lk(e->mu);
+    while (true) {
+        if (!e->pool_free.empty()) { out = std::move(e->pool_free.back()); e->pool_free.pop_back(); return SVSB_OK; }
+        if (e->ctx_total < e->ctx_max) { ++e->ctx_total; break; }
+        e->cv.wait(lk);
+    }
+    lk.unlock();
+    int rc = ctx_create(e, out);
+    if (rc != SVSB_OK) { lk.lock(); --e->ctx_total; e->cv.notify_one(); }
+    return rc;
+}
+static void ctx_release(svsb_engine* e, std::unique_ptr<QueryCtx>& c) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->pool_free.push_back(std::move(c));
+    e->cv.notify_one();
+}
+struct CtxLease {
+    svsb_engine* e; std::unique_ptr<QueryCtx> c;
+    explicit CtxLease(svsb_engine* e_) : e(e_) {}
+    ~CtxLease() { if (c) ctx_release(e, c); }
+};
+
+static int ctx_ensure_host(QueryCtx* c, int ld, int64_t k) {
+    if (ld > c->h_q_cap) { if (c->h_q) cudaFreeHost(c->h_q); c->h_q = nullptr; CU(cudaMallocHost(&c->h_q, (size_t)ld * 4)); c->h_q_cap = ld; }
+    if (!c->h_count) CU(cudaMallocHost(&c->h_count, 64));
+    if (k > c->h_out_cap) {
+        if (c->h_scores) cudaFreeHost(c->h_scores); if (c->h_ids) cudaFreeHost(c->h_ids);
+        c->h_scores = nullptr; c->h_ids = nullptr; c->h_out_cap = 0;
+        CU(cudaMallocHost(&c->h_scores, (size_t)k * 4));
+        CU(cudaMallocHost(&c->h_ids, (size_t)k * 8));
+        c->h_out_cap = k;
+    }
+    return SVSB_OK;
+}
+static int ctx_ensure_gather(svsb_engine* e, QueryCtx* c, int64_t k) {
+    CU(cudaSetDevice(e->devs[0]));
+    const int64_t nd = (int64_t)e->devs.size();
+    if (!c->g_counts) {
+        CU(cudaMalloc(&c->g_counts, (size_t)nd * 4)); CU(cudaMalloc(&c->m_count, 64));
+        CU(cudaEventCreateWithFlags(&c->ev_merge, cudaEventDisableTiming));
+    }
+    if (k > c->g_stride) {
+        void* ptrs[] = {c->g_keys, c->g_ids, c->m_scores, c->m_ids};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        c->g_keys = nullptr; c->g_ids = nullptr; c->m_scores = nullptr; c->m_ids = nullptr; c->g_stride = 0;
+        CU(cudaMalloc(&c->g_keys, (size_t)(nd * k) * 8));
+        CU(cudaMalloc(&c->g_ids, (size_t)(nd * k) * 8));
+        CU(cudaMalloc(&c->m_scores, (size_t)k * 4));
+        CU(cudaMalloc(&c->m_ids, (size_t)k * 8));
+        c->g_stride = k; c->m_cap = k;
+    }
+    return SVSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int svsb_create(const int* device_ids, int n_dev, svsb_t** out) {
+    if (!out) return fail(SVSB_E_INVALID, "svsb_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        return fail(SVSB_E_NO_DEVICE, std::string("no CUDA device available (") +
+                    (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0") + "); svs_b200 has no CPU path");
+    }
+    std::unique_ptr<svsb_engine> e(new svsb_engine());
+    if (!device_ids || n_dev <= 0) e->devs.push_back(0);
+    else for (int i = 0; i < n_dev; ++i) {
+        if (device_ids[i] < 0 || device_ids[i] >= count) return fail(SVSB_E_INVALID, "svsb_create: device id out of range");
+        // duplicates = several "virtual shards" on one GPU: only for testing the multi-shard path on one device
+        const char* dup = getenv("SVSB_ALLOW_DUP_DEVICES");
+        for (int j = 0; j < i; ++j)
+            if (device_ids[j] == device_ids[i] && !(dup && dup[0] == '1'))
+                return fail(SVSB_E_INVALID, "svsb_create: duplicate device id");
+        e->devs.push_back(device_ids[i]);
+    }
+    if (const char* s = getenv("SVSB_MAX_CONTEXTS")) { int v = atoi(s); if (v >= 1 && v <= 64) e->ctx_max = v; }
+    for (size_t i = 0; i < e->devs.size(); ++i) {
+        CU(cudaSetDevice(e->devs[i]));
+        int major = 0, minor = 0;
+        CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, e->devs[i]));
+        CU(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, e->devs[i]));
+        if (major != 10) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "device %d has compute capability %d.%d; svs_b200 is built for sm_100a (B200) only",
+                     e->devs[i], major, minor);
+            return fail(SVSB_E_NO_DEVICE, buf);
+        }
+        cudaStream_t st;
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        e->copy_st.push_back(st);
+        // peer access to device 0 for the candidate gather (ignored if unsupported: copies then stage via host)
+        if (i > 0 && e->devs[i] != e->devs[0]) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, e->devs[i], e->devs[0]) == cudaSuccess && can) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(e->devs[0], 0);
+                if (pe != cudaSuccess) (void)cudaGetLastError();
+            }
+            CU(cudaSetDevice(e->devs[0]));
+            if (cudaDeviceCanAccessPeer(&can, e->devs[0], e->devs[i]) == cudaSuccess && can) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(e->devs[i], 0);
+                if (pe != cudaSuccess) (void)cudaGetLastError();
+            }
+        }
+    }
+    *out = e.release();
+    return SVSB_OK;
+}
+
+static void free_slabs(svsb_engine* e) {
+    for (auto& s : e->slabs) {
+        if (s.rows) cudaFreeHost(s.rows);
+        if (s.ids) cudaFreeHost(s.ids);
+        for (auto ev : s.ev) if (ev) cudaEventDestroy(ev);
+    }
+    e->slabs.clear(); e->slab_bytes_rows = 0; e->slab_ids_cap = 0;
+}
+
+extern "C" void svsb_destroy(svsb_t* e) {
+    if (!e) return;
+    for (size_t i = 0; i < e->devs.size(); ++i) { cudaSetDevice(e->devs[i]); cudaDeviceSynchronize(); }
+    e->loading.reset();
+    e->current.reset();
+    for (auto& c : e->pool_free) ctx_destroy(e, c.get());
+    e->pool_free.clear();
+    if (e->bench_ctx) ctx_destroy(e, e->bench_ctx.get());
+    for (size_t i = 0; i < e->bench_q.size(); ++i) if (e->bench_q[i]) { cudaSetDevice(e->devs[i]); cudaFree(e->bench_q[i]); }
+    free_slabs(e);
+    for (size_t i = 0; i < e->copy_st.size(); ++i) { cudaSetDevice(e->devs[i]); cudaStreamDestroy(e->copy_st[i]); }
+    delete e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// load path
+// ------------------------------------------------------------------------------------------------
+static int alloc_generation(svsb_engine* e, int64_t n, int d, std::shared_ptr<Generation>& out) {
+    std::shared_ptr<Generation> g(new Generation());
+    g->n = n; g->d = d; g->ld = round_up4(d);
+    const int64_t nd = (int64_t)e->devs.size();
+    const int64_t per = (n + nd - 1) / nd;
+    for (int64_t i = 0; i < nd; ++i) {
+        Shard s; s.dev = e->devs[i];
+        s.row0 = std::min(n, i * per);
+        s.n = std::min(n, (i + 1) * per) - s.row0;
+        if (s.n > 0xfffffff0ll) return fail(SVSB_E_INVALID, "more than 2^32 rows per device are not supported");
+        g->shards.push_back(s);
+    }
+    if (n > 0xfffffff0ll) return fail(SVSB_E_INVALID, "more than 2^32 rows in total are not supported");
+    for (auto& s : g->shards) {
+        if (s.n == 0 || g->ld == 0) continue;
+        CU(cudaSetDevice(s.dev));
+        CU(cudaMalloc(&s.M, (size_t)s.n * g->ld * 4));
+        CU(cudaMalloc(&s.ids, (size_t)s.n * 8));
+    }
+    out = g;
+    return SVSB_OK;
+}
+
+static int ensure_slabs(svsb_engine* e, int d) {
+    // ~32 MB of rows per slab, 3 slabs
+    int64_t rows = d > 0 ? (32ll << 20) / ((int64_t)d * 4) : 1024;
+    if (rows < 16) rows = 16;
+    if (rows > (1 << 20)) rows = 1 << 20;
+    const int64_t bytes = rows * (int64_t)(d > 0 ? d : 1) * 4;
+    if (e->slabs.size() == 3 && e->slab_bytes_rows >= bytes && e->slab_ids_cap >= rows) return SVSB_OK;
+    free_slabs(e);
+    e->slabs.resize(3);
+    for (auto& s : e->slabs) {
+        CU(cudaMallocHost(&s.rows, (size_t)bytes));
+        CU(cudaMallocHost(&s.ids, (size_t)rows * 8));
+        s.ev.assign(e->devs.size(), nullptr);
+        s.pending.assign(e->devs.size(), 0);
+        for (size_t i = 0; i < e->devs.size(); ++i) {
+            CU(cudaSetDevice(e->devs[i]));
+            CU(cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming));
+        }
+    }
+    e->slab_bytes_rows = bytes; e->slab_ids_cap = rows;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_load_begin(svsb_t* e, int64_t n, int32_t d, int32_t norm_mode) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (n < 0 || d < 0) return fail(SVSB_E_INVALID, "svsb_load_begin: negative shape");
+    if (norm_mode != SVSB_NORM_CHECK && norm_mode != SVSB_NORM_NORMALIZE) return fail(SVSB_E_INVALID, "svsb_load_begin: bad norm_mode");
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->loading.reset();
+    std::unique_ptr<Loading> L(new Loading());
+    int rc = alloc_generation(e, n, d, L->gen);
+    if (rc != SVSB_OK) return rc;
+    L->norm_mode = norm_mode;
+    if (n > 0 && d > 0) {
+        rc = ensure_slabs(e, d);
+        if (rc != SVSB_OK) return rc;
+        L->slab_rows = e->slab_bytes_rows / ((int64_t)d * 4);
+        if (L->slab_rows > e->slab_ids_cap) L->slab_rows = e->slab_ids_cap;
+        if (L->gen->ld != d)                       // zero the padding columns once
+            for (auto& s : L->gen->shards) if (s.n) { CU(cudaSetDevice(s.dev)); CU(cudaMemset(s.M, 0, (size_t)s.n * L->gen->ld * 4)); }
+    }
+    e->loading = std::move(L);
+    return SVSB_OK;
+}
+
+static int slab_wait(svsb_engine* e, Slab& s) {
+    for (size_t i = 0; i < s.pending.size(); ++i)
+        if (s.pending[i]) { CU(cudaSetDevice(e->devs[i])); CU(cudaEventSynchronize(s.ev[i])); s.pending[i] = 0; }
+    return SVSB_OK;
+}
+
+// copy `count` rows sitting at the start of slab `s` to their shards, asynchronously
+static int slab_flush(svsb_engine* e, Loading* L, Slab& s, int64_t count) {
+    Generation* g = L->gen.get();
+    int64_t done = 0;
+    while (done < count) {
+        const int64_t grow = L->loaded + done;
+        size_t si = 0;
+        while (si + 1 < g->shards.size() && grow >= g->shards[si].row0 + g->shards[si].n) ++si;
+        Shard& sh = g->shards[si];
+        const int64_t local = grow - sh.row0;
+        const int64_t take = std::min(count - done, sh.n - local);
+        CU(cudaSetDevice(sh.dev));
+        cudaStream_t st = e->copy_st[si];
+        const float* src = s.rows + done * g->d;
+        if (g->ld == g->d)
+            CU(cudaMemcpyAsync(sh.M + local * g->ld, src, (size_t)take * g->d * 4, cudaMemcpyHostToDevice, st));
+        else
+            CU(cudaMemcpy2DAsync(sh.M + local * g->ld, (size_t)g->ld * 4, src, (size_t)g->d * 4, (size_t)g->d * 4,
+                                 (size_t)take, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(sh.ids + local, s.ids + done, (size_t)take * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(s.ev[si], st));
+        s.pending[si] = 1;
+        done += take;
+    }
+    L->loaded += count;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_load_acquire_slab(svsb_t* e, float** rows, int64_t** emb_ids, int64_t* capacity_rows) {
+    if (!e || !rows || !emb_ids || !capacity_rows) return fail(SVSB_E_INVALID, "svsb_load_acquire_slab: NULL argument");
+    Loading* L = e->loading.get();
+    if (!L) return fail(SVSB_E_STATE, "svsb_load_acquire_slab without svsb_load_begin");
+    if (L->borrowed) return fail(SVSB_E_STATE, "a slab is already borrowed");
+    if (L->slab_rows == 0) { *rows = nullptr; *emb_ids = nullptr; *capacity_rows = 0; return SVSB_OK; }
+    Slab& s = e->slabs[L->cur];
+    int rc = slab_wait(e, s);
+    if (rc != SVSB_OK) return rc;
+    *rows = s.rows; *emb_ids = s.ids;
+    *capacity_rows = std::min(L->slab_rows, L->gen->n - L->loaded);
+    L->borrowed = true;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_load_commit_slab(svsb_t* e, int64_t count) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    Loading* L = e->loading.get();
+    if (!L || !L->borrowed) return fail(SVSB_E_STATE, "svsb_load_commit_slab without a borrowed slab");
+    L->borrowed = false;
+    if (count < 0 || count > L->slab_rows) return fail(SVSB_E_INVALID, "svsb_load_commit_slab: bad count");
+    if (L->loaded + count > L->gen->n) return fail(SVSB_E_STATE, "more rows supplied than announced in svsb_load_begin");
+    if (count == 0) return SVSB_OK;
+    int rc = slab_flush(e, L, e->slabs[L->cur], count);
+    L->cur = (L->cur + 1) % (int)e->slabs.size();
+    return rc;
+}
+
+extern "C" int svsb_load_rows(svsb_t* e, const float* rows, const int64_t* emb_ids, int64_t count) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    Loading* L = e->loading.get();
+    if (!L) return fail(SVSB_E_STATE, "svsb_load_rows without svsb_load_begin");
+    if (count < 0) return fail(SVSB_E_INVALID, "svsb_load_rows: negative count");
+    if (count == 0) return SVSB_OK;
+    if (!emb_ids || (!rows && L->gen->d > 0)) return fail(SVSB_E_INVALID, "svsb_load_rows: NULL buffer");
+    if (L->loaded + count > L->gen->n) return fail(SVSB_E_STATE, "more rows supplied than announced in svsb_load_begin");
+    if (L->gen->d == 0) { L->loaded += count; return SVSB_OK; }
+    const int d = L->gen->d;
+    int64_t done = 0;
+    while (done < count) {
+        float* srows; int64_t* sids; int64_t cap;
+        int rc = svsb_load_acquire_slab(e, &srows, &sids, &cap);
+        if (rc != SVSB_OK) return rc;
+        const int64_t take = std::min(cap, count - done);
+        memcpy(srows, rows + done * d, (size_t)take * d * 4);
+        memcpy(sids, emb_ids + done, (size_t)take * 8);
+        rc = svsb_load_commit_slab(e, take);
+        if (rc != SVSB_OK) return rc;
+        done += take;
+    }
+    return SVSB_OK;
+}
+
+static int finish_generation(svsb_engine* e, Generation* g, int norm_mode) {
+    // row norms on every shard; stats reduced on the host (two words per shard)
+    g->max_dev = 0.f; g->n_out_of_tol = 0;
+    std::vector<u64*> stats(g->shards.size(), nullptr);
+    for (size_t i = 0; i < g->shards.size(); ++i) {
+        Shard& s = g->shards[i];
+        if (s.n == 0 || g->ld == 0) continue;
+        CU(cudaSetDevice(s.dev));
+        CU(cudaMalloc(&stats[i], 16));
+        CU(cudaMemsetAsync(stats[i], 0, 16, e->copy_st[i]));
+        CU(launch_row_norms(e->copy_st[i], s.dev, s.M, s.n, g->d, g->ld, norm_mode == SVSB_NORM_NORMALIZE ? 1 : 0,
+                            0.001f, nullptr, stats[i]));
+    }
+    for (size_t i = 0; i < g->shards.size(); ++i) {
+        if (!stats[i]) continue;
+        CU(cudaSetDevice(g->shards[i].dev));
+        u64 h[2] = {0, 0};
+        CU(cudaMemcpyAsync(h, stats[i], 16, cudaMemcpyDeviceToHost, e->copy_st[i]));
+        CU(cudaStreamSynchronize(e->copy_st[i]));
+        CU(cudaFree(stats[i]));
+        const float md = bits_f32((uint32_t)h[0]);
+        if (md > g->max_dev || md != md) g->max_dev = md;
+        g->n_out_of_tol += (int64_t)h[1];
+    }
+    return SVSB_OK;
+}
+
+extern "C" int svsb_load_end(svsb_t* e, uint64_t* generation) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    Loading* L = e->loading.get();
+    if (!L) return fail(SVSB_E_STATE, "svsb_load_end without svsb_load_begin");
+    if (L->borrowed) { e->loading.reset(); return fail(SVSB_E_STATE, "svsb_load_end with a borrowed slab"); }
+    if (L->loaded != L->gen->n) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "svsb_load_end: %lld rows supplied, %lld announced", (long long)L->loaded, (long long)L->gen->n);
+        e->loading.reset();
+        return fail(SVSB_E_STATE, buf);
+    }
+    for (auto& s : e->slabs) { int rc = slab_wait(e, s); if (rc != SVSB_OK) { e->loading.reset(); return rc; } }
+    int rc = finish_generation(e, L->gen.get(), L->norm_mode);
+    if (rc != SVSB_OK) { e->loading.reset(); return rc; }
+    std::lock_guard<std::mutex> lk(e->mu);
+    L->gen->id = e->next_gen++;
+    e->current = L->gen;
+    if (generation) *generation = L->gen->id;
+    e->loading.reset();
+    return SVSB_OK;
+}
+
+extern "C" int svsb_load_abort(svsb_t* e) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    e->loading.reset();          // frees the half-built generation (cudaFree waits for pending copies)
+    for (auto& s : e->slabs) std::fill(s.pending.begin(), s.pending.end(), 0);
+    return SVSB_OK;
+}
+
+extern "C" int svsb_load_synthetic(svsb_t* e, int64_t n, int32_t d, uint64_t seed, int64_t id0, int64_t id_step,
+                                   uint64_t* generation) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (n < 0 || d <= 0) return fail(SVSB_E_INVALID, "svsb_load_synthetic: bad shape");
+    std::shared_ptr<Generation> g;
+    int rc = alloc_generation(e, n, d, g);
+    if (rc != SVSB_OK) return rc;
+    for (size_t i = 0; i < g->shards.size(); ++i) {
+        Shard& s = g->shards[i];
+        if (!s.n) continue;
+        CU(cudaSetDevice(s.dev));
+        CU(launch_synth(e->copy_st[i], s.dev, s.M, s.n, d, g->ld, seed, s.row0, s.ids, id0, id_step));
+    }
+    rc = finish_generation(e, g.get(), SVSB_NORM_NORMALIZE);
+    if (rc != SVSB_OK) return rc;
+    // after normalisation the deviation statistics describe the raw rows; recompute for the stored ones
+    rc = finish_generation(e, g.get(), SVSB_NORM_CHECK);
+    if (rc != SVSB_OK) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    g->id = e->next_gen++;
+    e->current = g;
+    if (generation) *generation = g->id;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_invalidate(svsb_t* e) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    std::shared_ptr<Generation> old;
+    { std::lock_guard<std::mutex> lk(e->mu); old.swap(e->current); }
+    return SVSB_OK;          // `old` (and its device memory) dies here unless a query still pins it
+}
+
+extern "C" int svsb_is_loaded(svsb_t* e) {
+    if (!e) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return e->current ? 1 : 0;
+}
+
+static std::shared_ptr<Generation> pin(svsb_engine* e) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    return e->current;
+}
+
+extern "C" int svsb_shape(svsb_t* e, int64_t* n, int32_t* d) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (n) *n = g->n;
+    if (d) *d = g->d;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_norm_stats(svsb_t* e, float* max_abs_dev, int64_t* n_out_of_tolerance) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (max_abs_dev) *max_abs_dev = g->max_dev;
+    if (n_out_of_tolerance) *n_out_of_tolerance = g->n_out_of_tol;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_read_rows(svsb_t* e, int64_t row0, int64_t count, float* rows, int64_t* emb_ids) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (row0 < 0 || count < 0 || row0 + count > g->n) return fail(SVSB_E_INVALID, "svsb_read_rows: range out of bounds");
+    for (auto& s : g->shards) {
+        const int64_t a = std::max(row0, s.row0), b = std::min(row0 + count, s.row0 + s.n);
+        if (a >= b) continue;
+        CU(cudaSetDevice(s.dev));
+        if (rows && g->d > 0)
+            CU(cudaMemcpy2D(rows + (a - row0) * g->d, (size_t)g->d * 4, s.M + (a - s.row0) * g->ld, (size_t)g->ld * 4,
+                            (size_t)g->d * 4, (size_t)(b - a), cudaMemcpyDeviceToHost));
+        if (emb_ids) CU(cudaMemcpy(emb_ids + (a - row0), s.ids + (a - s.row0), (size_t)(b - a) * 8, cudaMemcpyDeviceToHost));
+    }
+    return SVSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the hot path
+// ------------------------------------------------------------------------------------------------
+// Enqueue GEMV + local top-k for one shard on its workspace stream.  d_q: device query (ld floats).
+static int enqueue_local(DevWs& w, const Generation* g, const Shard& s, const float* d_q, int64_t kk) {
+    const int shift = group_shift_for(s.n);
+    CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, d_q, w.scores, w.gmax, shift));
+    if (kk <= K_FAST_MAX)
+        CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
+                         w.out_keys, w.out_scores, w.out_ids, w.out_count));
+    else
+        CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
+                                w.out_keys, w.out_scores, w.out_ids, w.out_count));
+    return SVSB_OK;
+}
+
+static int prepare_ws(DevWs& w, const Generation* g, const Shard& s, int64_t kk) {
+    int rc;
+    if ((rc = w.ensure_rows(s.n)) != SVSB_OK) return rc;
+    if ((rc = w.ensure_q(g->ld)) != SVSB_OK) return rc;
+    if ((rc = w.ensure_out(std::max<int64_t>(kk, 128))) != SVSB_OK) return rc;
+    if (kk > K_FAST_MAX && (rc = w.ensure_sort(s.n)) != SVSB_OK) return rc;
+    return SVSB_OK;
+}
+
+// Gather per-device lists on device 0 and merge.  Results land in c->m_scores / m_ids / m_count (device 0).
+static int enqueue_gather_merge(svsb_engine* e, QueryCtx* c, const Generation* g, int64_t kk) {
+    const int nd = (int)e->devs.size();
+    DevWs& w0 = c->ws[0];
+    int live = 0;
+    for (int i = 0; i < nd; ++i) {
+        const Shard& s = g->shards[i];
+        DevWs& w = c->ws[i];
+        CU(cudaSetDevice(w.dev));
+        if (s.n == 0) { CU(cudaSetDevice(w0.dev)); CU(cudaMemsetAsync(c->g_counts + i, 0, 4, w0.st)); continue; }
+        ++live;
+        const int64_t kl = std::min(kk, s.n);
+        if (i == 0) {
+            CU(cudaMemcpyAsync(c->g_keys, w.out_keys, (size_t)kl * 8, cudaMemcpyDeviceToDevice, w.st));
+            CU(cudaMemcpyAsync(c->g_ids, w.out_ids, (size_t)kl * 8, cudaMemcpyDeviceToDevice, w.st));
+            CU(cudaMemcpyAsync(c->g_counts, w.out_count, 4, cudaMemcpyDeviceToDevice, w.st));
+        } else if (w.dev == w0.dev) {                     // virtual shard on the same GPU (tests)
+            if (c->merge_recorded) CU(cudaStreamWaitEvent(w.st, c->ev_merge, 0));
+            CU(cudaMemcpyAsync(c->g_keys + (int64_t)i * c->g_stride, w.out_keys, (size_t)kl * 8, cudaMemcpyDeviceToDevice, w.st));
+            CU(cudaMemcpyAsync(c->g_ids + (int64_t)i * c->g_stride, w.out_ids, (size_t)kl * 8, cudaMemcpyDeviceToDevice, w.st));
+            CU(cudaMemcpyAsync(c->g_counts + i, w.out_count, 4, cudaMemcpyDeviceToDevice, w.st));
+        } else {
+            // the previous merge on device 0 must have finished reading the gather buffers
+            if (c->merge_recorded) CU(cudaStreamWaitEvent(w.st, c->ev_merge, 0));
+            CU(cudaMemcpyPeerAsync(c->g_keys + (int64_t)i * c->g_stride, w0.dev, w.out_keys, w.dev, (size_t)kl * 8, w.st));
+            CU(cudaMemcpyPeerAsync(c->g_ids + (int64_t)i * c->g_stride, w0.dev, w.out_ids, w.dev, (size_t)kl * 8, w.st));
+            CU(cudaMemcpyPeerAsync(c->g_counts + i, w0.dev, w.out_count, w.dev, 4, w.st));
+        }
+        if (i != 0) { CU(cudaEventRecord(w.ev, w.st)); CU(cudaSetDevice(w0.dev)); CU(cudaStreamWaitEvent(w0.st, w.ev, 0)); }
+    }
+    (void)live;
+    CU(cudaSetDevice(w0.dev));
+    CU(launch_merge(w0.st, c->g_keys, c->g_ids, c->g_counts, nd, (int)c->g_stride, (int)kk, w0.mscr_keys, w0.mscr_ids,
+                    c->m_scores, c->m_ids, c->m_count));
+    CU(cudaEventRecord(c->ev_merge, w0.st));
+    c->merge_recorded = true;
+    return SVSB_OK;
+}
+
+static int query_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, const float* q, int32_t d, int32_t k,
+                     float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    if (!out_count) return fail(SVSB_E_INVALID, "svsb_query: out_count is NULL");
+    *out_count = 0;
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident (call svsb_load_* first)");
+    if (g->n == 0 || d != g->d) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "shapes (%lld,%d) and (%d,) not aligned: %d (dim 1) != %d (dim 0)",
+                 (long long)g->n, g->n == 0 ? 0 : g->d, d, g->n == 0 ? 0 : g->d, d);
+        return fail(SVSB_E_SHAPE, buf);
+    }
+    if (k <= 0) return SVSB_OK;                                   // util.py:200-201
+    if (!q || !out_scores || !out_emb_ids) return fail(SVSB_E_INVALID, "svsb_query: NULL buffer");
+    const int64_t kk = std::min<int64_t>(k, g->n);               // util.py:198-199
+    const int nd = (int)e->devs.size();
+    if (nd > 1 && kk > K_FAST_MAX) return fail(SVSB_E_INVALID, "k > 2048 is not supported with more than one device yet");
+
+    CtxLease lease(e);
+    int rc = ctx_acquire(e, lease.c);
+    if (rc != SVSB_OK) return rc;
+    QueryCtx* c = lease.c.get();
+    if ((rc = ctx_ensure_host(c, g->ld, kk)) != SVSB_OK) return rc;
+    memcpy(c->h_q, q, (size_t)d * 4);
+    for (int i = d; i < g->ld; ++i) c->h_q[i] = 0.f;
+
+    for (int i = 0; i < nd; ++i) {
+        const Shard& s = g->shards[i];
+        if (s.n == 0) continue;
+        DevWs& w = c->ws[i];
+        if ((rc = prepare_ws(w, g.get(), s, kk)) != SVSB_OK) return rc;
+        CU(cudaSetDevice(w.dev));
+        CU(cudaMemcpyAsync(w.d_q, c->h_q, (size_t)g->ld * 4, cudaMemcpyHostToDevice, w.st));
+        if ((rc = enqueue_local(w, g.get(), s, w.d_q, kk)) != SVSB_OK) return rc;
+    }
+    DevWs& w0 = c->ws[0];
+    if (nd == 1) {
+        CU(cudaMemcpyAsync(c->h_scores, w0.out_scores, (size_t)kk * 4, cudaMemcpyDeviceToHost, w0.st));
+        CU(cudaMemcpyAsync(c->h_ids, w0.out_ids, (size_t)kk * 8, cudaMemcpyDeviceToHost, w0.st));
+        CU(cudaMemcpyAsync(c->h_count, w0.out_count, 4, cudaMemcpyDeviceToHost, w0.st));
+    } else {
+        if ((rc = ctx_ensure_gather(e, c, std::max<int64_t>(kk, 128))) != SVSB_OK) return rc;
+        if ((int64_t)nd * c->g_stride > K_FAST_MAX && (rc = w0.ensure_merge_scratch((int64_t)nd * c->g_stride)) != SVSB_OK) return rc;
+        if ((rc = enqueue_gather_merge(e, c, g.get(), kk)) != SVSB_OK) return rc;
+        CU(cudaMemcpyAsync(c->h_scores, c->m_scores, (size_t)kk * 4, cudaMemcpyDeviceToHost, w0.st));
+        CU(cudaMemcpyAsync(c->h_ids, c->m_ids, (size_t)kk * 8, cudaMemcpyDeviceToHost, w0.st));
+        CU(cudaMemcpyAsync(c->h_count, c->m_count, 4, cudaMemcpyDeviceToHost, w0.st));
+    }
+    CU(cudaSetDevice(w0.dev));
+    CU(cudaStreamSynchronize(w0.st));
+    const int32_t cnt = *c->h_count;
+    if (cnt != (int32_t)kk) {
+        char buf[120]; snprintf(buf, sizeof buf, "internal: selection returned %d results, expected %lld", cnt, (long long)kk);
+        return fail(SVSB_E_CUDA, buf);
+    }
+    memcpy(out_scores, c->h_scores, (size_t)kk * 4);
+    memcpy(out_emb_ids, c->h_ids, (size_t)kk * 8);
+    *out_count = cnt;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_query(svsb_t* e, const float* q, int32_t d, int32_t k,
+                          float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    return query_gen(e, pin(e), q, d, k, out_scores, out_emb_ids, out_count);
+}
+
+// ---- snapshots: a query handle that keeps "the arrays it fetched" alive across an invalidate ----
+struct svsb_snapshot { std::shared_ptr<Generation> gen; };
+
+extern "C" int svsb_snapshot_acquire(svsb_t* e, svsb_snap_t** out) {
+    if (!e || !out) return fail(SVSB_E_INVALID, "svsb_snapshot_acquire: NULL argument");
+    *out = nullptr;
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    *out = new svsb_snapshot{g};
+    return SVSB_OK;
+}
+extern "C" void svsb_snapshot_release(svsb_snap_t* s) { delete s; }
+extern "C" int svsb_snapshot_shape(svsb_snap_t* s, int64_t* n, int32_t* d, uint64_t* generation) {
+    if (!s || !s->gen) return fail(SVSB_E_INVALID, "snapshot is NULL");
+    if (n) *n = s->gen->n;
+    if (d) *d = s->gen->d;
+    if (generation) *generation = s->gen->id;
+    return SVSB_OK;
+}
+extern "C" int svsb_snapshot_query(svsb_t* e, svsb_snap_t* s, const float* q, int32_t d, int32_t k,
+                                   float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    if (!e || !s) return fail(SVSB_E_INVALID, "svsb_snapshot_query: NULL argument");
+    return query_gen(e, s->gen, q, d, k, out_scores, out_emb_ids, out_count);
+}
+
+extern "C" int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
+                                float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
+    // First implementation: the exact single-query path per row of Q (same kernels, same results).
+    // The tensor-core contraction (K2) replaces this loop; see DESIGN.md.
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (b < 0) return fail(SVSB_E_INVALID, "svsb_query_batch: negative batch");
+    if (b > 0 && (!Q || !out_counts)) return fail(SVSB_E_INVALID, "svsb_query_batch: NULL buffer");
+    const int64_t kstride = k > 0 ? k : 0;
+    for (int32_t i = 0; i < b; ++i) {
+        int rc = svsb_query(e, Q + (int64_t)i * d, d, k, out_scores ? out_scores + i * kstride : nullptr,
+                            out_emb_ids ? out_emb_ids + i * kstride : nullptr, out_counts + i);
+        if (rc != SVSB_OK) return rc;
+    }
+    return SVSB_OK;
+}
+
+extern "C" int svsb_topk_scores(svsb_t* e, const float* scores, int64_t n, int32_t k,
+                                float* out_scores, int64_t* out_index, int32_t* out_count) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (!out_count) return fail(SVSB_E_INVALID, "svsb_topk_scores: out_count is NULL");
+    *out_count = 0;
+    if (n < 0) return fail(SVSB_E_INVALID, "svsb_topk_scores: negative n");
+    if (n > 0xfffffff0ll) return fail(SVSB_E_INVALID, "svsb_topk_scores: more than 2^32 scores");
+    const int64_t kk = std::min<int64_t>(k, n);
+    if (kk <= 0) return SVSB_OK;
+    if (!scores || !out_scores || !out_index) return fail(SVSB_E_INVALID, "svsb_topk_scores: NULL buffer");
+    CtxLease lease(e);
+    int rc = ctx_acquire(e, lease.c);
+    if (rc != SVSB_OK) return rc;
+    QueryCtx* c = lease.c.get();
+    DevWs& w = c->ws[0];
+    if ((rc = ctx_ensure_host(c, 4, kk)) != SVSB_OK) return rc;
+    if ((rc = w.ensure_rows(n)) != SVSB_OK) return rc;
+    if ((rc = w.ensure_out(std::max<int64_t>(kk, 128))) != SVSB_OK) return rc;
+    if (kk > K_FAST_MAX && (rc = w.ensure_sort(n)) != SVSB_OK) return rc;
+    CU(cudaSetDevice(w.dev));
+    const int shift = group_shift_for(n);
+    CU(cudaMemcpyAsync(w.scores, scores, (size_t)n * 4, cudaMemcpyHostToDevice, w.st));
+    if (kk <= K_FAST_MAX) {
+        CU(launch_groupmax(w.st, w.dev, w.scores, n, w.gmax, shift));
+        CU(launch_select(w.st, w.scores, n, w.gmax, shift, (int)kk, nullptr, 0, w.cand, w.cand_cap,
+                         w.out_keys, w.out_scores, w.out_ids, w.out_count));
+    } else {
+        CU(launch_fullsort_topk(w.st, w.scores, n, w.gmax, shift, kk, nullptr, 0, w.sortbuf,
+                                w.out_keys, w.out_scores, w.out_ids, w.out_count));
+    }
+    CU(cudaMemcpyAsync(c->h_scores, w.out_scores, (size_t)kk * 4, cudaMemcpyDeviceToHost, w.st));
+    CU(cudaMemcpyAsync(c->h_ids, w.out_ids, (size_t)kk * 8, cudaMemcpyDeviceToHost, w.st));
+    CU(cudaMemcpyAsync(c->h_count, w.out_count, 4, cudaMemcpyDeviceToHost, w.st));
+    CU(cudaStreamSynchronize(w.st));
+    memcpy(out_scores, c->h_scores, (size_t)kk * 4);
+    memcpy(out_index, c->h_ids, (size_t)kk * 8);
+    *out_count = *c->h_count;
+    return SVSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement support
+// ------------------------------------------------------------------------------------------------
+extern "C" int svsb_bench_set_queries(svsb_t* e, const float* Q, int32_t nq, int32_t d) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (!Q || nq <= 0 || d <= 0) return fail(SVSB_E_INVALID, "svsb_bench_set_queries: bad arguments");
+    const int ld = round_up4(d);
+    std::vector<float> padded((size_t)nq * ld, 0.f);
+    for (int i = 0; i < nq; ++i) memcpy(&padded[(size_t)i * ld], Q + (size_t)i * d, (size_t)d * 4);
+    if (e->bench_q.size() != e->devs.size()) e->bench_q.assign(e->devs.size(), nullptr);
+    for (size_t i = 0; i < e->devs.size(); ++i) {
+        CU(cudaSetDevice(e->devs[i]));
+        if (e->bench_q[i]) { cudaFree(e->bench_q[i]); e->bench_q[i] = nullptr; }
+        CU(cudaMalloc(&e->bench_q[i], padded.size() * 4));
+        CU(cudaMemcpy(e->bench_q[i], padded.data(), padded.size() * 4, cudaMemcpyHostToDevice));
+    }
+    e->bench_nq = nq; e->bench_d = d; e->bench_ld = ld;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* gemv_ms, int64_t* launches) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (e->bench_nq == 0 || e->bench_d != g->d) return fail(SVSB_E_SHAPE, "svsb_bench_run: upload queries of the matrix's d first");
+    if (k <= 0 || iters <= 0 || g->n == 0) return fail(SVSB_E_INVALID, "svsb_bench_run: bad arguments");
+    const int64_t kk = std::min<int64_t>(k, g->n);
+    const int nd = (int)e->devs.size();
+    if (nd > 1 && kk > K_FAST_MAX) return fail(SVSB_E_INVALID, "k > 2048 is not supported with more than one device yet");
+    int rc;
+    if (!e->bench_ctx) { if ((rc = ctx_create(e, e->bench_ctx)) != SVSB_OK) return rc; }
+    QueryCtx* c = e->bench_ctx.get();
+    for (int i = 0; i < nd; ++i) if (g->shards[i].n && (rc = prepare_ws(c->ws[i], g.get(), g->shards[i], kk)) != SVSB_OK) return rc;
+    if (nd > 1) {
+        if ((rc = ctx_ensure_gather(e, c, std::max<int64_t>(kk, 128))) != SVSB_OK) return rc;
+        if ((int64_t)nd * c->g_stride > K_FAST_MAX && (rc = c->ws[0].ensure_merge_scratch((int64_t)nd * c->g_stride)) != SVSB_OK) return rc;
+    }
+    const int64_t l0 = g_launches.load();
+    for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaStreamSynchronize(c->ws[i].st)); }
+    for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaEventRecord(c->ws[i].ev0, c->ws[i].st)); }
+    for (int it = 0; it < iters; ++it) {
+        const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
+        for (int i = 0; i < nd; ++i) {
+            if (!g->shards[i].n) continue;
+            CU(cudaSetDevice(c->ws[i].dev));
+            if ((rc = enqueue_local(c->ws[i], g.get(), g->shards[i], e->bench_q[i] + qoff, kk)) != SVSB_OK) return rc;
+        }
+        if (nd > 1 && (rc = enqueue_gather_merge(e, c, g.get(), kk)) != SVSB_OK) return rc;
+    }
+    float best = 0.f;
+    for (int i = 0; i < nd; ++i) {
+        CU(cudaSetDevice(c->ws[i].dev));
+        CU(cudaEventRecord(c->ws[i].ev1, c->ws[i].st));
+    }
+    for (int i = 0; i < nd; ++i) {
+        CU(cudaSetDevice(c->ws[i].dev));
+        CU(cudaEventSynchronize(c->ws[i].ev1));
+        float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ws[i].ev0, c->ws[i].ev1));
+        if (ms > best) best = ms;
+    }
+    if (total_ms) *total_ms = best;
+    if (launches) *launches = g_launches.load() - l0;
+    if (gemv_ms) {
+        // the similarity kernel alone, same queries, same stream (group maxima accumulate; reset afterwards)
+        float gbest = 0.f;
+        for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaEventRecord(c->ws[i].ev0, c->ws[i].st)); }
+        for (int it = 0; it < iters; ++it) {
+            const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
+            for (int i = 0; i < nd; ++i) {
+                const Shard& s = g->shards[i];
+                if (!s.n) continue;
+                DevWs& w = c->ws[i];
+                CU(cudaSetDevice(w.dev));
+                CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[i] + qoff, w.scores, w.gmax, group_shift_for(s.n)));
+            }
+        }
+        for (int i = 0; i < nd; ++i) {
+            DevWs& w = c->ws[i];
+            CU(cudaSetDevice(w.dev));
+            CU(cudaEventRecord(w.ev1, w.st));
+            if (w.gmax) CU(cudaMemsetAsync(w.gmax, 0, (size_t)w.g_cap * 8, w.st));
+        }
+        for (int i = 0; i < nd; ++i) {
+            CU(cudaSetDevice(c->ws[i].dev));
+            CU(cudaStreamSynchronize(c->ws[i].st));
+            float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ws[i].ev0, c->ws[i].ev1));
+            if (ms > gbest) gbest = ms;
+        }
+        *gemv_ms = gbest;
+    }
+    return SVSB_OK;
+}
+
+extern "C" int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, int64_t* launches) {
+    (void)e; (void)k; (void)iters; (void)total_ms; (void)launches;
+    return fail(SVSB_E_INVALID, "svsb_bench_run_batch: the batched tensor-core path is not built yet");
+}
+
+extern "C" int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    if (!e || !e->bench_ctx) return fail(SVSB_E_STATE, "svsb_bench_last_result: no bench run yet");
+    if (!out_scores || !out_emb_ids || !out_count) return fail(SVSB_E_INVALID, "svsb_bench_last_result: NULL buffer");
+    QueryCtx* c = e->bench_ctx.get();
+    DevWs& w0 = c->ws[0];
+    CU(cudaSetDevice(w0.dev));
+    CU(cudaStreamSynchronize(w0.st));
+    const bool multi = e->devs.size() > 1;
+    int32_t cnt = 0;
+    CU(cudaMemcpy(&cnt, multi ? c->m_count : w0.out_count, 4, cudaMemcpyDeviceToHost));
+    if (cnt < 0 || cnt > k) return fail(SVSB_E_INVALID, "svsb_bench_last_result: k smaller than the result");
+    CU(cudaMemcpy(out_scores, multi ? c->m_scores : w0.out_scores, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_emb_ids, multi ? c->m_ids : w0.out_ids, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
+    *out_count = cnt;
+    return SVSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stateless launchers (one process per GPU; torch owns memory and streams)
+// ------------------------------------------------------------------------------------------------
+extern "C" int svsb_ws_create(int device, int64_t n_rows, int32_t k_max, svsb_ws_t** out) {
+    if (!out) return fail(SVSB_E_INVALID, "svsb_ws_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        (void)cudaGetLastError();
+        return fail(SVSB_E_NO_DEVICE, "svsb_ws_create: no such CUDA device; svs_b200 has no CPU path");
+    }
+    if (n_rows < 0 || n_rows > 0xfffffff0ll) return fail(SVSB_E_INVALID, "svsb_ws_create: bad n_rows");
+    std::unique_ptr<svsb_workspace> w(new svsb_workspace());
+    w->dev = device;
+    int rc;
+    if (n_rows > 0 && (rc = w->ensure_rows(n_rows)) != SVSB_OK) { w->release(); return rc; }
+    const int64_t kcap = std::max<int64_t>(k_max, 128);
+    if ((rc = w->ensure_out(kcap)) != SVSB_OK) { w->release(); return rc; }
+    if (k_max > K_FAST_MAX && n_rows > 0 && (rc = w->ensure_sort(n_rows)) != SVSB_OK) { w->release(); return rc; }
+    *out = w.release();
+    return SVSB_OK;
+}
+
+extern "C" void svsb_ws_destroy(svsb_ws_t* ws) {
+    if (!ws) return;
+    ws->release();
+    delete ws;
+}
+
+extern "C" int svsb_launch_local_topk(svsb_ws_t* ws, void* stream, const float* d_matrix, int64_t n, int32_t d,
+                                      int32_t ld, const int64_t* d_emb_ids, int64_t global_row0, const float* d_query,
+                                      int32_t k, uint64_t* d_out_keys, int64_t* d_out_ids, int32_t* d_out_count) {
+    if (!ws) return fail(SVSB_E_INVALID, "workspace is NULL");
+    if (n <= 0 || d <= 0 || ld < d || (ld & 3)) return fail(SVSB_E_INVALID, "svsb_launch_local_topk: bad shape (ld must be a multiple of 4, >= d)");
+    if (k <= 0) return fail(SVSB_E_INVALID, "svsb_launch_local_topk: k must be positive");
+    if (!d_matrix || !d_query || !d_out_keys || !d_out_ids || !d_out_count) return fail(SVSB_E_INVALID, "svsb_launch_local_topk: NULL pointer");
+    const int64_t kk = std::min<int64_t>(k, n);
+    int rc;
+    if ((rc = ws->ensure_rows(n)) != SVSB_OK) return rc;
+    if ((rc = ws->ensure_out(std::max<int64_t>(kk, 128))) != SVSB_OK) return rc;
+    if (kk > K_FAST_MAX && (rc = ws->ensure_sort(n)) != SVSB_OK) return rc;
+    CU(cudaSetDevice(ws->dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int shift = group_shift_for(n);
+    CU(launch_gemv(st, ws->dev, d_matrix, n, d, ld, d_query, ws->scores, ws->gmax, shift));
+    if (kk <= K_FAST_MAX)
+        CU(launch_select(st, ws->scores, n, ws->gmax, shift, (int)kk, d_emb_ids, global_row0, ws->cand, ws->cand_cap,
+                         (u64*)d_out_keys, ws->out_scores, d_out_ids, d_out_count));
+    else
+        CU(launch_fullsort_topk(st, ws->scores, n, ws->gmax, shift, kk, d_emb_ids, global_row0, ws->sortbuf,
+                                (u64*)d_out_keys, ws->out_scores, d_out_ids, d_out_count));
+    return SVSB_OK;
+}
+
+extern "C" int svsb_launch_merge(svsb_ws_t* ws, void* stream, const uint64_t* d_keys, const int64_t* d_ids,
+                                 const int32_t* d_counts, int32_t n_lists, int32_t stride, int32_t k,
+                                 float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_count) {
+    if (!ws) return fail(SVSB_E_INVALID, "workspace is NULL");
+    if (n_lists < 1 || stride < 1 || k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_launch_merge: bad arguments (k <= 2048)");
+    if (!d_keys || !d_ids || !d_counts || !d_out_scores || !d_out_ids || !d_out_count) return fail(SVSB_E_INVALID, "svsb_launch_merge: NULL pointer");
+    int rc;
+    if ((int64_t)n_lists * stride > K_FAST_MAX && (rc = ws->ensure_merge_scratch((int64_t)n_lists * stride)) != SVSB_OK) return rc;
+    CU(cudaSetDevice(ws->dev));
+    CU(launch_merge((cudaStream_t)stream, (const u64*)d_keys, d_ids, d_counts, n_lists, stride, k,
+                    ws->mscr_keys, ws->mscr_ids, d_out_scores, d_out_ids, d_out_count));
+    return SVSB_OK;
+}
+
+extern "C" const char* svsb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* svsb_version(void) { return "svs_b200 0.1.0 (sm_100a)"; }
+extern "C" int64_t svsb_launch_count(void) { return g_launches.load(); }

@@ -1,0 +1,55 @@
+// Internal C++ interface between the engine (engine.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace svsb {
+
+// Launch counter (svsb_launch_count): every kernel launch of the library goes through count_launch().
+void count_launch(int n = 1);
+
+// ---- K1: similarity (fp32 GEMV) -------------------------------------------------------------
+// scores[r] = dot(M[r, :], q) for r < n, and gmax[r >> group_shift] = max(key(score, r)) via atomics.
+// M is row-major with leading dimension ld floats (ld % 4 == 0, rows 16-byte aligned, padding zero);
+// q has ld floats (padding zero).  gmax must be zero on entry.
+// variant: 0 = auto, 1 = LDG.128 streaming kernel, 2 = TMA-bulk (cp.async.bulk + mbarrier ring) kernel.
+// tune_a/tune_b: variant-specific knobs (0 = default), see gemv.cu.
+cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld,
+                        const float* q, float* scores, u64* gmax, int group_shift,
+                        int variant = 0, int tune_a = 0, int tune_b = 0);
+
+// ---- K3/K4: exact top-k ---------------------------------------------------------------------
+// Inputs: scores[n], gmax[ceil(n >> shift)] (consumed and reset to zero), ids[n] (may be null: ids = rows).
+// Outputs (device): out_keys[k] (key with GLOBAL row = row0 + local row), out_scores[k], out_ids[k],
+// *out_count = min(k, n).  cand is scratch of cand_cap entries, cand_cap >= min(n, K_FAST_MAX << shift).
+// Requires 1 <= k <= K_FAST_MAX.
+cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
+                          int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
+                          u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count);
+
+// Large-k path (k > K_FAST_MAX): sort all n keys.  sortbuf has next_pow2(n) entries.  Also zeroes gmax.
+cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
+                                 int64_t k, const int64_t* ids, int64_t row0, u64* sortbuf,
+                                 u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count);
+
+// gmax from a score vector alone (svsb_topk_scores: selection without the GEMV).
+cudaError_t launch_groupmax(cudaStream_t st, int device, const float* scores, int64_t n, u64* gmax, int group_shift);
+
+// Merge n_lists candidate lists (keys carry global rows; ids are the payload) into the top-k.
+// scratch: u64[next_pow2(n_lists * stride)] + int64[same] when n_lists * stride > K_FAST_MAX (else unused).
+cudaError_t launch_merge(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,
+                         int n_lists, int stride, int k, u64* scratch_keys, int64_t* scratch_ids,
+                         float* out_scores, int64_t* out_ids, int32_t* out_count);
+
+// ---- K0: load path ---------------------------------------------------------------------------
+// Row L2 norms; optionally divide rows by their norm.  stats[0] = float bits of max | ||row|| - 1 |
+// (atomicMax on non-negative floats), stats[1] = number of rows with deviation > tol.  stats must be zeroed.
+cudaError_t launch_row_norms(cudaStream_t st, int device, float* M, int64_t n, int d, int ld, int normalize,
+                             float tol, float* norms_or_null, u64* stats);
+// Counter-based synthetic rows (oracle/svs_oracle.py counter_uniform_rows) + ids.
+cudaError_t launch_synth(cudaStream_t st, int device, float* M, int64_t n, int d, int ld, uint64_t seed,
+                         int64_t global_row0, int64_t* ids, int64_t id0, int64_t id_step);
+
+int sm_count(int device);
+inline int64_t next_pow2(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace svsb

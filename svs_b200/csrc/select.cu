@@ -1,0 +1,494 @@
+// K3/K4 -- exact top-k over the fp32 scores, plus the cross-shard candidate merge (K5's compute half).
+//
+// Replaces get_top_k (reference src/svs/util.py:190-203: np.argpartition + sorted) and the
+// `emb_id_lookup[index]` gather (src/svs/kb.py:1188, 1626).
+//
+// Scheme ("group maxima + exact refilter"), all in ONE single-CTA kernel after the GEMV:
+//   The GEMV leaves, next to scores[n], the maximum KEY of every group of m = 2^shift consecutive rows
+//   (G = ceil(n/m) <= 32768 entries).  Let tau be the k-th largest group maximum.  There are k distinct
+//   rows with key >= tau, so tau is a lower bound on the k-th largest key overall, and every row with
+//   key >= tau lives in one of the k groups whose maximum is >= tau.  The kernel therefore
+//     1. finds tau among the G group maxima (range-adaptive radix select in shared memory),
+//     2. rescans only those k groups (k*m scores, not n) and collects the rows with key >= tau
+//        (typically k + a handful; never more than k*m),
+//     3. selects/sorts the candidates exactly (bitonic sort in shared memory), and
+//     4. writes (score, embeddings.id) pairs, resetting the group maxima for the next query.
+//   Keys are unique per row (common.cuh), so the result is the exact top-k under the order
+//   (score desc, row asc) whatever the data looks like -- ties, sorted input, NaNs included.
+//   Work: ~3 passes over G*8 bytes + k*m*4 bytes, all L2 hits; no pass over the n scores.
+//
+// k > K_FAST_MAX (e.g. the notebooks' n = len(kb) full ranking) takes a plain global bitonic sort.
+#include "kernels.cuh"
+
+namespace svsb {
+
+constexpr int SEL_THREADS = 1024;
+constexpr int HIST_BITS = 11;
+constexpr int HIST_BINS = 1 << HIST_BITS;           // 2048
+constexpr int SORT_CAP = K_FAST_MAX;                // 2048 keys sorted in shared memory
+
+struct SelectSmem {
+    u64 sortbuf[SORT_CAP];
+    int64_t payload[SORT_CAP];                       // merge kernel only
+    uint32_t hist[HIST_BINS];
+    u64 red_a[32];
+    u64 red_b[32];
+    u64 bcast64[2];
+    uint32_t counter;
+    int32_t bcast32[4];
+};
+
+__device__ __forceinline__ int bitlen64(u64 v) { return v ? 64 - __clzll((long long)v) : 0; }
+
+// Bitonic sort, descending, of buf[0..npow2) (npow2 a power of two <= SORT_CAP); optional payload.
+template <bool PAYLOAD>
+__device__ void block_bitonic_desc(u64* buf, int64_t* pay, int npow2) {
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const u64 a = buf[i], b = buf[ixj];
+                    const bool desc = ((i & k) == 0);
+                    if (desc ? (a < b) : (a > b)) {
+                        buf[i] = b; buf[ixj] = a;
+                        if (PAYLOAD) { int64_t t = pay[i]; pay[i] = pay[ixj]; pay[ixj] = t; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// kk-th largest (1-based) of keys[0..count), count >= kk >= 1.  All threads of the block call it and
+// all receive the result.  keys may be in global or shared memory.  Uses sm.hist / sm.sortbuf.
+__device__ u64 block_kth_largest(const u64* keys, int64_t count, int kk, SelectSmem& sm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    // pass 0: range of the keys
+    u64 mn = ~0ull, mx = 0ull;
+    for (int64_t i = tid; i < count; i += blockDim.x) { const u64 v = keys[i]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+    mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+    if (lane == 0) { sm.red_a[warp] = mn; sm.red_b[warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+        mn = lane < nwarps ? sm.red_a[lane] : ~0ull;
+        mx = lane < nwarps ? sm.red_b[lane] : 0ull;
+        mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+        if (lane == 0) { sm.bcast64[0] = mn; sm.bcast64[1] = mx; }
+    }
+    __syncthreads();
+    u64 lo = sm.bcast64[0], hi = sm.bcast64[1];
+    int remaining = kk;
+    __syncthreads();
+
+    while (true) {
+        const int shift = max(0, bitlen64(hi - lo) - HIST_BITS);
+        for (int i = tid; i < HIST_BINS; i += blockDim.x) sm.hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < count; i += blockDim.x) {
+            const u64 v = keys[i];
+            if (v >= lo && v <= hi) atomicAdd(&sm.hist[(uint32_t)((v - lo) >> shift)], 1u);
+        }
+        __syncthreads();
+        // find, from the top, the bin where the cumulative count reaches `remaining` (warp 0)
+        if (warp == 0) {
+            constexpr int PER = HIST_BINS / 32;            // 64 bins per lane; lane 0 owns the TOP chunk
+            const int top = HIST_BINS - 1 - lane * PER;    // highest bin of this lane's chunk
+            uint32_t mysum = 0;
+            for (int b = 0; b < PER; ++b) mysum += sm.hist[top - b];
+            uint32_t incl = mysum;                         // inclusive prefix over lanes (top-down)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const uint32_t excl = incl - mysum;
+            const bool mine = (excl < (uint32_t)remaining) && (incl >= (uint32_t)remaining);
+            if (mine) {
+                uint32_t cum = excl; int b = 0;
+                for (; b < PER; ++b) { const uint32_t h = sm.hist[top - b]; if (cum + h >= (uint32_t)remaining) break; cum += h; }
+                sm.bcast32[0] = top - b;                   // the bin
+                sm.bcast32[1] = (int)cum;                  // keys strictly above the bin
+            }
+        }
+        __syncthreads();
+        const int bin = sm.bcast32[0];
+        const int above = sm.bcast32[1];
+        const uint32_t inbin = sm.hist[bin];
+        remaining -= above;
+        const u64 nlo = lo + ((u64)bin << shift);
+        u64 nhi = nlo + (((u64)1 << shift) - 1);
+        if (nhi > hi || nhi < nlo) nhi = hi;
+        lo = nlo; hi = nhi;
+        __syncthreads();
+        if (shift == 0) return lo;                          // bin holds one key value: that is the answer
+        if (inbin <= (uint32_t)SORT_CAP) break;
+    }
+    // finish in shared memory: collect the keys of the final bin and sort them
+    if (tid == 0) sm.counter = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < count; i += blockDim.x) {
+        const u64 v = keys[i];
+        if (v >= lo && v <= hi) { const uint32_t p = atomicAdd(&sm.counter, 1u); if (p < (uint32_t)SORT_CAP) sm.sortbuf[p] = v; }
+    }
+    __syncthreads();
+    const int c = (int)min(sm.counter, (uint32_t)SORT_CAP);
+    int np2 = 1; while (np2 < c) np2 <<= 1;
+    for (int i = c + tid; i < np2; i += blockDim.x) sm.sortbuf[i] = 0ull;
+    __syncthreads();
+    block_bitonic_desc<false>(sm.sortbuf, nullptr, np2);
+    const u64 ans = sm.sortbuf[remaining - 1];
+    __syncthreads();
+    return ans;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The selection kernel (one CTA).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int group_shift,
+                   int k, const int64_t* __restrict__ ids, int64_t row0, u64* cand, int64_t cand_cap,
+                   u64* __restrict__ out_keys, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                   int32_t* __restrict__ out_count)
+{
+    extern __shared__ __align__(16) unsigned char sel_smem_raw[];
+    SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int kk = (int)min((int64_t)k, n);
+    const int64_t G = (n + ((int64_t)1 << group_shift) - 1) >> group_shift;
+    const int64_t m = (int64_t)1 << group_shift;
+
+    // 1. threshold: the kk-th largest group maximum (0 = "every group" when there are <= kk groups)
+    u64 tau = 0;
+    if (G > kk) tau = block_kth_largest(gmax, G, kk, sm);
+
+    // 2. candidates: rows with key >= tau inside the groups whose maximum is >= tau; reset gmax
+    if (tid == 0) sm.counter = 0;
+    __syncthreads();
+    for (int64_t gbase = (int64_t)warp * 32; gbase < G; gbase += (int64_t)nwarps * 32) {
+        const int64_t g = gbase + lane;
+        u64 gm = 0;
+        if (g < G) { gm = gmax[g]; gmax[g] = 0ull; }
+        unsigned hit = __ballot_sync(0xffffffffu, g < G && gm >= tau);
+        while (hit) {
+            const int b = __ffs(hit) - 1; hit &= hit - 1;
+            const int64_t rbeg = (gbase + b) << group_shift;
+            const int64_t rend = min(n, rbeg + m);
+            for (int64_t r = rbeg + lane; r < rbeg + m; r += 32) {     // uniform trip count for the ballot
+                u64 key = 0; bool take = false;
+                if (r < rend) { key = make_key(scores[r], (uint32_t)r); take = key >= tau; }
+                const unsigned msk = __ballot_sync(0xffffffffu, take);
+                if (msk) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.counter, (uint32_t)__popc(msk));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) {
+                        const uint32_t p = base + __popc(msk & ((1u << lane) - 1));
+                        if ((int64_t)p < cand_cap) cand[p] = key;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_block();
+    const int64_t C = min((int64_t)sm.counter, cand_cap);
+    __syncthreads();
+
+    // 3. exact top-kk of the candidates, sorted
+    if (C > SORT_CAP) {
+        // rare (adversarial order / massive ties): second-level select, then keep keys >= tau2
+        const u64 tau2 = block_kth_largest(cand, C, kk, sm);
+        if (tid == 0) sm.counter = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < C; i += blockDim.x) {
+            const u64 v = cand[i];
+            if (v >= tau2) { const uint32_t p = atomicAdd(&sm.counter, 1u); if (p < (uint32_t)SORT_CAP) sm.sortbuf[p] = v; }
+        }
+        __syncthreads();
+    } else {
+        for (int64_t i = tid; i < C; i += blockDim.x) sm.sortbuf[i] = cand[i];
+        if (tid == 0) sm.counter = (uint32_t)C;
+        __syncthreads();
+    }
+    const int c = (int)min(sm.counter, (uint32_t)SORT_CAP);
+    int np2 = 1; while (np2 < c) np2 <<= 1;
+    for (int i = c + tid; i < np2; i += blockDim.x) sm.sortbuf[i] = 0ull;
+    __syncthreads();
+    block_bitonic_desc<false>(sm.sortbuf, nullptr, np2);
+
+    // 4. epilogue: (score, embeddings.id), keys re-based to global rows for the cross-shard merge
+    for (int i = tid; i < kk; i += blockDim.x) {
+        const u64 key = sm.sortbuf[i];
+        const uint32_t row = key_row(key);
+        const int64_t grow = row0 + (int64_t)row;
+        out_keys[i] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
+        out_scores[i] = key_score(key);
+        out_ids[i] = ids ? ids[row] : grow;
+    }
+    if (tid == 0) *out_count = kk;
+}
+
+cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
+                          int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
+                          u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count)
+{
+    if (k < 1 || k > K_FAST_MAX || n < 1) return cudaErrorInvalidValue;
+    static bool attr_set[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem));
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    select_topk_kernel<<<1, SEL_THREADS, sizeof(SelectSmem), st>>>(scores, n, gmax, group_shift, k, ids, row0,
+                                                                  cand, cand_cap, out_keys, out_scores, out_ids, out_count);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// group maxima from a score vector (selection-only entry point)
+// ---------------------------------------------------------------------------------------------
+__global__ void groupmax_kernel(const float* __restrict__ scores, int64_t n, u64* __restrict__ gmax, int group_shift) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nchunks = (n + 31) / 32;                       // 32 rows per warp step; 32 | group size
+    for (int64_t c = warp_global; c < nchunks; c += nwarps) {
+        const int64_t r = c * 32 + lane;
+        u64 key = r < n ? make_key(scores[r], (uint32_t)r) : 0ull;
+        key = warp_max_u64(key);
+        if (lane == 0) atomicMax(&gmax[(c * 32) >> group_shift], key);
+    }
+}
+
+cudaError_t launch_groupmax(cudaStream_t st, int device, const float* scores, int64_t n, u64* gmax, int group_shift) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count(device) * 8;
+    if (blocks > cap) blocks = cap;
+    groupmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(scores, n, gmax, group_shift);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// large-k path: sort every key (global bitonic sort, shared-memory fused inner steps)
+// ---------------------------------------------------------------------------------------------
+constexpr int BS_CHUNK = 2048;                                  // keys per CTA in the fused steps
+constexpr int BS_THREADS = 1024;
+
+__global__ void fs_make_keys_kernel(const float* __restrict__ scores, int64_t n, int64_t np2, u64* __restrict__ keys,
+                                    u64* __restrict__ gmax, int64_t G) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np2; i += stride) {
+        keys[i] = i < n ? make_key(scores[i], (uint32_t)i) : 0ull;
+        if (i < G) gmax[i] = 0ull;
+    }
+}
+// sort each BS_CHUNK-sized chunk completely (k = 2 .. BS_CHUNK); direction alternates per chunk as bitonic needs
+__global__ void __launch_bounds__(BS_THREADS) fs_sort_chunks_kernel(u64* __restrict__ keys) {
+    __shared__ u64 s[BS_CHUNK];
+    const int64_t base = (int64_t)blockIdx.x * BS_CHUNK;
+    for (int i = threadIdx.x; i < BS_CHUNK; i += BS_THREADS) s[i] = keys[base + i];
+    __syncthreads();
+    for (int k = 2; k <= BS_CHUNK; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < BS_CHUNK; i += BS_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int64_t gi = base + i;
+                    const bool desc = ((gi & k) == 0);
+                    const u64 a = s[i], b = s[ixj];
+                    if (desc ? (a < b) : (a > b)) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < BS_CHUNK; i += BS_THREADS) keys[base + i] = s[i];
+}
+// one global compare-exchange step (j >= BS_CHUNK)
+__global__ void fs_global_step_kernel(u64* __restrict__ keys, int64_t np2, int64_t j, int64_t k) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (np2 >> 1); t += stride) {
+        // t enumerates the pairs: insert a zero bit at position log2(j)
+        const int64_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int64_t ixj = i | j;
+        const u64 a = keys[i], b = keys[ixj];
+        const bool desc = ((i & k) == 0);
+        if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+    }
+}
+// the remaining steps j = BS_CHUNK/2 .. 1 of merge level k, fused in shared memory
+__global__ void __launch_bounds__(BS_THREADS) fs_merge_chunks_kernel(u64* __restrict__ keys, int64_t k) {
+    __shared__ u64 s[BS_CHUNK];
+    const int64_t base = (int64_t)blockIdx.x * BS_CHUNK;
+    for (int i = threadIdx.x; i < BS_CHUNK; i += BS_THREADS) s[i] = keys[base + i];
+    __syncthreads();
+    const bool desc = ((base & k) == 0);
+    for (int j = BS_CHUNK >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < BS_CHUNK; i += BS_THREADS) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+                const u64 a = s[i], b = s[ixj];
+                if (desc ? (a < b) : (a > b)) { s[i] = b; s[ixj] = a; }
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < BS_CHUNK; i += BS_THREADS) keys[base + i] = s[i];
+}
+__global__ void fs_emit_kernel(const u64* __restrict__ keys, int64_t kk, const int64_t* __restrict__ ids, int64_t row0,
+                               u64* __restrict__ out_keys, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                               int32_t* __restrict__ out_count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < kk; i += stride) {
+        const u64 key = keys[i];
+        const uint32_t row = key_row(key);
+        const int64_t grow = row0 + (int64_t)row;
+        out_keys[i] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
+        out_scores[i] = key_score(key);
+        out_ids[i] = ids ? ids[row] : grow;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = (int32_t)kk;
+}
+
+cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
+                                 int64_t k, const int64_t* ids, int64_t row0, u64* sortbuf,
+                                 u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count)
+{
+    if (n < 1 || k < 1) return cudaErrorInvalidValue;
+    const int64_t kk = k < n ? k : n;
+    int64_t np2 = next_pow2(n);
+    if (np2 < BS_CHUNK) np2 = BS_CHUNK;
+    const int64_t G = (n + ((int64_t)1 << group_shift) - 1) >> group_shift;
+    const unsigned gblocks = (unsigned)((np2 / 256 < 4096) ? (np2 / 256) : 4096);
+    fs_make_keys_kernel<<<gblocks, 256, 0, st>>>(scores, n, np2, sortbuf, gmax, G);
+    const unsigned chunks = (unsigned)(np2 / BS_CHUNK);
+    fs_sort_chunks_kernel<<<chunks, BS_THREADS, 0, st>>>(sortbuf);
+    int launches = 2;
+    for (int64_t kl = (int64_t)BS_CHUNK << 1; kl <= np2; kl <<= 1) {
+        for (int64_t j = kl >> 1; j >= BS_CHUNK; j >>= 1) {
+            fs_global_step_kernel<<<gblocks, 256, 0, st>>>(sortbuf, np2, j, kl);
+            ++launches;
+        }
+        fs_merge_chunks_kernel<<<chunks, BS_THREADS, 0, st>>>(sortbuf, kl);
+        ++launches;
+    }
+    const unsigned eblocks = (unsigned)((kk + 255) / 256 < 1024 ? (kk + 255) / 256 : 1024);
+    fs_emit_kernel<<<eblocks, 256, 0, st>>>(sortbuf, kk, ids, row0, out_keys, out_scores, out_ids, out_count);
+    count_launch(launches + 1);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-shard merge: n_lists sorted candidate lists -> global top-k   (one CTA)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
+                   int n_lists, int stride, int k, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                   int32_t* __restrict__ out_count)
+{
+    extern __shared__ __align__(16) unsigned char sel_smem_raw[];
+    SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
+    const int tid = threadIdx.x;
+    // total number of valid candidates
+    if (tid == 0) {
+        int64_t tot = 0;
+        for (int l = 0; l < n_lists; ++l) tot += min(counts[l], stride);
+        sm.bcast32[2] = (int32_t)min(tot, (int64_t)0x7fffffff);
+        sm.counter = 0;
+    }
+    __syncthreads();
+    const int total = sm.bcast32[2];              // <= SORT_CAP: the host picks merge_lists_big_kernel otherwise
+    const int kk = min(k, total);
+    const int64_t span = (int64_t)n_lists * stride;
+    {
+        for (int64_t i = tid; i < span; i += blockDim.x) {
+            const int l = (int)(i / stride), p = (int)(i % stride);
+            if (p < min(counts[l], stride)) {
+                const uint32_t slot = atomicAdd(&sm.counter, 1u);
+                sm.sortbuf[slot] = keys[i]; sm.payload[slot] = ids[i];
+            }
+        }
+        __syncthreads();
+        int np2 = 1; while (np2 < total) np2 <<= 1;
+        for (int i = total + tid; i < np2; i += blockDim.x) { sm.sortbuf[i] = 0ull; sm.payload[i] = -1; }
+        __syncthreads();
+        block_bitonic_desc<true>(sm.sortbuf, sm.payload, np2);
+        for (int i = tid; i < kk; i += blockDim.x) { out_scores[i] = key_score(sm.sortbuf[i]); out_ids[i] = sm.payload[i]; }
+        if (tid == 0) *out_count = kk;
+    }
+}
+
+// Generic merge for n_lists * stride > SORT_CAP: compact valid entries into scratch, select, sort.
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+merge_lists_big_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
+                       int n_lists, int stride, int k, u64* sk, int64_t* sp,
+                       float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int32_t* __restrict__ out_count)
+{
+    extern __shared__ __align__(16) unsigned char sel_smem_raw[];
+    SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
+    const int tid = threadIdx.x;
+    if (tid == 0) sm.counter = 0;
+    __syncthreads();
+    const int64_t span = (int64_t)n_lists * stride;
+    for (int64_t i = tid; i < span; i += blockDim.x) {
+        const int l = (int)(i / stride), p = (int)(i % stride);
+        if (p < min(counts[l], stride)) {
+            const uint32_t slot = atomicAdd(&sm.counter, 1u);
+            sk[slot] = keys[i]; sp[slot] = ids[i];
+        }
+    }
+    __syncthreads();
+    __threadfence_block();
+    const int total = (int)sm.counter;
+    const int kk = min(k, total);
+    __syncthreads();
+    if (kk == 0) { if (tid == 0) *out_count = 0; return; }
+    u64 tau = 0;
+    if (total > kk) tau = block_kth_largest(sk, total, kk, sm);
+    if (tid == 0) sm.counter = 0;
+    __syncthreads();
+    for (int i = tid; i < total; i += blockDim.x) {
+        const u64 v = sk[i];
+        if (v >= tau) { const uint32_t slot = atomicAdd(&sm.counter, 1u); if (slot < (uint32_t)SORT_CAP) { sm.sortbuf[slot] = v; sm.payload[slot] = sp[i]; } }
+    }
+    __syncthreads();
+    const int c = (int)min(sm.counter, (uint32_t)SORT_CAP);
+    int np2 = 1; while (np2 < c) np2 <<= 1;
+    for (int i = c + tid; i < np2; i += blockDim.x) { sm.sortbuf[i] = 0ull; sm.payload[i] = -1; }
+    __syncthreads();
+    block_bitonic_desc<true>(sm.sortbuf, sm.payload, np2);
+    for (int i = tid; i < kk; i += blockDim.x) { out_scores[i] = key_score(sm.sortbuf[i]); out_ids[i] = sm.payload[i]; }
+    if (tid == 0) *out_count = kk;
+}
+
+cudaError_t launch_merge(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,
+                         int n_lists, int stride, int k, u64* scratch_keys, int64_t* scratch_ids,
+                         float* out_scores, int64_t* out_ids, int32_t* out_count)
+{
+    if (n_lists < 1 || stride < 1 || k < 1 || k > K_FAST_MAX) return cudaErrorInvalidValue;
+    static bool attr_set[64][2] = {{false}};
+    int dev = 0; cudaGetDevice(&dev);
+    const bool big = (int64_t)n_lists * stride > SORT_CAP;
+    if (dev >= 0 && dev < 64 && !attr_set[dev][big]) {
+        cudaError_t e = big
+            ? cudaFuncSetAttribute(merge_lists_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem))
+            : cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem));
+        if (e != cudaSuccess) return e;
+        attr_set[dev][big] = true;
+    }
+    if (big) {
+        if (!scratch_keys || !scratch_ids) return cudaErrorInvalidValue;
+        merge_lists_big_kernel<<<1, SEL_THREADS, sizeof(SelectSmem), st>>>(keys, ids, counts, n_lists, stride, k,
+                                                                          scratch_keys, scratch_ids, out_scores, out_ids, out_count);
+    } else {
+        merge_lists_kernel<<<1, SEL_THREADS, sizeof(SelectSmem), st>>>(keys, ids, counts, n_lists, stride, k,
+                                                                      out_scores, out_ids, out_count);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace svsb

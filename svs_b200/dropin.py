@@ -1,0 +1,118 @@
+"""Make an imported `svs` package (Rhobota/svs 0.7.x) answer `retrieve` on the GPU.
+
+    import svs, svs_b200
+    svs_b200.install(svs)            # or install(svs, devices=[0, 1, 2, 3])
+    kb = svs.KB('my.sqlite')         # unchanged public API, unchanged SQLite schema
+    kb.retrieve('query', n=100)      # similarity + top-n now run in libsvsb200.so
+
+What is replaced -- and nothing else:
+  * `svs.kb._EmbeddingsMatrix` (reference src/svs/kb.py:856-893) gains a `.device` member, a
+    `DeviceEmbeddingsMatrix`; `invalidate()` drops both caches, so every invalidation site of the
+    reference (kb.py:984,1062,1086,1455,1523,1541) keeps working untouched.  The host NumPy cache
+    stays in place for `document_top_pairwise_scores` (kb.py:1208-1243, 1642-1671), which is out of
+    scope and keeps running the reference's own code.
+  * `KB.retrieve` (kb.py:1608-1640), `AsyncKB.retrieve` (kb.py:1171-1206): same orchestration --
+    cache fetch, query embedding through the magnitude guard, SQL fetch of the n documents -- with the
+    `superheavy()` closure (np.dot + get_top_k + emb_id_lookup) replaced by one engine call.
+  * `AsyncKB.load` (kb.py:964-967) pre-warms the device cache instead of the host one.
+
+INTEGRATION.md shows the same change as a source patch to kb.py for a maintainer who prefers that.
+"""
+from __future__ import annotations
+
+import asyncio
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+
+from .matrix import DeviceEmbeddingsMatrix
+
+_ORIGINALS: dict = {}
+
+
+def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, normalize: bool = False) -> None:
+    """Patch `svs` in place.  Idempotent.  `devices`: CUDA devices to row-shard the matrix over."""
+    if svs_module is None:
+        import svs as svs_module                         # type: ignore  (the host application)
+    kb = svs_module.kb if hasattr(svs_module, "kb") else __import__(svs_module.__name__ + ".kb", fromlist=["kb"])
+    if _ORIGINALS.get("module") is kb:
+        return
+    host_cls = kb._EmbeddingsMatrix
+    log = kb._LOG
+
+    class _EmbeddingsMatrix(host_cls):                   # type: ignore
+        """Host cache (pairwise path, untouched) + device cache (retrieve path)."""
+
+        def __init__(self) -> None:
+            super().__init__()
+            self.device = DeviceEmbeddingsMatrix(devices, normalize)
+
+        def invalidate(self) -> None:
+            super().invalidate()
+            self.device.invalidate()
+
+    def _fetch_docs(q: Any, emb_ids: List[Any], n: int) -> List[Any]:
+        res = []
+        for score, emb_id in emb_ids:
+            doc_id = q.fetch_doc_with_emb_id(emb_id)
+            res.append({'score': score, 'doc': q.fetch_doc(doc_id, include_embedding=False)})
+        log.info(f"retrieved top {n} documents")
+        return res
+
+    def retrieve(self: Any, query: str, n: int) -> List[Any]:
+        log.info(f"retrieving {n} documents with query string: {query}")
+        assert self.db is not None
+        matrix = self.embeddings_matrix.device.get_sync(self.db)
+        func = self._get_embedding_func()
+        awaitable = func([query])
+        assert asyncio.iscoroutine(awaitable)
+        query_vec = np.array(asyncio.run_coroutine_threadsafe(awaitable, self.loop).result()[0], dtype=np.float32)
+        log.info("got embedding for query!")
+        emb_ids = matrix.retrieve(query_vec, n)          # superheavy(), on the GPU
+        log.info(f"computed {matrix.shape[0]} cosine similarities")
+        with self.db as q:
+            return _fetch_docs(q, emb_ids, n)
+
+    async def aretrieve(self: Any, query: str, n: int) -> List[Any]:
+        log.info(f"retrieving {n} documents with query string: {query}")
+        loop = asyncio.get_running_loop()
+        async with self._get_lock():
+            db = await self._ensure_db()
+            matrix = await self.embeddings_matrix.device.get(db)
+        func = await self._get_embedding_func()
+        query_vec = np.array((await func([query]))[0], dtype=np.float32)
+        log.info("got embedding for query!")
+        # the lock is NOT held here (as in the reference): `matrix` pins its generation, so a
+        # concurrent bulk_add/bulk_del may invalidate the cache while this runs
+        emb_ids = await loop.run_in_executor(None, matrix.retrieve, query_vec, n)
+        log.info(f"computed {matrix.shape[0]} cosine similarities")
+        async with self._get_lock():
+            db = await self._ensure_db()
+            async with db as q:
+                return await loop.run_in_executor(None, _fetch_docs, q, emb_ids, n)
+
+    async def aload(self: Any) -> None:
+        async with self._get_lock():
+            db = await self._ensure_db()
+            await self.embeddings_matrix.device.get(db)
+
+    _ORIGINALS.update({
+        "module": kb, "_EmbeddingsMatrix": host_cls, "KB.retrieve": kb.KB.retrieve,
+        "AsyncKB.retrieve": kb.AsyncKB.retrieve, "AsyncKB.load": kb.AsyncKB.load,
+    })
+    kb._EmbeddingsMatrix = _EmbeddingsMatrix
+    kb.KB.retrieve = retrieve
+    kb.AsyncKB.retrieve = aretrieve
+    kb.AsyncKB.load = aload
+
+
+def uninstall() -> None:
+    """Undo install()."""
+    kb = _ORIGINALS.get("module")
+    if kb is None:
+        return
+    kb._EmbeddingsMatrix = _ORIGINALS["_EmbeddingsMatrix"]
+    kb.KB.retrieve = _ORIGINALS["KB.retrieve"]
+    kb.AsyncKB.retrieve = _ORIGINALS["AsyncKB.retrieve"]
+    kb.AsyncKB.load = _ORIGINALS["AsyncKB.load"]
+    _ORIGINALS.clear()

@@ -1,0 +1,249 @@
+"""`Engine`: a thin, torch-free Python face of the C ABI (include/svsb200.h).
+
+Everything numeric happens in libsvsb200.so on the GPU; this module only marshals NumPy buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def _f32c(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Engine:
+    """One engine == one cached device matrix (the replacement of `_EmbeddingsMatrix`' two arrays,
+    reference src/svs/kb.py:856-893) plus the kernels that query it.
+
+    devices: list of CUDA device indices; more than one row-shards the matrix across them.
+    """
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        if devices is None:
+            check(self._lib.svsb_create(None, 0, C.byref(self._h)))
+            self.devices = [0]
+        else:
+            devs = (C.c_int32 * len(devices))(*devices)
+            check(self._lib.svsb_create(devs, len(devices), C.byref(self._h)))
+            self.devices = list(devices)
+
+    # ---- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.svsb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- load path --------------------------------------------------------------------------
+    def load_begin(self, n: int, d: int, normalize: bool = False) -> None:
+        check(self._lib.svsb_load_begin(self._h, n, d, _lib.NORM_NORMALIZE if normalize else _lib.NORM_CHECK))
+
+    def load_rows(self, rows: np.ndarray, emb_ids: np.ndarray) -> None:
+        rows = _f32c(rows)
+        emb_ids = np.ascontiguousarray(emb_ids, dtype=np.int64)
+        if rows.ndim != 2 or emb_ids.ndim != 1 or rows.shape[0] != emb_ids.shape[0]:
+            raise ValueError("rows must be (count, d) and emb_ids (count,)")
+        check(self._lib.svsb_load_rows(self._h, rows.ctypes.data, emb_ids.ctypes.data, rows.shape[0]))
+
+    def acquire_slab(self, d: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Borrow a pinned staging slab: returns (rows_u8 view of capacity*d*4 bytes, ids view)."""
+        p_rows, p_ids, cap = C.c_void_p(), C.c_void_p(), C.c_int64()
+        check(self._lib.svsb_load_acquire_slab(self._h, C.byref(p_rows), C.byref(p_ids), C.byref(cap)))
+        n = cap.value
+        if n == 0:
+            return np.empty(0, dtype=np.uint8), np.empty(0, dtype=np.int64)
+        rows = np.ctypeslib.as_array((C.c_uint8 * (n * d * 4)).from_address(p_rows.value))
+        ids = np.ctypeslib.as_array((C.c_int64 * n).from_address(p_ids.value))
+        return rows, ids
+
+    def commit_slab(self, count: int) -> None:
+        check(self._lib.svsb_load_commit_slab(self._h, count))
+
+    def load_end(self) -> int:
+        gen = C.c_uint64()
+        check(self._lib.svsb_load_end(self._h, C.byref(gen)))
+        return gen.value
+
+    def load_abort(self) -> None:
+        check(self._lib.svsb_load_abort(self._h))
+
+    def load(self, rows: np.ndarray, emb_ids: Optional[np.ndarray] = None, normalize: bool = False) -> int:
+        """Load a whole host matrix (n, d) float32 and its ids (default 0..n-1)."""
+        rows = _f32c(rows)
+        if rows.ndim != 2:
+            raise ValueError("rows must be 2-D")
+        n, d = rows.shape
+        if emb_ids is None:
+            emb_ids = np.arange(n, dtype=np.int64)
+        self.load_begin(n, d, normalize)
+        if n:
+            self.load_rows(rows, emb_ids)
+        return self.load_end()
+
+    def load_chunks(self, n: int, d: int, chunks: Iterable[Tuple[np.ndarray, np.ndarray]], normalize: bool = False) -> int:
+        self.load_begin(n, d, normalize)
+        for rows, ids in chunks:
+            self.load_rows(rows, ids)
+        return self.load_end()
+
+    def load_synthetic(self, n: int, d: int, seed: int = 0, id0: int = 0, id_step: int = 1) -> int:
+        gen = C.c_uint64()
+        check(self._lib.svsb_load_synthetic(self._h, n, d, seed, id0, id_step, C.byref(gen)))
+        return gen.value
+
+    def invalidate(self) -> None:
+        check(self._lib.svsb_invalidate(self._h))
+
+    def is_loaded(self) -> bool:
+        return bool(self._lib.svsb_is_loaded(self._h))
+
+    @property
+    def shape(self) -> Tuple[int, int]:
+        n, d = C.c_int64(), C.c_int32()
+        check(self._lib.svsb_shape(self._h, C.byref(n), C.byref(d)))
+        # the reference's empty matrix has shape (0, 0) (src/svs/kb.py:595-601)
+        return (n.value, d.value)
+
+    def norm_stats(self) -> Tuple[float, int]:
+        dev, bad = C.c_float(), C.c_int64()
+        check(self._lib.svsb_norm_stats(self._h, C.byref(dev), C.byref(bad)))
+        return dev.value, bad.value
+
+    def read_rows(self, row0: int, count: int) -> Tuple[np.ndarray, np.ndarray]:
+        n, d = self.shape
+        rows = np.empty((count, d), dtype=np.float32)
+        ids = np.empty(count, dtype=np.int64)
+        check(self._lib.svsb_read_rows(self._h, row0, count, rows.ctypes.data, ids.ctypes.data))
+        return rows, ids
+
+    # ---- hot path ---------------------------------------------------------------------------
+    def query(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Top-k of M @ q.  Returns (scores float32[c], emb_ids int64[c]), c = min(k, N); k <= 0 -> empty."""
+        q = _f32c(q)
+        if q.ndim != 1:
+            raise ValueError("query vector must be 1-D")
+        cap = max(int(k), 0)
+        scores = np.empty(cap, dtype=np.float32)
+        ids = np.empty(cap, dtype=np.int64)
+        cnt = C.c_int32()
+        check(self._lib.svsb_query(self._h, q.ctypes.data, q.shape[0], int(k), scores.ctypes.data, ids.ctypes.data, C.byref(cnt)))
+        return scores[:cnt.value], ids[:cnt.value]
+
+    def snapshot(self) -> "Snapshot":
+        """Pin the resident generation (the reference's `embeddings_matrix, emb_id_lookup` references)."""
+        return Snapshot(self)
+
+    def query_batch(self, Q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        Q = _f32c(Q)
+        if Q.ndim != 2:
+            raise ValueError("Q must be (b, d)")
+        b, d = Q.shape
+        cap = max(int(k), 0)
+        scores = np.zeros((b, cap), dtype=np.float32)
+        ids = np.full((b, cap), -1, dtype=np.int64)
+        counts = np.zeros(b, dtype=np.int32)
+        check(self._lib.svsb_query_batch(self._h, Q.ctypes.data, b, d, int(k), scores.ctypes.data, ids.ctypes.data, counts.ctypes.data))
+        return scores, ids, counts
+
+    def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
+        """The reference's `superheavy()` result shape: [(score: float, emb_id: int), ...]
+        (src/svs/kb.py:1622-1627)."""
+        scores, ids = self.query(query_vec, n)
+        return [(float(s), int(i)) for s, i in zip(scores, ids)]
+
+    def topk_scores(self, scores: np.ndarray, k: int) -> List[Tuple[float, int]]:
+        """get_top_k (src/svs/util.py:190-203) run by the device selection kernels on a host score
+        vector; ties are ordered by ascending index (the engine's order), not descending."""
+        scores = np.asarray(scores)
+        assert scores.ndim == 1
+        s32 = _f32c(scores)
+        cap = max(min(int(k), len(s32)), 0)
+        out_s = np.empty(cap, dtype=np.float32)
+        out_i = np.empty(cap, dtype=np.int64)
+        cnt = C.c_int32()
+        check(self._lib.svsb_topk_scores(self._h, s32.ctypes.data, len(s32), int(k), out_s.ctypes.data, out_i.ctypes.data, C.byref(cnt)))
+        return [(float(s), int(i)) for s, i in zip(out_s[:cnt.value], out_i[:cnt.value])]
+
+    # ---- measurement ------------------------------------------------------------------------
+    def bench_set_queries(self, Q: np.ndarray) -> None:
+        Q = _f32c(Q)
+        check(self._lib.svsb_bench_set_queries(self._h, Q.ctypes.data, Q.shape[0], Q.shape[1]))
+
+    def bench_run(self, k: int, iters: int, with_gemv: bool = False) -> dict:
+        total, gemv, launches = C.c_float(), C.c_float(), C.c_int64()
+        check(self._lib.svsb_bench_run(self._h, k, iters, C.byref(total), C.byref(gemv) if with_gemv else None, C.byref(launches)))
+        return {"total_ms": total.value, "gemv_ms": gemv.value if with_gemv else None, "launches": launches.value}
+
+    def bench_last_result(self, k: int) -> List[Tuple[float, int]]:
+        s = np.empty(k, dtype=np.float32)
+        i = np.empty(k, dtype=np.int64)
+        cnt = C.c_int32()
+        check(self._lib.svsb_bench_last_result(self._h, k, s.ctypes.data, i.ctypes.data, C.byref(cnt)))
+        return [(float(a), int(b)) for a, b in zip(s[:cnt.value], i[:cnt.value])]
+
+
+class Snapshot:
+    """A pinned generation: queries through it see the matrix that was resident when it was taken,
+    even if the engine has been invalidated or re-loaded since (reference src/svs/kb.py:1178-1190)."""
+
+    def __init__(self, engine: Engine):
+        self._engine = engine
+        self._lib = engine._lib
+        self._s = C.c_void_p()
+        check(self._lib.svsb_snapshot_acquire(engine._h, C.byref(self._s)))
+        n, d, gen = C.c_int64(), C.c_int32(), C.c_uint64()
+        check(self._lib.svsb_snapshot_shape(self._s, C.byref(n), C.byref(d), C.byref(gen)))
+        self.shape = (n.value, d.value if n.value else 0)
+        self.generation = gen.value
+
+    def query(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        q = _f32c(q)
+        if q.ndim != 1:
+            raise ValueError("query vector must be 1-D")
+        if not self._engine._h.value:
+            raise _lib.EngineError(_lib.SVSB_E_STATE, "engine is closed")
+        cap = max(int(k), 0)
+        scores = np.empty(cap, dtype=np.float32)
+        ids = np.empty(cap, dtype=np.int64)
+        cnt = C.c_int32()
+        check(self._lib.svsb_snapshot_query(self._engine._h, self._s, q.ctypes.data, q.shape[0], int(k),
+                                            scores.ctypes.data, ids.ctypes.data, C.byref(cnt)))
+        return scores[:cnt.value], ids[:cnt.value]
+
+    def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
+        scores, ids = self.query(query_vec, n)
+        return [(float(s), int(i)) for s, i in zip(scores, ids)]
+
+    def release(self) -> None:
+        if self._s is not None and self._s.value:
+            self._lib.svsb_snapshot_release(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def launch_count() -> int:
+    return int(_lib.load().svsb_launch_count())
