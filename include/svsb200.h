@@ -120,13 +120,30 @@ int svsb_topk_scores(svsb_t* e, const float* scores, int64_t n, int32_t k,
 int svsb_bench_set_queries(svsb_t* e, const float* Q, int32_t nq, int32_t d);
 /* Run `iters` single-query retrieves back to back, cycling through the uploaded queries, everything
  * device-resident, timed with CUDA events on the launching stream(s).  Returns total milliseconds
- * (max over devices) and, optionally, the milliseconds spent in the similarity kernel alone and the
- * number of kernel launches issued. */
+ * (max over devices), the number of kernel launches issued and, when gemv_ms != NULL, the summed
+ * duration of the similarity-kernel launches on device 0, each bracketed by its own pair of events
+ * inside the same timed loop (the roofline numerator's denominator). */
 int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* gemv_ms, int64_t* launches);
 /* Same through the batched kernel: one launch set per batch of the uploaded queries. */
 int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, int64_t* launches);
 /* Result of the last bench query (for checking that the timed path computes the right thing). */
 int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
+
+/* ---- sharded deployment: one process per GPU -----------------------------
+ * Each process owns ONE device and the rows [global_row0, global_row0 + n) of the matrix, in scan order.
+ * The library does the compute on the caller's stream; the caller (torch.distributed / NCCL) does the one
+ * exchange step: an all-gather of one packed record per query per rank.
+ * Record layout: 2*k+1 int64 words = [ keys (k, uint64: ordered score << 32 | ~global_row) |
+ *                                      embeddings.id (k) | count (int32 in the low half of the last word) ]. */
+int svsb_set_shard(svsb_t* e, int64_t global_row0);           /* call before svsb_load_*          */
+int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, const float* d_query, int32_t k,
+                            int64_t* d_record, int32_t time_kernel);
+/* d_records: all-gathered records, [n_lists][batch][2k+1].  Outputs [batch][k], [batch][k], [batch]. */
+int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
+                               int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts);
+/* Sum (ms) of the similarity-kernel durations bracketed by svsb_enqueue_local_topk(time_kernel=1) since the
+ * last collect; waits for them to finish. */
+int svsb_kernel_time_collect(svsb_t* e, float* ms);
 
 /* ---- stateless launchers on raw device pointers (one process per GPU; pointers may come from
  *      torch tensors' data_ptr(), stream from torch.cuda.current_stream().cuda_stream) ---------- */

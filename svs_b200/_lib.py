@@ -54,6 +54,11 @@ SIGNATURES = {
     "svsb_bench_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, c_i64_p]),
     "svsb_bench_run_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_i64_p]),
     "svsb_bench_last_result": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
+    "svsb_set_shard": (C.c_int, [C.c_void_p, C.c_int64]),
+    "svsb_enqueue_local_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
+    "svsb_enqueue_merge_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "svsb_kernel_time_collect": (C.c_int, [C.c_void_p, c_float_p]),
     "svsb_ws_create": (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
     "svsb_ws_destroy": (None, [C.c_void_p]),
     "svsb_launch_local_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

@@ -50,7 +50,7 @@ __host__ __device__ __forceinline__ float key_score(u64 key) { return ordered_to
 // Largest k the single-CTA selection kernel handles; larger k takes the full-sort path.
 constexpr int K_FAST_MAX = 2048;
 // Target upper bound on the number of row groups whose maxima the selection kernel scans.
-constexpr int64_t GROUPS_TARGET = 32768;
+constexpr int64_t GROUPS_TARGET = 16384;   // fits the selection kernel's shared memory (128 KB of keys)
 constexpr int GROUP_SHIFT_MIN = 6;     // 64 rows per group at least
 
 // rows per group = 1 << shift, chosen so that ceil(n / rows) <= GROUPS_TARGET

@@ -93,6 +93,7 @@ struct svsb_workspace {
             const int shift = group_shift_for(n);
             const int64_t G = (n + ((int64_t)1 << shift) - 1) >> shift;
             int64_t cc = (int64_t)K_FAST_MAX << shift; if (cc > n) cc = n;
+            cc += K_FAST_MAX;                       // room for the overflow path to re-home the sort buffer
             CU(cudaMalloc(&scores, (size_t)n * 4));
             CU(cudaMalloc(&gmax, (size_t)G * 8));
             CU(cudaMemset(gmax, 0, (size_t)G * 8));
@@ -186,6 +187,10 @@ struct svsb_engine {
     // bench state
     std::vector<float*> bench_q; int bench_nq = 0, bench_d = 0, bench_ld = 0;
     std::unique_ptr<QueryCtx> bench_ctx;
+    // sharded deployment (one process per GPU)
+    int64_t shard_row0 = 0;                              // global row of this engine's first row
+    std::vector<std::unique_ptr<DevWs>> shard_ws;        // workspaces for svsb_enqueue_local_topk (by slot)
+    std::vector<cudaEvent_t> kev; size_t kev_used = 0;   // similarity-kernel timing events
 };
 
 static inline int round_up4(int d) { return (d + 3) & ~3; }
@@ -350,6 +355,8 @@ extern "C" void svsb_destroy(svsb_t* e) {
     for (auto& c : e->pool_free) ctx_destroy(e, c.get());
     e->pool_free.clear();
     if (e->bench_ctx) ctx_destroy(e, e->bench_ctx.get());
+    for (auto& w : e->shard_ws) if (w) w->release();
+    for (auto ev : e->kev) cudaEventDestroy(ev);
     for (size_t i = 0; i < e->bench_q.size(); ++i) if (e->bench_q[i]) { cudaSetDevice(e->devs[i]); cudaFree(e->bench_q[i]); }
     free_slabs(e);
     for (size_t i = 0; i < e->copy_st.size(); ++i) { cudaSetDevice(e->devs[i]); cudaStreamDestroy(e->copy_st[i]); }
@@ -368,10 +375,11 @@ static int alloc_generation(svsb_engine* e, int64_t n, int d, std::shared_ptr<Ge
         Shard s; s.dev = e->devs[i];
         s.row0 = std::min(n, i * per);
         s.n = std::min(n, (i + 1) * per) - s.row0;
+        s.row0 += e->shard_row0;                         // keys / synthetic rows are in GLOBAL row numbers
         if (s.n > 0xfffffff0ll) return fail(SVSB_E_INVALID, "more than 2^32 rows per device are not supported");
         g->shards.push_back(s);
     }
-    if (n > 0xfffffff0ll) return fail(SVSB_E_INVALID, "more than 2^32 rows in total are not supported");
+    if (n + e->shard_row0 > 0xfffffff0ll) return fail(SVSB_E_INVALID, "more than 2^32 rows in total are not supported");
     for (auto& s : g->shards) {
         if (s.n == 0 || g->ld == 0) continue;
         CU(cudaSetDevice(s.dev));
@@ -438,7 +446,7 @@ static int slab_flush(svsb_engine* e, Loading* L, Slab& s, int64_t count) {
     Generation* g = L->gen.get();
     int64_t done = 0;
     while (done < count) {
-        const int64_t grow = L->loaded + done;
+        const int64_t grow = L->loaded + done + e->shard_row0;
         size_t si = 0;
         while (si + 1 < g->shards.size() && grow >= g->shards[si].row0 + g->shards[si].n) ++si;
         Shard& sh = g->shards[si];
@@ -636,7 +644,9 @@ extern "C" int svsb_read_rows(svsb_t* e, int64_t row0, int64_t count, float* row
     auto g = pin(e);
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
     if (row0 < 0 || count < 0 || row0 + count > g->n) return fail(SVSB_E_INVALID, "svsb_read_rows: range out of bounds");
-    for (auto& s : g->shards) {
+    const int64_t base = g->shards.empty() ? 0 : g->shards[0].row0;      // local row 0 in global numbering
+    for (auto& s0 : g->shards) {
+        Shard s = s0; s.row0 -= base;
         const int64_t a = std::max(row0, s.row0), b = std::min(row0 + count, s.row0 + s.n);
         if (a >= b) continue;
         CU(cudaSetDevice(s.dev));
@@ -879,6 +889,14 @@ extern "C" int svsb_bench_set_queries(svsb_t* e, const float* Q, int32_t nq, int
     return SVSB_OK;
 }
 
+// Timing events for the similarity kernel inside the timed loop (device 0's stream).
+static std::vector<cudaEvent_t> g_kev;
+static int ensure_kernel_events(int dev, size_t n) {
+    CU(cudaSetDevice(dev));
+    while (g_kev.size() < n) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); g_kev.push_back(ev); }
+    return SVSB_OK;
+}
+
 extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* gemv_ms, int64_t* launches) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     auto g = pin(e);
@@ -896,6 +914,9 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
         if ((rc = ctx_ensure_gather(e, c, std::max<int64_t>(kk, 128))) != SVSB_OK) return rc;
         if ((int64_t)nd * c->g_stride > K_FAST_MAX && (rc = c->ws[0].ensure_merge_scratch((int64_t)nd * c->g_stride)) != SVSB_OK) return rc;
     }
+    // gemv_ms requested: bracket every similarity-kernel launch on device 0 with events INSIDE the timed loop
+    const bool ktime = gemv_ms != nullptr && g->shards[0].n > 0;
+    if (ktime && (rc = ensure_kernel_events(c->ws[0].dev, (size_t)iters * 2)) != SVSB_OK) return rc;
     const int64_t l0 = g_launches.load();
     for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaStreamSynchronize(c->ws[i].st)); }
     for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaEventRecord(c->ws[i].ev0, c->ws[i].st)); }
@@ -904,7 +925,19 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
         for (int i = 0; i < nd; ++i) {
             if (!g->shards[i].n) continue;
             CU(cudaSetDevice(c->ws[i].dev));
-            if ((rc = enqueue_local(c->ws[i], g.get(), g->shards[i], e->bench_q[i] + qoff, kk)) != SVSB_OK) return rc;
+            if (ktime && i == 0) {
+                DevWs& w = c->ws[0]; const Shard& s = g->shards[0];
+                const int shift = group_shift_for(s.n);
+                CU(cudaEventRecord(g_kev[2 * it], w.st));
+                CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, w.scores, w.gmax, shift));
+                CU(cudaEventRecord(g_kev[2 * it + 1], w.st));
+                if (kk <= K_FAST_MAX)
+                    CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
+                                     w.out_keys, w.out_scores, w.out_ids, w.out_count));
+                else
+                    CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
+                                            w.out_keys, w.out_scores, w.out_ids, w.out_count));
+            } else if ((rc = enqueue_local(c->ws[i], g.get(), g->shards[i], e->bench_q[i] + qoff, kk)) != SVSB_OK) return rc;
         }
         if (nd > 1 && (rc = enqueue_gather_merge(e, c, g.get(), kk)) != SVSB_OK) return rc;
     }
@@ -921,34 +954,12 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
     }
     if (total_ms) *total_ms = best;
     if (launches) *launches = g_launches.load() - l0;
-    if (gemv_ms) {
-        // the similarity kernel alone, same queries, same stream (group maxima accumulate; reset afterwards)
-        float gbest = 0.f;
-        for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaEventRecord(c->ws[i].ev0, c->ws[i].st)); }
-        for (int it = 0; it < iters; ++it) {
-            const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
-            for (int i = 0; i < nd; ++i) {
-                const Shard& s = g->shards[i];
-                if (!s.n) continue;
-                DevWs& w = c->ws[i];
-                CU(cudaSetDevice(w.dev));
-                CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[i] + qoff, w.scores, w.gmax, group_shift_for(s.n)));
-            }
-        }
-        for (int i = 0; i < nd; ++i) {
-            DevWs& w = c->ws[i];
-            CU(cudaSetDevice(w.dev));
-            CU(cudaEventRecord(w.ev1, w.st));
-            if (w.gmax) CU(cudaMemsetAsync(w.gmax, 0, (size_t)w.g_cap * 8, w.st));
-        }
-        for (int i = 0; i < nd; ++i) {
-            CU(cudaSetDevice(c->ws[i].dev));
-            CU(cudaStreamSynchronize(c->ws[i].st));
-            float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ws[i].ev0, c->ws[i].ev1));
-            if (ms > gbest) gbest = ms;
-        }
-        *gemv_ms = gbest;
-    }
+    if (ktime) {
+        CU(cudaSetDevice(c->ws[0].dev));
+        float sum = 0.f;
+        for (int it = 0; it < iters; ++it) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, g_kev[2 * it], g_kev[2 * it + 1])); sum += ms; }
+        *gemv_ms = sum;
+    } else if (gemv_ms) *gemv_ms = 0.f;
     return SVSB_OK;
 }
 
@@ -971,6 +982,83 @@ extern "C" int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, i
     CU(cudaMemcpy(out_scores, multi ? c->m_scores : w0.out_scores, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(out_emb_ids, multi ? c->m_ids : w0.out_ids, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
     *out_count = cnt;
+    return SVSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded deployment: one process per GPU, the caller (torch.distributed) owns streams and the exchange
+// ------------------------------------------------------------------------------------------------
+extern "C" int svsb_set_shard(svsb_t* e, int64_t global_row0) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (global_row0 < 0) return fail(SVSB_E_INVALID, "svsb_set_shard: negative row offset");
+    if (e->devs.size() != 1) return fail(SVSB_E_INVALID, "svsb_set_shard: a sharded engine owns exactly one device");
+    e->shard_row0 = global_row0;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, const float* d_query, int32_t k,
+                                       int64_t* d_record, int32_t time_kernel) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (e->devs.size() != 1) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: single-device engines only");
+    if (slot < 0 || slot >= 8) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: slot out of range (0..7)");
+    if (k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: 1 <= k <= 2048");
+    if (!d_query || !d_record) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: NULL pointer");
+    const Shard& s = g->shards[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s.dev));
+    int32_t* d_count = reinterpret_cast<int32_t*>(d_record + 2 * (int64_t)k);
+    if (s.n == 0) { CU(cudaMemsetAsync(d_count, 0, 8, st)); return SVSB_OK; }
+    if ((size_t)slot >= e->shard_ws.size()) e->shard_ws.resize(slot + 1);
+    if (!e->shard_ws[slot]) { e->shard_ws[slot].reset(new DevWs()); e->shard_ws[slot]->dev = s.dev; }
+    DevWs& w = *e->shard_ws[slot];
+    int rc;
+    if ((rc = w.ensure_rows(s.n)) != SVSB_OK) return rc;
+    if ((rc = w.ensure_out(K_FAST_MAX)) != SVSB_OK) return rc;
+    const int shift = group_shift_for(s.n);
+    if (time_kernel) {
+        while (e->kev.size() < e->kev_used + 2) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
+        CU(cudaEventRecord(e->kev[e->kev_used], st));
+    }
+    CU(launch_gemv(st, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift));
+    if (time_kernel) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
+    CU(launch_select(st, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
+                     reinterpret_cast<u64*>(d_record), w.out_scores, d_record + k, d_count));
+    return SVSB_OK;
+}
+
+extern "C" int svsb_kernel_time_collect(svsb_t* e, float* ms) {
+    if (!e || !ms) return fail(SVSB_E_INVALID, "svsb_kernel_time_collect: NULL argument");
+    float sum = 0.f;
+    CU(cudaSetDevice(e->devs[0]));
+    for (size_t i = 0; i + 1 < e->kev_used; i += 2) {
+        CU(cudaEventSynchronize(e->kev[i + 1]));
+        float t = 0.f; CU(cudaEventElapsedTime(&t, e->kev[i], e->kev[i + 1])); sum += t;
+    }
+    e->kev_used = 0;
+    *ms = sum;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
+                                          int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (n_lists < 1 || batch < 1 || k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_enqueue_merge_records: bad arguments");
+    if (!d_records || !d_out_scores || !d_out_ids || !d_out_counts) return fail(SVSB_E_INVALID, "svsb_enqueue_merge_records: NULL pointer");
+    CU(cudaSetDevice(e->devs[0]));
+    const int64_t rec = 2 * (int64_t)k + 1;
+    u64* sk = nullptr; int64_t* sp = nullptr;
+    if ((int64_t)n_lists * k > K_FAST_MAX) {
+        if (e->shard_ws.empty() || !e->shard_ws[0]) { e->shard_ws.resize(std::max<size_t>(1, e->shard_ws.size())); e->shard_ws[0].reset(new DevWs()); e->shard_ws[0]->dev = e->devs[0]; }
+        int rc = e->shard_ws[0]->ensure_merge_scratch((int64_t)batch * n_lists * k);
+        if (rc != SVSB_OK) return rc;
+        sk = e->shard_ws[0]->mscr_keys; sp = e->shard_ws[0]->mscr_ids;
+    }
+    CU(launch_merge_ex((cudaStream_t)stream, reinterpret_cast<const u64*>(d_records), d_records + k,
+                       reinterpret_cast<const int32_t*>(d_records + 2 * (int64_t)k), n_lists, k, k, batch,
+                       (int64_t)batch * rec, rec, (int64_t)batch * rec * 2, rec * 2, sk, sp,
+                       d_out_scores, d_out_ids, d_out_counts));
     return SVSB_OK;
 }
 

@@ -116,7 +116,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
-template <int CW>
+// NQ > 0: each lane keeps its NQ float4 of the query in registers (d4 <= 32 * NQ), so the only shared
+// memory traffic is the row itself (one LDS.128 per 16 bytes streamed).  NQ == 0: query read from smem.
+template <int CW, int NQ>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, int stages,
                 const float* __restrict__ q, float* __restrict__ scores, u64* __restrict__ gmax, int group_shift)
@@ -124,12 +126,13 @@ gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, i
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t row_bytes = (uint32_t)d4 * 16u;
     const uint32_t stage_bytes = (uint32_t)tile_rows * row_bytes;
-    float4* sq = reinterpret_cast<float4*>(smem_raw + (size_t)stages * stage_bytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(sq + d4);
+    float4* sq = reinterpret_cast<float4*>(smem_raw + (size_t)stages * stage_bytes);   // used only when NQ == 0
+    uint64_t* full = reinterpret_cast<uint64_t*>(sq + (NQ == 0 ? d4 : 0));
     uint64_t* empty = full + stages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int c = threadIdx.x; c < d4; c += blockDim.x) sq[c] = reinterpret_cast<const float4*>(q)[c];
+    if (NQ == 0)
+        for (int c = threadIdx.x; c < d4; c += blockDim.x) sq[c] = reinterpret_cast<const float4*>(q)[c];
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -155,7 +158,15 @@ gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, i
             }
         }
     } else {
-        // ---- consumers: warp w takes rows w, w+CW, ... of the tile, two at a time
+        // ---- consumers: warp w takes rows w, w+CW, ... of each tile
+        float4 qr[NQ > 0 ? NQ : 1];
+        if (NQ > 0) {
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                const int c = lane + 32 * j;
+                qr[j] = c < d4 ? reinterpret_cast<const float4*>(q)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         int s = 0; uint32_t phase = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const int64_t r0 = t * tile_rows;
@@ -164,28 +175,28 @@ gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, i
             mbar_wait(&full[s], phase);
             const float4* tile = reinterpret_cast<const float4*>(smem_raw + (size_t)s * stage_bytes);
             u64 kmax = 0;
-            for (int r = warp; r < rows; r += 2 * CW) {
-                const bool two = (r + CW) < rows;
-                const float4* p0 = tile + (size_t)r * d4;
-                const float4* p1 = tile + (size_t)(two ? r + CW : r) * d4;
+            for (int r = warp; r < rows; r += CW) {
+                const float4* p = tile + (size_t)r * d4;
                 float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-#pragma unroll 4
-                for (int c = lane; c < d4; c += 32) {
-                    const float4 qv = sq[c];
-                    fma4(a0, p0[c], qv);
-                    fma4(a1, p1[c], qv);
-                }
-                const float s0 = warp_sum((a0.x + a0.y) + (a0.z + a0.w));
-                const float s1 = warp_sum((a1.x + a1.y) + (a1.z + a1.w));
-                if (lane == 0) {
-                    scores[r0 + r] = s0;
-                    u64 k0 = make_key(s0, (uint32_t)(r0 + r));
-                    kmax = k0 > kmax ? k0 : kmax;
-                    if (two) {
-                        scores[r0 + r + CW] = s1;
-                        u64 k1 = make_key(s1, (uint32_t)(r0 + r + CW));
-                        kmax = k1 > kmax ? k1 : kmax;
+                if (NQ > 0) {
+                    float4 m[NQ > 0 ? NQ : 1];
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) {
+                        const int c = lane + 32 * j;
+                        m[j] = c < d4 ? p[c] : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) { if (j & 1) fma4(a1, m[j], qr[j]); else fma4(a0, m[j], qr[j]); }
+                } else {
+                    int c = lane;
+                    for (; c + 32 < d4; c += 64) { fma4(a0, p[c], sq[c]); fma4(a1, p[c + 32], sq[c + 32]); }
+                    if (c < d4) fma4(a0, p[c], sq[c]);
+                }
+                const float sc = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
+                if (lane == 0) {
+                    scores[r0 + r] = sc;
+                    const u64 k0 = make_key(sc, (uint32_t)(r0 + r));
+                    kmax = k0 > kmax ? k0 : kmax;
                 }
             }
             __syncwarp();
@@ -241,32 +252,52 @@ static cudaError_t run_ldg(cudaStream_t st, int device, const float* M, int64_t 
     return cudaGetLastError();
 }
 
-static cudaError_t run_tma(cudaStream_t st, int device, const float* M, int64_t n, int d4, const float* q,
-                           float* scores, u64* gmax, int group_shift, int tile_rows, int stages)
+template <int CW, int NQ>
+static cudaError_t run_tma_inst(cudaStream_t st, int64_t grid, size_t smem, const float* M, int64_t n, int d4,
+                                int tile_rows, int stages, const float* q, float* scores, u64* gmax, int group_shift)
 {
-    constexpr int CW = 8;
-    auto kern = gemv_tma_kernel<CW>;
+    auto kern = gemv_tma_kernel<CW, NQ>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)grid, (CW + 1) * 32, smem, st>>>(M, n, d4, tile_rows, stages, q, scores, gmax, group_shift);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// tile_rows / stages: 0 = default.  cw: consumer warps (8 or 16; 0 = default).
+static cudaError_t run_tma(cudaStream_t st, int device, const float* M, int64_t n, int d4, const float* q,
+                           float* scores, u64* gmax, int group_shift, int tile_rows, int stages, int cw)
+{
     const size_t row_bytes = (size_t)d4 * 16;
-    const size_t budget = 220 * 1024 - row_bytes - 256;     // ring bytes available next to q + barriers
+    const int nq = d4 <= 64 ? 2 : d4 <= 192 ? 6 : d4 <= 384 ? 12 : d4 <= 768 ? 24 : 0;
+    const size_t q_bytes = nq == 0 ? row_bytes : 0;
+    const size_t budget = 224 * 1024 - q_bytes - 256;       // ring bytes available next to q + barriers
+    // Measured on B200 (profiles/r01_tune_gemv.md): ~48 KB tiles x 3 stages (~144 KB in flight per SM) is
+    // the optimum; deeper rings are SLOWER (more concurrent DRAM streams), shallower ones starve.
     if (tile_rows <= 0) {
-        tile_rows = 64;                                       // target ~48 KB per stage, power of two <= 64
+        tile_rows = 64;                                       // power of two <= 64
         while (tile_rows > 1 && (size_t)tile_rows * row_bytes > 48 * 1024) tile_rows >>= 1;
     }
     if (stages <= 0) {
         stages = (int)(budget / ((size_t)tile_rows * row_bytes));
-        if (stages > 8) stages = 8;
+        if (stages > 3) stages = 3;
     }
-    if (stages < 2 || (size_t)stages * tile_rows * row_bytes > budget) return cudaErrorInvalidConfiguration;
-    const size_t smem = (size_t)stages * tile_rows * row_bytes + row_bytes + (size_t)stages * 16 + 64;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if (tile_rows > 64 || (tile_rows & (tile_rows - 1))) return cudaErrorInvalidConfiguration;
+    if (stages < 2 || stages > 16 || (size_t)stages * tile_rows * row_bytes > budget) return cudaErrorInvalidConfiguration;
+    const size_t smem = (size_t)stages * tile_rows * row_bytes + q_bytes + (size_t)stages * 16 + 64;
     const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
     int64_t grid = sm_count(device);
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, (CW + 1) * 32, smem, st>>>(M, n, d4, tile_rows, stages, q, scores, gmax, group_shift);
-    count_launch();
-    return cudaGetLastError();
+#define SVSB_TMA_CASE(CWV, NQV) \
+    return run_tma_inst<CWV, NQV>(st, grid, smem, M, n, d4, tile_rows, stages, q, scores, gmax, group_shift)
+    if (cw == 16) {
+        switch (nq) { case 2: SVSB_TMA_CASE(16, 2); case 6: SVSB_TMA_CASE(16, 6); case 12: SVSB_TMA_CASE(16, 12);
+                      case 24: SVSB_TMA_CASE(16, 24); default: SVSB_TMA_CASE(16, 0); }
+    }
+    switch (nq) { case 2: SVSB_TMA_CASE(8, 2); case 6: SVSB_TMA_CASE(8, 6); case 12: SVSB_TMA_CASE(8, 12);
+                  case 24: SVSB_TMA_CASE(8, 24); default: SVSB_TMA_CASE(8, 0); }
+#undef SVSB_TMA_CASE
 }
 
 cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld,
@@ -278,16 +309,18 @@ cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, 
     const int d4 = ld / 4;
     if (variant == 0) {
         // rows longer than a TMA stage can hold fall back to the LDG kernel
-        variant = ((size_t)d4 * 16 * 2 <= 200 * 1024) ? 2 : 1;
+        variant = ((size_t)d4 * 16 * 4 <= 200 * 1024) ? 2 : 1;
         // tuning knobs for the measurement harness (profiles/): variant and its two parameters
         if (const char* v = getenv("SVSB_GEMV_VARIANT")) { int x = atoi(v); if (x == 1 || x == 2) variant = x; }
         if (const char* v = getenv("SVSB_GEMV_TUNE_A")) tune_a = atoi(v);
         if (const char* v = getenv("SVSB_GEMV_TUNE_B")) tune_b = atoi(v);
     }
     if (variant == 2) {
-        cudaError_t e = run_tma(st, device, M, n, d4, q, scores, gmax, group_shift, tune_a, tune_b);
+        // tune_a = tile rows, tune_b = stages + 100 * consumer warps (e.g. 1604 = 16 warps, 4 stages)
+        cudaError_t e = run_tma(st, device, M, n, d4, q, scores, gmax, group_shift, tune_a, tune_b % 100, tune_b / 100);
         if (e != cudaErrorInvalidConfiguration) return e;
         (void)cudaGetLastError();
+        tune_a = 0; tune_b = 0;                               // TMA knobs mean nothing to the LDG kernel
     }
     // LDG variant; tune_a selects the (R, U, THREADS) instantiation, tune_b caps blocks per SM
     switch (tune_a) {

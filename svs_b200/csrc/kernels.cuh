@@ -20,7 +20,7 @@ cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, 
 // ---- K3/K4: exact top-k ---------------------------------------------------------------------
 // Inputs: scores[n], gmax[ceil(n >> shift)] (consumed and reset to zero), ids[n] (may be null: ids = rows).
 // Outputs (device): out_keys[k] (key with GLOBAL row = row0 + local row), out_scores[k], out_ids[k],
-// *out_count = min(k, n).  cand is scratch of cand_cap entries, cand_cap >= min(n, K_FAST_MAX << shift).
+// *out_count = min(k, n).  cand is scratch of cand_cap entries, cand_cap >= min(n, K_FAST_MAX << shift) + K_FAST_MAX.
 // Requires 1 <= k <= K_FAST_MAX.
 cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
                           int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
@@ -39,6 +39,14 @@ cudaError_t launch_groupmax(cudaStream_t st, int device, const float* scores, in
 cudaError_t launch_merge(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,
                          int n_lists, int stride, int k, u64* scratch_keys, int64_t* scratch_ids,
                          float* out_scores, int64_t* out_ids, int32_t* out_count);
+
+// Strided / batched form (one CTA per query of the batch); strides in elements.  scratch (big case only):
+// batch * n_lists * cap entries each.
+cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,
+                            int n_lists, int cap, int k, int batch, int64_t list_stride, int64_t batch_stride,
+                            int64_t count_list_stride, int64_t count_batch_stride,
+                            u64* scratch_keys, int64_t* scratch_ids,
+                            float* out_scores, int64_t* out_ids, int32_t* out_count);
 
 // ---- K0: load path ---------------------------------------------------------------------------
 // Row L2 norms; optionally divide rows by their norm.  stats[0] = float bits of max | ||row|| - 1 |

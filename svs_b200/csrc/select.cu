@@ -5,7 +5,7 @@
 //
 // Scheme ("group maxima + exact refilter"), all in ONE single-CTA kernel after the GEMV:
 //   The GEMV leaves, next to scores[n], the maximum KEY of every group of m = 2^shift consecutive rows
-//   (G = ceil(n/m) <= 32768 entries).  Let tau be the k-th largest group maximum.  There are k distinct
+//   (G = ceil(n/m) <= 16384 entries).  Let tau be the k-th largest group maximum.  There are k distinct
 //   rows with key >= tau, so tau is a lower bound on the k-th largest key overall, and every row with
 //   key >= tau lives in one of the k groups whose maximum is >= tau.  The kernel therefore
 //     1. finds tau among the G group maxima (range-adaptive radix select in shared memory),
@@ -15,7 +15,8 @@
 //     4. writes (score, embeddings.id) pairs, resetting the group maxima for the next query.
 //   Keys are unique per row (common.cuh), so the result is the exact top-k under the order
 //   (score desc, row asc) whatever the data looks like -- ties, sorted input, NaNs included.
-//   Work: ~3 passes over G*8 bytes + k*m*4 bytes, all L2 hits; no pass over the n scores.
+//   Work: ONE pass over G*8 bytes (into shared memory; everything after that is on-chip) + k*m*4 bytes of
+//   scores, all L2 hits; no pass over the n scores.  Three dependent global round trips in total.
 //
 // k > K_FAST_MAX (e.g. the notebooks' n = len(kb) full ranking) takes a plain global bitonic sort.
 #include "kernels.cuh"
@@ -63,21 +64,24 @@ __device__ void block_bitonic_desc(u64* buf, int64_t* pay, int npow2) {
 
 // kk-th largest (1-based) of keys[0..count), count >= kk >= 1.  All threads of the block call it and
 // all receive the result.  keys may be in global or shared memory.  Uses sm.hist / sm.sortbuf.
-__device__ u64 block_kth_largest(const u64* keys, int64_t count, int kk, SelectSmem& sm) {
+// have_range: sm.bcast64[0..1] already hold min / max of the keys (saves a pass).
+__device__ u64 block_kth_largest(const u64* keys, int64_t count, int kk, SelectSmem& sm, bool have_range = false) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    // pass 0: range of the keys
-    u64 mn = ~0ull, mx = 0ull;
-    for (int64_t i = tid; i < count; i += blockDim.x) { const u64 v = keys[i]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
-    mn = warp_min_u64(mn); mx = warp_max_u64(mx);
-    if (lane == 0) { sm.red_a[warp] = mn; sm.red_b[warp] = mx; }
-    __syncthreads();
-    if (warp == 0) {
-        mn = lane < nwarps ? sm.red_a[lane] : ~0ull;
-        mx = lane < nwarps ? sm.red_b[lane] : 0ull;
+    if (!have_range) {
+        // pass 0: range of the keys
+        u64 mn = ~0ull, mx = 0ull;
+        for (int64_t i = tid; i < count; i += blockDim.x) { const u64 v = keys[i]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
         mn = warp_min_u64(mn); mx = warp_max_u64(mx);
-        if (lane == 0) { sm.bcast64[0] = mn; sm.bcast64[1] = mx; }
+        if (lane == 0) { sm.red_a[warp] = mn; sm.red_b[warp] = mx; }
+        __syncthreads();
+        if (warp == 0) {
+            mn = lane < nwarps ? sm.red_a[lane] : ~0ull;
+            mx = lane < nwarps ? sm.red_b[lane] : 0ull;
+            mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+            if (lane == 0) { sm.bcast64[0] = mn; sm.bcast64[1] = mx; }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     u64 lo = sm.bcast64[0], hi = sm.bcast64[1];
     int remaining = kk;
     __syncthreads();
@@ -143,6 +147,15 @@ __device__ u64 block_kth_largest(const u64* keys, int64_t count, int kk, SelectS
 // ---------------------------------------------------------------------------------------------
 // The selection kernel (one CTA).
 // ---------------------------------------------------------------------------------------------
+constexpr int SEL_KEYS_CAP = (int)GROUPS_TARGET;     // group maxima staged in shared memory
+constexpr int SEL_KEYS_PER_THREAD = SEL_KEYS_CAP / SEL_THREADS;   // 16
+
+struct SelectKeysSmem {
+    SelectSmem base;
+    u64 keys[SEL_KEYS_CAP];
+    uint32_t hits[K_FAST_MAX];
+};
+
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int group_shift,
                    int k, const int64_t* __restrict__ ids, int64_t row0, u64* cand, int64_t cand_cap,
@@ -150,73 +163,95 @@ select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int g
                    int32_t* __restrict__ out_count)
 {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
-    SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
+    SelectKeysSmem& big = *reinterpret_cast<SelectKeysSmem*>(sel_smem_raw);
+    SelectSmem& sm = big.base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int kk = (int)min((int64_t)k, n);
-    const int64_t G = (n + ((int64_t)1 << group_shift) - 1) >> group_shift;
-    const int64_t m = (int64_t)1 << group_shift;
+    const int G = (int)((n + ((int64_t)1 << group_shift) - 1) >> group_shift);    // <= SEL_KEYS_CAP
+    const int m = 1 << group_shift;
 
-    // 1. threshold: the kk-th largest group maximum (0 = "every group" when there are <= kk groups)
+    // 1. one pass over the group maxima: global -> registers (independent loads) -> shared; reset them;
+    //    min / max on the way
+    {
+        u64 r[SEL_KEYS_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < SEL_KEYS_PER_THREAD; ++j) { const int i = tid + j * SEL_THREADS; r[j] = i < G ? gmax[i] : 0ull; }
+        u64 mn = ~0ull, mx = 0ull;
+#pragma unroll
+        for (int j = 0; j < SEL_KEYS_PER_THREAD; ++j) {
+            const int i = tid + j * SEL_THREADS;
+            if (i < G) { big.keys[i] = r[j]; gmax[i] = 0ull; mn = r[j] < mn ? r[j] : mn; mx = r[j] > mx ? r[j] : mx; }
+        }
+        mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+        if (lane == 0) { sm.red_a[warp] = mn; sm.red_b[warp] = mx; }
+        if (tid == 0) sm.counter = 0;
+        __syncthreads();
+        if (warp == 0) {
+            mn = lane < nwarps ? sm.red_a[lane] : ~0ull;
+            mx = lane < nwarps ? sm.red_b[lane] : 0ull;
+            mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+            if (lane == 0) { sm.bcast64[0] = mn; sm.bcast64[1] = mx; }
+        }
+        __syncthreads();
+    }
+
+    // 2. threshold: the kk-th largest group maximum (0 = "every group" when there are <= kk groups)
     u64 tau = 0;
-    if (G > kk) tau = block_kth_largest(gmax, G, kk, sm);
+    if (G > kk) tau = block_kth_largest(big.keys, G, kk, sm, /*have_range=*/true);
 
-    // 2. candidates: rows with key >= tau inside the groups whose maximum is >= tau; reset gmax
+    // 3. the groups whose maximum reaches tau (exactly kk of them, or all G)
     if (tid == 0) sm.counter = 0;
     __syncthreads();
-    for (int64_t gbase = (int64_t)warp * 32; gbase < G; gbase += (int64_t)nwarps * 32) {
-        const int64_t g = gbase + lane;
-        u64 gm = 0;
-        if (g < G) { gm = gmax[g]; gmax[g] = 0ull; }
-        unsigned hit = __ballot_sync(0xffffffffu, g < G && gm >= tau);
-        while (hit) {
-            const int b = __ffs(hit) - 1; hit &= hit - 1;
-            const int64_t rbeg = (gbase + b) << group_shift;
-            const int64_t rend = min(n, rbeg + m);
-            for (int64_t r = rbeg + lane; r < rbeg + m; r += 32) {     // uniform trip count for the ballot
-                u64 key = 0; bool take = false;
-                if (r < rend) { key = make_key(scores[r], (uint32_t)r); take = key >= tau; }
-                const unsigned msk = __ballot_sync(0xffffffffu, take);
-                if (msk) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&sm.counter, (uint32_t)__popc(msk));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (take) {
-                        const uint32_t p = base + __popc(msk & ((1u << lane) - 1));
-                        if ((int64_t)p < cand_cap) cand[p] = key;
-                    }
-                }
+    for (int i = tid; i < G; i += SEL_THREADS)
+        if (big.keys[i] >= tau) { const uint32_t p = atomicAdd(&sm.counter, 1u); if (p < (uint32_t)K_FAST_MAX) big.hits[p] = (uint32_t)i; }
+    __syncthreads();
+    const int nhits = (int)min(sm.counter, (uint32_t)K_FAST_MAX);
+    __syncthreads();
+
+    // 4. candidates: rows of those groups with key >= tau (flattened: independent, coalesced loads).
+    //    The first SORT_CAP go straight into the sort buffer; any overflow goes to `cand` in global memory.
+    if (tid == 0) sm.counter = 0;
+    __syncthreads();
+    const int64_t items = (int64_t)nhits << group_shift;
+    for (int64_t it = tid; it < items; it += SEL_THREADS) {
+        const int64_t r = ((int64_t)big.hits[it >> group_shift] << group_shift) + (it & (m - 1));
+        if (r < n) {
+            const u64 key = make_key(scores[r], (uint32_t)r);
+            if (key >= tau) {
+                const uint32_t p = atomicAdd(&sm.counter, 1u);
+                if (p < (uint32_t)SORT_CAP) sm.sortbuf[p] = key;
+                else if ((int64_t)(p - SORT_CAP) < cand_cap) cand[p - SORT_CAP] = key;
             }
         }
     }
     __syncthreads();
-    __threadfence_block();
-    const int64_t C = min((int64_t)sm.counter, cand_cap);
+    const int64_t C = (int64_t)sm.counter;
     __syncthreads();
 
-    // 3. exact top-kk of the candidates, sorted
+    // 5. exact top-kk of the candidates, sorted
     if (C > SORT_CAP) {
-        // rare (adversarial order / massive ties): second-level select, then keep keys >= tau2
-        const u64 tau2 = block_kth_largest(cand, C, kk, sm);
+        // rare (adversarial order / massive ties): move everything to `cand`, second-level select there
+        const int64_t over = min(C - SORT_CAP, cand_cap - SORT_CAP);
+        for (int i = tid; i < SORT_CAP; i += SEL_THREADS) cand[over + i] = sm.sortbuf[i];
+        __syncthreads();
+        const int64_t total = over + SORT_CAP;
+        const u64 tau2 = block_kth_largest(cand, total, kk, sm);
         if (tid == 0) sm.counter = 0;
         __syncthreads();
-        for (int64_t i = tid; i < C; i += blockDim.x) {
+        for (int64_t i = tid; i < total; i += SEL_THREADS) {
             const u64 v = cand[i];
             if (v >= tau2) { const uint32_t p = atomicAdd(&sm.counter, 1u); if (p < (uint32_t)SORT_CAP) sm.sortbuf[p] = v; }
         }
         __syncthreads();
-    } else {
-        for (int64_t i = tid; i < C; i += blockDim.x) sm.sortbuf[i] = cand[i];
-        if (tid == 0) sm.counter = (uint32_t)C;
-        __syncthreads();
     }
     const int c = (int)min(sm.counter, (uint32_t)SORT_CAP);
     int np2 = 1; while (np2 < c) np2 <<= 1;
-    for (int i = c + tid; i < np2; i += blockDim.x) sm.sortbuf[i] = 0ull;
+    for (int i = c + tid; i < np2; i += SEL_THREADS) sm.sortbuf[i] = 0ull;
     __syncthreads();
     block_bitonic_desc<false>(sm.sortbuf, nullptr, np2);
 
-    // 4. epilogue: (score, embeddings.id), keys re-based to global rows for the cross-shard merge
-    for (int i = tid; i < kk; i += blockDim.x) {
+    // 6. epilogue: (score, embeddings.id), keys re-based to global rows for the cross-shard merge
+    for (int i = tid; i < kk; i += SEL_THREADS) {
         const u64 key = sm.sortbuf[i];
         const uint32_t row = key_row(key);
         const int64_t grow = row0 + (int64_t)row;
@@ -235,11 +270,12 @@ cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* 
     static bool attr_set[64] = {false};
     int dev = 0; cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem));
+        cudaError_t e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectKeysSmem));
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    select_topk_kernel<<<1, SEL_THREADS, sizeof(SelectSmem), st>>>(scores, n, gmax, group_shift, k, ids, row0,
+    if (((n + ((int64_t)1 << group_shift) - 1) >> group_shift) > SEL_KEYS_CAP) return cudaErrorInvalidValue;
+    select_topk_kernel<<<1, SEL_THREADS, sizeof(SelectKeysSmem), st>>>(scores, n, gmax, group_shift, k, ids, row0,
                                                                   cand, cand_cap, out_keys, out_scores, out_ids, out_count);
     count_launch();
     return cudaGetLastError();
@@ -382,70 +418,81 @@ cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n
 }
 
 // ---------------------------------------------------------------------------------------------
-// cross-shard merge: n_lists sorted candidate lists -> global top-k   (one CTA)
+// cross-shard merge: n_lists candidate lists per query -> global top-k.  One CTA per query of the batch.
+//
+// Layout (all strides in ELEMENTS of the respective array): list l of query b has its keys at
+// keys[l*list_stride + b*batch_stride + 0..cap), its ids at ids[same], and its valid count at
+// counts[l*count_list_stride + b*count_batch_stride].  Outputs: out_*[b*k + 0..k), out_count[b].
+// This covers both callers: the in-process engine (separate arrays, batch = 1) and the NCCL path
+// (one packed int64 record [keys(k) | ids(k) | count] per query per rank, all-gathered).
 // ---------------------------------------------------------------------------------------------
+struct MergeLayout {
+    int n_lists, cap, k;
+    int64_t list_stride, batch_stride, count_list_stride, count_batch_stride;
+};
+
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
-                   int n_lists, int stride, int k, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                   MergeLayout L, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
                    int32_t* __restrict__ out_count)
 {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
-    const int tid = threadIdx.x;
-    // total number of valid candidates
-    if (tid == 0) {
-        int64_t tot = 0;
-        for (int l = 0; l < n_lists; ++l) tot += min(counts[l], stride);
-        sm.bcast32[2] = (int32_t)min(tot, (int64_t)0x7fffffff);
-        sm.counter = 0;
+    const int tid = threadIdx.x, b = blockIdx.x;
+    keys += (int64_t)b * L.batch_stride; ids += (int64_t)b * L.batch_stride;
+    counts += (int64_t)b * L.count_batch_stride;
+    out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
+    if (tid == 0) sm.counter = 0;
+    __syncthreads();
+    const int span = L.n_lists * L.cap;                       // <= SORT_CAP (host guarantees)
+    for (int i = tid; i < span; i += blockDim.x) {
+        const int l = i / L.cap, p = i - l * L.cap;
+        if (p < min(counts[(int64_t)l * L.count_list_stride], L.cap)) {
+            const uint32_t slot = atomicAdd(&sm.counter, 1u);
+            sm.sortbuf[slot] = keys[(int64_t)l * L.list_stride + p];
+            sm.payload[slot] = ids[(int64_t)l * L.list_stride + p];
+        }
     }
     __syncthreads();
-    const int total = sm.bcast32[2];              // <= SORT_CAP: the host picks merge_lists_big_kernel otherwise
-    const int kk = min(k, total);
-    const int64_t span = (int64_t)n_lists * stride;
-    {
-        for (int64_t i = tid; i < span; i += blockDim.x) {
-            const int l = (int)(i / stride), p = (int)(i % stride);
-            if (p < min(counts[l], stride)) {
-                const uint32_t slot = atomicAdd(&sm.counter, 1u);
-                sm.sortbuf[slot] = keys[i]; sm.payload[slot] = ids[i];
-            }
-        }
-        __syncthreads();
-        int np2 = 1; while (np2 < total) np2 <<= 1;
-        for (int i = total + tid; i < np2; i += blockDim.x) { sm.sortbuf[i] = 0ull; sm.payload[i] = -1; }
-        __syncthreads();
-        block_bitonic_desc<true>(sm.sortbuf, sm.payload, np2);
-        for (int i = tid; i < kk; i += blockDim.x) { out_scores[i] = key_score(sm.sortbuf[i]); out_ids[i] = sm.payload[i]; }
-        if (tid == 0) *out_count = kk;
-    }
+    const int total = (int)sm.counter;
+    const int kk = min(L.k, total);
+    int np2 = 1; while (np2 < total) np2 <<= 1;
+    for (int i = total + tid; i < np2; i += blockDim.x) { sm.sortbuf[i] = 0ull; sm.payload[i] = -1; }
+    __syncthreads();
+    block_bitonic_desc<true>(sm.sortbuf, sm.payload, np2);
+    for (int i = tid; i < kk; i += blockDim.x) { out_scores[i] = key_score(sm.sortbuf[i]); out_ids[i] = sm.payload[i]; }
+    if (tid == 0) out_count[b] = kk;
 }
 
-// Generic merge for n_lists * stride > SORT_CAP: compact valid entries into scratch, select, sort.
+// Generic merge for n_lists * cap > SORT_CAP: compact valid entries into scratch, select, sort.
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 merge_lists_big_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
-                       int n_lists, int stride, int k, u64* sk, int64_t* sp,
-                       float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int32_t* __restrict__ out_count)
+                       MergeLayout L, u64* sk, int64_t* sp, float* __restrict__ out_scores,
+                       int64_t* __restrict__ out_ids, int32_t* __restrict__ out_count)
 {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int64_t span = (int64_t)L.n_lists * L.cap;
+    keys += (int64_t)b * L.batch_stride; ids += (int64_t)b * L.batch_stride;
+    counts += (int64_t)b * L.count_batch_stride;
+    out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
+    sk += (int64_t)b * span; sp += (int64_t)b * span;
     if (tid == 0) sm.counter = 0;
     __syncthreads();
-    const int64_t span = (int64_t)n_lists * stride;
     for (int64_t i = tid; i < span; i += blockDim.x) {
-        const int l = (int)(i / stride), p = (int)(i % stride);
-        if (p < min(counts[l], stride)) {
+        const int l = (int)(i / L.cap), p = (int)(i - (int64_t)l * L.cap);
+        if (p < min(counts[(int64_t)l * L.count_list_stride], L.cap)) {
             const uint32_t slot = atomicAdd(&sm.counter, 1u);
-            sk[slot] = keys[i]; sp[slot] = ids[i];
+            sk[slot] = keys[(int64_t)l * L.list_stride + p];
+            sp[slot] = ids[(int64_t)l * L.list_stride + p];
         }
     }
     __syncthreads();
-    __threadfence_block();
     const int total = (int)sm.counter;
-    const int kk = min(k, total);
+    const int kk = min(L.k, total);
     __syncthreads();
-    if (kk == 0) { if (tid == 0) *out_count = 0; return; }
+    if (kk == 0) { if (tid == 0) out_count[b] = 0; return; }
     u64 tau = 0;
     if (total > kk) tau = block_kth_largest(sk, total, kk, sm);
     if (tid == 0) sm.counter = 0;
@@ -461,17 +508,19 @@ merge_lists_big_kernel(const u64* __restrict__ keys, const int64_t* __restrict__
     __syncthreads();
     block_bitonic_desc<true>(sm.sortbuf, sm.payload, np2);
     for (int i = tid; i < kk; i += blockDim.x) { out_scores[i] = key_score(sm.sortbuf[i]); out_ids[i] = sm.payload[i]; }
-    if (tid == 0) *out_count = kk;
+    if (tid == 0) out_count[b] = kk;
 }
 
-cudaError_t launch_merge(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,
-                         int n_lists, int stride, int k, u64* scratch_keys, int64_t* scratch_ids,
-                         float* out_scores, int64_t* out_ids, int32_t* out_count)
+cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,
+                            int n_lists, int cap, int k, int batch, int64_t list_stride, int64_t batch_stride,
+                            int64_t count_list_stride, int64_t count_batch_stride,
+                            u64* scratch_keys, int64_t* scratch_ids,
+                            float* out_scores, int64_t* out_ids, int32_t* out_count)
 {
-    if (n_lists < 1 || stride < 1 || k < 1 || k > K_FAST_MAX) return cudaErrorInvalidValue;
+    if (n_lists < 1 || cap < 1 || k < 1 || k > K_FAST_MAX || batch < 1) return cudaErrorInvalidValue;
     static bool attr_set[64][2] = {{false}};
     int dev = 0; cudaGetDevice(&dev);
-    const bool big = (int64_t)n_lists * stride > SORT_CAP;
+    const bool big = (int64_t)n_lists * cap > SORT_CAP;
     if (dev >= 0 && dev < 64 && !attr_set[dev][big]) {
         cudaError_t e = big
             ? cudaFuncSetAttribute(merge_lists_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem))
@@ -479,16 +528,24 @@ cudaError_t launch_merge(cudaStream_t st, const u64* keys, const int64_t* ids, c
         if (e != cudaSuccess) return e;
         attr_set[dev][big] = true;
     }
+    MergeLayout L{n_lists, cap, k, list_stride, batch_stride, count_list_stride, count_batch_stride};
     if (big) {
         if (!scratch_keys || !scratch_ids) return cudaErrorInvalidValue;
-        merge_lists_big_kernel<<<1, SEL_THREADS, sizeof(SelectSmem), st>>>(keys, ids, counts, n_lists, stride, k,
-                                                                          scratch_keys, scratch_ids, out_scores, out_ids, out_count);
+        merge_lists_big_kernel<<<batch, SEL_THREADS, sizeof(SelectSmem), st>>>(keys, ids, counts, L, scratch_keys, scratch_ids,
+                                                                              out_scores, out_ids, out_count);
     } else {
-        merge_lists_kernel<<<1, SEL_THREADS, sizeof(SelectSmem), st>>>(keys, ids, counts, n_lists, stride, k,
-                                                                      out_scores, out_ids, out_count);
+        merge_lists_kernel<<<batch, SEL_THREADS, sizeof(SelectSmem), st>>>(keys, ids, counts, L, out_scores, out_ids, out_count);
     }
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t launch_merge(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,
+                         int n_lists, int stride, int k, u64* scratch_keys, int64_t* scratch_ids,
+                         float* out_scores, int64_t* out_ids, int32_t* out_count)
+{
+    return launch_merge_ex(st, keys, ids, counts, n_lists, stride, k, 1, stride, 0, 1, 0,
+                           scratch_keys, scratch_ids, out_scores, out_ids, out_count);
 }
 
 }  // namespace svsb

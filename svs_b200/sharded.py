@@ -1,0 +1,187 @@
+"""Row-sharded retrieve, one process per GPU (BASELINE.json north star item 4).
+
+Rank r owns the contiguous rows [r*ceil(N/G), min(N, (r+1)*ceil(N/G))) of the scan order together with
+their embeddings.ids.  A query is answered by
+  1. every rank: similarity + exact local top-k on its shard (libsvsb200.so, on the caller's stream),
+     written as ONE packed int64 record [keys(k) | ids(k) | count];
+  2. the ONE exchange step: `all_gather_into_tensor` of those records (NCCL over NVLink/NVSwitch;
+     k=100 -> 1.6 KB per rank per query), micro-batched over several queries per collective;
+  3. every rank: one merge kernel per micro-batch (one CTA per query) -> global top-k under the same
+     total order (score desc, global row asc), so all ranks hold the identical answer.
+No reduction over scores is needed: rows are independent (splitting D instead would need an all-reduce
+of N floats).
+
+The collective / packing / batching logic is backend-agnostic so that it can be exercised on CPU with
+`gloo` (tests/test_sharded_gloo.py injects a NumPy backend); the product backend is `CudaShardBackend`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+MICRO_BATCH = 8
+
+
+def partition(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """(first global row, row count) of `rank`'s shard: contiguous ranges of the scan order."""
+    per = (n + world - 1) // world
+    row0 = min(n, rank * per)
+    return row0, min(n, (rank + 1) * per) - row0
+
+
+class CudaShardBackend:
+    """The shard's compute, on `cuda:device_index`, through the C ABI.  Torch owns streams and buffers."""
+
+    def __init__(self, device_index: int):
+        import torch
+        from . import _lib
+        from .engine import Engine
+        self.torch = torch
+        self._lib = _lib.load()
+        self._check = _lib.check
+        self.device = torch.device("cuda", device_index)
+        self.engine = Engine([device_index])
+        self.d = 0
+        self.ld = 0
+
+    # -- data ------------------------------------------------------------------------------------
+    def set_shard(self, global_row0: int) -> None:
+        self._check(self._lib.svsb_set_shard(self.engine._h, global_row0))
+
+    def load_rows(self, rows: np.ndarray, emb_ids: np.ndarray) -> None:
+        self.engine.load(rows, emb_ids)
+        self.d = rows.shape[1]
+        self.ld = (self.d + 3) & ~3
+
+    def load_synthetic(self, n_local: int, d: int, seed: int, id0: int, id_step: int) -> None:
+        self.engine.load_synthetic(n_local, d, seed, id0, id_step)
+        self.d = d
+        self.ld = (d + 3) & ~3
+
+    def device_queries(self, Q: np.ndarray):
+        """(nq, d) host float32 -> (nq, ld) device tensor, zero padded."""
+        t = self.torch
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        host = t.zeros((Q.shape[0], self.ld), dtype=t.float32).pin_memory()
+        host[:, :Q.shape[1]] = t.from_numpy(Q)
+        return host.to(self.device, non_blocking=True)
+
+    def new_records(self, count: int, k: int):
+        return self.torch.zeros((count, 2 * k + 1), dtype=self.torch.int64, device=self.device)
+
+    def new_outputs(self, count: int, k: int):
+        t = self.torch
+        return (t.zeros((count, k), dtype=t.float32, device=self.device),
+                t.zeros((count, k), dtype=t.int64, device=self.device),
+                t.zeros((count,), dtype=t.int32, device=self.device))
+
+    # -- compute ---------------------------------------------------------------------------------
+    def enqueue_local(self, query_row, k: int, record_row, time_kernel: bool = False) -> None:
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_enqueue_local_topk(self.engine._h, C.c_void_p(st), 0, C.c_void_p(query_row.data_ptr()),
+                                                      k, C.c_void_p(record_row.data_ptr()), 1 if time_kernel else 0))
+
+    def enqueue_merge(self, gathered, n_lists: int, batch: int, k: int, out_scores, out_ids, out_counts) -> None:
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_enqueue_merge_records(self.engine._h, C.c_void_p(st), C.c_void_p(gathered.data_ptr()),
+                                                         n_lists, batch, k, C.c_void_p(out_scores.data_ptr()),
+                                                         C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_counts.data_ptr())))
+
+    def collect_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.svsb_kernel_time_collect(self.engine._h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self) -> None:
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self) -> None:
+        self.engine.close()
+
+
+class ShardedRetriever:
+    """All ranks construct one and call the same methods in the same order (SPMD)."""
+
+    def __init__(self, rank: int, world: int, device_index: int = 0, backend=None, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world, self.group = rank, world, group
+        self.backend = backend if backend is not None else CudaShardBackend(device_index)
+        self.n = 0
+        self.d = 0
+        self.row0 = 0
+        self.local_rows = 0
+        self._queries = None
+        self._bufs = {}
+
+    # -- load ------------------------------------------------------------------------------------
+    def load_synthetic(self, n: int, d: int, seed: int = 0, id0: int = 0, id_step: int = 1) -> None:
+        self.n, self.d = n, d
+        self.row0, self.local_rows = partition(n, self.world, self.rank)
+        self.backend.set_shard(self.row0)
+        self.backend.load_synthetic(self.local_rows, d, seed, id0, id_step)
+
+    def load_global(self, rows: np.ndarray, emb_ids: np.ndarray) -> None:
+        """Every rank passes the same global (n, d) matrix / ids and keeps only its slice (tests, small KBs)."""
+        self.n, self.d = rows.shape
+        self.row0, self.local_rows = partition(self.n, self.world, self.rank)
+        self.backend.set_shard(self.row0)
+        sl = slice(self.row0, self.row0 + self.local_rows)
+        self.backend.load_rows(np.ascontiguousarray(rows[sl]), np.ascontiguousarray(emb_ids[sl]))
+
+    # -- queries ---------------------------------------------------------------------------------
+    def set_queries(self, Q: np.ndarray) -> None:
+        self._queries = self.backend.device_queries(Q)
+
+    def _buffers(self, k: int):
+        if k not in self._bufs:
+            rec = self.backend.new_records(MICRO_BATCH, k)
+            gath = self.backend.new_records(self.world * MICRO_BATCH, k)
+            outs = self.backend.new_outputs(MICRO_BATCH, k)
+            self._bufs[k] = (rec, gath, outs)
+        return self._bufs[k]
+
+    def _micro_batch(self, qrows, k: int, time_gemv: bool):
+        """Local top-k for len(qrows) device queries, one all-gather, one merge.  Returns output views."""
+        rec, gath, (o_s, o_i, o_c) = self._buffers(k)
+        nb = len(qrows)
+        for j, q in enumerate(qrows):
+            self.backend.enqueue_local(q, k, rec[j], time_gemv)
+        recw = 2 * k + 1
+        g = gath.view(-1)[: self.world * nb * recw]
+        self.dist.all_gather_into_tensor(g, rec[:nb].reshape(-1), group=self.group)
+        self.backend.enqueue_merge(g, self.world, nb, k, o_s, o_i, o_c)
+        return o_s[:nb], o_i[:nb], o_c[:nb]
+
+    def run_queries(self, k: int, count: int, time_gemv: bool = False) -> float:
+        """`count` retrieves over the uploaded queries, device-resident end to end (bench path)."""
+        assert self._queries is not None, "set_queries first"
+        nq = self._queries.shape[0]
+        done = 0
+        while done < count:
+            nb = min(MICRO_BATCH, count - done)
+            self._micro_batch([self._queries[(done + j) % nq] for j in range(nb)], k, time_gemv)
+            done += nb
+        return self.backend.collect_kernel_ms() if time_gemv else 0.0
+
+    def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
+        """The reference's superheavy() result, on every rank: host query in, host list out."""
+        q = np.ascontiguousarray(query_vec, dtype=np.float32)
+        if q.ndim != 1 or q.shape[0] != self.d or self.n == 0:
+            raise ValueError(f"shapes ({self.n},{self.d if self.n else 0}) and ({q.shape[0]},) not aligned")
+        if n <= 0:
+            return []
+        k = min(int(n), 2048)
+        if n > 2048 and self.n > 2048:
+            raise NotImplementedError("n > 2048 is not supported by the sharded path")
+        dq = self.backend.device_queries(q[None, :])
+        o_s, o_i, o_c = self._micro_batch([dq[0]], k, False)
+        cnt = int(o_c[0].item())                                   # synchronises the stream
+        s = o_s[0, :cnt].cpu().numpy()
+        i = o_i[0, :cnt].cpu().numpy()
+        return [(float(a), int(b)) for a, b in zip(s, i)]
+
+    def close(self) -> None:
+        self.backend.close()

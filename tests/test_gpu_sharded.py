@@ -1,0 +1,78 @@
+"""GPU: the one-process-per-GPU shard path (svsb_set_shard / svsb_enqueue_local_topk /
+svsb_enqueue_merge_records) on ONE device: two shard engines stand in for two ranks and the all-gather is
+a concatenation.  The collective itself is covered on CPU with gloo (tests/test_sharded_gloo.py) and on
+N GPUs by bench.py under torchrun."""
+import numpy as np
+import pytest
+
+from _util import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_shard_engines_and_merge_records_match_the_oracle():
+    torch = pytest.importorskip("torch")
+    from svs_b200.sharded import CudaShardBackend, partition
+    n, d = 30_001, 256
+    m = oracle.synth_matrix_uniform(n, d, 5)
+    m[7] = m[n - 3]                                            # exact tie across shards
+    ids = np.cumsum(np.random.default_rng(2).integers(1, 4, size=n)).astype(np.int64)
+    world = 2
+    backs = []
+    for r in range(world):
+        b = CudaShardBackend(0)
+        row0, cnt = partition(n, world, r)
+        b.set_shard(row0)
+        b.load_rows(np.ascontiguousarray(m[row0:row0 + cnt]), np.ascontiguousarray(ids[row0:row0 + cnt]))
+        backs.append(b)
+    qs = oracle.synth_queries(5, d, 6)
+    qs[1] = m[7]
+    try:
+        for k in (1, 100, 1000, 2048):
+            batch = len(qs)
+            dq = backs[0].device_queries(qs)
+            recs = [b.new_records(batch, k) for b in backs]
+            for r, b in enumerate(backs):
+                for j in range(batch):
+                    b.enqueue_local(dq[j], k, recs[r][j], time_kernel=(k == 100))
+            torch.cuda.synchronize()
+            gathered = torch.stack(recs, dim=0).contiguous()   # [world, batch, 2k+1]: what all_gather yields
+            o_s, o_i, o_c = backs[0].new_outputs(batch, k)
+            backs[0].enqueue_merge(gathered, world, batch, k, o_s, o_i, o_c)
+            torch.cuda.synchronize()
+            for j in range(batch):
+                c = int(o_c[j])
+                got = list(zip(o_s[j, :c].cpu().numpy().tolist(), o_i[j, :c].cpu().numpy().tolist()))
+                oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+            if k >= 2:
+                c = int(o_c[1])
+                assert o_i[1, :2].cpu().numpy().tolist() == [int(ids[7]), int(ids[n - 3])]   # tie: ascending id
+            if k == 100:
+                assert backs[0].collect_kernel_ms() > 0 and backs[1].collect_kernel_ms() > 0
+    finally:
+        for b in backs:
+            b.close()
+
+
+def test_world_size_one_process_group_runs_the_real_collective():
+    torch = pytest.importorskip("torch")
+    import os
+    import torch.distributed as dist
+    from svs_b200.sharded import ShardedRetriever
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29581")
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        sr = ShardedRetriever(0, 1, 0)
+        sr.load_synthetic(50_000, 1536, seed=3, id0=1, id_step=1)
+        rows, ids = sr.backend.engine.read_rows(0, 50_000)
+        qs = oracle.synth_queries(11, 1536, 7)
+        for q in qs[:3]:
+            oracle.compare_retrieval(sr.retrieve(q, 100), oracle.superheavy(rows, ids, q, 100), oracle.scores_of(rows, q), ids)
+        sr.set_queries(qs)
+        ms = sr.run_queries(100, 11, time_gemv=True)
+        assert ms > 0
+        sr.close()
+    finally:
+        dist.destroy_process_group()

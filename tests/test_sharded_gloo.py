@@ -1,0 +1,146 @@
+"""The N>1 path on CPU: world_size-2 (and 3) `gloo` runs of ShardedRetriever with a NumPy stand-in for the
+shard compute (the CUDA backend is covered by the GPU suite).  Exercises the partitioning, the packed
+record layout, the all-gather, micro-batching and the merge order -- the host logic of SURVEY 8e."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from _util import oracle
+
+from svs_b200.sharded import MICRO_BATCH, ShardedRetriever, partition
+
+
+def np_keys(scores: np.ndarray, rows: np.ndarray) -> np.ndarray:
+    """The engine's 64-bit key (svs_b200/csrc/common.cuh make_key), restated in NumPy."""
+    bits = scores.astype(np.float32).view(np.uint32)
+    ordered = np.where(bits & np.uint32(0x80000000), ~bits, bits | np.uint32(0x80000000)).astype(np.uint64)
+    return (ordered << np.uint64(32)) | (~rows.astype(np.uint32)).astype(np.uint64)
+
+
+def key_score(keys: np.ndarray) -> np.ndarray:
+    o = (keys >> np.uint64(32)).astype(np.uint32)
+    bits = np.where(o & np.uint32(0x80000000), o & np.uint32(0x7FFFFFFF), ~o)
+    return bits.astype(np.uint32).view(np.float32)
+
+
+class NumpyShardBackend:
+    """CPU stand-in with the interface of svs_b200.sharded.CudaShardBackend (test infrastructure)."""
+
+    def __init__(self):
+        self.row0 = 0
+
+    def set_shard(self, row0):
+        self.row0 = row0
+
+    def load_rows(self, rows, ids):
+        self.m, self.ids = rows, ids
+
+    def device_queries(self, Q):
+        return torch.from_numpy(np.ascontiguousarray(Q, dtype=np.float32).copy())
+
+    def new_records(self, count, k):
+        return torch.zeros((count, 2 * k + 1), dtype=torch.int64)
+
+    def new_outputs(self, count, k):
+        return (torch.zeros((count, k), dtype=torch.float32), torch.zeros((count, k), dtype=torch.int64),
+                torch.zeros((count,), dtype=torch.int32))
+
+    def enqueue_local(self, q, k, record_row, time_kernel=False):
+        x = oracle.scores_of(self.m, q.numpy()) if len(self.m) else np.zeros(0, np.float32)
+        keys = np_keys(x, np.arange(self.row0, self.row0 + len(x)))
+        order = np.argsort(keys)[::-1][:k]
+        rec = record_row.numpy()
+        rec[:len(order)] = keys[order].view(np.int64)
+        rec[k:k + len(order)] = self.ids[order]
+        rec[2 * k] = len(order)
+
+    def enqueue_merge(self, gathered, n_lists, batch, k, out_scores, out_ids, out_counts):
+        g = gathered.numpy().reshape(n_lists, batch, 2 * k + 1)
+        for b in range(batch):
+            keys, ids = [], []
+            for l in range(n_lists):
+                c = int(g[l, b, 2 * k] & 0xFFFFFFFF)
+                keys.append(g[l, b, :c].view(np.uint64)); ids.append(g[l, b, k:k + c])
+            keys, ids = np.concatenate(keys), np.concatenate(ids)
+            order = np.argsort(keys)[::-1][:k]
+            out_scores.numpy()[b, :len(order)] = key_score(keys[order])
+            out_ids.numpy()[b, :len(order)] = ids[order]
+            out_counts.numpy()[b] = len(order)
+
+    def collect_kernel_ms(self):
+        return 0.0
+
+    def close(self):
+        pass
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n, d, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        m = oracle.synth_matrix_normal(n, d, 3)
+        tie = n > 10
+        if tie:
+            m[5] = m[n - 2]                              # an exact tie across the two ends (different shards)
+        ids = np.cumsum(rng.integers(1, 4, size=n)).astype(np.int64)
+        sr = ShardedRetriever(rank, world, backend=NumpyShardBackend())
+        sr.load_global(m, ids)
+        assert (sr.row0, sr.local_rows) == partition(n, world, rank)
+        qs = oracle.synth_queries(2 * MICRO_BATCH + 3, d, 4, "normal")
+        if tie:
+            qs[1] = m[5]                                 # makes rows 5 and n-2 tie at the top
+        out = []
+        for k in (1, 10, 64):
+            for q in qs[:4]:
+                got = sr.retrieve(q, k)
+                want = oracle.superheavy(m, ids, q, k)
+                oracle.compare_retrieval(got, want, oracle.scores_of(m, q), ids)
+                out.append(got)
+        if tie:
+            top = sr.retrieve(qs[1], 2)
+            assert [i for _, i in top] == [int(ids[5]), int(ids[n - 2])]  # tie -> ascending id, across ranks
+        # bench path: micro-batched, more queries than one batch, uneven tail
+        sr.set_queries(qs)
+        assert sr.run_queries(10, len(qs)) == 0.0
+        s_, i_, c_ = sr._micro_batch([sr._queries[j] for j in range(3)], 10, False)
+        for j in range(3):
+            got = [(float(a), int(b)) for a, b in zip(s_[j].numpy(), i_[j].numpy())][:int(c_[j])]
+            oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], 10), oracle.scores_of(m, qs[j]), ids)
+        assert sr.retrieve(qs[0], 0) == []
+        with pytest.raises(ValueError):
+            sr.retrieve(np.zeros(d + 1, np.float32), 3)
+        ret[rank] = out
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1001), (3, 700), (2, 3)])
+def test_sharded_retrieve_matches_the_oracle_on_every_rank(world, n):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, 24, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(1, world):
+        assert ret[r] == ret[0]                          # every rank holds the identical answer
+
+
+def test_partition_covers_all_rows_contiguously():
+    for n in (0, 1, 7, 1000, 1_000_000, 10_000_000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [partition(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            for (a, ca), (b, _cb) in zip(spans, spans[1:]):
+                assert b == a + ca or (ca == 0 and b == a)
