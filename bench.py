@@ -102,8 +102,8 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 def _reference_get_top_k():
     """svs.util.get_top_k from the byte-compiled reference (oracle/_ref) if present, else the oracle port."""
-    ref = os.path.join(ROOT, "oracle", "_ref")
-    if os.path.isfile(os.path.join(ref, "svs", "__init__.pyc")):
+    ref = os.path.join(ROOT, "oracle", "_ref", "svs_ref.bin")    # zip of the byte-compiled reference
+    if os.path.isfile(ref):
         try:
             sys.path.insert(0, ref)
             from svs.util import get_top_k          # the reference's own code

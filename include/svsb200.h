@@ -126,6 +126,8 @@ int svsb_bench_set_queries(svsb_t* e, const float* Q, int32_t nq, int32_t d);
 int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* gemv_ms, int64_t* launches);
 /* Same through the batched kernel: one launch set per batch of the uploaded queries. */
 int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, int64_t* launches);
+/* Development aid: %globaltimer phase stamps (ns) of one selection-kernel run with uploaded query qi. */
+int svsb_debug_select_phases(svsb_t* e, int32_t qi, int32_t k, uint64_t* stamps16);
 /* Result of the last bench query (for checking that the timed path computes the right thing). */
 int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
 

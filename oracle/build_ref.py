@@ -27,6 +27,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
+ZIP = os.path.join(OUT, "svs_ref.bin")     # a zip archive; neutral extension so that snapshots keep it
 
 
 def build(reference_root: str = "/root/reference") -> bool:
@@ -47,14 +48,23 @@ def build(reference_root: str = "/root/reference") -> bool:
                                    cfile=os.path.join(dst_dir, fn + "c"),
                                    dfile=f"<reference>/src/svs/{rel}/{fn}",
                                    doraise=True)
+    # The GPU-box snapshot drops *.pyc files, so the importable artefact is a zip of them
+    # (zipimport loads sourceless .pyc); the loose tree is removed again.
+    import zipfile
+    with zipfile.ZipFile(ZIP, "w", zipfile.ZIP_DEFLATED) as z:
+        for dirpath, _dirnames, filenames in os.walk(dst_pkg):
+            for fn in filenames:
+                full = os.path.join(dirpath, fn)
+                z.write(full, os.path.relpath(full, OUT))
+    shutil.rmtree(dst_pkg)
     with open(os.path.join(OUT, "BUILD_INFO.txt"), "w") as f:
         f.write(f"byte-compiled from {src_pkg} with python {sys.version.split()[0]}\n")
     return True
 
 
 def import_path() -> str | None:
-    """Directory to put on sys.path to import the built reference, or None if not built."""
-    return OUT if os.path.isfile(os.path.join(OUT, "svs", "__init__.pyc")) else None
+    """Entry to put on sys.path to import the built reference (a zip of .pyc files), or None if not built."""
+    return ZIP if os.path.isfile(ZIP) else None
 
 
 if __name__ == "__main__":

@@ -53,6 +53,7 @@ SIGNATURES = {
     "svsb_bench_set_queries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "svsb_bench_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, c_i64_p]),
     "svsb_bench_run_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_i64_p]),
+    "svsb_debug_select_phases": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_u64_p]),
     "svsb_bench_last_result": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_set_shard": (C.c_int, [C.c_void_p, C.c_int64]),
     "svsb_enqueue_local_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),

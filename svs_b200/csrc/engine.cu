@@ -963,6 +963,34 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
     return SVSB_OK;
 }
 
+// Phase timestamps (ns, %globaltimer) of one selection-kernel run on the resident matrix with uploaded
+// query `qi`: stamps[0..6] = entry, keys staged, threshold found, hit list, candidates, sorted, done;
+// stamps[8] = candidate count, stamps[9] = groups rescanned.  Development aid for profiles/.
+extern "C" int svsb_debug_select_phases(svsb_t* e, int32_t qi, int32_t k, uint64_t* stamps16) {
+    if (!e || !stamps16) return fail(SVSB_E_INVALID, "svsb_debug_select_phases: NULL argument");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (e->bench_nq == 0 || qi < 0 || qi >= e->bench_nq || k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_debug_select_phases: bad arguments");
+    int rc;
+    if (!e->bench_ctx) { if ((rc = ctx_create(e, e->bench_ctx)) != SVSB_OK) return rc; }
+    DevWs& w = e->bench_ctx->ws[0];
+    const Shard& s = g->shards[0];
+    const int64_t kk = std::min<int64_t>(k, s.n);
+    if ((rc = prepare_ws(w, g.get(), s, kk)) != SVSB_OK) return rc;
+    CU(cudaSetDevice(w.dev));
+    u64* dbg = nullptr;
+    CU(cudaMalloc(&dbg, 16 * 8));
+    CU(cudaMemsetAsync(dbg, 0, 16 * 8, w.st));
+    const int shift = group_shift_for(s.n);
+    CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + (int64_t)qi * e->bench_ld, w.scores, w.gmax, shift));
+    CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
+                     w.out_keys, w.out_scores, w.out_ids, w.out_count, dbg));
+    CU(cudaMemcpyAsync(stamps16, dbg, 16 * 8, cudaMemcpyDeviceToHost, w.st));
+    CU(cudaStreamSynchronize(w.st));
+    CU(cudaFree(dbg));
+    return SVSB_OK;
+}
+
 extern "C" int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, int64_t* launches) {
     (void)e; (void)k; (void)iters; (void)total_ms; (void)launches;
     return fail(SVSB_E_INVALID, "svsb_bench_run_batch: the batched tensor-core path is not built yet");

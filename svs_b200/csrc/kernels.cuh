@@ -24,7 +24,8 @@ cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, 
 // Requires 1 <= k <= K_FAST_MAX.
 cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
                           int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
-                          u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count);
+                          u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count,
+                          u64* dbg = nullptr);   // dbg: optional 16 x u64 of %globaltimer phase stamps
 
 // Large-k path (k > K_FAST_MAX): sort all n keys.  sortbuf has next_pow2(n) entries.  Also zeroes gmax.
 cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,

@@ -42,6 +42,9 @@ struct SelectSmem {
 __device__ __forceinline__ int bitlen64(u64 v) { return v ? 64 - __clzll((long long)v) : 0; }
 
 // Bitonic sort, descending, of buf[0..npow2) (npow2 a power of two <= SORT_CAP); optional payload.
+// Thread t owns elements t, t + blockDim, ...: for j < 32 both partners of a compare-exchange live in the
+// same 32-aligned block, i.e. in the same warp, so those steps need only __syncwarp(); block-wide barriers
+// are paid only around the j >= 32 steps (6 instead of 28 for 128 keys, 27 instead of 66 for 2048).
 template <bool PAYLOAD>
 __device__ void block_bitonic_desc(u64* buf, int64_t* pay, int npow2) {
     for (int k = 2; k <= npow2; k <<= 1) {
@@ -57,9 +60,24 @@ __device__ void block_bitonic_desc(u64* buf, int64_t* pay, int npow2) {
                     }
                 }
             }
-            __syncthreads();
+            if (j > 32 || (j == 32) || (j == 1 && (k << 1) > 32)) __syncthreads();   // next step crosses warps
+            else __syncwarp();
         }
     }
+    __syncthreads();
+}
+
+// Sort c <= RANK_SORT_MAX distinct keys descending by counting: rank(i) = #{j : key_j > key_i}.
+// One barrier, c broadcast shared-memory reads per participating thread.  src and dst must not alias.
+constexpr int RANK_SORT_MAX = 256;
+__device__ void block_rank_sort_desc(const u64* src, u64* dst, int c) {
+    if ((int)threadIdx.x < c) {
+        const u64 mine = src[threadIdx.x];
+        int rank = 0;
+        for (int j = 0; j < c; ++j) rank += (src[j] > mine) ? 1 : 0;
+        dst[rank] = mine;
+    }
+    __syncthreads();
 }
 
 // kk-th largest (1-based) of keys[0..count), count >= kk >= 1.  All threads of the block call it and
@@ -95,23 +113,40 @@ __device__ u64 block_kth_largest(const u64* keys, int64_t count, int kk, SelectS
             if (v >= lo && v <= hi) atomicAdd(&sm.hist[(uint32_t)((v - lo) >> shift)], 1u);
         }
         __syncthreads();
-        // find, from the top, the bin where the cumulative count reaches `remaining` (warp 0)
+        // Find, from the top, the bin where the cumulative count reaches `remaining`.
+        // Level 1: 32 chunks of 64 bins, chunk c = bins [64c, 64c+64); each warp sums chunks (conflict-free).
+        for (int cidx = warp; cidx < 32; cidx += nwarps) {
+            uint32_t v = sm.hist[cidx * 64 + lane] + sm.hist[cidx * 64 + 32 + lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sm.red_a[cidx] = (u64)v;
+        }
+        __syncthreads();
         if (warp == 0) {
-            constexpr int PER = HIST_BINS / 32;            // 64 bins per lane; lane 0 owns the TOP chunk
-            const int top = HIST_BINS - 1 - lane * PER;    // highest bin of this lane's chunk
-            uint32_t mysum = 0;
-            for (int b = 0; b < PER; ++b) mysum += sm.hist[top - b];
-            uint32_t incl = mysum;                         // inclusive prefix over lanes (top-down)
+            // lane l looks at chunk (31 - l): top-down inclusive prefix over chunks
+            const uint32_t mysum = (uint32_t)sm.red_a[31 - lane];
+            uint32_t incl = mysum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
             const uint32_t excl = incl - mysum;
-            const bool mine = (excl < (uint32_t)remaining) && (incl >= (uint32_t)remaining);
-            if (mine) {
-                uint32_t cum = excl; int b = 0;
-                for (; b < PER; ++b) { const uint32_t h = sm.hist[top - b]; if (cum + h >= (uint32_t)remaining) break; cum += h; }
-                sm.bcast32[0] = top - b;                   // the bin
-                sm.bcast32[1] = (int)cum;                  // keys strictly above the bin
-            }
+            const unsigned hitmask = __ballot_sync(0xffffffffu, excl < (uint32_t)remaining && incl >= (uint32_t)remaining);
+            const int src = __ffs(hitmask) - 1;                       // exactly one lane qualifies
+            const int chunk = 31 - src;
+            const uint32_t above_chunk = __shfl_sync(0xffffffffu, excl, src);
+            // Level 2: inside the chunk, lane l looks at bins (top - l) and (top - 32 - l)
+            const int top = chunk * 64 + 63;
+            const uint32_t h0 = sm.hist[top - lane], h1 = sm.hist[top - 32 - lane];
+            uint32_t p0 = h0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, p0, o); if (lane >= o) p0 += t; }
+            const uint32_t first_half = __shfl_sync(0xffffffffu, p0, 31);
+            uint32_t p1 = h1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, p1, o); if (lane >= o) p1 += t; }
+            const uint32_t need = (uint32_t)remaining - above_chunk;   // 1-based position inside the chunk
+            const uint32_t e0 = p0 - h0, e1 = first_half + p1 - h1;    // exclusive prefixes (top-down)
+            if (e0 < need && p0 >= need) { sm.bcast32[0] = top - lane; sm.bcast32[1] = (int)(above_chunk + e0); }
+            if (e1 < need && first_half + p1 >= need) { sm.bcast32[0] = top - 32 - lane; sm.bcast32[1] = (int)(above_chunk + e1); }
         }
         __syncthreads();
         const int bin = sm.bcast32[0];
@@ -124,22 +159,25 @@ __device__ u64 block_kth_largest(const u64* keys, int64_t count, int kk, SelectS
         lo = nlo; hi = nhi;
         __syncthreads();
         if (shift == 0) return lo;                          // bin holds one key value: that is the answer
-        if (inbin <= (uint32_t)SORT_CAP) break;
+        if (inbin <= (uint32_t)RANK_SORT_MAX) break;
     }
-    // finish in shared memory: collect the keys of the final bin and sort them
+    // finish in shared memory: collect the (few) keys of the final bin, pick the remaining-th by rank
     if (tid == 0) sm.counter = 0;
     __syncthreads();
     for (int64_t i = tid; i < count; i += blockDim.x) {
         const u64 v = keys[i];
-        if (v >= lo && v <= hi) { const uint32_t p = atomicAdd(&sm.counter, 1u); if (p < (uint32_t)SORT_CAP) sm.sortbuf[p] = v; }
+        if (v >= lo && v <= hi) { const uint32_t p = atomicAdd(&sm.counter, 1u); if (p < (uint32_t)RANK_SORT_MAX) sm.sortbuf[p] = v; }
     }
     __syncthreads();
-    const int c = (int)min(sm.counter, (uint32_t)SORT_CAP);
-    int np2 = 1; while (np2 < c) np2 <<= 1;
-    for (int i = c + tid; i < np2; i += blockDim.x) sm.sortbuf[i] = 0ull;
+    const int c = (int)min(sm.counter, (uint32_t)RANK_SORT_MAX);
+    if (tid < c) {
+        const u64 mine = sm.sortbuf[tid];
+        int rank = 0;
+        for (int j = 0; j < c; ++j) rank += (sm.sortbuf[j] > mine) ? 1 : 0;
+        if (rank == remaining - 1) sm.bcast64[0] = mine;
+    }
     __syncthreads();
-    block_bitonic_desc<false>(sm.sortbuf, nullptr, np2);
-    const u64 ans = sm.sortbuf[remaining - 1];
+    const u64 ans = sm.bcast64[0];
     __syncthreads();
     return ans;
 }
@@ -160,10 +198,12 @@ __global__ void __launch_bounds__(SEL_THREADS, 1)
 select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int group_shift,
                    int k, const int64_t* __restrict__ ids, int64_t row0, u64* cand, int64_t cand_cap,
                    u64* __restrict__ out_keys, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                   int32_t* __restrict__ out_count)
+                   int32_t* __restrict__ out_count, u64* __restrict__ dbg)
 {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelectKeysSmem& big = *reinterpret_cast<SelectKeysSmem*>(sel_smem_raw);
+#define SEL_STAMP(i) do { if (dbg && threadIdx.x == 0) { u64 t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[i] = t_; } } while (0)
+    SEL_STAMP(0);
     SelectSmem& sm = big.base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int kk = (int)min((int64_t)k, n);
@@ -195,9 +235,11 @@ select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int g
         __syncthreads();
     }
 
+    SEL_STAMP(1);
     // 2. threshold: the kk-th largest group maximum (0 = "every group" when there are <= kk groups)
     u64 tau = 0;
     if (G > kk) tau = block_kth_largest(big.keys, G, kk, sm, /*have_range=*/true);
+    SEL_STAMP(2);
 
     // 3. the groups whose maximum reaches tau (exactly kk of them, or all G)
     if (tid == 0) sm.counter = 0;
@@ -207,16 +249,31 @@ select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int g
     __syncthreads();
     const int nhits = (int)min(sm.counter, (uint32_t)K_FAST_MAX);
     __syncthreads();
+    SEL_STAMP(3);
 
     // 4. candidates: rows of those groups with key >= tau (flattened: independent, coalesced loads).
     //    The first SORT_CAP go straight into the sort buffer; any overflow goes to `cand` in global memory.
     if (tid == 0) sm.counter = 0;
     __syncthreads();
     const int64_t items = (int64_t)nhits << group_shift;
-    for (int64_t it = tid; it < items; it += SEL_THREADS) {
-        const int64_t r = ((int64_t)big.hits[it >> group_shift] << group_shift) + (it & (m - 1));
-        if (r < n) {
-            const u64 key = make_key(scores[r], (uint32_t)r);
+    constexpr int CB = 8;                                   // loads in flight per thread
+    for (int64_t it0 = tid; it0 < items; it0 += (int64_t)SEL_THREADS * CB) {
+        int64_t rr[CB]; float sc[CB];
+#pragma unroll
+        for (int u = 0; u < CB; ++u) {
+            const int64_t it = it0 + (int64_t)u * SEL_THREADS;
+            rr[u] = -1;
+            if (it < items) {
+                const int64_t r = ((int64_t)big.hits[it >> group_shift] << group_shift) + (it & (m - 1));
+                if (r < n) rr[u] = r;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CB; ++u) sc[u] = rr[u] >= 0 ? scores[rr[u]] : 0.f;
+#pragma unroll
+        for (int u = 0; u < CB; ++u) {
+            if (rr[u] < 0) continue;
+            const u64 key = make_key(sc[u], (uint32_t)rr[u]);
             if (key >= tau) {
                 const uint32_t p = atomicAdd(&sm.counter, 1u);
                 if (p < (uint32_t)SORT_CAP) sm.sortbuf[p] = key;
@@ -227,6 +284,8 @@ select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int g
     __syncthreads();
     const int64_t C = (int64_t)sm.counter;
     __syncthreads();
+    SEL_STAMP(4);
+    if (dbg && tid == 0) { dbg[8] = (u64)C; dbg[9] = (u64)nhits; }
 
     // 5. exact top-kk of the candidates, sorted
     if (C > SORT_CAP) {
@@ -245,14 +304,22 @@ select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int g
         __syncthreads();
     }
     const int c = (int)min(sm.counter, (uint32_t)SORT_CAP);
-    int np2 = 1; while (np2 < c) np2 <<= 1;
-    for (int i = c + tid; i < np2; i += SEL_THREADS) sm.sortbuf[i] = 0ull;
-    __syncthreads();
-    block_bitonic_desc<false>(sm.sortbuf, nullptr, np2);
+    const u64* sorted = sm.sortbuf;
+    if (c <= RANK_SORT_MAX) {
+        u64* dst = reinterpret_cast<u64*>(sm.payload);       // unused by this kernel otherwise
+        block_rank_sort_desc(sm.sortbuf, dst, c);
+        sorted = dst;
+    } else {
+        int np2 = 1; while (np2 < c) np2 <<= 1;
+        for (int i = c + tid; i < np2; i += SEL_THREADS) sm.sortbuf[i] = 0ull;
+        __syncthreads();
+        block_bitonic_desc<false>(sm.sortbuf, nullptr, np2);
+    }
+    SEL_STAMP(5);
 
     // 6. epilogue: (score, embeddings.id), keys re-based to global rows for the cross-shard merge
     for (int i = tid; i < kk; i += SEL_THREADS) {
-        const u64 key = sm.sortbuf[i];
+        const u64 key = sorted[i];
         const uint32_t row = key_row(key);
         const int64_t grow = row0 + (int64_t)row;
         out_keys[i] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
@@ -260,11 +327,13 @@ select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int g
         out_ids[i] = ids ? ids[row] : grow;
     }
     if (tid == 0) *out_count = kk;
+    SEL_STAMP(6);
+#undef SEL_STAMP
 }
 
 cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
                           int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
-                          u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count)
+                          u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count, u64* dbg)
 {
     if (k < 1 || k > K_FAST_MAX || n < 1) return cudaErrorInvalidValue;
     static bool attr_set[64] = {false};
@@ -276,7 +345,7 @@ cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* 
     }
     if (((n + ((int64_t)1 << group_shift) - 1) >> group_shift) > SEL_KEYS_CAP) return cudaErrorInvalidValue;
     select_topk_kernel<<<1, SEL_THREADS, sizeof(SelectKeysSmem), st>>>(scores, n, gmax, group_shift, k, ids, row0,
-                                                                  cand, cand_cap, out_keys, out_scores, out_ids, out_count);
+                                                                  cand, cand_cap, out_keys, out_scores, out_ids, out_count, dbg);
     count_launch();
     return cudaGetLastError();
 }

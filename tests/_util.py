@@ -31,5 +31,5 @@ def stub_vector(text: str, d: int) -> list:
 
 def reference_import_path():
     """sys.path entry for the byte-compiled reference (oracle/_ref), or None."""
-    p = os.path.join(ROOT, "oracle", "_ref")
-    return p if os.path.isfile(os.path.join(p, "svs", "__init__.pyc")) else None
+    p = os.path.join(ROOT, "oracle", "_ref", "svs_ref.bin")       # zip of the reference's .pyc files
+    return p if os.path.isfile(p) else None
