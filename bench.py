@@ -36,9 +36,23 @@ WORKLOADS = {
     # name: (rows, dims, k, description)
     "c1": (10_548, 1536, 10, "10,548 x 1536 fp32 top-10 (dad-jokes shape, synthetic unit rows)"),
     "c2": (1_000_000, 1536, 100, "1M x 1536 fp32 top-100 (README 'One Million Documents' shape)"),
+    "c3": (1_000_000, 768, 100, "1M x 768 fp32, batches of 1024 queries, top-100 (batched tensor-core path)"),
     "c4": (10_000_000, 1536, 100, "10M x 1536 fp32 top-100, row-sharded"),
     "c5": (1_000_000, 3072, 1000, "1M x 3072 fp32 top-1000"),
 }
+
+
+BATCH = 1024          # queries per step of the batched workload (c3)
+
+
+def measured_peak_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained, cuBLAS 16-bit dense, kernel timed inside a long step)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
 
 
 def measured_peak_gbs():
@@ -180,6 +194,85 @@ def run_reference_arm(args, n, d, k, desc):
 
 
 # ---------------------------------------------------------------------------------------------------
+# our arm, batched workload (c3): one step = one batch of BATCH queries through svsb_query_batch's pipeline
+# ---------------------------------------------------------------------------------------------------
+def run_batch_arm(args, n, d, k, desc):
+    import svs_b200
+    from svs_b200.engine import Engine
+    rng = np.random.default_rng(2)
+    queries = rng.random((BATCH, d), dtype=np.float32)
+    queries /= np.sqrt((queries * queries).sum(axis=1))[:, None]
+    peak, peak_src = measured_peak_tflops()
+    eng = Engine([0])
+    t_load = time.perf_counter()
+    eng.load_synthetic(n, d, seed=0, id0=1, id_step=1)
+    load_s = time.perf_counter() - t_load
+    eng.bench_set_queries(queries)
+    for _ in range(args.warmup):
+        eng.bench_run_batch(k, 1)
+    sampler = ClockSampler(0)
+    sampler.start()
+    total_ms = coarse_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        r = eng.bench_run_batch(k, 1, with_coarse=True)
+        total_ms += r["total_ms"]; coarse_ms += r["coarse_ms"]; launches += r["launches"]
+    clocks = sampler.stop()
+    cand, resc, flags = eng.batch_stats(BATCH)
+    # the timed path must compute the answer: compare a few queries with the single-query kernels
+    agree = True
+    for qi in (0, BATCH // 2, BATCH - 1):
+        got, flag = eng.bench_batch_result(qi, k)
+        agree = agree and flag == 0 and got == eng.retrieve(queries[qi], k)
+    # e2e: the public C-ABI call with host buffers (H2D of the batch, D2H of the results inside every call)
+    eng.query_batch(queries, k)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        eng.query_batch(queries, k)
+    e2e_qps = args.steps * BATCH / (time.perf_counter() - t0)
+    nq = args.steps * BATCH
+    flop = 2.0 * n * d * BATCH
+    achieved = flop * args.steps / (coarse_ms / 1e3) / 1e12
+    line = {
+        "metric": "retrieve_queries_per_sec", "value": nq / (total_ms / 1e3), "unit": "queries/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 results (f16 tensor-core coarse pass + exact f32 re-score)",
+        "data": "synthetic",
+        "config": {"workload": desc, "rows": n, "dims": d, "k": k, "queries_per_step": BATCH,
+                   "l2": "inputs larger than L2 (f16 shadow matrix %.2f GB)" % (n * d * 2 / 1e9), "parallelism": "1 GPU"},
+        "ms_per_query": total_ms / nq,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "coarse_gemm_kernel<0> (filter pass)", "peak_source": peak_src,
+                     "algorithmic_flop_per_launch": flop, "coarse_ms_per_batch": coarse_ms / args.steps,
+                     "hbm_floor_ms": n * d * 2 / 1e9 / measured_peak_gbs()[0] * 1e3},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": BATCH * d * 4, "d2h_bytes_per_step": BATCH * (k * 12 + 8)},
+        "gpu_launches": int(launches), "clocks": clocks, "load_synthetic_s": load_s,
+        "batch_stats": {"candidates_mean": float(cand.mean()), "candidates_max": int(cand.max()), "rescored_mean": float(resc.mean()),
+                        "rescored_max": int(resc.max()), "fallback_queries": int((flags != 0).sum()),
+                        "agrees_with_single_query_bits": bool(agree)},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            line["roofline"]["traffic"] = json.load(open(traffic_file)).get(args.workload)
+        except Exception:
+            pass
+    if not args.no_cpu_baseline:
+        rows, one_query, kind = cpu_arm(n, d, k)
+        for i in range(2):
+            one_query(queries[i])
+        t0 = time.perf_counter(); cnt = 0
+        while cnt < 10 or (time.perf_counter() - t0 < 5.0 and cnt < 64):
+            one_query(queries[cnt % len(queries)]); cnt += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": cnt / dt * (rows / n), "unit": "queries/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"{cnt} of the {BATCH} queries, each np.dot + get_top_k on {rows} x {d} host rows (the reference has no batched API)"}
+    eng.close()
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def main():
@@ -210,6 +303,10 @@ def main():
     queries /= np.sqrt((queries * queries).sum(axis=1))[:, None]
     peak, peak_src = measured_peak_gbs()
     l0 = svs_b200.launch_count()
+
+    if world == 1 and args.workload == "c3":
+        run_batch_arm(args, n, d, k, desc)
+        return
 
     if world == 1:
         from svs_b200.engine import Engine

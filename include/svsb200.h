@@ -106,9 +106,16 @@ void svsb_snapshot_release(svsb_snap_t* s);
 int  svsb_snapshot_shape(svsb_snap_t* s, int64_t* n, int32_t* d, uint64_t* generation);
 int  svsb_snapshot_query(svsb_t* e, svsb_snap_t* s, const float* q, int32_t d, int32_t k,
                          float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
-/* Batched queries (new; the reference has no batched API): Q is row-major (b, d); outputs (b, k). */
+/* Batched queries (new; the reference has no batched API -- a batch is a Python loop over retrieve,
+ * src/svs/kb.py:1608-1640): Q is row-major (b, d); outputs (b, k), out_counts (b).  Same results, bit for bit, as b
+ * calls of svsb_query.  Large batches on a single-device engine run as ONE dense contraction on the tensor cores
+ * (fp16 coarse pass with a proven error margin, then exact fp32 re-scoring of the surviving candidates); small
+ * batches, k > 1024 and multi-device engines loop over the single-query kernels. */
 int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
                      float* out_scores, int64_t* out_emb_ids, int32_t* out_counts);
+/* Diagnostics of the last batch chunk (<= 2048 queries): coarse candidates per query, rows re-scored exactly per
+ * query, flag word per query (0 = answered by the coarse path; otherwise it took the single-query kernels). */
+int svsb_batch_stats(svsb_t* e, int32_t b, int32_t* candidates, int32_t* rescored, int32_t* flags);
 /* Selection only: get_top_k (src/svs/util.py:190-203) on a host score vector, run by the same
  * selection kernels.  out_index receives row indices. */
 int svsb_topk_scores(svsb_t* e, const float* scores, int64_t n, int32_t k,
@@ -124,8 +131,12 @@ int svsb_bench_set_queries(svsb_t* e, const float* Q, int32_t nq, int32_t d);
  * duration of the similarity-kernel launches on device 0, each bracketed by its own pair of events
  * inside the same timed loop (the roofline numerator's denominator). */
 int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* gemv_ms, int64_t* launches);
-/* Same through the batched kernel: one launch set per batch of the uploaded queries. */
-int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, int64_t* launches);
+/* Same through the batched path: per iteration ONE batch of all uploaded queries (<= 2048), device-resident.
+ * coarse_ms (optional): summed duration of the tensor-core filter pass, bracketed by its own events. */
+int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* coarse_ms, int64_t* launches);
+/* Result of query qi of the last svsb_bench_run_batch iteration (checks that the timed path computes the answer). */
+int svsb_bench_batch_result(svsb_t* e, int32_t qi, int32_t k, float* out_scores, int64_t* out_emb_ids, int32_t* out_count,
+                            int32_t* out_flag);
 /* Development aid: %globaltimer phase stamps (ns) of one selection-kernel run with uploaded query qi. */
 int svsb_debug_select_phases(svsb_t* e, int32_t qi, int32_t k, uint64_t* stamps16);
 /* Result of the last bench query (for checking that the timed path computes the right thing). */

@@ -1,0 +1,206 @@
+// K2 (second half) -- thresholds for the coarse pass and the exact refine of its candidates.
+//
+// Why the result is exact.  For one query let e(r) = coarse(r) - exact(r) and |e(r)| <= eps
+// for every row r (the bound computed on the host, see engine.cu: two fp16 roundings per product, a generous
+// bound on the tensor core's fp32 accumulation and on the exact kernel's own fp32 rounding).  Let tau~ be the
+// kk-th largest COARSE score.  kk rows have coarse >= tau~, hence exact >= tau~ - eps, so the kk-th largest EXACT
+// score s_k >= tau~ - eps.  Any row in the exact top-kk has exact >= s_k, hence coarse >= tau~ - 2 eps.  The refine
+// kernel therefore re-scores every candidate with coarse >= tau~ - 2 eps in fp32 -- with the very summation
+// order of the similarity kernel (gemv.cu, TMA variant), so scores are bit-identical to svsb_query's -- and the
+// exact top-kk of those is the exact top-kk of all rows, under the same total order (score desc, row asc).
+// The candidate list holds every row with coarse >= tau~ - 2 eps because the filter threshold is (the kk-th largest
+// coarse score of a SAMPLE of the rows) - 2 eps, and the sample's kk-th largest can only be lower than tau~.
+#include "select_common.cuh"
+
+namespace svsb {
+
+constexpr int RF_THREADS = 512;
+constexpr int RF_BINS = 2048;
+
+// kk-th largest (1-based) of the 32-bit ordered values load(i), i < count (count >= kk >= 1), by three
+// most-significant-first radix passes (11 + 11 + 10 bits).  All threads call it; all get the result.
+// hist: RF_BINS words of shared memory; scratch: 40 words of shared memory.
+template <class Load>
+__device__ uint32_t block_kth_largest_o32(Load load, int64_t count, int kk, uint32_t* hist, uint32_t* scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t prefix = 0, known = 0;
+    uint32_t remaining = (uint32_t)kk;
+    const int shifts[3] = {21, 10, 0};
+    const int bits[3] = {11, 11, 10};
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass];
+        const uint32_t nb = 1u << bits[pass];
+        for (int i = tid; i < RF_BINS; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < count; i += blockDim.x) {
+            const uint32_t o = load(i);
+            if ((o & known) == prefix) atomicAdd(&hist[(o >> shift) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns bins [64 l, 64 l + 64); top-down: lane 31 first
+            uint32_t mine = 0;
+            for (int j = 0; j < 64; ++j) mine += hist[lane * 64 + j];
+            // suffix sums: above(l) = sum of lanes > l
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
+            const uint32_t above = incl - mine;
+            const bool hit = above < remaining && incl >= remaining;       // exactly one lane
+            if (hit) {
+                uint32_t acc = above;
+                int bin = lane * 64 + 63;
+                for (; bin > lane * 64; --bin) { if (acc + hist[bin] >= remaining) break; acc += hist[bin]; }
+                scratch[0] = (uint32_t)bin; scratch[1] = acc;
+            }
+        }
+        __syncthreads();
+        const uint32_t bin = scratch[0], acc = scratch[1];
+        prefix |= bin << shift;
+        known |= (nb - 1) << shift;
+        remaining -= acc;
+        __syncthreads();
+    }
+    return prefix;
+}
+
+// ---------------------------------------------------------------------------------------------
+// thresholds from the sample: thr[q] = kk-th largest coarse score among the sampled rows
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RF_THREADS)
+sample_threshold_kernel(const float* __restrict__ sample, int64_t sample_rows, int kk, const float* __restrict__ eps,
+                        float* __restrict__ thr)
+{
+    __shared__ uint32_t hist[RF_BINS];
+    __shared__ uint32_t scratch[40];
+    const int q = blockIdx.x;
+    const float* s = sample + (size_t)q * sample_rows;
+    const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(s[i]); }, sample_rows, kk, hist, scratch);
+    // The filter must let through every row with coarse >= tau~ - 2 eps; the sample's kk-th largest is <= tau~.
+    if (threadIdx.x == 0) thr[q] = ordered_to_f32(o) - 2.0f * eps[q];
+}
+
+cudaError_t launch_sample_threshold(cudaStream_t st, const float* sample, int64_t sample_rows, int b, int kk, const float* eps,
+                                    float* thr)
+{
+    if (b <= 0) return cudaSuccess;
+    if (kk < 1 || kk > sample_rows) return cudaErrorInvalidValue;
+    sample_threshold_kernel<<<b, RF_THREADS, 0, st>>>(sample, sample_rows, kk, eps, thr);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// refine
+// ---------------------------------------------------------------------------------------------
+struct RefineSmem {
+    u64 keys[REFINE_SURVIVOR_CAP];
+    uint32_t rows[REFINE_SURVIVOR_CAP];
+    uint32_t hist[RF_BINS];
+    uint32_t scratch[40];
+    uint32_t counter;
+    // float4 q[ld / 4] follows
+};
+
+__global__ void __launch_bounds__(RF_THREADS)
+refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __restrict__ ids, int64_t row0,
+              const float* __restrict__ Q, int ldq, int k, const u64* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+              int cand_cap, const float* __restrict__ eps, int32_t* __restrict__ flags,
+              float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int32_t* __restrict__ out_counts,
+              int32_t* __restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char rf_smem_raw[];
+    RefineSmem& sm = *reinterpret_cast<RefineSmem*>(rf_smem_raw);
+    float4* sq = reinterpret_cast<float4*>(rf_smem_raw + ((sizeof(RefineSmem) + 15) & ~(size_t)15));
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RF_THREADS / 32;
+    const int kk = (int)min((int64_t)k, n);
+    if (tid == 0) { out_counts[q] = 0; if (stats) stats[q] = 0; }
+    if (flags[q] != 0) return;                                       // already routed to the exact path
+    const int total = cand_cnt[q];
+    if (total > cand_cap || total < kk) {
+        if (tid == 0) flags[q] = total > cand_cap ? 2 : 4;
+        return;
+    }
+    const u64* cq = cand + (size_t)q * cand_cap;
+    for (int c = tid; c < d4; c += RF_THREADS) sq[c] = reinterpret_cast<const float4*>(Q + (size_t)q * ldq)[c];
+    if (tid == 0) sm.counter = 0;
+    __syncthreads();
+
+    // tau~: the kk-th largest coarse score among the candidates (the key's high word IS the ordered score)
+    const uint32_t tau_o = block_kth_largest_o32([&](int64_t i) { return (uint32_t)(cq[i] >> 32); }, total, kk, sm.hist, sm.scratch);
+    const float cutoff = ordered_to_f32(tau_o) - 2.0f * eps[q];
+
+    for (int i = tid; i < total; i += RF_THREADS) {
+        const u64 key = cq[i];
+        if (key_score(key) >= cutoff) {
+            const uint32_t p = atomicAdd(&sm.counter, 1u);
+            if (p < (uint32_t)REFINE_SURVIVOR_CAP) sm.rows[p] = key_row(key);
+        }
+    }
+    __syncthreads();
+    const int C = (int)sm.counter;
+    if (C > REFINE_SURVIVOR_CAP) { if (tid == 0) flags[q] = 8; return; }
+    if (tid == 0 && stats) stats[q] = C;
+
+    // exact fp32 re-score, one warp per survivor.  Summation order == gemv_tma_kernel: lane l takes the float4
+    // chunks l, l+32, ...; even chunks accumulate into a0, odd ones into a1; then the same combine + xor tree.
+    const float4* M4 = reinterpret_cast<const float4*>(M);
+    for (int i = warp; i < C; i += nwarps) {
+        const uint32_t row = sm.rows[i];
+        const float4* p = M4 + ((int64_t)row - row0) * d4;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        int c = lane;
+        for (; c + 96 < d4; c += 128) {
+            const float4 m0 = ldg_stream(p + c), m1 = ldg_stream(p + c + 32), m2 = ldg_stream(p + c + 64), m3 = ldg_stream(p + c + 96);
+            fma4(a0, m0, sq[c]); fma4(a1, m1, sq[c + 32]); fma4(a0, m2, sq[c + 64]); fma4(a1, m3, sq[c + 96]);
+        }
+        for (; c + 32 < d4; c += 64) {
+            const float4 m0 = ldg_stream(p + c), m1 = ldg_stream(p + c + 32);
+            fma4(a0, m0, sq[c]); fma4(a1, m1, sq[c + 32]);
+        }
+        if (c < d4) { const float4 m0 = ldg_stream(p + c); fma4(a0, m0, sq[c]); }
+        const float sc = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
+        if (lane == 0) sm.keys[i] = make_key(sc, row);
+    }
+    __syncthreads();
+
+    int np2 = 1; while (np2 < C) np2 <<= 1;
+    for (int i = C + tid; i < np2; i += RF_THREADS) sm.keys[i] = 0ull;
+    __syncthreads();
+    block_bitonic_desc<false>(sm.keys, nullptr, np2);
+
+    for (int i = tid; i < kk; i += RF_THREADS) {
+        const u64 key = sm.keys[i];
+        const uint32_t row = key_row(key);
+        out_scores[(size_t)q * k + i] = key_score(key);
+        out_ids[(size_t)q * k + i] = ids ? ids[(int64_t)row - row0] : (int64_t)row;
+    }
+    if (tid == 0) out_counts[q] = kk;
+}
+
+cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
+                          const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
+                          const float* eps, int32_t* flags, float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                          int32_t* stats)
+{
+    if (b <= 0) return cudaSuccess;
+    if (k < 1 || (ld & 3) || ldq < ld) return cudaErrorInvalidValue;
+    const int64_t kk = k < n ? k : n;
+    if (kk > REFINE_SURVIVOR_CAP) return cudaErrorInvalidValue;
+    const size_t smem = ((sizeof(RefineSmem) + 15) & ~(size_t)15) + (size_t)ld * 4;
+    static bool attr_set[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    refine_kernel<<<b, RF_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, flags,
+                                              out_scores, out_ids, out_counts, stats);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace svsb

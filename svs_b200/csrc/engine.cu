@@ -61,12 +61,16 @@ struct Generation {
     std::vector<Shard> shards;
     float max_dev = 0.f;
     int64_t n_out_of_tol = 0;
+    // fp16 shadow of shard 0 for the batched coarse contraction (built lazily by the first batch)
+    std::mutex m16_mu;
+    void* M16 = nullptr; int ld16 = 0;
     ~Generation() {
         for (auto& s : shards) {
             if (s.M || s.ids) cudaSetDevice(s.dev);
             if (s.M) cudaFree(s.M);
             if (s.ids) cudaFree(s.ids);
         }
+        if (M16 && !shards.empty()) { cudaSetDevice(shards[0].dev); cudaFree(M16); }
     }
 };
 
@@ -173,6 +177,38 @@ struct Loading {
     bool borrowed = false;
 };
 
+// workspace of the batched path: coarse operands, thresholds, candidate lists, outputs (device) + pinned staging
+struct BatchWs {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // capacities
+    int cap_b = 0, cap_ld = 0, cap_k = 0; int64_t cap_sample = 0; int cand_cap = 0;
+    float* dQ = nullptr; void* dQ16 = nullptr;
+    float* eps = nullptr; float* thr = nullptr; int32_t* flags = nullptr; int32_t* cand_cnt = nullptr; int32_t* stats = nullptr;
+    float* sample = nullptr; u64* cand = nullptr;
+    float* o_scores = nullptr; int64_t* o_ids = nullptr; int32_t* o_counts = nullptr;
+    float* h_Q = nullptr; float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_counts = nullptr;
+    int32_t* h_flags = nullptr; int32_t* h_stats = nullptr; int32_t* h_cnt = nullptr;
+
+    void release_device() {
+        cudaSetDevice(dev);
+        void* ptrs[] = {dQ, dQ16, eps, thr, flags, cand_cnt, stats, sample, cand, o_scores, o_ids, o_counts};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        void* hp[] = {h_Q, h_scores, h_ids, h_counts, h_flags, h_stats, h_cnt};
+        for (void* p : hp) if (p) cudaFreeHost(p);
+        dQ = nullptr; dQ16 = nullptr; eps = thr = nullptr; flags = cand_cnt = stats = nullptr; sample = nullptr; cand = nullptr;
+        o_scores = nullptr; o_ids = nullptr; o_counts = nullptr;
+        h_Q = h_scores = nullptr; h_ids = nullptr; h_counts = h_flags = h_stats = h_cnt = nullptr;
+        cap_b = cap_ld = cap_k = 0; cap_sample = 0; cand_cap = 0;
+    }
+    void release() {
+        release_device();
+        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (st) { cudaStreamDestroy(st); st = nullptr; }
+    }
+};
+
 struct svsb_engine {
     std::vector<int> devs;
     std::mutex mu;                          // guards current, loading, pool bookkeeping
@@ -184,6 +220,9 @@ struct svsb_engine {
     std::vector<cudaStream_t> copy_st;      // per device
     std::vector<std::unique_ptr<QueryCtx>> pool_free;
     int ctx_total = 0, ctx_max = 4;
+    // batched path (one batch at a time)
+    std::mutex batch_mu;
+    std::unique_ptr<struct BatchWs> batch_ws;
     // bench state
     std::vector<float*> bench_q; int bench_nq = 0, bench_d = 0, bench_ld = 0;
     std::unique_ptr<QueryCtx> bench_ctx;
@@ -355,6 +394,7 @@ extern "C" void svsb_destroy(svsb_t* e) {
     for (auto& c : e->pool_free) ctx_destroy(e, c.get());
     e->pool_free.clear();
     if (e->bench_ctx) ctx_destroy(e, e->bench_ctx.get());
+    if (e->batch_ws) e->batch_ws->release();
     for (auto& w : e->shard_ws) if (w) w->release();
     for (auto ev : e->kev) cudaEventDestroy(ev);
     for (size_t i = 0; i < e->bench_q.size(); ++i) if (e->bench_q[i]) { cudaSetDevice(e->devs[i]); cudaFree(e->bench_q[i]); }
@@ -813,19 +853,198 @@ extern "C" int svsb_snapshot_query(svsb_t* e, svsb_snap_t* s, const float* q, in
     return query_gen(e, s->gen, q, d, k, out_scores, out_emb_ids, out_count);
 }
 
-extern "C" int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
-                                float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
-    // First implementation: the exact single-query path per row of Q (same kernels, same results).
-    // The tensor-core contraction (K2) replaces this loop; see DESIGN.md.
-    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
-    if (b < 0) return fail(SVSB_E_INVALID, "svsb_query_batch: negative batch");
-    if (b > 0 && (!Q || !out_counts)) return fail(SVSB_E_INVALID, "svsb_query_batch: NULL buffer");
+// ------------------------------------------------------------------------------------------------
+// batched queries: coarse tensor-core contraction + exact refine (coarse.cu, batch.cu)
+// ------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
+
+struct BatchPlan {
+    int64_t n = 0; int d = 0, ld = 0, ld16 = 0, kk = 0, k = 0;
+    int n_tiles = 0, s_tiles = 0, tile_stride = 1; int64_t sample_rows = 0;
+    int cand_cap = 0;
+    float eps_coef = 0.f, max_row_norm = 1.f;
+};
+
+// Can this generation / k take the coarse path at all?  (Purely a performance gate: both paths return the same bits.)
+static bool batch_plan(svsb_engine* e, const Generation* g, int32_t k, BatchPlan& P) {
+    if (e->devs.size() != 1 || g->shards.size() != 1) return false;
+    const Shard& s = g->shards[0];
+    if (s.n != g->n || g->n < env_int("SVSB_BATCH_MIN_ROWS", 4096) || g->n > 0x7fffff00ll || g->d < 16) return false;
+    const int64_t kk = std::min<int64_t>(k, g->n);
+    if (kk < 1 || kk > 1024) return false;
+    const float R = 1.0f + g->max_dev;
+    if (!(R <= 8.0f)) return false;                               // huge / non-finite rows: fp16 operands are not safe
+    P.n = g->n; P.d = g->d; P.ld = g->ld; P.ld16 = (g->d + 7) & ~7; P.kk = (int)kk; P.k = k;
+    P.n_tiles = (int)((g->n + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS);
+    P.cand_cap = env_int("SVSB_BATCH_CAND_CAP", 32768);
+    // sample size: the filter lets through roughly n * kk / sample_rows candidates per query (more once the 2 eps
+    // margin is subtracted); keep the expectation below cap / 4
+    int64_t want = std::max<int64_t>(320 * kk, (int64_t)(4.0 * (double)g->n * (double)kk / (double)P.cand_cap) + 1);
+    if (const char* v = getenv("SVSB_BATCH_SAMPLE_ROWS")) want = atoll(v);
+    int64_t st = (want + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS;
+    st = std::max<int64_t>(st, 32);
+    st = std::min<int64_t>(st, P.n_tiles);
+    P.s_tiles = (int)st;
+    P.tile_stride = std::max(1, P.n_tiles / P.s_tiles);
+    P.sample_rows = (int64_t)P.s_tiles * COARSE_TILE_ROWS;
+    // |coarse - exact| <= eps_coef * ||q|| * max||row|| + 1e-8: two fp16 roundings per product (2u + u^2, u = 2^-11),
+    // fp32 accumulation inside the tensor core (d * 2^-22, generous) and the exact kernel's own rounding (d * 2^-23)
+    P.eps_coef = 9.765625e-4f + 2.384185791015625e-7f + (float)g->d * (2.384185791015625e-7f + 1.1920928955078125e-7f);
+    P.max_row_norm = R * 1.000001f;
+    return true;
+}
+
+static int batch_ws_get(svsb_engine* e, BatchWs*& out) {
+    if (!e->batch_ws) {
+        std::unique_ptr<BatchWs> w(new BatchWs());
+        w->dev = e->devs[0];
+        CU(cudaSetDevice(w->dev));
+        CU(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
+        for (auto& ev : w->ev) CU(cudaEventCreate(&ev));
+        e->batch_ws = std::move(w);
+    }
+    out = e->batch_ws.get();
+    return SVSB_OK;
+}
+
+static int batch_ws_ensure(BatchWs* w, const BatchPlan& P, int b_pad) {
+    CU(cudaSetDevice(w->dev));
+    if (b_pad > w->cap_b || P.ld > w->cap_ld || P.k > w->cap_k || P.sample_rows > w->cap_sample || P.cand_cap != w->cand_cap) {
+        CU(cudaStreamSynchronize(w->st));
+        const int nb = std::max(b_pad, w->cap_b), nld = std::max(P.ld, w->cap_ld), nk = std::max(P.k, w->cap_k);
+        const int64_t ns = std::max(P.sample_rows, w->cap_sample);
+        w->release_device();
+        const int ld16 = (nld + 7) & ~7;
+        CU(cudaMalloc(&w->dQ, (size_t)nb * nld * 4));
+        CU(cudaMalloc(&w->dQ16, (size_t)nb * ld16 * 2));
+        CU(cudaMalloc(&w->eps, (size_t)nb * 4)); CU(cudaMalloc(&w->thr, (size_t)nb * 4));
+        CU(cudaMalloc(&w->flags, (size_t)nb * 4)); CU(cudaMalloc(&w->cand_cnt, (size_t)nb * 4)); CU(cudaMalloc(&w->stats, (size_t)nb * 4));
+        CU(cudaMalloc(&w->sample, (size_t)nb * ns * 4));
+        CU(cudaMalloc(&w->cand, (size_t)nb * P.cand_cap * 8));
+        CU(cudaMalloc(&w->o_scores, (size_t)nb * nk * 4)); CU(cudaMalloc(&w->o_ids, (size_t)nb * nk * 8)); CU(cudaMalloc(&w->o_counts, (size_t)nb * 4));
+        CU(cudaMallocHost(&w->h_Q, (size_t)nb * nld * 4));
+        CU(cudaMallocHost(&w->h_scores, (size_t)nb * nk * 4)); CU(cudaMallocHost(&w->h_ids, (size_t)nb * nk * 8));
+        CU(cudaMallocHost(&w->h_counts, (size_t)nb * 4)); CU(cudaMallocHost(&w->h_flags, (size_t)nb * 4));
+        CU(cudaMallocHost(&w->h_stats, (size_t)nb * 4)); CU(cudaMallocHost(&w->h_cnt, (size_t)nb * 4));
+        w->cap_b = nb; w->cap_ld = nld; w->cap_k = nk; w->cap_sample = ns; w->cand_cap = P.cand_cap;
+    }
+    return SVSB_OK;
+}
+
+// fp16 shadow of the matrix, built once per generation
+static int ensure_m16(Generation* g, const BatchPlan& P, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g->m16_mu);
+    if (g->M16) return SVSB_OK;
+    const Shard& s = g->shards[0];
+    CU(cudaSetDevice(s.dev));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, (size_t)s.n * P.ld16 * 2));
+    cudaError_t ce = launch_rows_to_f16(st, s.dev, s.M, s.n, g->ld, p, P.ld16);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { cudaFree(p); (void)cudaGetLastError(); return fail(SVSB_E_CUDA, std::string("fp16 shadow: ") + cudaGetErrorString(ce)); }
+    g->M16 = p; g->ld16 = P.ld16;
+    return SVSB_OK;
+}
+
+// Enqueue the whole pipeline for b (<= COARSE_MAX_BATCH) device-resident fp32 queries dQ[b][ld] on w->st.
+// Results: w->o_scores / o_ids [b][k], w->o_counts[b], w->flags[b] (!= 0: the query needs the exact path).
+// time_coarse: bracket the filter pass with w->ev[2], w->ev[3].
+static int batch_enqueue(BatchWs* w, const Generation* g, const BatchPlan& P, const float* dQ, int b, bool time_coarse) {
+    const Shard& s = g->shards[0];
+    const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+    CU(cudaSetDevice(w->dev));
+    CU(launch_queries_to_f16(w->st, dQ, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags));
+    CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, w->st));
+    CU(launch_coarse_gemm(w->st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
+                          nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
+    CU(launch_sample_threshold(w->st, w->sample, P.sample_rows, b, P.kk, w->eps, w->thr));
+    if (time_coarse) CU(cudaEventRecord(w->ev[2], w->st));
+    CU(launch_coarse_gemm(w->st, w->dev, 0, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.n_tiles, 1,
+                          w->thr, w->cand, w->cand_cnt, P.cand_cap, nullptr, 0));
+    if (time_coarse) CU(cudaEventRecord(w->ev[3], w->st));
+    CU(launch_refine(w->st, s.M, P.n, P.ld, s.ids, 0, dQ, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->flags,
+                     w->o_scores, w->o_ids, w->o_counts, w->stats));
+    return SVSB_OK;
+}
+
+static int query_batch_loop(svsb_engine* e, const std::shared_ptr<Generation>& g, const float* Q, int32_t b, int32_t d, int32_t k,
+                            float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
     const int64_t kstride = k > 0 ? k : 0;
     for (int32_t i = 0; i < b; ++i) {
-        int rc = svsb_query(e, Q + (int64_t)i * d, d, k, out_scores ? out_scores + i * kstride : nullptr,
-                            out_emb_ids ? out_emb_ids + i * kstride : nullptr, out_counts + i);
+        int rc = query_gen(e, g, Q + (int64_t)i * d, d, k, out_scores ? out_scores + i * kstride : nullptr,
+                           out_emb_ids ? out_emb_ids + i * kstride : nullptr, out_counts + i);
         if (rc != SVSB_OK) return rc;
     }
+    return SVSB_OK;
+}
+
+extern "C" int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
+                                float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (b < 0) return fail(SVSB_E_INVALID, "svsb_query_batch: negative batch");
+    if (b == 0) return SVSB_OK;
+    if (!Q || !out_counts) return fail(SVSB_E_INVALID, "svsb_query_batch: NULL buffer");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident (call svsb_load_* first)");
+    for (int32_t i = 0; i < b; ++i) out_counts[i] = 0;
+    BatchPlan P;
+    const bool coarse = g->n > 0 && d == g->d && k > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
+    if (!coarse)                                      // same results, one similarity pass per query
+        return query_batch_loop(e, g, Q, b, d, k, out_scores, out_emb_ids, out_counts);
+    if (!out_scores || !out_emb_ids) return fail(SVSB_E_INVALID, "svsb_query_batch: NULL buffer");
+
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = nullptr;
+    int rc = batch_ws_get(e, w);
+    if (rc != SVSB_OK) return rc;
+    if ((rc = ensure_m16(g.get(), P, w->st)) != SVSB_OK) {
+        if (rc == SVSB_E_NOMEM) return query_batch_loop(e, g, Q, b, d, k, out_scores, out_emb_ids, out_counts);
+        return rc;
+    }
+    for (int32_t c0 = 0; c0 < b; c0 += COARSE_MAX_BATCH) {
+        const int bc = std::min<int32_t>(COARSE_MAX_BATCH, b - c0);
+        const int b_pad = (bc + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+        if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
+        for (int i = 0; i < bc; ++i) {
+            float* dst = w->h_Q + (size_t)i * P.ld;
+            memcpy(dst, Q + (size_t)(c0 + i) * d, (size_t)d * 4);
+            for (int c = d; c < P.ld; ++c) dst[c] = 0.f;
+        }
+        CU(cudaSetDevice(w->dev));
+        CU(cudaMemcpyAsync(w->dQ, w->h_Q, (size_t)bc * P.ld * 4, cudaMemcpyHostToDevice, w->st));
+        if ((rc = batch_enqueue(w, g.get(), P, w->dQ, bc, false)) != SVSB_OK) return rc;
+        CU(cudaMemcpyAsync(w->h_scores, w->o_scores, (size_t)bc * k * 4, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaMemcpyAsync(w->h_ids, w->o_ids, (size_t)bc * k * 8, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaMemcpyAsync(w->h_counts, w->o_counts, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaMemcpyAsync(w->h_flags, w->flags, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaStreamSynchronize(w->st));
+        for (int i = 0; i < bc; ++i) {
+            const int64_t o = (int64_t)(c0 + i) * k;
+            if (w->h_flags[i] == 0 && w->h_counts[i] == P.kk) {
+                memcpy(out_scores + o, w->h_scores + (size_t)i * k, (size_t)P.kk * 4);
+                memcpy(out_emb_ids + o, w->h_ids + (size_t)i * k, (size_t)P.kk * 8);
+                out_counts[c0 + i] = P.kk;
+            } else {                                   // overflowed / untrusted query: exact single-query kernels
+                rc = query_gen(e, g, Q + (size_t)(c0 + i) * d, d, k, out_scores + o, out_emb_ids + o, out_counts + c0 + i);
+                if (rc != SVSB_OK) return rc;
+            }
+        }
+    }
+    return SVSB_OK;
+}
+
+// Diagnostics of the last svsb_query_batch / svsb_bench_run_batch chunk: per query the number of coarse candidates,
+// the number of rows re-scored exactly, and the flag word (0 = answered by the coarse path).
+extern "C" int svsb_batch_stats(svsb_t* e, int32_t b, int32_t* candidates, int32_t* rescored, int32_t* flags) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = e->batch_ws.get();
+    if (!w || b < 0 || b > w->cap_b) return fail(SVSB_E_STATE, "svsb_batch_stats: no batch of that size has run");
+    CU(cudaSetDevice(w->dev));
+    CU(cudaStreamSynchronize(w->st));
+    if (candidates) CU(cudaMemcpy(candidates, w->cand_cnt, (size_t)b * 4, cudaMemcpyDeviceToHost));
+    if (rescored) CU(cudaMemcpy(rescored, w->stats, (size_t)b * 4, cudaMemcpyDeviceToHost));
+    if (flags) CU(cudaMemcpy(flags, w->flags, (size_t)b * 4, cudaMemcpyDeviceToHost));
     return SVSB_OK;
 }
 
@@ -991,9 +1210,62 @@ extern "C" int svsb_debug_select_phases(svsb_t* e, int32_t qi, int32_t k, uint64
     return SVSB_OK;
 }
 
-extern "C" int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, int64_t* launches) {
-    (void)e; (void)k; (void)iters; (void)total_ms; (void)launches;
-    return fail(SVSB_E_INVALID, "svsb_bench_run_batch: the batched tensor-core path is not built yet");
+extern "C" int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* coarse_ms, int64_t* launches) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (e->bench_nq == 0 || e->bench_d != g->d) return fail(SVSB_E_SHAPE, "svsb_bench_run_batch: upload queries of the matrix's d first");
+    if (k <= 0 || iters <= 0 || g->n == 0) return fail(SVSB_E_INVALID, "svsb_bench_run_batch: bad arguments");
+    if (e->bench_nq > COARSE_MAX_BATCH) return fail(SVSB_E_INVALID, "svsb_bench_run_batch: at most 2048 uploaded queries");
+    BatchPlan P;
+    if (!batch_plan(e, g.get(), k, P)) return fail(SVSB_E_INVALID, "svsb_bench_run_batch: this matrix / k does not take the coarse path");
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = nullptr;
+    int rc = batch_ws_get(e, w);
+    if (rc != SVSB_OK) return rc;
+    if ((rc = ensure_m16(g.get(), P, w->st)) != SVSB_OK) return rc;
+    const int b = e->bench_nq;
+    const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+    if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
+    CU(cudaSetDevice(w->dev));
+    const int64_t l0 = g_launches.load();
+    CU(cudaStreamSynchronize(w->st));
+    float csum = 0.f;
+    CU(cudaEventRecord(w->ev[0], w->st));
+    for (int it = 0; it < iters; ++it) {
+        if ((rc = batch_enqueue(w, g.get(), P, e->bench_q[0], b, coarse_ms != nullptr)) != SVSB_OK) return rc;
+        if (coarse_ms) {                                 // events are reused: collect before the next iteration records them
+            CU(cudaEventSynchronize(w->ev[3]));
+            float ms = 0.f; CU(cudaEventElapsedTime(&ms, w->ev[2], w->ev[3])); csum += ms;
+        }
+    }
+    CU(cudaEventRecord(w->ev[1], w->st));
+    CU(cudaEventSynchronize(w->ev[1]));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]));
+    if (total_ms) *total_ms = ms;
+    if (coarse_ms) *coarse_ms = csum;
+    if (launches) *launches = g_launches.load() - l0;
+    return SVSB_OK;
+}
+
+// Result of query qi of the last batch run (device-resident pipeline), for checking the timed path.
+extern "C" int svsb_bench_batch_result(svsb_t* e, int32_t qi, int32_t k, float* out_scores, int64_t* out_emb_ids, int32_t* out_count,
+                                       int32_t* out_flag) {
+    if (!e || !out_scores || !out_emb_ids || !out_count) return fail(SVSB_E_INVALID, "svsb_bench_batch_result: NULL argument");
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = e->batch_ws.get();
+    if (!w || qi < 0 || qi >= w->cap_b || k > w->cap_k) return fail(SVSB_E_STATE, "svsb_bench_batch_result: no such result");
+    CU(cudaSetDevice(w->dev));
+    CU(cudaStreamSynchronize(w->st));
+    int32_t cnt = 0, flag = 0;
+    CU(cudaMemcpy(&cnt, w->o_counts + qi, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&flag, w->flags + qi, 4, cudaMemcpyDeviceToHost));
+    if (cnt < 0 || cnt > k) return fail(SVSB_E_INVALID, "svsb_bench_batch_result: k does not match the run");
+    CU(cudaMemcpy(out_scores, w->o_scores + (size_t)qi * k, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_emb_ids, w->o_ids + (size_t)qi * k, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
+    *out_count = cnt;
+    if (out_flag) *out_flag = flag;
+    return SVSB_OK;
 }
 
 extern "C" int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {

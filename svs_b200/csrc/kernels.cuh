@@ -58,6 +58,38 @@ cudaError_t launch_row_norms(cudaStream_t st, int device, float* M, int64_t n, i
 cudaError_t launch_synth(cudaStream_t st, int device, float* M, int64_t n, int d, int ld, uint64_t seed,
                          int64_t global_row0, int64_t* ids, int64_t id0, int64_t id_step);
 
+// ---- K2: batched queries = coarse tensor-core contraction + exact refine (coarse.cu, batch.cu) -----------
+constexpr int COARSE_MAX_BATCH = 2048;              // queries per coarse launch (thresholds live in shared memory)
+constexpr int COARSE_TILE_ROWS = 128;               // rows per coarse tile (UMMA M)
+constexpr int COARSE_TILE_QUERIES = 256;            // queries per coarse tile (UMMA N); batches are padded to it
+constexpr float COARSE_OPERAND_SCALE = 4096.0f;     // 2^12 on both operands: keeps fp16 components normal, exact to undo
+constexpr int REFINE_SURVIVOR_CAP = 4096;           // exact re-scores per query the refine kernel can hold
+
+// M16[r][0..ld16) = fp16(M[r][.] * 2^12), zero padded.  ld % 4 == 0, ld16 % 8 == 0, ld16 >= ld.
+cudaError_t launch_rows_to_f16(cudaStream_t st, int device, const float* M, int64_t n, int ld, void* M16, int ld16);
+// Q16 (b_pad rows, rows >= b zero) from fp32 queries Q[b][ldq]; eps[q] = eps_coef * ||q|| * max_row_norm + 1e-8,
+// thr[q] = +inf, flags[q] = 1 for queries the coarse path must not handle (non-finite / huge norm).
+cudaError_t launch_queries_to_f16(cudaStream_t st, const float* Q, int b, int b_pad, int d, int ldq, void* Q16, int ld16,
+                                  float eps_coef, float max_row_norm, float* eps, float* thr, int32_t* flags);
+// mode 0: filter -- every (row, query) whose coarse score >= thr[query] is appended to cand[query][..cand_cap)
+//         (key = ordered coarse score << 32 | ~row), cand_cnt[query] counts ALL survivors (may exceed cand_cap).
+// mode 1: sample -- raw coarse scores of row tiles 0, tile_stride, 2*tile_stride, ... (n_tiles of them) go to
+//         sample[query][sample_rows]; rows beyond n read as -inf.
+cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void* M16, int64_t n, const void* Q16, int b_pad,
+                               int ld16, int n_tiles, int tile_stride, const float* thr, u64* cand, int32_t* cand_cnt,
+                               int cand_cap, float* sample, int64_t sample_rows);
+// thr[q] = (kk-th largest of sample[q][0..sample_rows)) - 2 eps[q] for q < b (one CTA per query).
+cudaError_t launch_sample_threshold(cudaStream_t st, const float* sample, int64_t sample_rows, int b, int kk, const float* eps,
+                                    float* thr);
+// One CTA per query: tau~ = kk-th largest coarse candidate; keep candidates with coarse >= tau~ - 2*eps[q]; re-score
+// them exactly (fp32, the similarity kernel's summation order); sort; write (score, embeddings.id) x kk.
+// flags[q] |= 2 candidate list overflowed, 4 fewer than kk candidates, 8 survivor list overflowed: such queries
+// are left to the caller's exact single-query path.  stats[q] (optional) = survivors re-scored.
+cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
+                          const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
+                          const float* eps, int32_t* flags, float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                          int32_t* stats);
+
 int sm_count(int device);
 inline int64_t next_pow2(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return p; }
 

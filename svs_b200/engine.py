@@ -153,6 +153,8 @@ class Engine:
         return Snapshot(self)
 
     def query_batch(self, Q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """b queries at once: (scores (b, k), emb_ids (b, k), counts (b,)).  Bit-identical to b calls of query();
+        large batches run as one tensor-core contraction + exact refine (include/svsb200.h: svsb_query_batch)."""
         Q = _f32c(Q)
         if Q.ndim != 2:
             raise ValueError("Q must be (b, d)")
@@ -192,6 +194,28 @@ class Engine:
         total, gemv, launches = C.c_float(), C.c_float(), C.c_int64()
         check(self._lib.svsb_bench_run(self._h, k, iters, C.byref(total), C.byref(gemv) if with_gemv else None, C.byref(launches)))
         return {"total_ms": total.value, "gemv_ms": gemv.value if with_gemv else None, "launches": launches.value}
+
+    def bench_run_batch(self, k: int, iters: int, with_coarse: bool = False) -> dict:
+        """`iters` batches of ALL uploaded queries through the batched (tensor-core) path, device-resident."""
+        total, coarse, launches = C.c_float(), C.c_float(), C.c_int64()
+        check(self._lib.svsb_bench_run_batch(self._h, k, iters, C.byref(total), C.byref(coarse) if with_coarse else None,
+                                             C.byref(launches)))
+        return {"total_ms": total.value, "coarse_ms": coarse.value if with_coarse else None, "launches": launches.value}
+
+    def bench_batch_result(self, qi: int, k: int) -> Tuple[List[Tuple[float, int]], int]:
+        s = np.empty(k, dtype=np.float32)
+        i = np.empty(k, dtype=np.int64)
+        cnt, flag = C.c_int32(), C.c_int32()
+        check(self._lib.svsb_bench_batch_result(self._h, qi, k, s.ctypes.data, i.ctypes.data, C.byref(cnt), C.byref(flag)))
+        return [(float(a), int(b)) for a, b in zip(s[:cnt.value], i[:cnt.value])], flag.value
+
+    def batch_stats(self, b: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(coarse candidates, rows re-scored exactly, flag) per query of the last batch chunk."""
+        cand = np.zeros(b, dtype=np.int32)
+        resc = np.zeros(b, dtype=np.int32)
+        flags = np.zeros(b, dtype=np.int32)
+        check(self._lib.svsb_batch_stats(self._h, b, cand.ctypes.data, resc.ctypes.data, flags.ctypes.data))
+        return cand, resc, flags
 
     def bench_last_result(self, k: int) -> List[Tuple[float, int]]:
         s = np.empty(k, dtype=np.float32)

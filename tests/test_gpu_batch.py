@@ -1,0 +1,117 @@
+"""GPU: svsb_query_batch (tensor-core coarse contraction + exact fp32 refine) against the single-query path and the
+oracle.  The batched path promises the SAME BITS as b calls of svsb_query, so scores are
+compared as uint32 and ids exactly; one configuration is also checked against the oracle's superheavy()
+(reference src/svs/kb.py:1622-1627) under the usual tolerance."""
+import numpy as np
+import pytest
+
+from _util import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import svs_b200
+    e = svs_b200.Engine()
+    yield e
+    e.close()
+
+
+def _unit(rng, shape, dist):
+    m = rng.random(shape, dtype=np.float32) if dist == "uniform" else rng.standard_normal(shape).astype(np.float32)
+    m /= np.maximum(np.sqrt((m * m).sum(axis=1)), 1e-12)[:, None]
+    return m
+
+
+def _assert_same_as_single(engine, q, k, s, i, c, check=None):
+    n = engine.shape[0]
+    assert (c == min(k, n)).all()
+    for j in (range(len(q)) if check is None else check):
+        ss, ii = engine.query(q[j], k)
+        assert np.array_equal(ss.view(np.uint32), s[j, :len(ss)].view(np.uint32)), f"scores differ for query {j}"
+        assert np.array_equal(ii, i[j, :len(ii)]), f"ids differ for query {j}"
+
+
+@pytest.mark.parametrize("n,d,k,b,dist", [
+    (20_000, 768, 100, 300, "uniform"),        # the README recipe's distribution: scores 0.75 +- 0.007, a hard case
+    (20_000, 768, 100, 300, "normal"),
+    (5_000, 96, 10, 8, "normal"),              # one partial query tile
+    (70_001, 1536, 100, 64, "uniform"),        # ragged last row tile
+    (30_000, 100, 7, 33, "normal"),            # d not a multiple of 8
+    (12_345, 3072, 1000, 20, "uniform"),       # large k
+    (40_000, 256, 1, 513, "normal"),           # k = 1, three query tiles
+])
+def test_batch_equals_single_query_bits(engine, n, d, k, b, dist):
+    rng = np.random.default_rng(n + d + k)
+    m = _unit(rng, (n, d), dist)
+    ids = np.cumsum(rng.integers(1, 4, size=n)).astype(np.int64)
+    q = _unit(rng, (b, d), dist)
+    engine.load(m, ids)
+    s, i, c = engine.query_batch(q, k)
+    cand, resc, flags = engine.batch_stats(b)
+    assert (flags == 0).all(), "these inputs must be answered by the coarse path, not the fallback"
+    assert (resc >= min(k, n)).all() and (cand >= resc).all()
+    _assert_same_as_single(engine, q, k, s, i, c, check=range(0, b, max(1, b // 24)))
+
+
+def test_batch_against_the_oracle(engine):
+    rng = np.random.default_rng(5)
+    n, d, k, b = 50_000, 768, 100, 16
+    m = _unit(rng, (n, d), "uniform")
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    q = _unit(rng, (b, d), "uniform")
+    engine.load(m, ids)
+    s, i, c = engine.query_batch(q, k)
+    for j in range(b):
+        got = [(float(a), int(x)) for a, x in zip(s[j, :c[j]], i[j, :c[j]])]
+        rep = oracle.compare_retrieval(got, oracle.superheavy(m, ids, q[j], k), oracle.scores_of(m, q[j]), ids)
+        assert rep["max_rel_score_err"] <= 1e-5
+
+
+def test_batch_with_massive_ties_falls_back_and_stays_exact(engine):
+    """Every row identical: all coarse scores tie, candidate lists overflow, the exact kernels answer."""
+    rng = np.random.default_rng(9)
+    n, d, k, b = 40_000, 128, 50, 8
+    row = _unit(rng, (1, d), "normal")
+    m = np.repeat(row, n, axis=0)
+    ids = np.arange(n, dtype=np.int64)
+    q = _unit(rng, (b, d), "normal")
+    engine.load(m, ids)
+    s, i, c = engine.query_batch(q, k)
+    cand, resc, flags = engine.batch_stats(b)
+    assert (flags != 0).all()
+    assert (i == np.arange(k)[None, :]).all()                     # ties: ascending row / id
+    _assert_same_as_single(engine, q, k, s, i, c)
+
+
+def test_batch_edge_cases(engine):
+    rng = np.random.default_rng(11)
+    n, d = 6_000, 64
+    m = _unit(rng, (n, d), "normal")
+    engine.load(m, np.arange(n, dtype=np.int64))
+    q = _unit(rng, (10, d), "normal")
+    s, i, c = engine.query_batch(q, 0)                             # k <= 0 -> no results (util.py:200-201)
+    assert (c == 0).all() and s.shape == (10, 0)
+    s, i, c = engine.query_batch(q[:2], 5)                         # tiny batch: loops the single-query kernels
+    _assert_same_as_single(engine, q[:2], 5, s, i, c)
+    s, i, c = engine.query_batch(q, 3000)                          # k above the coarse path's limit
+    _assert_same_as_single(engine, q, 3000, s, i, c, check=[0, 9])
+    with pytest.raises(ValueError):
+        engine.query_batch(_unit(rng, (10, d + 1), "normal"), 5)   # d mismatch, as np.dot
+    big = q.copy(); big[3] *= 100.0                                # a query far from unit norm: exact path for it only
+    s, i, c = engine.query_batch(big, 5)
+    cand, resc, flags = engine.batch_stats(10)
+    assert flags[3] != 0 and (np.delete(flags, 3) == 0).all()
+    _assert_same_as_single(engine, big, 5, s, i, c)
+
+
+def test_batch_after_reload_uses_the_new_generation(engine):
+    rng = np.random.default_rng(13)
+    d, k, b = 128, 10, 16
+    q = _unit(rng, (b, d), "normal")
+    for n in (8_000, 9_000):
+        m = _unit(rng, (n, d), "normal")
+        engine.load(m, np.arange(100, 100 + n, dtype=np.int64))
+        s, i, c = engine.query_batch(q, k)
+        _assert_same_as_single(engine, q, k, s, i, c)
