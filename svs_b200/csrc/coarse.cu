@@ -8,12 +8,13 @@
 //
 //   operands   M16 = fp16(M * 2^12) [n][ld16], Q16 = fp16(Q * 2^12) [b_pad][ld16]   (K-major, zero padded)
 //   kernel     persistent, warp-specialised, one CTA per SM, cta_group::1:
-//                warp 4   TMA producer: cp.async.bulk.tensor 2-D boxes (64 halfs x 128 rows of M16, 64 x 256 rows of
+//                warp 16  TMA producer: cp.async.bulk.tensor 2-D boxes (64 halfs x 128 rows of M16, 64 x 256 rows of
 //                         Q16), 128-byte swizzle, 4-stage shared-memory ring on mbarriers
-//                warp 5   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (rows) x N=256 (queries) x K=16, fp32
+//                warp 17  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (rows) x N=256 (queries) x K=16, fp32
 //                         accumulators in TMEM, two accumulator buffers (2 x 256 columns) so that the epilogue of tile
 //                         i overlaps the MMAs of tile i+1; tcgen05.commit releases ring slots / publishes accumulators
-//                warps 0-3 epilogue: tcgen05.ld 32 lanes x 32 columns at a time; S~ is NEVER written out:
+//                warps 0-15 epilogue (4 per TMEM lane quarter, 2 column chunks each): tcgen05.ld 32 lanes x 32 columns
+//                         at a time; S~ is NEVER written out:
 //                         MODE_FILTER  compare with the query's threshold (shared memory), append the rare survivors
 //                                      as 64-bit keys (ordered coarse score << 32 | ~row) to the query's candidate list
 //                         MODE_SAMPLE  dump raw coarse scores of the sampled row tiles (bootstrap of the thresholds)
@@ -94,9 +95,13 @@ constexpr int CG_STAGES = 4;
 constexpr uint32_t CG_A_BYTES = CG_BM * CG_BK * 2;      // 16 KB
 constexpr uint32_t CG_B_BYTES = CG_BN * CG_BK * 2;      // 32 KB
 constexpr uint32_t CG_STAGE_BYTES = CG_A_BYTES + CG_B_BYTES;
-constexpr int CG_THREADS = 192;            // 4 epilogue warps + producer warp + MMA warp
+constexpr int CG_EPI_WARPS = 16;           // 4 per TMEM lane quarter (= per SM sub-partition): latency hiding for the read-out
+constexpr int CG_THREADS = (CG_EPI_WARPS + 2) * 32;   // epilogue warps + producer warp + MMA warp
+constexpr int CG_CHUNKS_PER_WARP = (256 / 32) / (CG_EPI_WARPS / 4);   // 32-column chunks of a tile per epilogue warp
 constexpr int CG_TMEM_COLS = 512;          // two 256-column fp32 accumulators
-constexpr size_t CG_SMEM = 1024 /*align slack*/ + (size_t)CG_STAGES * CG_STAGE_BYTES + COARSE_MAX_BATCH * 4 + 256;
+constexpr int CG_LCAP = 128;               // staged survivors per epilogue warp before a flush to the global lists
+constexpr size_t CG_SMEM = 1024 /*align slack*/ + (size_t)CG_STAGES * CG_STAGE_BYTES + COARSE_MAX_BATCH * 4 + 256
+                         + CG_EPI_WARPS * (size_t)CG_LCAP * (8 + 2);
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=B=f16 (0), K-major both, N>>3 at [17,23),
 // M>>4 at [24,29)
@@ -129,6 +134,9 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     auto tfull_bar = [&](int b) { return bar0 + 8u * (uint32_t)(2 * CG_STAGES + b); };
     auto tempty_bar = [&](int b) { return bar0 + 8u * (uint32_t)(2 * CG_STAGES + 2 + b); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CG_STAGES + 4);
+    uint32_t* lcnt_all = tmem_slot + 4;                                 // per-warp staging counters (16 x 4 B)
+    u64* lkey_all = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(bars) + 256);
+    uint16_t* lq_all = reinterpret_cast<uint16_t*>(lkey_all + CG_EPI_WARPS * CG_LCAP);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float kScale = 16777216.0f;                                   // 2^24 = (2^12)^2, the operands' scaling
@@ -137,12 +145,13 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int nq = n_qblocks * CG_BN;
         for (int i = threadIdx.x; i < nq; i += CG_THREADS) thr_s[i] = thr[i] * kScale;
     }
-    if (warp == 4 && lane == 0) {
+    if (threadIdx.x < CG_EPI_WARPS) lcnt_all[threadIdx.x] = 0;
+    if (warp == CG_EPI_WARPS && lane == 0) {
         for (int s = 0; s < CG_STAGES; ++s) { mbarrier_init(full_bar(s), 1); mbarrier_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbarrier_init(tfull_bar(b), 1); mbarrier_init(tempty_bar(b), 4); }
+        for (int b = 0; b < 2; ++b) { mbarrier_init(tfull_bar(b), 1); mbarrier_init(tempty_bar(b), CG_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == CG_EPI_WARPS + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(cvta_smem(tmem_slot)), "n"(CG_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -154,7 +163,7 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     const int64_t total = (int64_t)n_tiles * n_qblocks;
 
-    if (warp == 4) {
+    if (warp == CG_EPI_WARPS) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0; uint32_t phase = 0;
@@ -172,7 +181,7 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == CG_EPI_WARPS + 1) {
         // ------------------------------------------------------------------ MMA issuer (one elected lane)
         if (lane == 0) {
             int s = 0; uint32_t phase = 0;
@@ -198,7 +207,38 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps 0..3 (TMEM lanes 32*warp ..)
+        // ------------------------------------------------------------------ epilogue warps: warp w reads TMEM lanes
+        // 32*(w%4).. (the hardware ties a warp to the lane quarter of its sub-partition) and the column chunks
+        // (w/4)*CG_CHUNKS_PER_WARP ...  Survivors are staged in a per-warp shared-memory list (shared-memory atomics: tens of cycles) and flushed
+        // to the per-query global lists by all 32 lanes at once, so the ~700-cycle global atomic round trip is
+        // paid once per ~128 survivors instead of once per survivor in the middle of the TMEM read-out.
+        u64* lkey = lkey_all + warp * CG_LCAP;
+        uint16_t* lq = lq_all + warp * CG_LCAP;
+        uint32_t* lcnt = lcnt_all + warp;
+        auto append_global = [&](int q, u64 key) {
+            const int slot = atomicAdd(&cand_cnt[q], 1);
+            if (slot < cand_cap) cand[(size_t)q * cand_cap + slot] = key;
+        };
+        auto flush = [&]() {
+            __syncwarp();
+            const int cnt = min((int)*reinterpret_cast<volatile uint32_t*>(lcnt), CG_LCAP);
+            for (int i0 = 0; i0 < cnt; i0 += 128) {                    // 4 independent atomics in flight per lane
+                int qs[4], slots[4]; u64 keys[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 32 + lane;
+                    qs[u] = -1;
+                    if (i < cnt) { qs[u] = lq[i]; keys[u] = lkey[i]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) slots[u] = qs[u] >= 0 ? atomicAdd(&cand_cnt[qs[u]], 1) : cand_cap;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (slots[u] < cand_cap) cand[(size_t)qs[u] * cand_cap + slots[u]] = keys[u];
+            }
+            __syncwarp();
+            if (lane == 0) *lcnt = 0;
+            __syncwarp();
+        };
         int64_t it = 0;
         for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
             const int t = (int)(w / n_qblocks), qb = (int)(w - (int64_t)t * n_qblocks);
@@ -206,14 +246,21 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t use = (uint32_t)(it >> 1);
             mbarrier_wait(tfull_bar(buf), use & 1u);
             tc_fence_after();
-            const int64_t row = (int64_t)t * tile_stride * CG_BM + warp * 32 + lane;
+            const int lq4 = warp & 3;                                  // TMEM lane quarter
+            const int64_t row = (int64_t)t * tile_stride * CG_BM + lq4 * 32 + lane;
             const bool row_ok = row < n;
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * CG_BN;
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(lq4 * 32) << 16) + (uint32_t)buf * CG_BN;
+            const int c_begin = (warp >> 2) * CG_CHUNKS_PER_WARP;
 #pragma unroll 1
-            for (int c = 0; c < CG_BN / 32; ++c) {
+            for (int c = c_begin; c < c_begin + CG_CHUNKS_PER_WARP; ++c) {
                 uint32_t v[32];
                 tc_ld_32x32(taddr0 + (uint32_t)c * 32, v);
                 tc_wait_ld();
+                if (c == c_begin + CG_CHUNKS_PER_WARP - 1) {           // this warp's share is read: one of 16 arrivals
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbarrier_arrive(tempty_bar(buf));
+                }
                 const int q0 = qb * CG_BN + c * 32;
                 if (MODE == 0) {
                     const float4* th4 = reinterpret_cast<const float4*>(thr_s + q0);
@@ -228,18 +275,23 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                     if (!row_ok) mask = 0;
                     if (mask) {
+                        const int hits = __popc(mask);
+                        const uint32_t pos0 = atomicAdd(lcnt, (uint32_t)hits);      // shared-memory atomic
+                        uint32_t pos = pos0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (mask & (1u << j)) {
-                                const int q = q0 + j;
-                                const int slot = atomicAdd(&cand_cnt[q], 1);
-                                if (slot < cand_cap)
-                                    cand[(size_t)q * cand_cap + slot] = make_key(__uint_as_float(v[j]) * (1.0f / kScale), (uint32_t)row);
+                                const u64 key = make_key(__uint_as_float(v[j]) * (1.0f / kScale), (uint32_t)row);
+                                if (pos < (uint32_t)CG_LCAP) { lkey[pos] = key; lq[pos] = (uint16_t)(q0 + j); }
+                                else append_global(q0 + j, key);       // staging full (loose thresholds): slow but correct
+                                ++pos;
                             }
                         }
                     }
+                    __syncwarp();
+                    if (*reinterpret_cast<volatile uint32_t*>(lcnt) >= (uint32_t)(CG_LCAP / 2)) flush();
                 } else {
-                    const int64_t srow = (int64_t)t * CG_BM + warp * 32 + lane;          // position inside the sample
+                    const int64_t srow = (int64_t)t * CG_BM + lq4 * 32 + lane;           // position inside the sample
                     if (srow < sample_rows) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -248,15 +300,13 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbarrier_arrive(tempty_bar(buf));
         }
+        if (MODE == 0) flush();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == CG_EPI_WARPS + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(CG_TMEM_COLS) : "memory");
     }
