@@ -208,8 +208,8 @@ def run_batch_arm(args, n, d, k, desc):
     eng.load_synthetic(n, d, seed=0, id0=1, id_step=1)
     load_s = time.perf_counter() - t_load
     eng.bench_set_queries(queries)
-    for _ in range(args.warmup):
-        eng.bench_run_batch(k, 1)
+    for _ in range(args.warmup):                                # a batch is ~2 ms: 10 per warm-up step lets the clocks ramp
+        eng.bench_run_batch(k, 10)
     sampler = ClockSampler(0)
     sampler.start()
     total_ms = coarse_ms = 0.0

@@ -39,7 +39,7 @@ def to_bytes(val, unit):
     return float(val.replace(",", "")) * mult if mult else None
 
 
-def summarise(rep, title, tag):
+def summarise(rep, title, tag, only=None):
     hdr, units, rows = raw_rows(rep)
     lines = [f"# {title}", "", f"Source: `gpurun_out/{os.path.basename(rep)}` (`ncu --set full --clock-control none --import-source on`), "
              "read with `ncu -i ... --page raw --csv`.  Times under ncu are serialised/cold-cache: use the shares, not the absolutes.", ""]
@@ -54,7 +54,8 @@ def summarise(rep, title, tag):
         rd = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
         wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
         if rd is not None and wr is not None:
-            traffic.append(rd + wr)
+            if only is None or only in name:
+                traffic.append(rd + wr)
             lines.append(f"| **traffic = dram read + write** | {rd + wr:.0f} | byte |")
         lines.append("")
     path = os.path.join(PROF, f"{tag}.md")
@@ -63,8 +64,8 @@ def summarise(rep, title, tag):
     return traffic
 
 
-def launches(tag):
-    src = os.path.join(OUT, "launches.csv")
+def launches(tag, src=None):
+    src = src or os.path.join(OUT, "launches.csv")
     rows = [r for r in csv.reader(open(src)) if len(r) > 10]
     hdr = rows[0]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -92,16 +93,20 @@ if __name__ == "__main__":
     rtag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     out = {}
-    for rep, title, key in (("prof_gemv.ncu-rep", "similarity kernel (gemv_tma_kernel), workload c2 = 1M x 1536 fp32", "c2"),
-                            ("prof_select.ncu-rep", "selection kernel (select_topk_kernel), workload c2, k = 100", None),
-                            ("prof_coarse.ncu-rep", "batched coarse contraction (coarse_gemm_kernel), workload c3", "c3")):
+    for rep, title, key, only in (
+            ("prof_gemv.ncu-rep", "similarity kernel (gemv_tma_kernel), workload c2 = 1M x 1536 fp32", "c2", None),
+            ("prof_select.ncu-rep", "selection kernel (select_topk_kernel), workload c2, k = 100", None, None),
+            ("prof_coarse.ncu-rep", "batched coarse contraction (coarse_gemm_kernel<1> sample pass, <0> filter pass), workload c3",
+             "c3", "coarse_gemm_kernel<0>")):
         p = os.path.join(OUT, rep)
         if os.path.exists(p):
-            t = summarise(p, title, f"{rtag}_{rep.split('.')[0][5:]}_ncu")
+            t = summarise(p, title, f"{rtag}_{rep.split('.')[0][5:]}_ncu", only)
             if key and t:
                 out[key] = sum(t) / len(t)
     if os.path.exists(os.path.join(OUT, "launches.csv")):
         launches(f"{rtag}_launches")
+    if os.path.exists(os.path.join(OUT, "launches_c3.csv")):
+        launches(f"{rtag}_launches_c3", os.path.join(OUT, "launches_c3.csv"))
     tf = os.path.join(PROF, f"{rtag}_traffic.json")
     old = json.load(open(tf)) if os.path.exists(tf) else {}
     old.update(out)

@@ -17,52 +17,87 @@ namespace svsb {
 constexpr int RF_THREADS = 512;
 constexpr int RF_BINS = 2048;
 
-// kk-th largest (1-based) of the 32-bit ordered values load(i), i < count (count >= kk >= 1), by three
-// most-significant-first radix passes (11 + 11 + 10 bits).  All threads call it; all get the result.
-// hist: RF_BINS words of shared memory; scratch: 40 words of shared memory.
+// kk-th largest (1-based, duplicates counted) of the 32-bit ordered values load(i), i < count (count >= kk >= 1).
+// Range-adaptive radix select: the 2048 bins always span [min, max] of the values still in play, so scores packed
+// into a narrow band (the README recipe: 0.75 +- 0.007) spread over all bins instead of hammering two of them with
+// shared-memory atomics; typically min/max pass + one histogram pass + one collect pass.
+// All threads call it; all get the result.  hist: RF_BINS words, scratch: 72 words, small: RF_SMALL words (shared).
+constexpr int RF_SMALL = 256;
 template <class Load>
-__device__ uint32_t block_kth_largest_o32(Load load, int64_t count, int kk, uint32_t* hist, uint32_t* scratch) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t prefix = 0, known = 0;
+__device__ uint32_t block_kth_largest_o32(Load load, int64_t count, int kk, uint32_t* hist, uint32_t* scratch, uint32_t* small) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int64_t i = tid; i < count; i += blockDim.x) { const uint32_t o = load(i); mn = min(mn, o); mx = max(mx, o); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if (lane == 0) { scratch[8 + warp] = mn; scratch[40 + warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+        mn = lane < nwarps ? scratch[8 + lane] : 0xffffffffu;
+        mx = lane < nwarps ? scratch[40 + lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        if (lane == 0) { scratch[4] = mn; scratch[5] = mx; }
+    }
+    __syncthreads();
+    uint32_t lo = scratch[4], hi = scratch[5];
     uint32_t remaining = (uint32_t)kk;
-    const int shifts[3] = {21, 10, 0};
-    const int bits[3] = {11, 11, 10};
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-        const int shift = shifts[pass];
-        const uint32_t nb = 1u << bits[pass];
+    __syncthreads();
+    while (true) {
+        const uint32_t span = hi - lo;
+        const int shift = max(0, (span ? 32 - __clz(span) : 0) - 11);
         for (int i = tid; i < RF_BINS; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         for (int64_t i = tid; i < count; i += blockDim.x) {
             const uint32_t o = load(i);
-            if ((o & known) == prefix) atomicAdd(&hist[(o >> shift) & (nb - 1)], 1u);
+            if (o >= lo && o <= hi) atomicAdd(&hist[(o - lo) >> shift], 1u);
         }
         __syncthreads();
         if (warp == 0) {
-            // lane l owns bins [64 l, 64 l + 64); top-down: lane 31 first
+            // lane l owns bins [64 l, 64 l + 64); scan from the top bin down
             uint32_t mine = 0;
             for (int j = 0; j < 64; ++j) mine += hist[lane * 64 + j];
-            // suffix sums: above(l) = sum of lanes > l
-            uint32_t incl = mine;
+            uint32_t incl = mine;                                      // suffix sum over lanes >= l
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
             const uint32_t above = incl - mine;
-            const bool hit = above < remaining && incl >= remaining;       // exactly one lane
-            if (hit) {
+            if (above < remaining && incl >= remaining) {              // exactly one lane
                 uint32_t acc = above;
                 int bin = lane * 64 + 63;
                 for (; bin > lane * 64; --bin) { if (acc + hist[bin] >= remaining) break; acc += hist[bin]; }
-                scratch[0] = (uint32_t)bin; scratch[1] = acc;
+                scratch[0] = (uint32_t)bin; scratch[1] = acc; scratch[2] = hist[bin];
             }
         }
         __syncthreads();
-        const uint32_t bin = scratch[0], acc = scratch[1];
-        prefix |= bin << shift;
-        known |= (nb - 1) << shift;
-        remaining -= acc;
+        const uint32_t bin = scratch[0], above = scratch[1], inbin = scratch[2];
+        remaining -= above;
+        const uint32_t nlo = lo + (bin << shift);
+        uint32_t nhi = nlo + ((1u << shift) - 1u);
+        if (nhi > hi || nhi < nlo) nhi = hi;
+        lo = nlo; hi = nhi;
         __syncthreads();
+        if (shift == 0) return lo;                                     // the bin is one value
+        if (inbin <= (uint32_t)RF_SMALL) break;
     }
-    return prefix;
+    // finish: the <= RF_SMALL values of the final bin, rank-selected (duplicates allowed)
+    if (tid == 0) scratch[3] = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < count; i += blockDim.x) {
+        const uint32_t o = load(i);
+        if (o >= lo && o <= hi) { const uint32_t p = atomicAdd(&scratch[3], 1u); if (p < (uint32_t)RF_SMALL) small[p] = o; }
+    }
+    __syncthreads();
+    const int c = (int)min(scratch[3], (uint32_t)RF_SMALL);
+    if (tid < c) {
+        const uint32_t mine = small[tid];
+        uint32_t gt = 0, ge = 0;
+        for (int j = 0; j < c; ++j) { gt += small[j] > mine ? 1u : 0u; ge += small[j] >= mine ? 1u : 0u; }
+        if (gt < remaining && ge >= remaining) scratch[6] = mine;      // equal values write the same word
+    }
+    __syncthreads();
+    const uint32_t ans = scratch[6];
+    __syncthreads();
+    return ans;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -73,10 +108,11 @@ sample_threshold_kernel(const float* __restrict__ sample, int64_t sample_rows, i
                         float* __restrict__ thr)
 {
     __shared__ uint32_t hist[RF_BINS];
-    __shared__ uint32_t scratch[40];
+    __shared__ uint32_t scratch[72];
+    __shared__ uint32_t small[RF_SMALL];
     const int q = blockIdx.x;
     const float* s = sample + (size_t)q * sample_rows;
-    const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(s[i]); }, sample_rows, kk, hist, scratch);
+    const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(s[i]); }, sample_rows, kk, hist, scratch, small);
     // The filter must let through every row with coarse >= tau~ - 2 eps; the sample's kk-th largest is <= tau~.
     if (threadIdx.x == 0) thr[q] = ordered_to_f32(o) - 2.0f * eps[q];
 }
@@ -98,7 +134,8 @@ struct RefineSmem {
     u64 keys[REFINE_SURVIVOR_CAP];
     uint32_t rows[REFINE_SURVIVOR_CAP];
     uint32_t hist[RF_BINS];
-    uint32_t scratch[40];
+    uint32_t scratch[72];
+    uint32_t small[RF_SMALL];
     uint32_t counter;
     // float4 q[ld / 4] follows
 };
@@ -128,7 +165,7 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
     __syncthreads();
 
     // tau~: the kk-th largest coarse score among the candidates (the key's high word IS the ordered score)
-    const uint32_t tau_o = block_kth_largest_o32([&](int64_t i) { return (uint32_t)(cq[i] >> 32); }, total, kk, sm.hist, sm.scratch);
+    const uint32_t tau_o = block_kth_largest_o32([&](int64_t i) { return (uint32_t)(cq[i] >> 32); }, total, kk, sm.hist, sm.scratch, sm.small);
     const float cutoff = ordered_to_f32(tau_o) - 2.0f * eps[q];
 
     for (int i = tid; i < total; i += RF_THREADS) {
@@ -145,23 +182,38 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
 
     // exact fp32 re-score, one warp per survivor.  Summation order == gemv_tma_kernel: lane l takes the float4
     // chunks l, l+32, ...; even chunks accumulate into a0, odd ones into a1; then the same combine + xor tree.
+    // Two survivors per warp iteration: twice the loads in flight, each row's own summation order untouched.
     const float4* M4 = reinterpret_cast<const float4*>(M);
-    for (int i = warp; i < C; i += nwarps) {
-        const uint32_t row = sm.rows[i];
-        const float4* p = M4 + ((int64_t)row - row0) * d4;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int i = warp; i < C; i += 2 * nwarps) {
+        const int i2 = i + nwarps;
+        const bool two = i2 < C;
+        const uint32_t rowa = sm.rows[i], rowb = sm.rows[two ? i2 : i];
+        const float4* pa = M4 + ((int64_t)rowa - row0) * d4;
+        const float4* pb = M4 + ((int64_t)rowb - row0) * d4;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
         int c = lane;
         for (; c + 96 < d4; c += 128) {
-            const float4 m0 = ldg_stream(p + c), m1 = ldg_stream(p + c + 32), m2 = ldg_stream(p + c + 64), m3 = ldg_stream(p + c + 96);
-            fma4(a0, m0, sq[c]); fma4(a1, m1, sq[c + 32]); fma4(a0, m2, sq[c + 64]); fma4(a1, m3, sq[c + 96]);
+            const float4 m0 = ldg_stream(pa + c), m1 = ldg_stream(pa + c + 32), m2 = ldg_stream(pa + c + 64), m3 = ldg_stream(pa + c + 96);
+            const float4 n0 = ldg_stream(pb + c), n1 = ldg_stream(pb + c + 32), n2 = ldg_stream(pb + c + 64), n3 = ldg_stream(pb + c + 96);
+            const float4 q0 = sq[c], q1 = sq[c + 32], q2 = sq[c + 64], q3 = sq[c + 96];
+            fma4(a0, m0, q0); fma4(a1, m1, q1); fma4(a0, m2, q2); fma4(a1, m3, q3);
+            fma4(b0, n0, q0); fma4(b1, n1, q1); fma4(b0, n2, q2); fma4(b1, n3, q3);
         }
         for (; c + 32 < d4; c += 64) {
-            const float4 m0 = ldg_stream(p + c), m1 = ldg_stream(p + c + 32);
-            fma4(a0, m0, sq[c]); fma4(a1, m1, sq[c + 32]);
+            const float4 m0 = ldg_stream(pa + c), m1 = ldg_stream(pa + c + 32);
+            const float4 n0 = ldg_stream(pb + c), n1 = ldg_stream(pb + c + 32);
+            const float4 q0 = sq[c], q1 = sq[c + 32];
+            fma4(a0, m0, q0); fma4(a1, m1, q1);
+            fma4(b0, n0, q0); fma4(b1, n1, q1);
         }
-        if (c < d4) { const float4 m0 = ldg_stream(p + c); fma4(a0, m0, sq[c]); }
-        const float sc = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
-        if (lane == 0) sm.keys[i] = make_key(sc, row);
+        if (c < d4) {
+            const float4 m0 = ldg_stream(pa + c), n0 = ldg_stream(pb + c);
+            const float4 q0 = sq[c];
+            fma4(a0, m0, q0); fma4(b0, n0, q0);
+        }
+        const float sa = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
+        const float sb = warp_sum(((b0.x + b1.x) + (b0.y + b1.y)) + ((b0.z + b1.z) + (b0.w + b1.w)));
+        if (lane == 0) { sm.keys[i] = make_key(sa, rowa); if (two) sm.keys[i2] = make_key(sb, rowb); }
     }
     __syncthreads();
 
