@@ -113,6 +113,8 @@ int  svsb_snapshot_query(svsb_t* e, svsb_snap_t* s, const float* q, int32_t d, i
  * batches, k > 1024 and multi-device engines loop over the single-query kernels. */
 int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
                      float* out_scores, int64_t* out_emb_ids, int32_t* out_counts);
+int svsb_snapshot_query_batch(svsb_t* e, svsb_snap_t* s, const float* Q, int32_t b, int32_t d, int32_t k,
+                              float* out_scores, int64_t* out_emb_ids, int32_t* out_counts);
 /* Diagnostics of the last batch chunk (<= 2048 queries): coarse candidates per query, rows re-scored exactly per
  * query, flag word per query (0 = answered by the coarse path; otherwise it took the single-query kernels). */
 int svsb_batch_stats(svsb_t* e, int32_t b, int32_t* candidates, int32_t* rescored, int32_t* flags);
@@ -149,8 +151,14 @@ int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, int64_t* out
  * Record layout: 2*k+1 int64 words = [ keys (k, uint64: ordered score << 32 | ~global_row) |
  *                                      embeddings.id (k) | count (int32 in the low half of the last word) ]. */
 int svsb_set_shard(svsb_t* e, int64_t global_row0);           /* call before svsb_load_*          */
+/* flags: bit 0 = bracket the similarity kernel with timing events (svsb_kernel_time_collect); bit 1 = pipelined:
+ * the similarity kernel runs on `stream` leaving one SM free and the one-CTA selection kernel runs on an engine-owned
+ * side stream, so the selection of query i overlaps the similarity pass of query i+1 when consecutive calls
+ * alternate `slot`.  With bit 1 the record is complete only after svsb_enqueue_join(e, stream). */
 int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, const float* d_query, int32_t k,
-                            int64_t* d_record, int32_t time_kernel);
+                            int64_t* d_record, int32_t flags);
+/* Make `stream` wait for every selection kernel the pipelined svsb_enqueue_local_topk calls have issued. */
+int svsb_enqueue_join(svsb_t* e, void* stream);
 /* d_records: all-gathered records, [n_lists][batch][2k+1].  Outputs [batch][k], [batch][k], [batch]. */
 int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
                                int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "svsb_snapshot_shape": (C.c_int, [C.c_void_p, c_i64_p, c_i32_p, c_u64_p]),
     "svsb_snapshot_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "svsb_snapshot_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
     "svsb_topk_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_bench_set_queries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "svsb_bench_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, c_i64_p]),
@@ -59,6 +61,7 @@ SIGNATURES = {
     "svsb_bench_last_result": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_set_shard": (C.c_int, [C.c_void_p, C.c_int64]),
     "svsb_enqueue_local_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
+    "svsb_enqueue_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "svsb_enqueue_merge_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "svsb_kernel_time_collect": (C.c_int, [C.c_void_p, c_float_p]),

@@ -87,7 +87,7 @@ struct svsb_workspace {
     u64* out_keys = nullptr; float* out_scores = nullptr; int64_t* out_ids = nullptr; int64_t out_cap = 0;
     int32_t* out_count = nullptr;
     u64* mscr_keys = nullptr; int64_t* mscr_ids = nullptr; int64_t mscr_cap = 0;   // merge scratch
-    cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr, ev_sel = nullptr;
 
     int ensure_rows(int64_t n) {
         cudaSetDevice(dev);
@@ -146,6 +146,7 @@ struct svsb_workspace {
         void* ptrs[] = {d_q, scores, gmax, cand, sortbuf, out_keys, out_scores, out_ids, out_count, mscr_keys, mscr_ids};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (ev) cudaEventDestroy(ev); if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
+        if (ev_sel) cudaEventDestroy(ev_sel);
         if (own_stream && st) cudaStreamDestroy(st);
     }
 };
@@ -153,6 +154,8 @@ typedef svsb_workspace DevWs;
 
 struct QueryCtx {
     std::vector<DevWs> ws;                 // one per engine device
+    std::unique_ptr<DevWs> alt;            // second buffer set + the selection stream of the pipelined bench loop (device 0)
+    DevWs* last = nullptr;                 // workspace holding the last single-device bench result
     // pinned host staging
     float* h_q = nullptr; int h_q_cap = 0;
     float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_count = nullptr; int64_t h_out_cap = 0;
@@ -230,6 +233,8 @@ struct svsb_engine {
     int64_t shard_row0 = 0;                              // global row of this engine's first row
     std::vector<std::unique_ptr<DevWs>> shard_ws;        // workspaces for svsb_enqueue_local_topk (by slot)
     std::vector<cudaEvent_t> kev; size_t kev_used = 0;   // similarity-kernel timing events
+    cudaStream_t side_st = nullptr;                      // selection kernels of the pipelined sharded path
+    std::vector<char> sel_pending;                       // per slot: a selection is (or was) in flight on side_st
 };
 
 static inline int round_up4(int d) { return (d + 3) & ~3; }
@@ -249,6 +254,7 @@ static int ctx_create(svsb_engine* e, std::unique_ptr<QueryCtx>& out) {
         CU(cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming));
         CU(cudaEventCreate(&w.ev0));
         CU(cudaEventCreate(&w.ev1));
+        CU(cudaEventCreateWithFlags(&w.ev_sel, cudaEventDisableTiming));
     }
     out = std::move(c);
     return SVSB_OK;
@@ -256,6 +262,7 @@ static int ctx_create(svsb_engine* e, std::unique_ptr<QueryCtx>& out) {
 static void ctx_destroy(svsb_engine* e, QueryCtx* c) {
     if (!c) return;
     for (auto& w : c->ws) w.release();
+    if (c->alt) c->alt->release();
     if (!e->devs.empty()) cudaSetDevice(e->devs[0]);
     if (c->h_q) cudaFreeHost(c->h_q);
     if (c->h_scores) cudaFreeHost(c->h_scores);
@@ -396,6 +403,7 @@ extern "C" void svsb_destroy(svsb_t* e) {
     if (e->bench_ctx) ctx_destroy(e, e->bench_ctx.get());
     if (e->batch_ws) e->batch_ws->release();
     for (auto& w : e->shard_ws) if (w) w->release();
+    if (e->side_st) { cudaSetDevice(e->devs[0]); cudaStreamDestroy(e->side_st); }
     for (auto ev : e->kev) cudaEventDestroy(ev);
     for (size_t i = 0; i < e->bench_q.size(); ++i) if (e->bench_q[i]) { cudaSetDevice(e->devs[i]); cudaFree(e->bench_q[i]); }
     free_slabs(e);
@@ -978,13 +986,11 @@ static int query_batch_loop(svsb_engine* e, const std::shared_ptr<Generation>& g
     return SVSB_OK;
 }
 
-extern "C" int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
-                                float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
-    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+static int query_batch_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, const float* Q, int32_t b, int32_t d, int32_t k,
+                           float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
     if (b < 0) return fail(SVSB_E_INVALID, "svsb_query_batch: negative batch");
     if (b == 0) return SVSB_OK;
     if (!Q || !out_counts) return fail(SVSB_E_INVALID, "svsb_query_batch: NULL buffer");
-    auto g = pin(e);
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident (call svsb_load_* first)");
     for (int32_t i = 0; i < b; ++i) out_counts[i] = 0;
     BatchPlan P;
@@ -1031,6 +1037,17 @@ extern "C" int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d,
         }
     }
     return SVSB_OK;
+}
+
+extern "C" int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
+                                float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    return query_batch_gen(e, pin(e), Q, b, d, k, out_scores, out_emb_ids, out_counts);
+}
+extern "C" int svsb_snapshot_query_batch(svsb_t* e, svsb_snap_t* s, const float* Q, int32_t b, int32_t d, int32_t k,
+                                         float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
+    if (!e || !s) return fail(SVSB_E_INVALID, "svsb_snapshot_query_batch: NULL argument");
+    return query_batch_gen(e, s->gen, Q, b, d, k, out_scores, out_emb_ids, out_counts);
 }
 
 // Diagnostics of the last svsb_query_batch / svsb_bench_run_batch chunk: per query the number of coarse candidates,
@@ -1136,29 +1153,70 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
     // gemv_ms requested: bracket every similarity-kernel launch on device 0 with events INSIDE the timed loop
     const bool ktime = gemv_ms != nullptr && g->shards[0].n > 0;
     if (ktime && (rc = ensure_kernel_events(c->ws[0].dev, (size_t)iters * 2)) != SVSB_OK) return rc;
+    // Single device, k <= 2048: software pipeline.  The similarity kernel of query i+1 (stream A, all SMs but one)
+    // runs while the one-CTA selection kernel of query i (stream B) finishes on the SM left free; two buffer sets.
+    const bool pipelined = nd == 1 && kk <= K_FAST_MAX && env_int("SVSB_PIPELINE", 1) != 0 && sm_count(c->ws[0].dev) > 8;
+    if (pipelined) {
+        if (!c->alt) {
+            c->alt.reset(new DevWs());
+            DevWs& a = *c->alt;
+            a.dev = c->ws[0].dev;
+            CU(cudaSetDevice(a.dev));
+            CU(cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking));
+            a.own_stream = true;
+            CU(cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&a.ev_sel, cudaEventDisableTiming));
+        }
+        if ((rc = prepare_ws(*c->alt, g.get(), g->shards[0], kk)) != SVSB_OK) return rc;
+    }
     const int64_t l0 = g_launches.load();
     for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaStreamSynchronize(c->ws[i].st)); }
+    if (pipelined) CU(cudaStreamSynchronize(c->alt->st));
     for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaEventRecord(c->ws[i].ev0, c->ws[i].st)); }
-    for (int it = 0; it < iters; ++it) {
-        const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
-        for (int i = 0; i < nd; ++i) {
-            if (!g->shards[i].n) continue;
-            CU(cudaSetDevice(c->ws[i].dev));
-            if (ktime && i == 0) {
-                DevWs& w = c->ws[0]; const Shard& s = g->shards[0];
-                const int shift = group_shift_for(s.n);
-                CU(cudaEventRecord(g_kev[2 * it], w.st));
-                CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, w.scores, w.gmax, shift));
-                CU(cudaEventRecord(g_kev[2 * it + 1], w.st));
-                if (kk <= K_FAST_MAX)
-                    CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
-                                     w.out_keys, w.out_scores, w.out_ids, w.out_count));
-                else
-                    CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
-                                            w.out_keys, w.out_scores, w.out_ids, w.out_count));
-            } else if ((rc = enqueue_local(c->ws[i], g.get(), g->shards[i], e->bench_q[i] + qoff, kk)) != SVSB_OK) return rc;
+    if (pipelined) {
+        DevWs& w0 = c->ws[0]; DevWs& w1 = *c->alt;
+        const Shard& s = g->shards[0];
+        const int shift = group_shift_for(s.n);
+        cudaStream_t sa = w0.st, sb = w1.st;
+        for (int it = 0; it < iters; ++it) {
+            DevWs& W = (it & 1) ? w1 : w0;
+            const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
+            if (it >= 2) CU(cudaStreamWaitEvent(sa, W.ev_sel, 0));           // selection of query it-2 is done with W
+            if (ktime) CU(cudaEventRecord(g_kev[2 * it], sa));
+            CU(launch_gemv(sa, W.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, W.scores, W.gmax, shift, 0, 0, 0, /*reserve_sms=*/1));
+            if (ktime) CU(cudaEventRecord(g_kev[2 * it + 1], sa));
+            CU(cudaEventRecord(W.ev, sa));
+            CU(cudaStreamWaitEvent(sb, W.ev, 0));
+            CU(launch_select(sb, W.scores, s.n, W.gmax, shift, (int)kk, s.ids, s.row0, W.cand, W.cand_cap,
+                             W.out_keys, W.out_scores, W.out_ids, W.out_count));
+            CU(cudaEventRecord(W.ev_sel, sb));
+            c->last = &W;
         }
-        if (nd > 1 && (rc = enqueue_gather_merge(e, c, g.get(), kk)) != SVSB_OK) return rc;
+        CU(cudaStreamWaitEvent(sa, w0.ev_sel, 0));
+        if (iters > 1) CU(cudaStreamWaitEvent(sa, w1.ev_sel, 0));
+    } else {
+        for (int it = 0; it < iters; ++it) {
+            const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
+            for (int i = 0; i < nd; ++i) {
+                if (!g->shards[i].n) continue;
+                CU(cudaSetDevice(c->ws[i].dev));
+                if (ktime && i == 0) {
+                    DevWs& w = c->ws[0]; const Shard& s = g->shards[0];
+                    const int shift = group_shift_for(s.n);
+                    CU(cudaEventRecord(g_kev[2 * it], w.st));
+                    CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, w.scores, w.gmax, shift));
+                    CU(cudaEventRecord(g_kev[2 * it + 1], w.st));
+                    if (kk <= K_FAST_MAX)
+                        CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
+                                         w.out_keys, w.out_scores, w.out_ids, w.out_count));
+                    else
+                        CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
+                                                w.out_keys, w.out_scores, w.out_ids, w.out_count));
+                } else if ((rc = enqueue_local(c->ws[i], g.get(), g->shards[i], e->bench_q[i] + qoff, kk)) != SVSB_OK) return rc;
+            }
+            if (nd > 1 && (rc = enqueue_gather_merge(e, c, g.get(), kk)) != SVSB_OK) return rc;
+        }
+        c->last = &c->ws[0];
     }
     float best = 0.f;
     for (int i = 0; i < nd; ++i) {
@@ -1272,10 +1330,11 @@ extern "C" int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, i
     if (!e || !e->bench_ctx) return fail(SVSB_E_STATE, "svsb_bench_last_result: no bench run yet");
     if (!out_scores || !out_emb_ids || !out_count) return fail(SVSB_E_INVALID, "svsb_bench_last_result: NULL buffer");
     QueryCtx* c = e->bench_ctx.get();
-    DevWs& w0 = c->ws[0];
-    CU(cudaSetDevice(w0.dev));
-    CU(cudaStreamSynchronize(w0.st));
     const bool multi = e->devs.size() > 1;
+    DevWs& w0 = (!multi && c->last) ? *c->last : c->ws[0];
+    CU(cudaSetDevice(w0.dev));
+    CU(cudaStreamSynchronize(c->ws[0].st));
+    if (c->alt) CU(cudaStreamSynchronize(c->alt->st));
     int32_t cnt = 0;
     CU(cudaMemcpy(&cnt, multi ? c->m_count : w0.out_count, 4, cudaMemcpyDeviceToHost));
     if (cnt < 0 || cnt > k) return fail(SVSB_E_INVALID, "svsb_bench_last_result: k smaller than the result");
@@ -1297,7 +1356,7 @@ extern "C" int svsb_set_shard(svsb_t* e, int64_t global_row0) {
 }
 
 extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, const float* d_query, int32_t k,
-                                       int64_t* d_record, int32_t time_kernel) {
+                                       int64_t* d_record, int32_t flags) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     auto g = pin(e);
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
@@ -1305,26 +1364,51 @@ extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, co
     if (slot < 0 || slot >= 8) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: slot out of range (0..7)");
     if (k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: 1 <= k <= 2048");
     if (!d_query || !d_record) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: NULL pointer");
+    const bool time_kernel = (flags & 1) != 0, pipelined = (flags & 2) != 0;
     const Shard& s = g->shards[0];
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s.dev));
     int32_t* d_count = reinterpret_cast<int32_t*>(d_record + 2 * (int64_t)k);
     if (s.n == 0) { CU(cudaMemsetAsync(d_count, 0, 8, st)); return SVSB_OK; }
     if ((size_t)slot >= e->shard_ws.size()) e->shard_ws.resize(slot + 1);
+    if (e->sel_pending.size() < e->shard_ws.size()) e->sel_pending.resize(e->shard_ws.size(), 0);
     if (!e->shard_ws[slot]) { e->shard_ws[slot].reset(new DevWs()); e->shard_ws[slot]->dev = s.dev; }
     DevWs& w = *e->shard_ws[slot];
     int rc;
     if ((rc = w.ensure_rows(s.n)) != SVSB_OK) return rc;
     if ((rc = w.ensure_out(K_FAST_MAX)) != SVSB_OK) return rc;
+    if (pipelined) {
+        if (!e->side_st) CU(cudaStreamCreateWithFlags(&e->side_st, cudaStreamNonBlocking));
+        if (!w.ev) CU(cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming));
+        if (!w.ev_sel) CU(cudaEventCreateWithFlags(&w.ev_sel, cudaEventDisableTiming));
+        // the slot's previous selection must have finished reading scores / group maxima before they are overwritten
+        if (e->sel_pending[slot]) CU(cudaStreamWaitEvent(st, w.ev_sel, 0));
+    }
     const int shift = group_shift_for(s.n);
     if (time_kernel) {
         while (e->kev.size() < e->kev_used + 2) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
         CU(cudaEventRecord(e->kev[e->kev_used], st));
     }
-    CU(launch_gemv(st, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift));
+    CU(launch_gemv(st, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, pipelined ? 1 : 0));
     if (time_kernel) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
-    CU(launch_select(st, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
+    cudaStream_t sel_st = st;
+    if (pipelined) {
+        CU(cudaEventRecord(w.ev, st));
+        CU(cudaStreamWaitEvent(e->side_st, w.ev, 0));
+        sel_st = e->side_st;
+    }
+    CU(launch_select(sel_st, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
                      reinterpret_cast<u64*>(d_record), w.out_scores, d_record + k, d_count));
+    if (pipelined) { CU(cudaEventRecord(w.ev_sel, e->side_st)); e->sel_pending[slot] = 1; }
+    return SVSB_OK;
+}
+
+extern "C" int svsb_enqueue_join(svsb_t* e, void* stream) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    CU(cudaSetDevice(e->devs[0]));
+    for (size_t i = 0; i < e->sel_pending.size(); ++i)
+        if (e->sel_pending[i] && e->shard_ws[i] && e->shard_ws[i]->ev_sel)
+            CU(cudaStreamWaitEvent((cudaStream_t)stream, e->shard_ws[i]->ev_sel, 0));
     return SVSB_OK;
 }
 

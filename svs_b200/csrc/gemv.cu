@@ -266,7 +266,7 @@ static cudaError_t run_tma_inst(cudaStream_t st, int64_t grid, size_t smem, cons
 
 // tile_rows / stages: 0 = default.  cw: consumer warps (8 or 16; 0 = default).
 static cudaError_t run_tma(cudaStream_t st, int device, const float* M, int64_t n, int d4, const float* q,
-                           float* scores, u64* gmax, int group_shift, int tile_rows, int stages, int cw)
+                           float* scores, u64* gmax, int group_shift, int tile_rows, int stages, int cw, int reserve_sms)
 {
     const size_t row_bytes = (size_t)d4 * 16;
     const int nq = d4 <= 64 ? 2 : d4 <= 192 ? 6 : d4 <= 384 ? 12 : d4 <= 768 ? 24 : 0;
@@ -286,7 +286,7 @@ static cudaError_t run_tma(cudaStream_t st, int device, const float* M, int64_t 
     if (stages < 2 || stages > 16 || (size_t)stages * tile_rows * row_bytes > budget) return cudaErrorInvalidConfiguration;
     const size_t smem = (size_t)stages * tile_rows * row_bytes + q_bytes + (size_t)stages * 16 + 64;
     const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
-    int64_t grid = sm_count(device);
+    int64_t grid = sm_count(device) - reserve_sms;          // reserve_sms: SMs left free for a concurrent selection kernel
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
 #define SVSB_TMA_CASE(CWV, NQV) \
@@ -302,7 +302,7 @@ static cudaError_t run_tma(cudaStream_t st, int device, const float* M, int64_t 
 
 cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld,
                         const float* q, float* scores, u64* gmax, int group_shift,
-                        int variant, int tune_a, int tune_b)
+                        int variant, int tune_a, int tune_b, int reserve_sms)
 {
     (void)d;
     if (n <= 0) return cudaSuccess;
@@ -317,7 +317,7 @@ cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, 
     }
     if (variant == 2) {
         // tune_a = tile rows, tune_b = stages + 100 * consumer warps (e.g. 1604 = 16 warps, 4 stages)
-        cudaError_t e = run_tma(st, device, M, n, d4, q, scores, gmax, group_shift, tune_a, tune_b % 100, tune_b / 100);
+        cudaError_t e = run_tma(st, device, M, n, d4, q, scores, gmax, group_shift, tune_a, tune_b % 100, tune_b / 100, reserve_sms);
         if (e != cudaErrorInvalidConfiguration) return e;
         (void)cudaGetLastError();
         tune_a = 0; tune_b = 0;                               // TMA knobs mean nothing to the LDG kernel

@@ -12,10 +12,11 @@ void count_launch(int n = 1);
 // M is row-major with leading dimension ld floats (ld % 4 == 0, rows 16-byte aligned, padding zero);
 // q has ld floats (padding zero).  gmax must be zero on entry.
 // variant: 0 = auto, 1 = LDG.128 streaming kernel, 2 = TMA-bulk (cp.async.bulk + mbarrier ring) kernel.
-// tune_a/tune_b: variant-specific knobs (0 = default), see gemv.cu.
+// tune_a/tune_b: variant-specific knobs (0 = default), see gemv.cu.  reserve_sms: SMs the persistent grid leaves
+// free (the pipelined paths run the previous query's selection kernel there, concurrently).
 cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld,
                         const float* q, float* scores, u64* gmax, int group_shift,
-                        int variant = 0, int tune_a = 0, int tune_b = 0);
+                        int variant = 0, int tune_a = 0, int tune_b = 0, int reserve_sms = 0);
 
 // ---- K3/K4: exact top-k ---------------------------------------------------------------------
 // Inputs: scores[n], gmax[ceil(n >> shift)] (consumed and reset to zero), ids[n] (may be null: ids = rows).

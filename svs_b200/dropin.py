@@ -91,6 +91,43 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
             async with db as q:
                 return await loop.run_in_executor(None, _fetch_docs, q, emb_ids, n)
 
+    def retrieve_many(self: Any, queries: List[str], n: int) -> List[List[Any]]:
+        """ADDITIVE API (the reference has none; its equivalent is a Python loop over retrieve, kb.py:1608-1640):
+        embed all queries with ONE call of the embedding function (it takes a list, types.py EmbeddingFunc), run ONE
+        engine batch, then fetch the documents.  Result j equals `retrieve(queries[j], n)`."""
+        log.info(f"retrieving {n} documents for each of {len(queries)} query strings")
+        assert self.db is not None
+        matrix = self.embeddings_matrix.device.get_sync(self.db)
+        if not queries:
+            return []
+        func = self._get_embedding_func()
+        awaitable = func(list(queries))
+        assert asyncio.iscoroutine(awaitable)
+        vecs = np.array(asyncio.run_coroutine_threadsafe(awaitable, self.loop).result(), dtype=np.float32)
+        log.info("got embeddings for the queries!")
+        all_ids = matrix.retrieve_many(vecs, n)
+        log.info(f"computed {matrix.shape[0]} x {len(queries)} cosine similarities")
+        with self.db as q:
+            return [_fetch_docs(q, emb_ids, n) for emb_ids in all_ids]
+
+    async def aretrieve_many(self: Any, queries: List[str], n: int) -> List[List[Any]]:
+        log.info(f"retrieving {n} documents for each of {len(queries)} query strings")
+        loop = asyncio.get_running_loop()
+        async with self._get_lock():
+            db = await self._ensure_db()
+            matrix = await self.embeddings_matrix.device.get(db)
+        if not queries:
+            return []
+        func = await self._get_embedding_func()
+        vecs = np.array(await func(list(queries)), dtype=np.float32)
+        log.info("got embeddings for the queries!")
+        all_ids = await loop.run_in_executor(None, matrix.retrieve_many, vecs, n)
+        log.info(f"computed {matrix.shape[0]} x {len(queries)} cosine similarities")
+        async with self._get_lock():
+            db = await self._ensure_db()
+            async with db as q:
+                return await loop.run_in_executor(None, lambda: [_fetch_docs(q, emb_ids, n) for emb_ids in all_ids])
+
     async def aload(self: Any) -> None:
         async with self._get_lock():
             db = await self._ensure_db()
@@ -104,6 +141,8 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
     kb.KB.retrieve = retrieve
     kb.AsyncKB.retrieve = aretrieve
     kb.AsyncKB.load = aload
+    kb.KB.retrieve_many = retrieve_many                  # additive: batched retrieve
+    kb.AsyncKB.retrieve_many = aretrieve_many
 
 
 def uninstall() -> None:
@@ -115,4 +154,7 @@ def uninstall() -> None:
     kb.KB.retrieve = _ORIGINALS["KB.retrieve"]
     kb.AsyncKB.retrieve = _ORIGINALS["AsyncKB.retrieve"]
     kb.AsyncKB.load = _ORIGINALS["AsyncKB.load"]
+    for cls in (kb.KB, kb.AsyncKB):
+        if "retrieve_many" in cls.__dict__:
+            delattr(cls, "retrieve_many")
     _ORIGINALS.clear()

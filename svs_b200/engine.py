@@ -257,6 +257,27 @@ class Snapshot:
         scores, ids = self.query(query_vec, n)
         return [(float(s), int(i)) for s, i in zip(scores, ids)]
 
+    def query_batch(self, Q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """b queries against the pinned generation: (scores (b, k), emb_ids (b, k), counts (b,))."""
+        Q = _f32c(Q)
+        if Q.ndim != 2:
+            raise ValueError("Q must be (b, d)")
+        if not self._engine._h.value:
+            raise _lib.EngineError(_lib.SVSB_E_STATE, "engine is closed")
+        b, d = Q.shape
+        cap = max(int(k), 0)
+        scores = np.zeros((b, cap), dtype=np.float32)
+        ids = np.full((b, cap), -1, dtype=np.int64)
+        counts = np.zeros(b, dtype=np.int32)
+        check(self._lib.svsb_snapshot_query_batch(self._engine._h, self._s, Q.ctypes.data, b, d, int(k),
+                                                  scores.ctypes.data, ids.ctypes.data, counts.ctypes.data))
+        return scores, ids, counts
+
+    def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
+        """superheavy() for every row of query_vecs, as ONE engine call."""
+        scores, ids, counts = self.query_batch(query_vecs, n)
+        return [[(float(s), int(i)) for s, i in zip(scores[j, :counts[j]], ids[j, :counts[j]])] for j in range(len(counts))]
+
     def release(self) -> None:
         if self._s is not None and self._s.value:
             self._lib.svsb_snapshot_release(self._s)

@@ -42,6 +42,11 @@ class DeviceMatrix:
         an empty matrix exactly where the reference's np.dot does."""
         return self._snap.retrieve(query_vec, n)
 
+    def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
+        """superheavy() for a batch of query vectors in one engine call (bit-identical to looping `retrieve`);
+        large batches run as one tensor-core contraction (include/svsb200.h: svsb_query_batch)."""
+        return self._snap.retrieve_many(query_vecs, n)
+
 
 def load_from_connection(engine: Engine, conn: sqlite3.Connection, normalize: bool = False) -> DeviceMatrix:
     """build_embeddings_matrix (src/svs/kb.py:573-618) into the device cache."""

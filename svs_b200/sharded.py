@@ -5,7 +5,7 @@ their embeddings.ids.  A query is answered by
   1. every rank: similarity + exact local top-k on its shard (libsvsb200.so, on the caller's stream),
      written as ONE packed int64 record [keys(k) | ids(k) | count];
   2. the ONE exchange step: `all_gather_into_tensor` of those records (NCCL over NVLink/NVSwitch;
-     k=100 -> 1.6 KB per rank per query), micro-batched over several queries per collective;
+     k=100 -> 1.6 KB per rank per query), micro-batched over 16 queries per collective;
   3. every rank: one merge kernel per micro-batch (one CTA per query) -> global top-k under the same
      total order (score desc, global row asc), so all ranks hold the identical answer.
 No reduction over scores is needed: rows are independent (splitting D instead would need an all-reduce
@@ -21,7 +21,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-MICRO_BATCH = 8
+MICRO_BATCH = 16
 
 
 def partition(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -78,10 +78,17 @@ class CudaShardBackend:
                 t.zeros((count,), dtype=t.int32, device=self.device))
 
     # -- compute ---------------------------------------------------------------------------------
-    def enqueue_local(self, query_row, k: int, record_row, time_kernel: bool = False) -> None:
+    def enqueue_local(self, query_row, k: int, record_row, time_kernel: bool = False, seq: int = 0) -> None:
+        """Similarity on the current stream, selection pipelined on the engine's side stream (slots alternate with
+        `seq`, so the selection of one query overlaps the similarity pass of the next).  Call join() before the
+        records are consumed."""
         st = self.torch.cuda.current_stream(self.device).cuda_stream
-        self._check(self._lib.svsb_enqueue_local_topk(self.engine._h, C.c_void_p(st), 0, C.c_void_p(query_row.data_ptr()),
-                                                      k, C.c_void_p(record_row.data_ptr()), 1 if time_kernel else 0))
+        self._check(self._lib.svsb_enqueue_local_topk(self.engine._h, C.c_void_p(st), seq & 1, C.c_void_p(query_row.data_ptr()),
+                                                      k, C.c_void_p(record_row.data_ptr()), (1 if time_kernel else 0) | 2))
+
+    def join(self) -> None:
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_enqueue_join(self.engine._h, C.c_void_p(st)))
 
     def enqueue_merge(self, gathered, n_lists: int, batch: int, k: int, out_scores, out_ids, out_counts) -> None:
         st = self.torch.cuda.current_stream(self.device).cuda_stream
@@ -148,7 +155,8 @@ class ShardedRetriever:
         rec, gath, (o_s, o_i, o_c) = self._buffers(k)
         nb = len(qrows)
         for j, q in enumerate(qrows):
-            self.backend.enqueue_local(q, k, rec[j], time_gemv)
+            self.backend.enqueue_local(q, k, rec[j], time_gemv, seq=j)
+        self.backend.join()                                        # records complete before the exchange
         recw = 2 * k + 1
         g = gath.view(-1)[: self.world * nb * recw]
         self.dist.all_gather_into_tensor(g, rec[:nb].reshape(-1), group=self.group)

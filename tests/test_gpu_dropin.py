@@ -137,3 +137,37 @@ def test_dropin_matches_the_unpatched_reference_on_a_real_kb(svs_patched, tmp_pa
         got = [(r['score'], doc_to_emb[r['doc']['id']]) for r in res]
         oracle.compare_retrieval(got, want, oracle.scores_of(m, q), ids)
     kb.close()
+
+
+def test_retrieve_many_equals_looping_retrieve(svs_patched, tmp_path):
+    """The additive batched API: result j of retrieve_many == retrieve(queries[j]) (sync and async), on a KB large
+    enough to take the tensor-core path (>= 4096 rows)."""
+    svs = svs_patched
+    path = str(tmp_path / "many.sqlite")
+    d = 128
+
+    async def embed(texts):
+        return [stub_vector(t, d) for t in texts]
+    kb = svs.KB(path, embed)
+    with kb.bulk_add_docs() as add_doc:
+        for i in range(5000):
+            add_doc(f"passage {i}")
+    queries = [f"passage {i * 37}" for i in range(20)] + ["something unseen", "another one"]
+    many = kb.retrieve_many(queries, 7)
+    assert len(many) == len(queries)
+    for qtext, res in zip(queries, many):
+        single = kb.retrieve(qtext, 7)
+        assert [(r['score'], r['doc']['id']) for r in res] == [(r['score'], r['doc']['id']) for r in single]
+    assert many[0][0]['doc']['text'] == "passage 0"
+    assert kb.retrieve_many([], 5) == []
+    assert kb.retrieve_many(queries[:3], 0) == [[], [], []]
+    kb.close()
+
+    async def go():
+        akb = svs.AsyncKB(path, embed)
+        res = await akb.retrieve_many(queries, 3)
+        for qtext, r in zip(queries, res):
+            s = await akb.retrieve(qtext, 3)
+            assert [(x['score'], x['doc']['id']) for x in r] == [(x['score'], x['doc']['id']) for x in s]
+        await akb.close()
+    asyncio.run(go())

@@ -26,6 +26,9 @@ class FakeSnapshot:
     def retrieve(self, q, n):
         return [(0.0, int(i)) for i in self._ids[:max(0, n)]]
 
+    def retrieve_many(self, qs, n):
+        return [self.retrieve(q, n) for q in qs]
+
 
 class FakeEngine:
     """Records what the host logic asks of the C ABI; slab capacity is tiny to force many slabs."""
@@ -227,6 +230,7 @@ def test_install_and_uninstall_patch_only_the_seam(fake_engine):
         svs_b200.uninstall()
     assert mod.kb._EmbeddingsMatrix is orig_cls and mod.kb.KB.retrieve is orig_retrieve
     assert mod.kb.KB().retrieve("q", 1) == "host"
+    assert not hasattr(mod.kb.KB, "retrieve_many") and not hasattr(mod.kb.AsyncKB, "retrieve_many")
 
 
 @pytest.mark.skipif(reference_import_path() is None, reason="oracle/_ref (byte-compiled reference) not built")
@@ -253,6 +257,9 @@ def test_install_on_the_real_reference_package(fake_engine, tmp_path, monkeypatc
         assert ("invalidate",) in fake_engine[0].calls            # kb.py:1541 reached the device cache
         assert [r["doc"]["text"] for r in kb.retrieve("q", 5)] == ["b", "c"]
         assert kb.document_top_pairwise_scores(1)[0][1]["text"] == "b"   # untouched host path still works
+        many = kb.retrieve_many(["q1", "q2", "q3"], 1)             # additive batched API: one embed call, one engine call
+        assert [[r["doc"]["text"] for r in res] for res in many] == [["b"], ["b"], ["b"]]
+        assert kb.retrieve_many([], 3) == []
         kb.close()
     finally:
         svs_b200.uninstall()

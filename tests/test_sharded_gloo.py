@@ -50,7 +50,10 @@ class NumpyShardBackend:
         return (torch.zeros((count, k), dtype=torch.float32), torch.zeros((count, k), dtype=torch.int64),
                 torch.zeros((count,), dtype=torch.int32))
 
-    def enqueue_local(self, q, k, record_row, time_kernel=False):
+    def join(self):
+        pass
+
+    def enqueue_local(self, q, k, record_row, time_kernel=False, seq=0):
         x = oracle.scores_of(self.m, q.numpy()) if len(self.m) else np.zeros(0, np.float32)
         keys = np_keys(x, np.arange(self.row0, self.row0 + len(x)))
         order = np.argsort(keys)[::-1][:k]
