@@ -157,6 +157,12 @@ int svsb_set_shard(svsb_t* e, int64_t global_row0);           /* call before svs
  * alternate `slot`.  With bit 1 the record is complete only after svsb_enqueue_join(e, stream). */
 int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, const float* d_query, int32_t k,
                             int64_t* d_record, int32_t flags);
+/* Batched form: local top-k records of b device-resident queries d_Q[b][ld] (ld = d rounded up to 4, zero padded)
+ * on `stream`.  Large batches take the tensor-core coarse pass + exact refine (same bits as the single-query kernels),
+ * flagged queries / small batches / k > 1024 take the single-query kernels.  *n_fallback = queries that did.
+ * Synchronises `stream` once per 2048 queries. */
+int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, int64_t* d_records,
+                             int32_t* n_fallback);
 /* Make `stream` wait for every selection kernel the pipelined svsb_enqueue_local_topk calls have issued. */
 int svsb_enqueue_join(svsb_t* e, void* stream);
 /* d_records: all-gathered records, [n_lists][batch][2k+1].  Outputs [batch][k], [batch][k], [batch]. */

@@ -143,8 +143,7 @@ struct RefineSmem {
 __global__ void __launch_bounds__(RF_THREADS)
 refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __restrict__ ids, int64_t row0,
               const float* __restrict__ Q, int ldq, int k, const u64* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
-              int cand_cap, const float* __restrict__ eps, int32_t* __restrict__ flags,
-              float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int32_t* __restrict__ out_counts,
+              int cand_cap, const float* __restrict__ eps, int32_t* __restrict__ flags, RefineOut out,
               int32_t* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char rf_smem_raw[];
@@ -152,7 +151,8 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
     float4* sq = reinterpret_cast<float4*>(rf_smem_raw + ((sizeof(RefineSmem) + 15) & ~(size_t)15));
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RF_THREADS / 32;
     const int kk = (int)min((int64_t)k, n);
-    if (tid == 0) { out_counts[q] = 0; if (stats) stats[q] = 0; }
+    int32_t* out_count = out.counts + (int64_t)q * out.count_stride;
+    if (tid == 0) { *out_count = 0; if (stats) stats[q] = 0; }
     if (flags[q] != 0) return;                                       // already routed to the exact path
     const int total = cand_cnt[q];
     if (total > cand_cap || total < kk) {
@@ -188,8 +188,8 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
         const int i2 = i + nwarps;
         const bool two = i2 < C;
         const uint32_t rowa = sm.rows[i], rowb = sm.rows[two ? i2 : i];
-        const float4* pa = M4 + ((int64_t)rowa - row0) * d4;
-        const float4* pb = M4 + ((int64_t)rowb - row0) * d4;
+        const float4* pa = M4 + (int64_t)rowa * d4;                  // candidate keys carry LOCAL rows
+        const float4* pb = M4 + (int64_t)rowb * d4;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
         int c = lane;
         for (; c + 96 < d4; c += 128) {
@@ -225,18 +225,20 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
     for (int i = tid; i < kk; i += RF_THREADS) {
         const u64 key = sm.keys[i];
         const uint32_t row = key_row(key);
-        out_scores[(size_t)q * k + i] = key_score(key);
-        out_ids[(size_t)q * k + i] = ids ? ids[(int64_t)row - row0] : (int64_t)row;
+        const int64_t grow = row0 + (int64_t)row;                    // global row (row0 = first row of this shard)
+        if (out.scores) out.scores[(int64_t)q * out.stride + i] = key_score(key);
+        if (out.keys) out.keys[(int64_t)q * out.stride + i] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
+        out.ids[(int64_t)q * out.stride + i] = ids ? ids[row] : grow;
     }
-    if (tid == 0) out_counts[q] = kk;
+    if (tid == 0) *out_count = kk;
 }
 
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
-                          const float* eps, int32_t* flags, float* out_scores, int64_t* out_ids, int32_t* out_counts,
-                          int32_t* stats)
+                          const float* eps, int32_t* flags, RefineOut out, int32_t* stats)
 {
     if (b <= 0) return cudaSuccess;
+    if (!out.ids || !out.counts) return cudaErrorInvalidValue;
     if (k < 1 || (ld & 3) || ldq < ld) return cudaErrorInvalidValue;
     const int64_t kk = k < n ? k : n;
     if (kk > REFINE_SURVIVOR_CAP) return cudaErrorInvalidValue;
@@ -249,8 +251,7 @@ cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, co
         attr_set[dev] = true;
     }
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    refine_kernel<<<b, RF_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, flags,
-                                              out_scores, out_ids, out_counts, stats);
+    refine_kernel<<<b, RF_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, flags, out, stats);
     count_launch();
     return cudaGetLastError();
 }

@@ -957,21 +957,26 @@ static int ensure_m16(Generation* g, const BatchPlan& P, cudaStream_t st) {
 // Enqueue the whole pipeline for b (<= COARSE_MAX_BATCH) device-resident fp32 queries dQ[b][ld] on w->st.
 // Results: w->o_scores / o_ids [b][k], w->o_counts[b], w->flags[b] (!= 0: the query needs the exact path).
 // time_coarse: bracket the filter pass with w->ev[2], w->ev[3].
-static int batch_enqueue(BatchWs* w, const Generation* g, const BatchPlan& P, const float* dQ, int b, bool time_coarse) {
+// st: the stream everything is enqueued on (the workspace's own, or the caller's in the sharded path).
+// out == nullptr: results go to w->o_scores / o_ids [b][k], w->o_counts[b].
+static int batch_enqueue(BatchWs* w, const Generation* g, const BatchPlan& P, const float* dQ, int b, bool time_coarse,
+                         cudaStream_t st, const RefineOut* out = nullptr) {
     const Shard& s = g->shards[0];
     const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
     CU(cudaSetDevice(w->dev));
-    CU(launch_queries_to_f16(w->st, dQ, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags));
-    CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, w->st));
-    CU(launch_coarse_gemm(w->st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
+    CU(launch_queries_to_f16(st, dQ, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags));
+    CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, st));
+    CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
                           nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
-    CU(launch_sample_threshold(w->st, w->sample, P.sample_rows, b, P.kk, w->eps, w->thr));
-    if (time_coarse) CU(cudaEventRecord(w->ev[2], w->st));
-    CU(launch_coarse_gemm(w->st, w->dev, 0, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.n_tiles, 1,
+    CU(launch_sample_threshold(st, w->sample, P.sample_rows, b, P.kk, w->eps, w->thr));
+    if (time_coarse) CU(cudaEventRecord(w->ev[2], st));
+    CU(launch_coarse_gemm(st, w->dev, 0, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.n_tiles, 1,
                           w->thr, w->cand, w->cand_cnt, P.cand_cap, nullptr, 0));
-    if (time_coarse) CU(cudaEventRecord(w->ev[3], w->st));
-    CU(launch_refine(w->st, s.M, P.n, P.ld, s.ids, 0, dQ, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->flags,
-                     w->o_scores, w->o_ids, w->o_counts, w->stats));
+    if (time_coarse) CU(cudaEventRecord(w->ev[3], st));
+    RefineOut o{w->o_scores, nullptr, w->o_ids, (int64_t)P.k, w->o_counts, 1};
+    if (out) o = *out;
+    CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, dQ, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->flags,
+                     o, w->stats));
     return SVSB_OK;
 }
 
@@ -1018,7 +1023,7 @@ static int query_batch_gen(svsb_engine* e, const std::shared_ptr<Generation>& g,
         }
         CU(cudaSetDevice(w->dev));
         CU(cudaMemcpyAsync(w->dQ, w->h_Q, (size_t)bc * P.ld * 4, cudaMemcpyHostToDevice, w->st));
-        if ((rc = batch_enqueue(w, g.get(), P, w->dQ, bc, false)) != SVSB_OK) return rc;
+        if ((rc = batch_enqueue(w, g.get(), P, w->dQ, bc, false, w->st)) != SVSB_OK) return rc;
         CU(cudaMemcpyAsync(w->h_scores, w->o_scores, (size_t)bc * k * 4, cudaMemcpyDeviceToHost, w->st));
         CU(cudaMemcpyAsync(w->h_ids, w->o_ids, (size_t)bc * k * 8, cudaMemcpyDeviceToHost, w->st));
         CU(cudaMemcpyAsync(w->h_counts, w->o_counts, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
@@ -1291,7 +1296,7 @@ extern "C" int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* 
     float csum = 0.f;
     CU(cudaEventRecord(w->ev[0], w->st));
     for (int it = 0; it < iters; ++it) {
-        if ((rc = batch_enqueue(w, g.get(), P, e->bench_q[0], b, coarse_ms != nullptr)) != SVSB_OK) return rc;
+        if ((rc = batch_enqueue(w, g.get(), P, e->bench_q[0], b, coarse_ms != nullptr, w->st)) != SVSB_OK) return rc;
         if (coarse_ms) {                                 // events are reused: collect before the next iteration records them
             CU(cudaEventSynchronize(w->ev[3]));
             float ms = 0.f; CU(cudaEventElapsedTime(&ms, w->ev[2], w->ev[3])); csum += ms;
@@ -1400,6 +1405,53 @@ extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, co
     CU(launch_select(sel_st, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
                      reinterpret_cast<u64*>(d_record), w.out_scores, d_record + k, d_count));
     if (pipelined) { CU(cudaEventRecord(w.ev_sel, e->side_st)); e->sel_pending[slot] = 1; }
+    return SVSB_OK;
+}
+
+// Batched form of svsb_enqueue_local_topk: local top-k records of b device-resident queries dQ[b][ld] (zero padded
+// to the matrix's leading dimension) on the caller's stream, through the tensor-core coarse pass + exact refine where
+// the shard / k allow it, else (and for queries the coarse pass flags) through the single-query kernels.  Synchronises
+// `stream` once per <= 2048 queries to read the flag words.
+extern "C" int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, int64_t* d_records,
+                                        int32_t* n_fallback) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (e->devs.size() != 1) return fail(SVSB_E_INVALID, "svsb_batch_local_records: single-device engines only");
+    if (b < 0 || k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_batch_local_records: bad arguments (1 <= k <= 2048)");
+    if (b == 0) return SVSB_OK;
+    if (!d_Q || !d_records) return fail(SVSB_E_INVALID, "svsb_batch_local_records: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rec = 2 * (int64_t)k + 1;
+    int fallbacks = 0;
+    BatchPlan P;
+    const bool coarse = g->n > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
+    std::vector<char> todo((size_t)b, coarse ? 0 : 1);
+    if (coarse) {
+        std::lock_guard<std::mutex> lk(e->batch_mu);
+        BatchWs* w = nullptr;
+        int rc = batch_ws_get(e, w);
+        if (rc != SVSB_OK) return rc;
+        if ((rc = ensure_m16(g.get(), P, st)) != SVSB_OK) return rc;
+        for (int32_t c0 = 0; c0 < b; c0 += COARSE_MAX_BATCH) {
+            const int bc = std::min<int32_t>(COARSE_MAX_BATCH, b - c0);
+            const int b_pad = (bc + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+            if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
+            int64_t* r0 = d_records + (int64_t)c0 * rec;
+            RefineOut o{nullptr, reinterpret_cast<u64*>(r0), r0 + k, rec, reinterpret_cast<int32_t*>(r0 + 2 * (int64_t)k), 2 * rec};
+            if ((rc = batch_enqueue(w, g.get(), P, d_Q + (int64_t)c0 * P.ld, bc, false, st, &o)) != SVSB_OK) return rc;
+            CU(cudaMemcpyAsync(w->h_flags, w->flags, (size_t)bc * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (int i = 0; i < bc; ++i) if (w->h_flags[i] != 0) todo[c0 + i] = 1;
+        }
+    }
+    for (int32_t i = 0; i < b; ++i) {
+        if (!todo[i]) continue;
+        ++fallbacks;
+        int rc = svsb_enqueue_local_topk(e, stream, 0, d_Q + (int64_t)i * g->ld, k, d_records + (int64_t)i * rec, 0);
+        if (rc != SVSB_OK) return rc;
+    }
+    if (n_fallback) *n_fallback = fallbacks;
     return SVSB_OK;
 }
 

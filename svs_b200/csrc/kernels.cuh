@@ -86,10 +86,16 @@ cudaError_t launch_sample_threshold(cudaStream_t st, const float* sample, int64_
 // them exactly (fp32, the similarity kernel's summation order); sort; write (score, embeddings.id) x kk.
 // flags[q] |= 2 candidate list overflowed, 4 fewer than kk candidates, 8 survivor list overflowed: such queries
 // are left to the caller's exact single-query path.  stats[q] (optional) = survivors re-scored.
+// Output layout: entry i of query q goes to scores / keys / ids [q * stride + i] (scores, keys optional), its count
+// to counts[q * count_stride].  Two users: plain (b, k) arrays, and the packed per-query records of the sharded
+// path ([keys(k) | ids(k) | count], 2k+1 int64 words) whose keys carry GLOBAL rows (row0 + local row).
+struct RefineOut {
+    float* scores; u64* keys; int64_t* ids; int64_t stride;
+    int32_t* counts; int64_t count_stride;
+};
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
-                          const float* eps, int32_t* flags, float* out_scores, int64_t* out_ids, int32_t* out_counts,
-                          int32_t* stats);
+                          const float* eps, int32_t* flags, RefineOut out, int32_t* stats);
 
 int sm_count(int device);
 inline int64_t next_pow2(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return p; }

@@ -86,6 +86,15 @@ class CudaShardBackend:
         self._check(self._lib.svsb_enqueue_local_topk(self.engine._h, C.c_void_p(st), seq & 1, C.c_void_p(query_row.data_ptr()),
                                                       k, C.c_void_p(record_row.data_ptr()), (1 if time_kernel else 0) | 2))
 
+    def batch_local(self, queries, k: int, records) -> int:
+        """Local top-k records of all rows of the device tensor `queries` (b, ld) in one call: tensor-core coarse pass
+        + exact refine where the shard allows it.  Returns how many queries took the single-query kernels."""
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        nfb = C.c_int32()
+        self._check(self._lib.svsb_batch_local_records(self.engine._h, C.c_void_p(st), C.c_void_p(queries.data_ptr()),
+                                                       queries.shape[0], k, C.c_void_p(records.data_ptr()), C.byref(nfb)))
+        return nfb.value
+
     def join(self) -> None:
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.svsb_enqueue_join(self.engine._h, C.c_void_p(st)))
@@ -122,6 +131,7 @@ class ShardedRetriever:
         self.local_rows = 0
         self._queries = None
         self._bufs = {}
+        self.last_fallbacks = 0
 
     # -- load ------------------------------------------------------------------------------------
     def load_synthetic(self, n: int, d: int, seed: int = 0, id0: int = 0, id_step: int = 1) -> None:
@@ -173,6 +183,41 @@ class ShardedRetriever:
             self._micro_batch([self._queries[(done + j) % nq] for j in range(nb)], k, time_gemv)
             done += nb
         return self.backend.collect_kernel_ms() if time_gemv else 0.0
+
+    # -- batches ---------------------------------------------------------------------------------
+    def _batch(self, dq, k: int):
+        """b device queries -> (scores (b, k), ids (b, k), counts (b,)) device tensors, identical on every rank:
+        per-rank batched local top-k, ONE all-gather of b records per rank, ONE merge launch (a CTA per query)."""
+        b = dq.shape[0]
+        key = ("batch", k, b)
+        if key not in self._bufs:
+            self._bufs[key] = (self.backend.new_records(b, k), self.backend.new_records(self.world * b, k),
+                               self.backend.new_outputs(b, k))
+        rec, gath, (o_s, o_i, o_c) = self._bufs[key]
+        self.last_fallbacks = self.backend.batch_local(dq, k, rec)
+        self.dist.all_gather_into_tensor(gath.view(-1), rec.view(-1), group=self.group)
+        self.backend.enqueue_merge(gath, self.world, b, k, o_s, o_i, o_c)
+        return o_s, o_i, o_c
+
+    def run_batch(self, k: int) -> None:
+        """One batch of ALL uploaded queries, device-resident end to end (bench path)."""
+        assert self._queries is not None, "set_queries first"
+        self._batch(self._queries, k)
+
+    def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
+        """superheavy() for every row of query_vecs on every rank: host queries in, host lists out."""
+        Q = np.ascontiguousarray(query_vecs, dtype=np.float32)
+        if Q.ndim != 2 or Q.shape[1] != self.d or self.n == 0:
+            raise ValueError(f"shapes ({self.n},{self.d if self.n else 0}) and {Q.shape} not aligned")
+        if n <= 0 or Q.shape[0] == 0:
+            return [[] for _ in range(Q.shape[0])]
+        if n > 2048 and self.n > 2048:
+            raise NotImplementedError("n > 2048 is not supported by the sharded path")
+        k = min(int(n), 2048)
+        o_s, o_i, o_c = self._batch(self.backend.device_queries(Q), k)
+        cnt = o_c.cpu().numpy()                                     # synchronises the stream
+        s, i = o_s.cpu().numpy(), o_i.cpu().numpy()
+        return [[(float(a), int(x)) for a, x in zip(s[j, :cnt[j]], i[j, :cnt[j]])] for j in range(Q.shape[0])]
 
     def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
         """The reference's superheavy() result, on every rank: host query in, host list out."""

@@ -54,6 +54,54 @@ def test_two_shard_engines_and_merge_records_match_the_oracle():
             b.close()
 
 
+def test_two_shard_engines_batched_records_equal_the_single_query_records():
+    """svsb_batch_local_records (tensor-core coarse pass + exact refine per shard) must give the same merged
+    answer, bit for bit, as the per-query records, and match the oracle."""
+    torch = pytest.importorskip("torch")
+    from svs_b200.sharded import CudaShardBackend, partition
+    n, d, k, batch = 24_001, 256, 50, 40
+    m = oracle.synth_matrix_uniform(n, d, 8)
+    m[11] = m[n - 5]                                           # exact tie across shards
+    ids = np.cumsum(np.random.default_rng(3).integers(1, 4, size=n)).astype(np.int64)
+    world = 2
+    backs = []
+    for r in range(world):
+        b = CudaShardBackend(0)
+        row0, cnt = partition(n, world, r)
+        b.set_shard(row0)
+        b.load_rows(np.ascontiguousarray(m[row0:row0 + cnt]), np.ascontiguousarray(ids[row0:row0 + cnt]))
+        backs.append(b)
+    qs = oracle.synth_queries(batch, d, 9)
+    qs[2] = m[11]
+    try:
+        dq = backs[0].device_queries(qs)
+        outs = []
+        for mode in ("batch", "single"):
+            recs = [b.new_records(batch, k) for b in backs]
+            for r, b in enumerate(backs):
+                if mode == "batch":
+                    assert b.batch_local(dq, k, recs[r]) == 0            # nobody needed the fallback
+                else:
+                    for j in range(batch):
+                        b.enqueue_local(dq[j], k, recs[r][j])
+            torch.cuda.synchronize()
+            gathered = torch.stack(recs, dim=0).contiguous()
+            o_s, o_i, o_c = backs[0].new_outputs(batch, k)
+            backs[0].enqueue_merge(gathered, world, batch, k, o_s, o_i, o_c)
+            torch.cuda.synchronize()
+            outs.append((o_s.cpu().numpy().copy(), o_i.cpu().numpy().copy(), o_c.cpu().numpy().copy()))
+        assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+        assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+        s, i, c = outs[0]
+        for j in range(0, batch, 5):
+            got = list(zip(s[j, :c[j]].tolist(), i[j, :c[j]].tolist()))
+            oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+        assert i[2, :2].tolist() == [int(ids[11]), int(ids[n - 5])]     # tie: ascending id, across shards
+    finally:
+        for b in backs:
+            b.close()
+
+
 def test_world_size_one_process_group_runs_the_real_collective():
     torch = pytest.importorskip("torch")
     import os
@@ -73,6 +121,10 @@ def test_world_size_one_process_group_runs_the_real_collective():
         sr.set_queries(qs)
         ms = sr.run_queries(100, 11, time_gemv=True)
         assert ms > 0
+        many = sr.retrieve_many(qs, 100)                        # batched: coarse pass + refine, all-gather, merge
+        assert sr.last_fallbacks == 0
+        for j in (0, 5, 10):
+            assert many[j] == sr.retrieve(qs[j], 100)
         sr.close()
     finally:
         dist.destroy_process_group()

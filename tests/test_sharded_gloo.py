@@ -53,6 +53,11 @@ class NumpyShardBackend:
     def join(self):
         pass
 
+    def batch_local(self, queries, k, records):
+        for j in range(queries.shape[0]):
+            self.enqueue_local(queries[j], k, records[j])
+        return 0
+
     def enqueue_local(self, q, k, record_row, time_kernel=False, seq=0):
         x = oracle.scores_of(self.m, q.numpy()) if len(self.m) else np.zeros(0, np.float32)
         keys = np_keys(x, np.arange(self.row0, self.row0 + len(x)))
@@ -123,6 +128,13 @@ def _worker(rank, world, port, n, d, ret):
         assert sr.retrieve(qs[0], 0) == []
         with pytest.raises(ValueError):
             sr.retrieve(np.zeros(d + 1, np.float32), 3)
+        # batched form: one all-gather and one merge for the whole batch; result j == retrieve(qs[j])
+        many = sr.retrieve_many(qs[:7], 10)
+        for j in range(7):
+            oracle.compare_retrieval(many[j], oracle.superheavy(m, ids, qs[j], 10), oracle.scores_of(m, qs[j]), ids)
+            assert many[j] == sr.retrieve(qs[j], 10)
+        assert sr.retrieve_many(qs[:2], 0) == [[], []]
+        out.append(many)
         ret[rank] = out
         dist.barrier()
     finally:
