@@ -118,6 +118,15 @@ int svsb_snapshot_query_batch(svsb_t* e, svsb_snap_t* s, const float* Q, int32_t
 /* Diagnostics of the last batch chunk (<= 2048 queries): coarse candidates per query, rows re-scored exactly per
  * query, flag word per query (0 = answered by the coarse path; otherwise it took the single-query kernels). */
 int svsb_batch_stats(svsb_t* e, int32_t b, int32_t* candidates, int32_t* rescored, int32_t* flags);
+/* Pairwise top pairs: the compute of document_top_pairwise_scores (src/svs/kb.py:1642-1671, 1208-1243) =
+ * np.dot(M, M.T) + get_top_pairs (src/svs/util.py:206-233) without ever materialising the N x N scores: tensor-core
+ * coarse pass over the upper triangle, one global threshold, exact fp32 re-score of the survivors.  Outputs have
+ * capacity n_pairs; *out_count = min(n_pairs, N(N-1)/2).  Order: score descending, then first row ascending, then
+ * second row ascending (the reference orders exact ties by descending flat index).  Single-device engines. */
+int svsb_top_pairs(svsb_t* e, int64_t n_pairs, float* out_scores, int64_t* out_emb_ids_a, int64_t* out_emb_ids_b,
+                   int64_t* out_count);
+int svsb_snapshot_top_pairs(svsb_t* e, svsb_snap_t* s, int64_t n_pairs, float* out_scores, int64_t* out_emb_ids_a,
+                            int64_t* out_emb_ids_b, int64_t* out_count);
 /* Selection only: get_top_k (src/svs/util.py:190-203) on a host score vector, run by the same
  * selection kernels.  out_index receives row indices. */
 int svsb_topk_scores(svsb_t* e, const float* scores, int64_t n, int32_t k,

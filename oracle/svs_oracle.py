@@ -134,6 +134,55 @@ def superheavy(embeddings_matrix: np.ndarray, emb_id_lookup: np.ndarray,
     return emb_ids
 
 
+def get_top_pairs(pairwise_scores_as_matrix: np.ndarray, top_k: int) -> List[Tuple[float, int, int]]:
+    """src/svs/util.py:206-233: upper triangle without the diagonal (np.triu_indices_from(k=1)) -> get_top_k on the
+    flattened values -> (score, row, col).  Exact ties come out by DESCENDING flat index (get_top_k's sort)."""
+    assert len(pairwise_scores_as_matrix.shape) == 2
+    rows, cols = pairwise_scores_as_matrix.shape
+    assert rows == cols
+    indices = np.triu_indices_from(pairwise_scores_as_matrix, k=1)
+    vals = pairwise_scores_as_matrix[indices]
+    top = get_top_k(vals, top_k=top_k)
+    return [(score, int(indices[0][ii]), int(indices[1][ii])) for score, ii in top]
+
+
+def top_pairwise(embeddings_matrix: np.ndarray, emb_id_lookup: np.ndarray, n: int) -> List[Tuple[float, int, int]]:
+    """The superheavy() closure of document_top_pairwise_scores, src/svs/kb.py:1650-1656 (sync), 1218-1224 (async)."""
+    pairwise = np.dot(embeddings_matrix, embeddings_matrix.T)
+    return [(score, int(emb_id_lookup[i1]), int(emb_id_lookup[i2])) for score, i1, i2 in get_top_pairs(pairwise, n)]
+
+
+def compare_pairs(engine: Sequence[Tuple[float, int, int]], oracle_list: Sequence[Tuple[float, int, int]],
+                  pairwise: np.ndarray, emb_id_lookup: np.ndarray,
+                  rtol: float = SCORE_RTOL, atol: float = SCORE_ATOL) -> dict:
+    """Tolerance-aware comparison of two top-pairs lists (same rules as compare_retrieval): same length; every
+    engine score within tolerance of the oracle matrix's entry for that pair; every rank either the same pair or a
+    near-tie swap; engine sorted by (score desc, first row asc, second row asc); pairs distinct and i < j in row order."""
+    assert len(engine) == len(oracle_list), (len(engine), len(oracle_list))
+    row_of = {int(e): r for r, e in enumerate(emb_id_lookup)}
+    seen = set()
+    exact = 0
+    max_rel = 0.0
+    prev = None
+    for r, ((s, a, b), (so, ao, bo)) in enumerate(zip(engine, oracle_list)):
+        i, j = row_of[a], row_of[b]
+        assert i < j, f"rank {r}: pair not in the upper triangle: rows {i}, {j}"
+        assert (i, j) not in seen, f"rank {r}: duplicate pair"
+        seen.add((i, j))
+        ref = float(pairwise[i, j])
+        tol = rtol * abs(ref) + atol
+        assert abs(s - ref) <= tol, f"rank {r}: score {s} vs oracle {ref}"
+        max_rel = max(max_rel, abs(s - ref) / max(abs(ref), 1e-30))
+        if (a, b) == (ao, bo):
+            exact += 1
+        else:
+            assert abs(ref - so) <= rtol * abs(so) + atol, f"rank {r}: pair ({a},{b}) is not a near-tie of the oracle's ({ao},{bo})"
+        key = (-s, i, j)
+        assert prev is None or prev <= key, f"rank {r}: not sorted by (score desc, row asc, row asc)"
+        prev = key
+    return {"n": len(engine), "exact_rank_matches": exact, "max_rel_score_err": max_rel}
+
+
 def query_vec_of(list_of_floats: Sequence[float]) -> np.ndarray:
     """src/svs/kb.py:1182 / 1620: the provider's float list -> float32, NOT re-normalised."""
     return np.array(list_of_floats, dtype=np.float32)

@@ -114,13 +114,19 @@ __device__ __forceinline__ u64 smem_desc_sw128(uint32_t smem_addr) {
     return (u64)((smem_addr >> 4) & 0x3FFFu) | ((u64)1 << 16) | ((u64)(1024 >> 4) << 32) | ((u64)1 << 46) | ((u64)2 << 61);
 }
 
+// Pairwise mode: a tile whose every row index is <= every query's row index lies on or below the diagonal.
+__device__ __forceinline__ bool tile_below_diagonal(int64_t tri_q0, int t, int tile_stride, int qb) {
+    return tri_q0 >= 0 && (int64_t)t * tile_stride * CG_BM + (CG_BM - 1) <= tri_q0 + (int64_t)qb * CG_BN;
+}
+
 template <int MODE>   // 0 = filter (main pass), 1 = sample dump
 __global__ void __launch_bounds__(CG_THREADS, 1)
 coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    int64_t n, int n_tiles, int tile_stride, int n_qblocks, int n_kblocks,
                    const float* __restrict__ thr,          // [b_pad] thresholds (unscaled coarse scores), MODE 0
                    u64* __restrict__ cand, int32_t* __restrict__ cand_cnt, int cand_cap,   // MODE 0
-                   float* __restrict__ sample, int64_t sample_rows)                        // MODE 1: [b_pad][sample_rows]
+                   float* __restrict__ sample, int64_t sample_rows,                        // MODE 1: [b_pad][sample_rows]
+                   int64_t tri_q0)   // >= 0: pairwise mode, query column q is matrix row tri_q0 + q; keep only row > that
 {
     extern __shared__ unsigned char cg_smem_raw[];
     const uint32_t raw = cvta_smem(cg_smem_raw);
@@ -169,6 +175,7 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int s = 0; uint32_t phase = 0;
             for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
                 const int t = (int)(w / n_qblocks), qb = (int)(w - (int64_t)t * n_qblocks);
+                if (tile_below_diagonal(tri_q0, t, tile_stride, qb)) continue;
                 const int row0 = t * tile_stride * CG_BM;             // < 2^31 rows per engine (checked on the host)
                 const int q0 = qb * CG_BN;
                 for (int kb = 0; kb < n_kblocks; ++kb) {
@@ -185,10 +192,15 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ------------------------------------------------------------------ MMA issuer (one elected lane)
         if (lane == 0) {
             int s = 0; uint32_t phase = 0;
-            int64_t it = 0;
-            for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+            int64_t it = 0;                                              // tiles actually processed by this CTA
+            for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+                if (tri_q0 >= 0) {
+                    const int t = (int)(w / n_qblocks), qb = (int)(w - (int64_t)t * n_qblocks);
+                    if (tile_below_diagonal(tri_q0, t, tile_stride, qb)) continue;
+                }
                 const int buf = (int)(it & 1);
                 const uint32_t use = (uint32_t)(it >> 1);
+                ++it;
                 mbarrier_wait(tempty_bar(buf), (use & 1u) ^ 1u);        // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * CG_BN;
@@ -240,10 +252,12 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             __syncwarp();
         };
         int64_t it = 0;
-        for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
             const int t = (int)(w / n_qblocks), qb = (int)(w - (int64_t)t * n_qblocks);
+            if (tile_below_diagonal(tri_q0, t, tile_stride, qb)) continue;
             const int buf = (int)(it & 1);
             const uint32_t use = (uint32_t)(it >> 1);
+            ++it;
             mbarrier_wait(tfull_bar(buf), use & 1u);
             tc_fence_after();
             const int lq4 = warp & 3;                                  // TMEM lane quarter
@@ -274,6 +288,10 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         mask |= (__uint_as_float(v[4 * j4 + 3]) >= th.w ? 1u : 0u) << (4 * j4 + 3);
                     }
                     if (!row_ok) mask = 0;
+                    if (tri_q0 >= 0) {                                 // upper triangle: column j allowed iff row > tri_q0 + q0 + j
+                        const int64_t lim = row - tri_q0 - q0;
+                        mask &= lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << (int)lim) - 1u));
+                    }
                     if (mask) {
                         const int hits = __popc(mask);
                         const uint32_t pos0 = atomicAdd(lcnt, (uint32_t)hits);      // shared-memory atomic
@@ -293,10 +311,11 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 } else {
                     const int64_t srow = (int64_t)t * CG_BM + lq4 * 32 + lane;           // position inside the sample
                     if (srow < sample_rows) {
+                        const int64_t lim = tri_q0 >= 0 ? row - tri_q0 - q0 : 32;   // pairwise: only columns j < lim count
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             sample[(size_t)(q0 + j) * sample_rows + srow] =
-                                row_ok ? __uint_as_float(v[j]) * (1.0f / kScale) : __int_as_float(0xff800000);
+                                (row_ok && j < lim) ? __uint_as_float(v[j]) * (1.0f / kScale) : __int_as_float(0xff800000);
                     }
                 }
             }
@@ -425,14 +444,14 @@ static cudaError_t make_map(CUtensorMap* map, const void* ptr, int64_t rows, int
 
 cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void* M16, int64_t n, const void* Q16, int b_pad,
                                int ld16, int n_tiles, int tile_stride, const float* thr, u64* cand, int32_t* cand_cnt,
-                               int cand_cap, float* sample, int64_t sample_rows)
+                               int cand_cap, float* sample, int64_t sample_rows, int64_t q_rows, int64_t tri_q0)
 {
     if (n <= 0 || b_pad <= 0 || b_pad % CG_BN || b_pad > COARSE_MAX_BATCH || ld16 % 8 || n_tiles <= 0) return cudaErrorInvalidValue;
     if (n > 0x7fffff00ll) return cudaErrorInvalidValue;
     CUtensorMap tmA, tmB;
     cudaError_t e = make_map(&tmA, M16, n, ld16, CG_BM);
     if (e != cudaSuccess) return e;
-    e = make_map(&tmB, Q16, b_pad, ld16, CG_BN);
+    e = make_map(&tmB, Q16, q_rows > 0 ? q_rows : b_pad, ld16, CG_BN);   // rows beyond the extent read as zero
     if (e != cudaSuccess) return e;
     const int n_qblocks = b_pad / CG_BN;
     const int n_kblocks = (ld16 + CG_BK - 1) / CG_BK;
@@ -448,10 +467,10 @@ cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void
     }
     if (mode)
         coarse_gemm_kernel<1><<<(unsigned)grid, CG_THREADS, CG_SMEM, st>>>(tmA, tmB, n, n_tiles, tile_stride, n_qblocks, n_kblocks,
-                                                                          thr, cand, cand_cnt, cand_cap, sample, sample_rows);
+                                                                          thr, cand, cand_cnt, cand_cap, sample, sample_rows, tri_q0);
     else
         coarse_gemm_kernel<0><<<(unsigned)grid, CG_THREADS, CG_SMEM, st>>>(tmA, tmB, n, n_tiles, tile_stride, n_qblocks, n_kblocks,
-                                                                          thr, cand, cand_cnt, cand_cap, sample, sample_rows);
+                                                                          thr, cand, cand_cnt, cand_cap, sample, sample_rows, tri_q0);
     count_launch();
     return cudaGetLastError();
 }

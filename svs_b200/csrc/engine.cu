@@ -1055,6 +1055,138 @@ extern "C" int svsb_snapshot_query_batch(svsb_t* e, svsb_snap_t* s, const float*
     return query_batch_gen(e, s->gen, Q, b, d, k, out_scores, out_emb_ids, out_counts);
 }
 
+// ------------------------------------------------------------------------------------------------
+// pairwise top pairs: document_top_pairwise_scores' compute (reference src/svs/kb.py:1642-1671, 1208-1243;
+// src/svs/util.py:206-233) on the coarse tensor-core pass + exact refine (pairs.cu)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DevBufs {                                  // frees everything it handed out
+    int dev; std::vector<void*> ptrs;
+    explicit DevBufs(int d) : dev(d) {}
+    ~DevBufs() { cudaSetDevice(dev); for (void* p : ptrs) cudaFree(p); }
+    template <class T> cudaError_t get(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) { ptrs.push_back(p); *out = reinterpret_cast<T*>(p); }
+        return e;
+    }
+};
+}  // namespace
+
+static int top_pairs_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, int64_t n_pairs, float* out_scores,
+                         int64_t* out_ids_a, int64_t* out_ids_b, int64_t* out_count) {
+    if (!out_count) return fail(SVSB_E_INVALID, "svsb_top_pairs: out_count is NULL");
+    *out_count = 0;
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident (call svsb_load_* first)");
+    const int64_t N = g->n;
+    if (n_pairs <= 0 || N < 2 || g->d == 0) return SVSB_OK;       // get_top_k: k <= 0 -> [] (util.py:200-201); no pairs
+    if (!out_scores || !out_ids_a || !out_ids_b) return fail(SVSB_E_INVALID, "svsb_top_pairs: NULL buffer");
+    if (e->devs.size() != 1 || g->shards.size() != 1) return fail(SVSB_E_INVALID, "svsb_top_pairs: single-device engines only");
+    if (N > 0x7fffff00ll) return fail(SVSB_E_INVALID, "svsb_top_pairs: too many rows");
+    const float R = 1.0f + g->max_dev;
+    if (!(R <= 8.0f)) return fail(SVSB_E_INVALID, "svsb_top_pairs: rows are too far from unit norm for the fp16 coarse pass");
+    const double total_pairs = 0.5 * (double)N * (double)(N - 1);
+    const int64_t n = (double)n_pairs < total_pairs ? n_pairs : (int64_t)total_pairs;       // util.py:198-199
+    if (n > (1ll << 22)) return fail(SVSB_E_INVALID, "svsb_top_pairs: at most 2^22 pairs per call");
+    const Shard& s = g->shards[0];
+
+    BatchPlan P;
+    P.n = N; P.d = g->d; P.ld = g->ld; P.ld16 = (g->d + 7) & ~7; P.kk = 1; P.k = 1;
+    P.n_tiles = (int)((N + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS);
+    P.cand_cap = env_int("SVSB_BATCH_CAND_CAP", 32768);
+    const int B = 1024;                                            // query rows per block
+    // bootstrap sample (only when a first block at threshold -inf would overflow the per-row lists)
+    const bool bootstrap = N >= 2048;
+    int64_t want_rows = std::max<int64_t>(std::max<int64_t>(4096, n / 16 + 1),
+                                          (int64_t)((double)N * (double)n / (64.0 * (double)P.cand_cap)) + 1);
+    int64_t st_ = std::max<int64_t>((want_rows + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS, 32);
+    st_ = std::min<int64_t>(st_, P.n_tiles);
+    P.s_tiles = (int)st_; P.tile_stride = std::max(1, P.n_tiles / P.s_tiles);
+    P.sample_rows = (int64_t)P.s_tiles * COARSE_TILE_ROWS;
+    const float eps = (9.765625e-4f + 2.384185791015625e-7f + (float)g->d * (2.384185791015625e-7f + 1.1920928955078125e-7f))
+                      * (R * 1.000001f) * (R * 1.000001f) + 1e-8f;
+    const float eps2 = 2.0f * eps;
+
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = nullptr;
+    int rc = batch_ws_get(e, w);
+    if (rc != SVSB_OK) return rc;
+    if ((rc = ensure_m16(g.get(), P, w->st)) != SVSB_OK) return rc;
+    {   // the sample buffer holds 256 x sample_rows floats: size it through the (b_pad x sample_rows) allocation
+        BatchPlan Pa = P;
+        Pa.sample_rows = std::max<int64_t>(1, (256 * P.sample_rows + B - 1) / B);
+        if ((rc = batch_ws_ensure(w, Pa, B)) != SVSB_OK) return rc;
+    }
+    CU(cudaSetDevice(w->dev));
+    cudaStream_t st = w->st;
+    DevBufs bufs(w->dev);
+    const int64_t LC = std::max<int64_t>(1ll << 22, 16 * n);
+    uint32_t* lo[2]; u64* lp[2]; unsigned long long* lstate[2]; float* thr_scalar;
+    for (int i = 0; i < 2; ++i) { CU(bufs.get(&lo[i], (size_t)LC)); CU(bufs.get(&lp[i], (size_t)LC)); CU(bufs.get(&lstate[i], 2)); }
+    CU(bufs.get(&thr_scalar, 1));
+    const uint32_t neg_inf = 0xff800000u;
+    CU(cudaMemcpyAsync(thr_scalar, &neg_inf, 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(lstate[0], 0, 16, st));
+    const char* m16 = reinterpret_cast<const char*>(g->M16);
+
+    if (bootstrap) {
+        CU(launch_coarse_gemm(st, w->dev, 1, g->M16, N, g->M16, 256, P.ld16, P.s_tiles, P.tile_stride, nullptr, nullptr, nullptr, 0,
+                              w->sample, P.sample_rows, /*q_rows=*/std::min<int64_t>(N, 256), /*tri_q0=*/0));
+        CU(launch_pairs_tau(st, nullptr, w->sample, 256 * P.sample_rows, nullptr, 0, (int)n, eps2, thr_scalar));
+    }
+    int cur = 0;
+    for (int64_t q0 = 0; q0 + 1 < N; q0 += B) {
+        const int bq = (int)std::min<int64_t>(B, N - q0);
+        const int b_pad = (bq + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+        CU(launch_pairs_fill_thr(st, w->thr, b_pad, bq, thr_scalar));
+        CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, st));
+        CU(launch_coarse_gemm(st, w->dev, 0, g->M16, N, m16 + (size_t)q0 * P.ld16 * 2, b_pad, P.ld16, P.n_tiles, 1, w->thr,
+                              w->cand, w->cand_cnt, P.cand_cap, nullptr, 0, /*q_rows=*/N - q0, /*tri_q0=*/q0));
+        CU(launch_pairs_gather(st, w->cand, w->cand_cnt, P.cand_cap, bq, q0, lo[cur], lp[cur], LC, lstate[cur]));
+        CU(launch_pairs_tau(st, lo[cur], nullptr, 0, lstate[cur], LC, (int)n, eps2, thr_scalar));
+        CU(cudaMemsetAsync(lstate[cur ^ 1], 0, 16, st));
+        CU(launch_pairs_compact(st, w->dev, lo[cur], lp[cur], lstate[cur], LC, lo[cur ^ 1], lp[cur ^ 1], lstate[cur ^ 1], thr_scalar));
+        cur ^= 1;
+    }
+    unsigned long long hstate[2] = {0, 0};
+    CU(cudaMemcpyAsync(hstate, lstate[cur], 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hstate[1] != 0)
+        return fail(SVSB_E_NOMEM, hstate[1] & 1 ? "svsb_top_pairs: a row has more than 32768 near-tied partners (raise SVSB_BATCH_CAND_CAP)"
+                                                : "svsb_top_pairs: too many near-tied pairs for the candidate list");
+    const int64_t C = (int64_t)hstate[0];
+    if (C < n) return fail(SVSB_E_CUDA, "internal: pair list shorter than the requested count");
+    int64_t np2 = next_pow2(C); if (np2 < 2048) np2 = 2048;
+    u64* keys; float* scores; u64* sortbuf; u64* gmax; u64* o_keys; float* o_scores; int64_t* o_sel; int32_t* o_cnt; int64_t* o_a; int64_t* o_b;
+    CU(bufs.get(&keys, (size_t)np2)); CU(bufs.get(&scores, (size_t)C)); CU(bufs.get(&sortbuf, (size_t)np2));
+    const int shift = group_shift_for(C);
+    const int64_t G = (C + ((int64_t)1 << shift) - 1) >> shift;
+    CU(bufs.get(&gmax, (size_t)G)); CU(bufs.get(&o_keys, (size_t)n)); CU(bufs.get(&o_scores, (size_t)n)); CU(bufs.get(&o_sel, (size_t)n));
+    CU(bufs.get(&o_cnt, 16)); CU(bufs.get(&o_a, (size_t)n)); CU(bufs.get(&o_b, (size_t)n));
+    CU(launch_pairs_sortkeys(st, lp[cur], C, np2, keys));
+    CU(launch_sort_keys_desc(st, keys, np2));                     // ascending (i, j)
+    CU(launch_pairs_rescore(st, w->dev, s.M, g->ld, keys, C, scores));
+    CU(launch_fullsort_topk(st, scores, C, gmax, shift, n, nullptr, 0, sortbuf, o_keys, o_scores, o_sel, o_cnt));
+    CU(launch_pairs_emit(st, o_sel, n, keys, s.ids, o_a, o_b));
+    CU(cudaMemcpyAsync(out_scores, o_scores, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_ids_a, o_a, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_ids_b, o_b, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out_count = n;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_top_pairs(svsb_t* e, int64_t n_pairs, float* out_scores, int64_t* out_ids_a, int64_t* out_ids_b,
+                              int64_t* out_count) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    return top_pairs_gen(e, pin(e), n_pairs, out_scores, out_ids_a, out_ids_b, out_count);
+}
+extern "C" int svsb_snapshot_top_pairs(svsb_t* e, svsb_snap_t* s, int64_t n_pairs, float* out_scores, int64_t* out_ids_a,
+                                       int64_t* out_ids_b, int64_t* out_count) {
+    if (!e || !s) return fail(SVSB_E_INVALID, "svsb_snapshot_top_pairs: NULL argument");
+    return top_pairs_gen(e, s->gen, n_pairs, out_scores, out_ids_a, out_ids_b, out_count);
+}
+
 // Diagnostics of the last svsb_query_batch / svsb_bench_run_batch chunk: per query the number of coarse candidates,
 // the number of rows re-scored exactly, and the flag word (0 = answered by the coarse path).
 extern "C" int svsb_batch_stats(svsb_t* e, int32_t b, int32_t* candidates, int32_t* rescored, int32_t* flags) {

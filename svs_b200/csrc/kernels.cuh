@@ -76,9 +76,12 @@ cudaError_t launch_queries_to_f16(cudaStream_t st, const float* Q, int b, int b_
 //         (key = ordered coarse score << 32 | ~row), cand_cnt[query] counts ALL survivors (may exceed cand_cap).
 // mode 1: sample -- raw coarse scores of row tiles 0, tile_stride, 2*tile_stride, ... (n_tiles of them) go to
 //         sample[query][sample_rows]; rows beyond n read as -inf.
+// q_rows > 0: Q16 holds only q_rows (<= b_pad) rows, the rest of the padded batch reads as zero.
+// tri_q0 >= 0: pairwise mode -- Q16 is the matrix itself from row tri_q0 on; only pairs (query row < matrix row)
+// count, tiles on or below the diagonal are skipped.
 cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void* M16, int64_t n, const void* Q16, int b_pad,
                                int ld16, int n_tiles, int tile_stride, const float* thr, u64* cand, int32_t* cand_cnt,
-                               int cand_cap, float* sample, int64_t sample_rows);
+                               int cand_cap, float* sample, int64_t sample_rows, int64_t q_rows = 0, int64_t tri_q0 = -1);
 // thr[q] = (kk-th largest of sample[q][0..sample_rows)) - 2 eps[q] for q < b (one CTA per query).
 cudaError_t launch_sample_threshold(cudaStream_t st, const float* sample, int64_t sample_rows, int b, int kk, const float* eps,
                                     float* thr);
@@ -96,6 +99,22 @@ struct RefineOut {
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
                           const float* eps, int32_t* flags, RefineOut out, int32_t* stats);
+
+// ---- pairwise top pairs (pairs.cu): global candidate list on top of the coarse pass's pairwise mode --------
+// Sort keys[0..np2) descending; np2 a power of two >= 2048 (pad with 0).
+cudaError_t launch_sort_keys_desc(cudaStream_t st, u64* keys, int64_t np2);
+cudaError_t launch_pairs_fill_thr(cudaStream_t st, float* thr, int b_pad, int b, const float* scalar);
+// state[0] = entries in the list, state[1] = error flags (1: a per-query list overflowed, 2: the pair list overflowed)
+cudaError_t launch_pairs_gather(cudaStream_t st, const u64* cand, const int32_t* cand_cnt, int cand_cap, int b, int64_t q0,
+                                uint32_t* list_o, u64* list_pair, int64_t list_cap, unsigned long long* state);
+// *thr_scalar = max(*thr_scalar, n-th largest coarse score - eps2) over the list (vals == nullptr) or a raw sample
+cudaError_t launch_pairs_tau(cudaStream_t st, const uint32_t* list_o, const float* vals, int64_t vals_count,
+                             const unsigned long long* state, int64_t list_cap, int n, float eps2, float* thr_scalar);
+cudaError_t launch_pairs_compact(cudaStream_t st, int device, const uint32_t* src_o, const u64* src_pair, const unsigned long long* src_state,
+                                 int64_t list_cap, uint32_t* dst_o, u64* dst_pair, unsigned long long* dst_state, const float* thr_scalar);
+cudaError_t launch_pairs_sortkeys(cudaStream_t st, const u64* list_pair, int64_t count, int64_t np2, u64* keys);
+cudaError_t launch_pairs_rescore(cudaStream_t st, int device, const float* M, int ld, const u64* keys, int64_t count, float* scores);
+cudaError_t launch_pairs_emit(cudaStream_t st, const int64_t* sel, int64_t k, const u64* keys, const int64_t* ids, int64_t* out_a, int64_t* out_b);
 
 int sm_count(int device);
 inline int64_t next_pow2(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return p; }

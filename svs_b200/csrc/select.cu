@@ -401,6 +401,26 @@ __global__ void fs_emit_kernel(const u64* __restrict__ keys, int64_t kk, const i
     if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = (int32_t)kk;
 }
 
+// Sort keys[0..np2) descending; np2 a power of two >= BS_CHUNK (pad with 0 = sorts last).
+cudaError_t launch_sort_keys_desc(cudaStream_t st, u64* keys, int64_t np2)
+{
+    if (np2 < BS_CHUNK || (np2 & (np2 - 1))) return cudaErrorInvalidValue;
+    const unsigned gblocks = (unsigned)((np2 / 256 < 4096) ? (np2 / 256) : 4096);
+    const unsigned chunks = (unsigned)(np2 / BS_CHUNK);
+    fs_sort_chunks_kernel<<<chunks, BS_THREADS, 0, st>>>(keys);
+    int launches = 1;
+    for (int64_t kl = (int64_t)BS_CHUNK << 1; kl <= np2; kl <<= 1) {
+        for (int64_t j = kl >> 1; j >= BS_CHUNK; j >>= 1) {
+            fs_global_step_kernel<<<gblocks, 256, 0, st>>>(keys, np2, j, kl);
+            ++launches;
+        }
+        fs_merge_chunks_kernel<<<chunks, BS_THREADS, 0, st>>>(keys, kl);
+        ++launches;
+    }
+    count_launch(launches);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
                                  int64_t k, const int64_t* ids, int64_t row0, u64* sortbuf,
                                  u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count)
@@ -412,20 +432,12 @@ cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n
     const int64_t G = (n + ((int64_t)1 << group_shift) - 1) >> group_shift;
     const unsigned gblocks = (unsigned)((np2 / 256 < 4096) ? (np2 / 256) : 4096);
     fs_make_keys_kernel<<<gblocks, 256, 0, st>>>(scores, n, np2, sortbuf, gmax, G);
-    const unsigned chunks = (unsigned)(np2 / BS_CHUNK);
-    fs_sort_chunks_kernel<<<chunks, BS_THREADS, 0, st>>>(sortbuf);
-    int launches = 2;
-    for (int64_t kl = (int64_t)BS_CHUNK << 1; kl <= np2; kl <<= 1) {
-        for (int64_t j = kl >> 1; j >= BS_CHUNK; j >>= 1) {
-            fs_global_step_kernel<<<gblocks, 256, 0, st>>>(sortbuf, np2, j, kl);
-            ++launches;
-        }
-        fs_merge_chunks_kernel<<<chunks, BS_THREADS, 0, st>>>(sortbuf, kl);
-        ++launches;
-    }
+    cudaError_t se = launch_sort_keys_desc(st, sortbuf, np2);
+    if (se != cudaSuccess) return se;
+    count_launch(1);
     const unsigned eblocks = (unsigned)((kk + 255) / 256 < 1024 ? (kk + 255) / 256 : 1024);
     fs_emit_kernel<<<eblocks, 256, 0, st>>>(sortbuf, kk, ids, row0, out_keys, out_scores, out_ids, out_count);
-    count_launch(launches + 1);
+    count_launch(1);
     return cudaGetLastError();
 }
 

@@ -61,4 +61,89 @@ __device__ inline void block_rank_sort_desc(const u64* src, u64* dst, int c) {
     __syncthreads();
 }
 
+constexpr int KTH_BINS = 2048;
+constexpr int KTH_SMALL = 256;
+
+// kk-th largest (1-based, duplicates counted) of the 32-bit ordered values load(i), i < count (count >= kk >= 1).
+// Range-adaptive radix select: the 2048 bins always span [min, max] of the values still in play, so scores packed
+// into a narrow band (the README recipe: 0.75 +- 0.007) spread over all bins instead of hammering two of them with
+// shared-memory atomics; typically min/max pass + one histogram pass + one collect pass.
+// All threads call it; all get the result.  hist: KTH_BINS words, scratch: 72 words, small: KTH_SMALL words (shared).
+template <class Load>
+__device__ inline uint32_t block_kth_largest_o32(Load load, int64_t count, int kk, uint32_t* hist, uint32_t* scratch, uint32_t* small) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int64_t i = tid; i < count; i += blockDim.x) { const uint32_t o = load(i); mn = min(mn, o); mx = max(mx, o); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if (lane == 0) { scratch[8 + warp] = mn; scratch[40 + warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+        mn = lane < nwarps ? scratch[8 + lane] : 0xffffffffu;
+        mx = lane < nwarps ? scratch[40 + lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        if (lane == 0) { scratch[4] = mn; scratch[5] = mx; }
+    }
+    __syncthreads();
+    uint32_t lo = scratch[4], hi = scratch[5];
+    uint32_t remaining = (uint32_t)kk;
+    __syncthreads();
+    while (true) {
+        const uint32_t span = hi - lo;
+        const int shift = max(0, (span ? 32 - __clz(span) : 0) - 11);
+        for (int i = tid; i < KTH_BINS; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < count; i += blockDim.x) {
+            const uint32_t o = load(i);
+            if (o >= lo && o <= hi) atomicAdd(&hist[(o - lo) >> shift], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns bins [64 l, 64 l + 64); scan from the top bin down
+            uint32_t mine = 0;
+            for (int j = 0; j < 64; ++j) mine += hist[lane * 64 + j];
+            uint32_t incl = mine;                                      // suffix sum over lanes >= l
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += t; }
+            const uint32_t above = incl - mine;
+            if (above < remaining && incl >= remaining) {              // exactly one lane
+                uint32_t acc = above;
+                int bin = lane * 64 + 63;
+                for (; bin > lane * 64; --bin) { if (acc + hist[bin] >= remaining) break; acc += hist[bin]; }
+                scratch[0] = (uint32_t)bin; scratch[1] = acc; scratch[2] = hist[bin];
+            }
+        }
+        __syncthreads();
+        const uint32_t bin = scratch[0], above = scratch[1], inbin = scratch[2];
+        remaining -= above;
+        const uint32_t nlo = lo + (bin << shift);
+        uint32_t nhi = nlo + ((1u << shift) - 1u);
+        if (nhi > hi || nhi < nlo) nhi = hi;
+        lo = nlo; hi = nhi;
+        __syncthreads();
+        if (shift == 0) return lo;                                     // the bin is one value
+        if (inbin <= (uint32_t)KTH_SMALL) break;
+    }
+    // finish: the <= KTH_SMALL values of the final bin, rank-selected (duplicates allowed)
+    if (tid == 0) scratch[3] = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < count; i += blockDim.x) {
+        const uint32_t o = load(i);
+        if (o >= lo && o <= hi) { const uint32_t p = atomicAdd(&scratch[3], 1u); if (p < (uint32_t)KTH_SMALL) small[p] = o; }
+    }
+    __syncthreads();
+    const int c = (int)min(scratch[3], (uint32_t)KTH_SMALL);
+    if (tid < c) {
+        const uint32_t mine = small[tid];
+        uint32_t gt = 0, ge = 0;
+        for (int j = 0; j < c; ++j) { gt += small[j] > mine ? 1u : 0u; ge += small[j] >= mine ? 1u : 0u; }
+        if (gt < remaining && ge >= remaining) scratch[6] = mine;      // equal values write the same word
+    }
+    __syncthreads();
+    const uint32_t ans = scratch[6];
+    __syncthreads();
+    return ans;
+}
+
 }  // namespace svsb

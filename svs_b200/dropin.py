@@ -9,12 +9,15 @@ What is replaced -- and nothing else:
   * `svs.kb._EmbeddingsMatrix` (reference src/svs/kb.py:856-893) gains a `.device` member, a
     `DeviceEmbeddingsMatrix`; `invalidate()` drops both caches, so every invalidation site of the
     reference (kb.py:984,1062,1086,1455,1523,1541) keeps working untouched.  The host NumPy cache
-    stays in place for `document_top_pairwise_scores` (kb.py:1208-1243, 1642-1671), which is out of
-    scope and keeps running the reference's own code.
+    stays in place (it is only filled if something still asks for it, e.g. the pairwise path of a
+    multi-device install).
   * `KB.retrieve` (kb.py:1608-1640), `AsyncKB.retrieve` (kb.py:1171-1206): same orchestration --
     cache fetch, query embedding through the magnitude guard, SQL fetch of the n documents -- with the
     `superheavy()` closure (np.dot + get_top_k + emb_id_lookup) replaced by one engine call.
   * `AsyncKB.load` (kb.py:964-967) pre-warms the device cache instead of the host one.
+  * `document_top_pairwise_scores` (kb.py:1642-1671, 1208-1243): same orchestration with `superheavy()` =
+    np.dot(M, M.T) + get_top_pairs replaced by `svsb_top_pairs` (single-device engines).
+  * additive: `KB.retrieve_many` / `AsyncKB.retrieve_many` (one embedding call, one engine batch).
 
 INTEGRATION.md shows the same change as a source patch to kb.py for a maintainer who prefers that.
 """
@@ -30,8 +33,13 @@ from .matrix import DeviceEmbeddingsMatrix
 _ORIGINALS: dict = {}
 
 
-def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, normalize: bool = False) -> None:
-    """Patch `svs` in place.  Idempotent.  `devices`: CUDA devices to row-shard the matrix over."""
+def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, normalize: bool = False,
+            pairwise: Optional[bool] = None) -> None:
+    """Patch `svs` in place.  Idempotent.  `devices`: CUDA devices to row-shard the matrix over.
+    `pairwise`: also route document_top_pairwise_scores to the engine (default: yes on a single device; the
+    multi-device engine keeps the reference's host NumPy path for it)."""
+    if pairwise is None:
+        pairwise = devices is None or len(devices) <= 1
     if svs_module is None:
         import svs as svs_module                         # type: ignore  (the host application)
     kb = svs_module.kb if hasattr(svs_module, "kb") else __import__(svs_module.__name__ + ".kb", fromlist=["kb"])
@@ -128,6 +136,44 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
             async with db as q:
                 return await loop.run_in_executor(None, lambda: [_fetch_docs(q, emb_ids, n) for emb_ids in all_ids])
 
+    def _pair_docs(q: Any, pairwise_scores: List[Any], n: int) -> List[Any]:
+        # the reference's document fetch for pairs, verbatim in behaviour (kb.py:1658-1671)
+        emb_id_to_doc_id = {}
+        for emb_id in set(emb_id for _, e1, e2 in pairwise_scores for emb_id in (e1, e2)):
+            emb_id_to_doc_id[emb_id] = q.fetch_doc_with_emb_id(emb_id)
+        doc_lookup = {}
+        for doc_id in emb_id_to_doc_id.values():
+            doc_lookup[doc_id] = q.fetch_doc(doc_id, include_embedding=False)
+        res = [(score, doc_lookup[emb_id_to_doc_id[e1]], doc_lookup[emb_id_to_doc_id[e2]]) for score, e1, e2 in pairwise_scores]
+        log.info(f"retrieved top {n} document pairs")
+        return res
+
+    def top_pairwise(self: Any, n: int) -> List[Any]:
+        """document_top_pairwise_scores (kb.py:1642-1671) with `superheavy()` = np.dot(M, M.T) + get_top_pairs replaced by
+        one engine call that never materialises the N x N scores."""
+        assert self.db is not None
+        matrix = self.embeddings_matrix.device.get_sync(self.db)
+        n_docs = matrix.shape[0]
+        log.info(f"computing pairwise similarity over {n_docs} documents")
+        pairwise_scores = matrix.top_pairs(n)
+        log.info(f"computed {n_docs * n_docs} pairwise cosine similarities")
+        with self.db as q:
+            return _pair_docs(q, pairwise_scores, n)
+
+    async def atop_pairwise(self: Any, n: int) -> List[Any]:
+        loop = asyncio.get_running_loop()
+        async with self._get_lock():
+            db = await self._ensure_db()
+            matrix = await self.embeddings_matrix.device.get(db)
+        n_docs = matrix.shape[0]
+        log.info(f"computing pairwise similarity over {n_docs} documents")
+        pairwise_scores = await loop.run_in_executor(None, matrix.top_pairs, n)
+        log.info(f"computed {n_docs * n_docs} pairwise cosine similarities")
+        async with self._get_lock():
+            db = await self._ensure_db()
+            async with db as q:
+                return await loop.run_in_executor(None, _pair_docs, q, pairwise_scores, n)
+
     async def aload(self: Any) -> None:
         async with self._get_lock():
             db = await self._ensure_db()
@@ -136,11 +182,15 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
     _ORIGINALS.update({
         "module": kb, "_EmbeddingsMatrix": host_cls, "KB.retrieve": kb.KB.retrieve,
         "AsyncKB.retrieve": kb.AsyncKB.retrieve, "AsyncKB.load": kb.AsyncKB.load,
+        "KB.pairs": kb.KB.document_top_pairwise_scores, "AsyncKB.pairs": kb.AsyncKB.document_top_pairwise_scores,
     })
     kb._EmbeddingsMatrix = _EmbeddingsMatrix
     kb.KB.retrieve = retrieve
     kb.AsyncKB.retrieve = aretrieve
     kb.AsyncKB.load = aload
+    if pairwise:
+        kb.KB.document_top_pairwise_scores = top_pairwise
+        kb.AsyncKB.document_top_pairwise_scores = atop_pairwise
     kb.KB.retrieve_many = retrieve_many                  # additive: batched retrieve
     kb.AsyncKB.retrieve_many = aretrieve_many
 
@@ -154,6 +204,8 @@ def uninstall() -> None:
     kb.KB.retrieve = _ORIGINALS["KB.retrieve"]
     kb.AsyncKB.retrieve = _ORIGINALS["AsyncKB.retrieve"]
     kb.AsyncKB.load = _ORIGINALS["AsyncKB.load"]
+    kb.KB.document_top_pairwise_scores = _ORIGINALS["KB.pairs"]
+    kb.AsyncKB.document_top_pairwise_scores = _ORIGINALS["AsyncKB.pairs"]
     for cls in (kb.KB, kb.AsyncKB):
         if "retrieve_many" in cls.__dict__:
             delattr(cls, "retrieve_many")

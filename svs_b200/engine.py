@@ -172,6 +172,20 @@ class Engine:
         scores, ids = self.query(query_vec, n)
         return [(float(s), int(i)) for s, i in zip(scores, ids)]
 
+    def top_pairs(self, n: int) -> List[Tuple[float, int, int]]:
+        """The `superheavy()` of document_top_pairwise_scores (src/svs/kb.py:1650-1656): [(score, emb_id_1, emb_id_2)]
+        of the n highest-scoring pairs of distinct rows (upper triangle), never materialising the N x N scores."""
+        cap = max(int(n), 0)
+        rows = self.shape[0]
+        cap = min(cap, rows * (rows - 1) // 2)
+        s = np.empty(cap, dtype=np.float32)
+        a = np.empty(cap, dtype=np.int64)
+        b = np.empty(cap, dtype=np.int64)
+        cnt = C.c_int64()
+        check(self._lib.svsb_top_pairs(self._h, cap, s.ctypes.data, a.ctypes.data, b.ctypes.data, C.byref(cnt)))
+        c = cnt.value
+        return [(float(x), int(y), int(z)) for x, y, z in zip(s[:c], a[:c], b[:c])]
+
     def topk_scores(self, scores: np.ndarray, k: int) -> List[Tuple[float, int]]:
         """get_top_k (src/svs/util.py:190-203) run by the device selection kernels on a host score
         vector; ties are ordered by ascending index (the engine's order), not descending."""
@@ -272,6 +286,21 @@ class Snapshot:
         check(self._lib.svsb_snapshot_query_batch(self._engine._h, self._s, Q.ctypes.data, b, d, int(k),
                                                   scores.ctypes.data, ids.ctypes.data, counts.ctypes.data))
         return scores, ids, counts
+
+    def top_pairs(self, n: int) -> List[Tuple[float, int, int]]:
+        """[(score, emb_id_1, emb_id_2)] of the n best pairs of distinct rows of the pinned generation."""
+        if not self._engine._h.value:
+            raise _lib.EngineError(_lib.SVSB_E_STATE, "engine is closed")
+        rows = self.shape[0]
+        cap = min(max(int(n), 0), rows * (rows - 1) // 2)
+        s = np.empty(cap, dtype=np.float32)
+        a = np.empty(cap, dtype=np.int64)
+        b = np.empty(cap, dtype=np.int64)
+        cnt = C.c_int64()
+        check(self._lib.svsb_snapshot_top_pairs(self._engine._h, self._s, cap, s.ctypes.data, a.ctypes.data, b.ctypes.data,
+                                                C.byref(cnt)))
+        c = cnt.value
+        return [(float(x), int(y), int(z)) for x, y, z in zip(s[:c], a[:c], b[:c])]
 
     def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
         """superheavy() for every row of query_vecs, as ONE engine call."""

@@ -42,6 +42,11 @@ class DeviceMatrix:
         an empty matrix exactly where the reference's np.dot does."""
         return self._snap.retrieve(query_vec, n)
 
+    def top_pairs(self, n: int) -> List[Tuple[float, int, int]]:
+        """The `superheavy()` of document_top_pairwise_scores (src/svs/kb.py:1650-1656): np.dot(M, M.T) + get_top_pairs
+        + emb_id_lookup, on the GPU, without materialising the N x N score matrix."""
+        return self._snap.top_pairs(n)
+
     def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
         """superheavy() for a batch of query vectors in one engine call (bit-identical to looping `retrieve`);
         large batches run as one tensor-core contraction (include/svsb200.h: svsb_query_batch)."""

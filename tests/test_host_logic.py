@@ -29,6 +29,9 @@ class FakeSnapshot:
     def retrieve_many(self, qs, n):
         return [self.retrieve(q, n) for q in qs]
 
+    def top_pairs(self, n):
+        return [(0.5, int(self._ids[0]), int(self._ids[1]))][:max(0, n)] if len(self._ids) > 1 else []
+
 
 class FakeEngine:
     """Records what the host logic asks of the C ABI; slab capacity is tiny to force many slabs."""
@@ -200,12 +203,18 @@ def _fake_svs_module():
         def retrieve(self, query, n):
             return "host"
 
+        def document_top_pairwise_scores(self, n):
+            return "host pairs"
+
     class AsyncKB(KB):
         async def retrieve(self, query, n):
             return "host"
 
         async def load(self):
             return "host"
+
+        async def document_top_pairwise_scores(self, n):
+            return "host pairs"
 
     import logging
     kb._EmbeddingsMatrix, kb.KB, kb.AsyncKB, kb._LOG = _EmbeddingsMatrix, KB, AsyncKB, logging.getLogger("fakesvs")
@@ -230,6 +239,7 @@ def test_install_and_uninstall_patch_only_the_seam(fake_engine):
         svs_b200.uninstall()
     assert mod.kb._EmbeddingsMatrix is orig_cls and mod.kb.KB.retrieve is orig_retrieve
     assert mod.kb.KB().retrieve("q", 1) == "host"
+    assert mod.kb.KB().document_top_pairwise_scores(1) == "host pairs"
     assert not hasattr(mod.kb.KB, "retrieve_many") and not hasattr(mod.kb.AsyncKB, "retrieve_many")
 
 
@@ -256,7 +266,8 @@ def test_install_on_the_real_reference_package(fake_engine, tmp_path, monkeypatc
             del_doc(1)
         assert ("invalidate",) in fake_engine[0].calls            # kb.py:1541 reached the device cache
         assert [r["doc"]["text"] for r in kb.retrieve("q", 5)] == ["b", "c"]
-        assert kb.document_top_pairwise_scores(1)[0][1]["text"] == "b"   # untouched host path still works
+        pair = kb.document_top_pairwise_scores(1)[0]               # pairwise now asks the (fake) engine for the pair
+        assert (pair[0], pair[1]["text"], pair[2]["text"]) == (0.5, "b", "c")
         many = kb.retrieve_many(["q1", "q2", "q3"], 1)             # additive batched API: one embed call, one engine call
         assert [[r["doc"]["text"] for r in res] for res in many] == [["b"], ["b"], ["b"]]
         assert kb.retrieve_many([], 3) == []

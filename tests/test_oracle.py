@@ -206,3 +206,31 @@ def test_synth_matrices_are_unit_norm():
         m = f(200, 64, 0)
         assert m.dtype == np.float32
         assert oracle.magnitude_ok(m.tolist(), 1e-5)
+
+
+def test_get_top_pairs_known_answers():
+    """The known-answer cases of the reference's tests/test_util.py:403-470 (get_top_pairs)."""
+    with pytest.raises(AssertionError):
+        oracle.get_top_pairs(np.zeros((3, 2, 5)), top_k=3)           # not 2-D
+    with pytest.raises(AssertionError):
+        oracle.get_top_pairs(np.zeros((3, 2)), top_k=3)              # not square
+    assert oracle.get_top_pairs(np.zeros((0, 0)), top_k=3) == []
+    assert oracle.get_top_pairs(np.array([[1]]), top_k=3) == []
+    assert oracle.get_top_pairs(np.array([[1, 2], [9, 4]]), top_k=3) == [(2, 0, 1)]
+    assert oracle.get_top_pairs(np.array([[1, 2, 3], [9, 5, 6], [9, 9, 9]]), top_k=3) == [(6, 1, 2), (3, 0, 2), (2, 0, 1)]
+    m = np.array([[1, 2, 3, 4], [20, 20, 7, 8], [20, 20, 20, 12], [20, 20, 20, 16]])
+    assert oracle.get_top_pairs(m, top_k=3) == [(12, 2, 3), (8, 1, 3), (7, 1, 2)]
+
+
+def test_top_pairwise_and_its_comparator():
+    rng = np.random.default_rng(21)
+    m = oracle.synth_matrix_normal(60, 12, 2)
+    ids = np.cumsum(rng.integers(1, 4, size=60)).astype(np.int64)
+    pairwise = np.dot(m, m.T)
+    want = oracle.top_pairwise(m, ids, 40)
+    assert len(want) == 40 and all(want[i][0] >= want[i + 1][0] for i in range(39))
+    oracle.compare_pairs(want, want, pairwise, ids)
+    wrong = list(want)
+    wrong[3] = (wrong[3][0], wrong[30][1], wrong[30][2])             # a far-away pair smuggled into rank 3
+    with pytest.raises(AssertionError):
+        oracle.compare_pairs(wrong, want, pairwise, ids)
