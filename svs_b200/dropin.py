@@ -33,11 +33,67 @@ from .matrix import DeviceEmbeddingsMatrix
 _ORIGINALS: dict = {}
 
 
+class _Coalescer:
+    """Dynamic batching of concurrent `AsyncKB.retrieve` calls.
+
+    The reference runs every retrieve's `superheavy()` in the default executor without holding the KB lock
+    (src/svs/kb.py:1190), so many can be in flight; on one GPU they would simply queue behind each other, one
+    full pass over the matrix each.  Here the calls that arrive while a batch is on the GPU are collected and go out
+    together as ONE `retrieve_many` (the tensor-core path from 4 queries up) -- results are bit-identical to the
+    single-query kernels', so only the scheduling changes.  No added latency when idle: a lone call is issued at
+    once.  Queries with different n share a batch (run at the largest n; a top-n list is a prefix of a top-k list).
+    """
+
+    def __init__(self) -> None:
+        self._pending: List[Any] = []          # (matrix, vec, n, future)
+        self._busy = False
+
+    async def submit(self, matrix: Any, vec: np.ndarray, n: int) -> List[Any]:
+        loop = asyncio.get_running_loop()
+        fut = loop.create_future()
+        self._pending.append((matrix, vec, n, fut))
+        if not self._busy:
+            self._busy = True
+            loop.create_task(self._drain())
+        return await fut
+
+    async def _drain(self) -> None:
+        loop = asyncio.get_running_loop()
+        try:
+            await asyncio.sleep(0)             # let every retrieve that is runnable in this tick join the batch
+            while self._pending:
+                matrix = self._pending[0][0]
+                dim = self._pending[0][1].shape
+                batch = [it for it in self._pending if it[0] is matrix and it[1].shape == dim]
+                self._pending = [it for it in self._pending if not (it[0] is matrix and it[1].shape == dim)]
+                k = max(it[2] for it in batch)
+                try:
+                    if len(batch) == 1:
+                        res = [await loop.run_in_executor(None, matrix.retrieve, batch[0][1], batch[0][2])]
+                    else:
+                        vecs = np.stack([it[1] for it in batch])
+                        full = await loop.run_in_executor(None, matrix.retrieve_many, vecs, k)
+                        res = [r[:max(it[2], 0)] for r, it in zip(full, batch)]
+                    for it, r in zip(batch, res):
+                        if not it[3].done():
+                            it[3].set_result(r)
+                except BaseException as ex:    # e.g. ValueError for a d mismatch: every caller of the batch sees it
+                    for it in batch:
+                        if not it[3].done():
+                            it[3].set_exception(ex)
+        finally:
+            self._busy = False
+            if self._pending:                  # arrivals that raced with the end of the loop
+                self._busy = True
+                loop.create_task(self._drain())
+
+
 def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, normalize: bool = False,
-            pairwise: Optional[bool] = None) -> None:
+            pairwise: Optional[bool] = None, coalesce: bool = True) -> None:
     """Patch `svs` in place.  Idempotent.  `devices`: CUDA devices to row-shard the matrix over.
     `pairwise`: also route document_top_pairwise_scores to the engine (default: yes on a single device; the
-    multi-device engine keeps the reference's host NumPy path for it)."""
+    multi-device engine keeps the reference's host NumPy path for it).
+    `coalesce`: batch concurrent AsyncKB.retrieve calls into one engine call (see _Coalescer)."""
     if pairwise is None:
         pairwise = devices is None or len(devices) <= 1
     if svs_module is None:
@@ -54,6 +110,7 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
         def __init__(self) -> None:
             super().__init__()
             self.device = DeviceEmbeddingsMatrix(devices, normalize)
+            self.coalescer = _Coalescer() if coalesce else None
 
         def invalidate(self) -> None:
             super().invalidate()
@@ -92,7 +149,11 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
         log.info("got embedding for query!")
         # the lock is NOT held here (as in the reference): `matrix` pins its generation, so a
         # concurrent bulk_add/bulk_del may invalidate the cache while this runs
-        emb_ids = await loop.run_in_executor(None, matrix.retrieve, query_vec, n)
+        co = getattr(self.embeddings_matrix, "coalescer", None)
+        if co is not None and query_vec.ndim == 1 and query_vec.shape[0] == matrix.shape[1] and matrix.shape[0] > 0:
+            emb_ids = await co.submit(matrix, query_vec, n)      # joins whatever else is waiting for the GPU
+        else:                                                    # shape errors surface exactly as in the single path
+            emb_ids = await loop.run_in_executor(None, matrix.retrieve, query_vec, n)
         log.info(f"computed {matrix.shape[0]} cosine similarities")
         async with self._get_lock():
             db = await self._ensure_db()

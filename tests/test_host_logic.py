@@ -17,6 +17,8 @@ from svs_b200 import matrix as matrix_mod
 
 
 class FakeSnapshot:
+    batches = []                                   # sizes of the retrieve_many calls seen (coalescer test)
+
     def __init__(self, eng):
         self.shape = (eng.n, eng.d if eng.n else 0)
         self.generation = eng.gen
@@ -27,6 +29,7 @@ class FakeSnapshot:
         return [(0.0, int(i)) for i in self._ids[:max(0, n)]]
 
     def retrieve_many(self, qs, n):
+        FakeSnapshot.batches.append(len(qs))
         return [self.retrieve(q, n) for q in qs]
 
     def top_pairs(self, n):
@@ -272,5 +275,37 @@ def test_install_on_the_real_reference_package(fake_engine, tmp_path, monkeypatc
         assert [[r["doc"]["text"] for r in res] for res in many] == [["b"], ["b"], ["b"]]
         assert kb.retrieve_many([], 3) == []
         kb.close()
+    finally:
+        svs_b200.uninstall()
+
+
+@pytest.mark.skipif(reference_import_path() is None, reason="oracle/_ref (byte-compiled reference) not built")
+def test_concurrent_async_retrieves_are_coalesced_into_batches(fake_engine, tmp_path, monkeypatch):
+    """AsyncKB.retrieve calls that are in flight together reach the engine as retrieve_many batches; every caller
+    still gets its own n results; a lone call goes out as a single query."""
+    import sys
+    monkeypatch.syspath_prepend(reference_import_path())
+    for k in [k for k in sys.modules if k == "svs" or k.startswith("svs.")]:
+        monkeypatch.delitem(sys.modules, k)
+    import svs
+    svs_b200.install(svs)
+    try:
+        async def embed(texts):
+            return [[1.0, 0.0, 0.0] for _ in texts]
+
+        async def go():
+            kb = svs.AsyncKB(str(tmp_path / "a.sqlite"), embed)
+            async with kb.bulk_add_docs() as add_doc:
+                for t in ("a", "b", "c", "d"):
+                    await add_doc(t)
+            FakeSnapshot.batches.clear()
+            one = await kb.retrieve("q", 2)
+            assert [r["doc"]["text"] for r in one] == ["a", "b"] and FakeSnapshot.batches == []
+            outs = await asyncio.gather(*[kb.retrieve(f"q{i}", 1 + i % 3) for i in range(12)])
+            assert [len(o) for o in outs] == [1 + i % 3 for i in range(12)]
+            assert all(o[0]["doc"]["text"] == "a" for o in outs)
+            assert sum(FakeSnapshot.batches) >= 8 and max(FakeSnapshot.batches) > 1       # most of them travelled together
+            await kb.close()
+        asyncio.run(go())
     finally:
         svs_b200.uninstall()
