@@ -12,6 +12,8 @@
 // coarse score of a SAMPLE of the rows) - 2 eps, and the sample's kk-th largest can only be lower than tau~.
 #include "select_common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace svsb {
 
 constexpr int RF_THREADS = 512;
@@ -22,25 +24,26 @@ constexpr int RF_SMALL = KTH_SMALL;
 // thresholds from the sample: thr[q] = kk-th largest coarse score among the sampled rows
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RF_THREADS)
-sample_threshold_kernel(const float* __restrict__ sample, int64_t sample_rows, int kk, const float* __restrict__ eps,
+sample_threshold_kernel(const __half* __restrict__ sample, int64_t sample_rows, int kk, const float* __restrict__ eps,
                         float* __restrict__ thr)
 {
     __shared__ uint32_t hist[RF_BINS];
     __shared__ uint32_t scratch[72];
     __shared__ uint32_t small[RF_SMALL];
     const int q = blockIdx.x;
-    const float* s = sample + (size_t)q * sample_rows;
-    const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(s[i]); }, sample_rows, kk, hist, scratch, small);
+    const __half* s = sample + (size_t)q * sample_rows;          // coarse scores rounded DOWN to fp16: still a lower bound
+    const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(__half2float(s[i])); }, sample_rows, kk,
+                                             hist, scratch, small);
     // The filter must let through every row with coarse >= tau~ - 2 eps; the sample's kk-th largest is <= tau~.
     if (threadIdx.x == 0) thr[q] = ordered_to_f32(o) - 2.0f * eps[q];
 }
 
-cudaError_t launch_sample_threshold(cudaStream_t st, const float* sample, int64_t sample_rows, int b, int kk, const float* eps,
+cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t sample_rows, int b, int kk, const float* eps,
                                     float* thr)
 {
     if (b <= 0) return cudaSuccess;
     if (kk < 1 || kk > sample_rows) return cudaErrorInvalidValue;
-    sample_threshold_kernel<<<b, RF_THREADS, 0, st>>>(sample, sample_rows, kk, eps, thr);
+    sample_threshold_kernel<<<b, RF_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, kk, eps, thr);
     count_launch();
     return cudaGetLastError();
 }
@@ -48,9 +51,11 @@ cudaError_t launch_sample_threshold(cudaStream_t st, const float* sample, int64_
 // ---------------------------------------------------------------------------------------------
 // refine
 // ---------------------------------------------------------------------------------------------
+constexpr int RF_CACHE = 8192;                  // candidates whose coarse scores are kept in shared memory across passes
 struct RefineSmem {
     u64 keys[REFINE_SURVIVOR_CAP];
     uint32_t rows[REFINE_SURVIVOR_CAP];
+    uint32_t cached[RF_CACHE];
     uint32_t hist[RF_BINS];
     uint32_t scratch[72];
     uint32_t small[RF_SMALL];
@@ -58,7 +63,7 @@ struct RefineSmem {
     // float4 q[ld / 4] follows
 };
 
-__global__ void __launch_bounds__(RF_THREADS)
+__global__ void __launch_bounds__(RF_THREADS, 2)
 refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __restrict__ ids, int64_t row0,
               const float* __restrict__ Q, int ldq, int k, const u64* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
               int cand_cap, const float* __restrict__ eps, int32_t* __restrict__ flags, RefineOut out,
@@ -80,17 +85,29 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
     const u64* cq = cand + (size_t)q * cand_cap;
     for (int c = tid; c < d4; c += RF_THREADS) sq[c] = reinterpret_cast<const float4*>(Q + (size_t)q * ldq)[c];
     if (tid == 0) sm.counter = 0;
+    // one trip to global memory for the coarse scores (the key's high word IS the ordered score); the select passes
+    // below then run out of shared memory
+    {
+        const int lim = min(total, RF_CACHE);
+        for (int i0 = tid; i0 < lim; i0 += RF_THREADS * 4) {
+            u64 kv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * RF_THREADS; kv[u] = i < lim ? cq[i] : 0ull; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * RF_THREADS; if (i < lim) sm.cached[i] = (uint32_t)(kv[u] >> 32); }
+        }
+    }
     __syncthreads();
+    auto score_o = [&](int64_t i) { return i < RF_CACHE ? sm.cached[i] : (uint32_t)(cq[i] >> 32); };
 
-    // tau~: the kk-th largest coarse score among the candidates (the key's high word IS the ordered score)
-    const uint32_t tau_o = block_kth_largest_o32([&](int64_t i) { return (uint32_t)(cq[i] >> 32); }, total, kk, sm.hist, sm.scratch, sm.small);
+    // tau~: the kk-th largest coarse score among the candidates
+    const uint32_t tau_o = block_kth_largest_o32(score_o, total, kk, sm.hist, sm.scratch, sm.small);
     const float cutoff = ordered_to_f32(tau_o) - 2.0f * eps[q];
 
     for (int i = tid; i < total; i += RF_THREADS) {
-        const u64 key = cq[i];
-        if (key_score(key) >= cutoff) {
+        if (ordered_to_f32(score_o(i)) >= cutoff) {
             const uint32_t p = atomicAdd(&sm.counter, 1u);
-            if (p < (uint32_t)REFINE_SURVIVOR_CAP) sm.rows[p] = key_row(key);
+            if (p < (uint32_t)REFINE_SURVIVOR_CAP) sm.rows[p] = key_row(cq[i]);
         }
     }
     __syncthreads();

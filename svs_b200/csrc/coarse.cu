@@ -125,7 +125,7 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                    int64_t n, int n_tiles, int tile_stride, int n_qblocks, int n_kblocks,
                    const float* __restrict__ thr,          // [b_pad] thresholds (unscaled coarse scores), MODE 0
                    u64* __restrict__ cand, int32_t* __restrict__ cand_cnt, int cand_cap,   // MODE 0
-                   float* __restrict__ sample, int64_t sample_rows,                        // MODE 1: [b_pad][sample_rows]
+                   __half* __restrict__ sample, int64_t sample_rows,                       // MODE 1: [b_pad][sample_rows]
                    int64_t tri_q0)   // >= 0: pairwise mode, query column q is matrix row tri_q0 + q; keep only row > that
 {
     extern __shared__ unsigned char cg_smem_raw[];
@@ -314,8 +314,8 @@ coarse_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const int64_t lim = tri_q0 >= 0 ? row - tri_q0 - q0 : 32;   // pairwise: only columns j < lim count
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            sample[(size_t)(q0 + j) * sample_rows + srow] =
-                                (row_ok && j < lim) ? __uint_as_float(v[j]) * (1.0f / kScale) : __int_as_float(0xff800000);
+                            sample[(size_t)(q0 + j) * sample_rows + srow] =      // rounded down: stays a lower bound
+                                __float2half_rd((row_ok && j < lim) ? __uint_as_float(v[j]) * (1.0f / kScale) : __int_as_float(0xff800000));
                     }
                 }
             }
@@ -444,7 +444,7 @@ static cudaError_t make_map(CUtensorMap* map, const void* ptr, int64_t rows, int
 
 cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void* M16, int64_t n, const void* Q16, int b_pad,
                                int ld16, int n_tiles, int tile_stride, const float* thr, u64* cand, int32_t* cand_cnt,
-                               int cand_cap, float* sample, int64_t sample_rows, int64_t q_rows, int64_t tri_q0)
+                               int cand_cap, void* sample, int64_t sample_rows, int64_t q_rows, int64_t tri_q0)
 {
     if (n <= 0 || b_pad <= 0 || b_pad % CG_BN || b_pad > COARSE_MAX_BATCH || ld16 % 8 || n_tiles <= 0) return cudaErrorInvalidValue;
     if (n > 0x7fffff00ll) return cudaErrorInvalidValue;
@@ -467,10 +467,10 @@ cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void
     }
     if (mode)
         coarse_gemm_kernel<1><<<(unsigned)grid, CG_THREADS, CG_SMEM, st>>>(tmA, tmB, n, n_tiles, tile_stride, n_qblocks, n_kblocks,
-                                                                          thr, cand, cand_cnt, cand_cap, sample, sample_rows, tri_q0);
+                                                                          thr, cand, cand_cnt, cand_cap, reinterpret_cast<__half*>(sample), sample_rows, tri_q0);
     else
         coarse_gemm_kernel<0><<<(unsigned)grid, CG_THREADS, CG_SMEM, st>>>(tmA, tmB, n, n_tiles, tile_stride, n_qblocks, n_kblocks,
-                                                                          thr, cand, cand_cnt, cand_cap, sample, sample_rows, tri_q0);
+                                                                          thr, cand, cand_cnt, cand_cap, reinterpret_cast<__half*>(sample), sample_rows, tri_q0);
     count_launch();
     return cudaGetLastError();
 }

@@ -74,16 +74,17 @@ cudaError_t launch_queries_to_f16(cudaStream_t st, const float* Q, int b, int b_
                                   float eps_coef, float max_row_norm, float* eps, float* thr, int32_t* flags);
 // mode 0: filter -- every (row, query) whose coarse score >= thr[query] is appended to cand[query][..cand_cap)
 //         (key = ordered coarse score << 32 | ~row), cand_cnt[query] counts ALL survivors (may exceed cand_cap).
-// mode 1: sample -- raw coarse scores of row tiles 0, tile_stride, 2*tile_stride, ... (n_tiles of them) go to
-//         sample[query][sample_rows]; rows beyond n read as -inf.
+// mode 1: sample -- coarse scores of row tiles 0, tile_stride, 2*tile_stride, ... (n_tiles of them), rounded DOWN to
+//         fp16, go to sample[query][sample_rows] (__half); rows beyond n read as -inf.
 // q_rows > 0: Q16 holds only q_rows (<= b_pad) rows, the rest of the padded batch reads as zero.
 // tri_q0 >= 0: pairwise mode -- Q16 is the matrix itself from row tri_q0 on; only pairs (query row < matrix row)
 // count, tiles on or below the diagonal are skipped.
 cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void* M16, int64_t n, const void* Q16, int b_pad,
                                int ld16, int n_tiles, int tile_stride, const float* thr, u64* cand, int32_t* cand_cnt,
-                               int cand_cap, float* sample, int64_t sample_rows, int64_t q_rows = 0, int64_t tri_q0 = -1);
+                               int cand_cap, void* sample, int64_t sample_rows, int64_t q_rows = 0, int64_t tri_q0 = -1);
 // thr[q] = (kk-th largest of sample[q][0..sample_rows)) - 2 eps[q] for q < b (one CTA per query).
-cudaError_t launch_sample_threshold(cudaStream_t st, const float* sample, int64_t sample_rows, int b, int kk, const float* eps,
+// sample: fp16 (coarse scores rounded down), as the coarse kernel's mode 1 writes it.
+cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t sample_rows, int b, int kk, const float* eps,
                                     float* thr);
 // One CTA per query: tau~ = kk-th largest coarse candidate; keep candidates with coarse >= tau~ - 2*eps[q]; re-score
 // them exactly (fp32, the similarity kernel's summation order); sort; write (score, embeddings.id) x kk.
@@ -108,7 +109,7 @@ cudaError_t launch_pairs_fill_thr(cudaStream_t st, float* thr, int b_pad, int b,
 cudaError_t launch_pairs_gather(cudaStream_t st, const u64* cand, const int32_t* cand_cnt, int cand_cap, int b, int64_t q0,
                                 uint32_t* list_o, u64* list_pair, int64_t list_cap, unsigned long long* state);
 // *thr_scalar = max(*thr_scalar, n-th largest coarse score - eps2) over the list (vals == nullptr) or a raw sample
-cudaError_t launch_pairs_tau(cudaStream_t st, const uint32_t* list_o, const float* vals, int64_t vals_count,
+cudaError_t launch_pairs_tau(cudaStream_t st, const uint32_t* list_o, const void* vals /*fp16 sample*/, int64_t vals_count,
                              const unsigned long long* state, int64_t list_cap, int n, float eps2, float* thr_scalar);
 cudaError_t launch_pairs_compact(cudaStream_t st, int device, const uint32_t* src_o, const u64* src_pair, const unsigned long long* src_state,
                                  int64_t list_cap, uint32_t* dst_o, u64* dst_pair, unsigned long long* dst_state, const float* thr_scalar);

@@ -14,6 +14,8 @@
 // (the reference orders exact ties by descending flat index of the upper triangle, src/svs/util.py:203).
 #include "select_common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace svsb {
 
 constexpr int PR_THREADS = 1024;
@@ -51,9 +53,9 @@ pairs_gather_kernel(const u64* __restrict__ cand, const int32_t* __restrict__ ca
 }
 
 // Single CTA: tighten the global threshold to (n-th largest coarse score in the list) - 2 eps.
-// Also usable on a raw fp32 sample (vals != nullptr): the bootstrap.
+// Also usable on the coarse kernel's fp16 sample dump (vals != nullptr): the bootstrap.
 __global__ void __launch_bounds__(PR_THREADS)
-pairs_tau_kernel(const uint32_t* __restrict__ list_o, const float* __restrict__ vals, int64_t vals_count,
+pairs_tau_kernel(const uint32_t* __restrict__ list_o, const __half* __restrict__ vals, int64_t vals_count,
                  const unsigned long long* __restrict__ state, int64_t list_cap, int n, float eps2, float* __restrict__ thr_scalar)
 {
     __shared__ uint32_t hist[PR_BINS];
@@ -62,7 +64,7 @@ pairs_tau_kernel(const uint32_t* __restrict__ list_o, const float* __restrict__ 
     int64_t count = vals ? vals_count : (int64_t)min(state[0], (unsigned long long)list_cap);
     if (count < n) return;
     uint32_t o;
-    if (vals) o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(vals[i]); }, count, n, hist, scratch, small);
+    if (vals) o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(__half2float(vals[i])); }, count, n, hist, scratch, small);
     else      o = block_kth_largest_o32([&](int64_t i) { return list_o[i]; }, count, n, hist, scratch, small);
     if (threadIdx.x == 0) {
         const float t = ordered_to_f32(o) - eps2;
@@ -154,9 +156,9 @@ cudaError_t launch_pairs_gather(cudaStream_t st, const u64* cand, const int32_t*
     count_launch();
     return cudaGetLastError();
 }
-cudaError_t launch_pairs_tau(cudaStream_t st, const uint32_t* list_o, const float* vals, int64_t vals_count,
+cudaError_t launch_pairs_tau(cudaStream_t st, const uint32_t* list_o, const void* vals, int64_t vals_count,
                              const unsigned long long* state, int64_t list_cap, int n, float eps2, float* thr_scalar) {
-    pairs_tau_kernel<<<1, PR_THREADS, 0, st>>>(list_o, vals, vals_count, state, list_cap, n, eps2, thr_scalar);
+    pairs_tau_kernel<<<1, PR_THREADS, 0, st>>>(list_o, reinterpret_cast<const __half*>(vals), vals_count, state, list_cap, n, eps2, thr_scalar);
     count_launch();
     return cudaGetLastError();
 }

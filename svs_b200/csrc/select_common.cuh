@@ -63,6 +63,7 @@ __device__ inline void block_rank_sort_desc(const u64* src, u64* dst, int c) {
 
 constexpr int KTH_BINS = 2048;
 constexpr int KTH_SMALL = 256;
+constexpr int KTH_UNROLL = 1;
 
 // kk-th largest (1-based, duplicates counted) of the 32-bit ordered values load(i), i < count (count >= kk >= 1).
 // Range-adaptive radix select: the 2048 bins always span [min, max] of the values still in play, so scores packed
@@ -73,7 +74,14 @@ template <class Load>
 __device__ inline uint32_t block_kth_largest_o32(Load load, int64_t count, int kk, uint32_t* hist, uint32_t* scratch, uint32_t* small) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     uint32_t mn = 0xffffffffu, mx = 0u;
-    for (int64_t i = tid; i < count; i += blockDim.x) { const uint32_t o = load(i); mn = min(mn, o); mx = max(mx, o); }
+    // every scan issues KTH_UNROLL independent loads before consuming them: the passes are latency-, not bandwidth-bound
+    for (int64_t i0 = tid; i0 < count; i0 += (int64_t)blockDim.x * KTH_UNROLL) {
+        uint32_t o[KTH_UNROLL];
+#pragma unroll
+        for (int u = 0; u < KTH_UNROLL; ++u) { const int64_t i = i0 + (int64_t)u * blockDim.x; o[u] = i < count ? load(i) : 0u; }
+#pragma unroll
+        for (int u = 0; u < KTH_UNROLL; ++u) if (i0 + (int64_t)u * blockDim.x < count) { mn = min(mn, o[u]); mx = max(mx, o[u]); }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
     if (lane == 0) { scratch[8 + warp] = mn; scratch[40 + warp] = mx; }
@@ -94,9 +102,13 @@ __device__ inline uint32_t block_kth_largest_o32(Load load, int64_t count, int k
         const int shift = max(0, (span ? 32 - __clz(span) : 0) - 11);
         for (int i = tid; i < KTH_BINS; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for (int64_t i = tid; i < count; i += blockDim.x) {
-            const uint32_t o = load(i);
-            if (o >= lo && o <= hi) atomicAdd(&hist[(o - lo) >> shift], 1u);
+        for (int64_t i0 = tid; i0 < count; i0 += (int64_t)blockDim.x * KTH_UNROLL) {
+            uint32_t o[KTH_UNROLL];
+#pragma unroll
+            for (int u = 0; u < KTH_UNROLL; ++u) { const int64_t i = i0 + (int64_t)u * blockDim.x; o[u] = i < count ? load(i) : 0u; }
+#pragma unroll
+            for (int u = 0; u < KTH_UNROLL; ++u)
+                if (i0 + (int64_t)u * blockDim.x < count && o[u] >= lo && o[u] <= hi) atomicAdd(&hist[(o[u] - lo) >> shift], 1u);
         }
         __syncthreads();
         if (warp == 0) {
@@ -128,9 +140,15 @@ __device__ inline uint32_t block_kth_largest_o32(Load load, int64_t count, int k
     // finish: the <= KTH_SMALL values of the final bin, rank-selected (duplicates allowed)
     if (tid == 0) scratch[3] = 0;
     __syncthreads();
-    for (int64_t i = tid; i < count; i += blockDim.x) {
-        const uint32_t o = load(i);
-        if (o >= lo && o <= hi) { const uint32_t p = atomicAdd(&scratch[3], 1u); if (p < (uint32_t)KTH_SMALL) small[p] = o; }
+    for (int64_t i0 = tid; i0 < count; i0 += (int64_t)blockDim.x * KTH_UNROLL) {
+        uint32_t o[KTH_UNROLL];
+#pragma unroll
+        for (int u = 0; u < KTH_UNROLL; ++u) { const int64_t i = i0 + (int64_t)u * blockDim.x; o[u] = i < count ? load(i) : 0u; }
+#pragma unroll
+        for (int u = 0; u < KTH_UNROLL; ++u)
+            if (i0 + (int64_t)u * blockDim.x < count && o[u] >= lo && o[u] <= hi) {
+                const uint32_t p = atomicAdd(&scratch[3], 1u); if (p < (uint32_t)KTH_SMALL) small[p] = o[u];
+            }
     }
     __syncthreads();
     const int c = (int)min(scratch[3], (uint32_t)KTH_SMALL);
