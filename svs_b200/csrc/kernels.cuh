@@ -64,6 +64,7 @@ constexpr int COARSE_MAX_BATCH = 2048;              // queries per coarse launch
 constexpr int COARSE_TILE_ROWS = 128;               // rows per coarse tile (UMMA M)
 constexpr int COARSE_TILE_QUERIES = 256;            // queries per coarse tile (UMMA N); batches are padded to it
 constexpr float COARSE_OPERAND_SCALE = 4096.0f;     // 2^12 on both operands: keeps fp16 components normal, exact to undo
+constexpr int COARSE_DEFAULT_CTAS = 1;               // 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2); env SVSB_COARSE_CTAS
 constexpr int REFINE_SURVIVOR_CAP = 4096;           // exact re-scores per query the refine kernel can hold
 
 // M16[r][0..ld16) = fp16(M[r][.] * 2^12), zero padded.  ld % 4 == 0, ld16 % 8 == 0, ld16 >= ld.
