@@ -969,6 +969,11 @@ static int batch_enqueue(BatchWs* w, const Generation* g, const BatchPlan& P, co
     CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
                           nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
     CU(launch_sample_threshold(st, w->sample, P.sample_rows, b, P.kk, w->eps, w->thr));
+    if (env_int("SVSB_DEBUG_NO_SURVIVORS", 0)) {          // measurement aid: thresholds +inf -> the filter pass keeps nothing
+        std::vector<uint32_t> inf((size_t)b_pad, 0x7f800000u);
+        CU(cudaMemcpyAsync(w->thr, inf.data(), (size_t)b_pad * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
     if (time_coarse) CU(cudaEventRecord(w->ev[2], st));
     CU(launch_coarse_gemm(st, w->dev, 0, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.n_tiles, 1,
                           w->thr, w->cand, w->cand_cnt, P.cand_cap, nullptr, 0));
