@@ -342,6 +342,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
+                    help="N>1, single queries: fused push over NVLink peer memory (default) or NCCL all-gather + merge")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     n, d, k, desc = WORKLOADS[args.workload]
@@ -445,7 +447,7 @@ def main():
     from svs_b200.sharded import ShardedRetriever
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sr = ShardedRetriever(rank, world, local_rank)
+    sr = ShardedRetriever(rank, world, local_rank, exchange=args.exchange)
     sr.load_synthetic(n, d, seed=0, id0=1, id_step=1)
     if args.workload == "c3":
         run_batch_arm_sharded(args, sr, dist, torch, rank, world, local_rank, n, d, k, desc, l0)
@@ -492,7 +494,10 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "rows": n, "dims": d, "k": k, "queries_per_step": QUERIES_PER_STEP,
                        "l2": "per-GPU shard %.2f GB, distinct queries" % (shard_bytes / 1e9),
-                       "parallelism": f"row-sharded over {world} GPUs, NCCL all-gather of k candidates + merge kernel"},
+                       "parallelism": (f"row-sharded over {world} GPUs, k-candidate records pushed into every rank's window over "
+                                       "NVLink peer memory by the selection kernel, merge kernel waits on flags (no collective call)"
+                                       if sr.exchange == "peer" else
+                                       f"row-sharded over {world} GPUs, NCCL all-gather of k candidates + merge kernel")},
             "ms_per_query": total_ms / nq,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "gemv_tma_kernel (per GPU, rank-max time)", "peak_source": peak_src,

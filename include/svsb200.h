@@ -118,6 +118,12 @@ int svsb_snapshot_query_batch(svsb_t* e, svsb_snap_t* s, const float* Q, int32_t
 /* Diagnostics of the last batch chunk (<= 2048 queries): coarse candidates per query, rows re-scored exactly per
  * query, flag word per query (0 = answered by the coarse path; otherwise it took the single-query kernels). */
 int svsb_batch_stats(svsb_t* e, int32_t b, int32_t* candidates, int32_t* rescored, int32_t* flags);
+/* How the resident generation picks the coarse pass's filter thresholds: 0 = an order statistic of a row sample that
+ * bounds the true cut-off with overwhelming probability and is VERIFIED per query after the pass (default; several
+ * times fewer candidates), 1 = a proven bound (the engine switches a generation to it when verification fails for
+ * many queries of a batch -- rows stored in an order correlated with the queries -- or SVSB_BATCH_GUARANTEED=1).
+ * Results are bit-identical in both modes.  Returns the mode, or a negative error code. */
+int svsb_batch_threshold_mode(svsb_t* e);
 /* Pairwise top pairs: the compute of document_top_pairwise_scores (src/svs/kb.py:1642-1671, 1208-1243) =
  * np.dot(M, M.T) + get_top_pairs (src/svs/util.py:206-233) without ever materialising the N x N scores: tensor-core
  * coarse pass over the upper triangle, one global threshold, exact fp32 re-score of the survivors.  Outputs have
@@ -172,6 +178,32 @@ int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, const float* 
  * Synchronises `stream` once per 2048 queries. */
 int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, int64_t* d_records,
                              int32_t* n_fallback);
+/* ---- peer exchange: the exchange step fused into the kernels, over NVLink / NVSwitch peer memory ----------
+ * Replaces "all-gather the records over NCCL, then merge" for single queries: every rank owns a GATHER WINDOW in its
+ * HBM (slots x world records + one flag word per record); the selection kernel's epilogue stores its record into the
+ * window of EVERY rank with plain peer stores and publishes it with a system-scope release store of the query's
+ * sequence number; the merge kernel of each rank acquires the `world` flags of its own window and merges.  No
+ * collective library call and no extra launch sit between a shard's local top-k and the global answer.
+ * SPMD contract: all ranks issue the same sequence of svsb_enqueue_query_peer / svsb_query_peer calls (the sequence
+ * number is implicit), each rank in stream order.
+ *   svsb_xchg_create        allocates this rank's window (k <= k_max <= 2048, world <= 16) and returns its CUDA IPC
+ *                           handle (64 bytes) for the launcher to all-gather (torch.distributed, any backend);
+ *   svsb_xchg_connect       opens the peers' windows: handles = world x 64 bytes, rank order (own entry ignored);
+ *   svsb_xchg_connect_local same for engines living in THIS process (tests; one process driving several GPUs). */
+int svsb_xchg_create(svsb_t* e, int32_t world, int32_t rank, int32_t k_max, void* ipc_handle_out);
+int svsb_xchg_connect(svsb_t* e, const void* ipc_handles);
+int svsb_xchg_connect_local(svsb_t* e, svsb_t* const* engines);
+/* One query, device resident: similarity on `stream`, selection + push + waiting merge on `stream` (flags bit 1 clear)
+ * or on the engine's side stream with one SM reserved for them (bit 1 set: overlaps the next query's similarity
+ * pass; outputs are complete after svsb_enqueue_join).  Bit 0: time the similarity kernel (svsb_kernel_time_collect).
+ * Outputs (device or pinned host pointers): GLOBAL top-k, identical on every rank; *d_out_count = min(k, N). */
+int svsb_enqueue_query_peer(svsb_t* e, void* stream, const float* d_query, int32_t k,
+                            float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_count, int32_t flags);
+/* One query, host buffers in and out, synchronous (the sharded counterpart of svsb_query; replaces a6 + a7 of
+ * SURVEY.md section 8 on a row-sharded matrix): H2D of the query, similarity, selection + push, waiting merge that
+ * writes the result straight into pinned host memory, one stream synchronize. */
+int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
+                    float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
 /* Make `stream` wait for every selection kernel the pipelined svsb_enqueue_local_topk calls have issued. */
 int svsb_enqueue_join(svsb_t* e, void* stream);
 /* d_records: all-gathered records, [n_lists][batch][2k+1].  Outputs [batch][k], [batch][k], [batch]. */

@@ -59,9 +59,15 @@ SIGNATURES = {
     "svsb_bench_run_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, c_i64_p]),
     "svsb_bench_batch_result": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p, c_i32_p]),
     "svsb_batch_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "svsb_batch_threshold_mode": (C.c_int, [C.c_void_p]),
     "svsb_debug_select_phases": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_u64_p]),
     "svsb_bench_last_result": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_set_shard": (C.c_int, [C.c_void_p, C.c_int64]),
+    "svsb_xchg_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "svsb_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "svsb_xchg_connect_local": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "svsb_enqueue_query_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "svsb_query_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_enqueue_local_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "svsb_batch_local_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, c_i32_p]),
     "svsb_enqueue_join": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -8,8 +8,13 @@
 // kernel therefore re-scores every candidate with coarse >= tau~ - 2 eps in fp32 -- with the very summation
 // order of the similarity kernel (gemv.cu, TMA variant), so scores are bit-identical to svsb_query's -- and the
 // exact top-kk of those is the exact top-kk of all rows, under the same total order (score desc, row asc).
-// The candidate list holds every row with coarse >= tau~ - 2 eps because the filter threshold is (the kk-th largest
-// coarse score of a SAMPLE of the rows) - 2 eps, and the sample's kk-th largest can only be lower than tau~.
+// The candidate list holds every row with coarse >= tau~ - 2 eps whenever the filter threshold T <= tau~ - 2 eps.
+// Guaranteed mode: T = (the kk-th largest coarse score of a SAMPLE of the rows) - 2 eps; the sample's kk-th largest
+// can only be lower than tau~.  Statistical mode (default): T = (the m-th largest of the sample) - 2 eps with
+// m < kk chosen on the host so that "the sample holds m of the overall top kk" has probability ~1e-9 for a random
+// sample -- several times fewer candidates -- and the refine kernel CHECKS T <= tau~ - 2 eps per query: tau~ is
+// exact as soon as the list holds kk entries (every row >= T is in it), so the check is exact; a query that fails
+// it (flag 16) is redone by the caller, never answered from an incomplete list.
 #include "select_common.cuh"
 
 #include <cuda_fp16.h>
@@ -24,7 +29,7 @@ constexpr int RF_SMALL = KTH_SMALL;
 // thresholds from the sample: thr[q] = kk-th largest coarse score among the sampled rows
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RF_THREADS)
-sample_threshold_kernel(const __half* __restrict__ sample, int64_t sample_rows, int kk, const float* __restrict__ eps,
+sample_threshold_kernel(const __half* __restrict__ sample, int64_t sample_rows, int rank, const float* __restrict__ eps,
                         float* __restrict__ thr)
 {
     __shared__ uint32_t hist[RF_BINS];
@@ -32,18 +37,19 @@ sample_threshold_kernel(const __half* __restrict__ sample, int64_t sample_rows, 
     __shared__ uint32_t small[RF_SMALL];
     const int q = blockIdx.x;
     const __half* s = sample + (size_t)q * sample_rows;          // coarse scores rounded DOWN to fp16: still a lower bound
-    const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(__half2float(s[i])); }, sample_rows, kk,
+    const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(__half2float(s[i])); }, sample_rows, rank,
                                              hist, scratch, small);
-    // The filter must let through every row with coarse >= tau~ - 2 eps; the sample's kk-th largest is <= tau~.
+    // The filter must let through every row with coarse >= tau~ - 2 eps; the sample's kk-th largest is <= tau~
+    // (rank < kk: with overwhelming probability, verified by refine_kernel).
     if (threadIdx.x == 0) thr[q] = ordered_to_f32(o) - 2.0f * eps[q];
 }
 
-cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t sample_rows, int b, int kk, const float* eps,
+cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t sample_rows, int b, int rank, const float* eps,
                                     float* thr)
 {
     if (b <= 0) return cudaSuccess;
-    if (kk < 1 || kk > sample_rows) return cudaErrorInvalidValue;
-    sample_threshold_kernel<<<b, RF_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, kk, eps, thr);
+    if (rank < 1 || rank > sample_rows) return cudaErrorInvalidValue;
+    sample_threshold_kernel<<<b, RF_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, rank, eps, thr);
     count_launch();
     return cudaGetLastError();
 }
@@ -66,8 +72,8 @@ struct RefineSmem {
 __global__ void __launch_bounds__(RF_THREADS, 2)
 refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __restrict__ ids, int64_t row0,
               const float* __restrict__ Q, int ldq, int k, const u64* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
-              int cand_cap, const float* __restrict__ eps, int32_t* __restrict__ flags, RefineOut out,
-              int32_t* __restrict__ stats)
+              int cand_cap, const float* __restrict__ eps, const float* __restrict__ thr, int32_t* __restrict__ flags,
+              RefineOut out, int32_t* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char rf_smem_raw[];
     RefineSmem& sm = *reinterpret_cast<RefineSmem*>(rf_smem_raw);
@@ -103,6 +109,9 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
     // tau~: the kk-th largest coarse score among the candidates
     const uint32_t tau_o = block_kth_largest_o32(score_o, total, kk, sm.hist, sm.scratch, sm.small);
     const float cutoff = ordered_to_f32(tau_o) - 2.0f * eps[q];
+    // The list holds exactly the rows with coarse >= thr[q] and at least kk of them, so tau_o IS the kk-th largest
+    // coarse score of all rows; rows with coarse in [cutoff, thr[q]) would be missing from the list.
+    if (thr && !(cutoff >= thr[q])) { if (tid == 0) flags[q] = REFINE_FLAG_THRESHOLD_HIGH; return; }
 
     for (int i = tid; i < total; i += RF_THREADS) {
         if (ordered_to_f32(score_o(i)) >= cutoff) {
@@ -170,7 +179,7 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
 
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
-                          const float* eps, int32_t* flags, RefineOut out, int32_t* stats)
+                          const float* eps, const float* thr, int32_t* flags, RefineOut out, int32_t* stats)
 {
     if (b <= 0) return cudaSuccess;
     if (!out.ids || !out.counts) return cudaErrorInvalidValue;
@@ -186,7 +195,7 @@ cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, co
         attr_set[dev] = true;
     }
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    refine_kernel<<<b, RF_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, flags, out, stats);
+    refine_kernel<<<b, RF_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, thr, flags, out, stats);
     count_launch();
     return cudaGetLastError();
 }

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -64,6 +65,9 @@ struct Generation {
     // fp16 shadow of shard 0 for the batched coarse contraction (built lazily by the first batch)
     std::mutex m16_mu;
     void* M16 = nullptr; int ld16 = 0;
+    // set once a batch saw its statistical filter thresholds fail verification (rows not in random order w.r.t. the
+    // queries): later batches of this generation use the guaranteed thresholds
+    std::atomic<bool> batch_guaranteed{false};
     ~Generation() {
         for (auto& s : shards) {
             if (s.M || s.ids) cudaSetDevice(s.dev);
@@ -212,6 +216,30 @@ struct BatchWs {
     }
 };
 
+// Peer exchange of the one-process-per-GPU deployment (kernels.cuh "peer exchange"): this rank's gather window,
+// the peers' windows opened over CUDA IPC (or plain pointers inside one process), and a synchronous query context.
+struct Xchg {
+    int world = 0, rank = 0, cap = 0, slots = 4;
+    int64_t rec_words = 0;
+    unsigned char* block = nullptr;                      // [flags: slots*world u64, padded to 256 B][window]
+    size_t flags_bytes = 0;
+    std::vector<unsigned char*> peer_block;              // per rank (own entry = block)
+    std::vector<void*> ipc_opened;
+    bool connected = false;
+    unsigned long long seq = 0;
+    unsigned long long timeout_ns = 30ull * 1000000000ull;   // merge kernel gives up waiting for a peer (SVSB_XCHG_TIMEOUT_MS)
+    // synchronous path (svsb_query_peer): own stream, device query, pinned staging; results land in pinned
+    // host memory straight from the merge kernel (mapped, no copy back)
+    cudaStream_t st = nullptr;
+    DevWs ws;
+    float* h_q = nullptr; int h_q_cap = 0;
+    float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_count = nullptr; int64_t h_cap = 0;
+    u64* flags_of(unsigned char* b, int slot) const { return reinterpret_cast<u64*>(b) + (size_t)slot * world; }
+    u64* rec_of(unsigned char* b, int slot, int src) const {
+        return reinterpret_cast<u64*>(b + flags_bytes) + ((size_t)slot * world + src) * rec_words;
+    }
+};
+
 struct svsb_engine {
     std::vector<int> devs;
     std::mutex mu;                          // guards current, loading, pool bookkeeping
@@ -235,6 +263,7 @@ struct svsb_engine {
     std::vector<cudaEvent_t> kev; size_t kev_used = 0;   // similarity-kernel timing events
     cudaStream_t side_st = nullptr;                      // selection kernels of the pipelined sharded path
     std::vector<char> sel_pending;                       // per slot: a selection is (or was) in flight on side_st
+    std::unique_ptr<Xchg> xchg;
 };
 
 static inline int round_up4(int d) { return (d + 3) & ~3; }
@@ -393,6 +422,22 @@ static void free_slabs(svsb_engine* e) {
     e->slabs.clear(); e->slab_bytes_rows = 0; e->slab_ids_cap = 0;
 }
 
+static void xchg_release(svsb_engine* e) {
+    Xchg* x = e->xchg.get();
+    if (!x) return;
+    cudaSetDevice(e->devs[0]);
+    if (x->st) cudaStreamSynchronize(x->st);
+    for (void* p : x->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (x->block) cudaFree(x->block);
+    x->ws.release();
+    if (x->st) cudaStreamDestroy(x->st);
+    if (x->h_q) cudaFreeHost(x->h_q);
+    if (x->h_scores) cudaFreeHost(x->h_scores);
+    if (x->h_ids) cudaFreeHost(x->h_ids);
+    if (x->h_count) cudaFreeHost(x->h_count);
+    e->xchg.reset();
+}
+
 extern "C" void svsb_destroy(svsb_t* e) {
     if (!e) return;
     for (size_t i = 0; i < e->devs.size(); ++i) { cudaSetDevice(e->devs[i]); cudaDeviceSynchronize(); }
@@ -403,6 +448,7 @@ extern "C" void svsb_destroy(svsb_t* e) {
     if (e->bench_ctx) ctx_destroy(e, e->bench_ctx.get());
     if (e->batch_ws) e->batch_ws->release();
     for (auto& w : e->shard_ws) if (w) w->release();
+    xchg_release(e);
     if (e->side_st) { cudaSetDevice(e->devs[0]); cudaStreamDestroy(e->side_st); }
     for (auto ev : e->kev) cudaEventDestroy(ev);
     for (size_t i = 0; i < e->bench_q.size(); ++i) if (e->bench_q[i]) { cudaSetDevice(e->devs[i]); cudaFree(e->bench_q[i]); }
@@ -795,17 +841,32 @@ static int query_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, const
     memcpy(c->h_q, q, (size_t)d * 4);
     for (int i = d; i < g->ld; ++i) c->h_q[i] = 0.f;
 
+    // Single device, k <= 2048: no copy-engine operation at all -- a small kernel reads the query from the pinned
+    // staging buffer and the selection kernel writes (score, id, count) straight into pinned host memory (both are
+    // device-accessible under unified addressing), so the call is 3 launches + 1 synchronize.
+    const bool zero_copy = nd == 1 && kk <= K_FAST_MAX;
     for (int i = 0; i < nd; ++i) {
         const Shard& s = g->shards[i];
         if (s.n == 0) continue;
         DevWs& w = c->ws[i];
         if ((rc = prepare_ws(w, g.get(), s, kk)) != SVSB_OK) return rc;
         CU(cudaSetDevice(w.dev));
+        if (zero_copy) {
+            const int shift = group_shift_for(s.n);
+            *c->h_count = -1;
+            CU(launch_stage_query(w.st, c->h_q, w.d_q, g->ld));
+            CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift));
+            CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
+                             w.out_keys, c->h_scores, c->h_ids, c->h_count));
+            continue;
+        }
         CU(cudaMemcpyAsync(w.d_q, c->h_q, (size_t)g->ld * 4, cudaMemcpyHostToDevice, w.st));
         if ((rc = enqueue_local(w, g.get(), s, w.d_q, kk)) != SVSB_OK) return rc;
     }
     DevWs& w0 = c->ws[0];
-    if (nd == 1) {
+    if (zero_copy) {
+        // results are already on their way to host memory
+    } else if (nd == 1) {
         CU(cudaMemcpyAsync(c->h_scores, w0.out_scores, (size_t)kk * 4, cudaMemcpyDeviceToHost, w0.st));
         CU(cudaMemcpyAsync(c->h_ids, w0.out_ids, (size_t)kk * 8, cudaMemcpyDeviceToHost, w0.st));
         CU(cudaMemcpyAsync(c->h_count, w0.out_count, 4, cudaMemcpyDeviceToHost, w0.st));
@@ -869,12 +930,17 @@ static int env_int(const char* name, int dflt) { const char* s = getenv(name); r
 struct BatchPlan {
     int64_t n = 0; int d = 0, ld = 0, ld16 = 0, kk = 0, k = 0;
     int n_tiles = 0, s_tiles = 0, tile_stride = 1; int64_t sample_rows = 0;
+    int64_t sample_alloc_rows = 0;    // sample buffer rows to allocate (covers both threshold modes)
+    int sample_rank = 0;              // which order statistic of the sample the filter threshold is (kk = guaranteed)
     int cand_cap = 0;
     float eps_coef = 0.f, max_row_norm = 1.f;
 };
 
 // Can this generation / k take the coarse path at all?  (Purely a performance gate: both paths return the same bits.)
-static bool batch_plan(svsb_engine* e, const Generation* g, int32_t k, BatchPlan& P) {
+// guaranteed: thresholds are a proven bound (the kk-th largest of the sample); else an order statistic of the sample
+// that is a bound except with probability ~1e-9 per query for a random sample, verified per query by the refine
+// kernel (flag 16 -> the caller redoes the batch with guaranteed thresholds).
+static bool batch_plan(svsb_engine* e, const Generation* g, int32_t k, BatchPlan& P, bool guaranteed = false) {
     if (e->devs.size() != 1 || g->shards.size() != 1) return false;
     const Shard& s = g->shards[0];
     if (s.n != g->n || g->n < env_int("SVSB_BATCH_MIN_ROWS", 4096) || g->n > 0x7fffff00ll || g->d < 16) return false;
@@ -885,16 +951,33 @@ static bool batch_plan(svsb_engine* e, const Generation* g, int32_t k, BatchPlan
     P.n = g->n; P.d = g->d; P.ld = g->ld; P.ld16 = (g->d + 7) & ~7; P.kk = (int)kk; P.k = k;
     P.n_tiles = (int)((g->n + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS);
     P.cand_cap = env_int("SVSB_BATCH_CAND_CAP", 32768);
-    // sample size: the filter lets through roughly n * kk / sample_rows candidates per query (more once the 2 eps
-    // margin is subtracted); keep the expectation below cap / 4
-    int64_t want = std::max<int64_t>(320 * kk, (int64_t)(4.0 * (double)g->n * (double)kk / (double)P.cand_cap) + 1);
+    // sample size: the proven-bound filter lets through roughly n * kk / sample_rows candidates per query (more once
+    // the 2 eps margin is subtracted); keep the expectation below cap / 4.  Statistical thresholds (below) pass about
+    // n * rank / sample_rows with rank ~ 6..10 for small samples, so far fewer sampled rows do: 80 * kk measured best
+    // at 1M x 768, k = 100 (profiles/r01_c3_threshold_modes.md).
+    const bool stat = !guaranteed && !g->batch_guaranteed.load(std::memory_order_relaxed) && env_int("SVSB_BATCH_GUARANTEED", 0) == 0;
+    auto tiles_for = [&](int64_t want) {
+        int64_t st = (want + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS;
+        st = std::max<int64_t>(st, 32);
+        return std::min<int64_t>(st, P.n_tiles);
+    };
+    const int64_t want_proven = std::max<int64_t>(320 * kk, (int64_t)(4.0 * (double)g->n * (double)kk / (double)P.cand_cap) + 1);
+    int64_t want = stat ? std::max<int64_t>(80 * kk, (int64_t)(4.0 * (double)g->n * 8.0 / (double)P.cand_cap) + 1) : want_proven;
     if (const char* v = getenv("SVSB_BATCH_SAMPLE_ROWS")) want = atoll(v);
-    int64_t st = (want + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS;
-    st = std::max<int64_t>(st, 32);
-    st = std::min<int64_t>(st, P.n_tiles);
-    P.s_tiles = (int)st;
+    P.s_tiles = (int)tiles_for(want);
     P.tile_stride = std::max(1, P.n_tiles / P.s_tiles);
     P.sample_rows = (int64_t)P.s_tiles * COARSE_TILE_ROWS;
+    // buffers are sized for whichever mode needs more, so a chunk can be redone in the other mode in place
+    P.sample_alloc_rows = std::max(P.sample_rows, tiles_for(want_proven) * COARSE_TILE_ROWS);
+    P.sample_rank = (int)kk;
+    if (stat) {
+        // X = how many of the overall top kk fall into the sample ~ Binomial(kk, f) <= Poisson-like tail;
+        // the threshold fails only if X >= rank.  rank = mean + 6 sigma + 4 puts that near 1e-9.
+        const double f = std::min(1.0, (double)P.sample_rows / (double)g->n);
+        const double lam = (double)kk * f;
+        const int64_t r = (int64_t)std::ceil(lam + 6.0 * std::sqrt(lam) + 4.0);
+        P.sample_rank = (int)std::max<int64_t>(1, std::min<int64_t>(kk, r));
+    }
     // |coarse - exact| <= eps_coef * ||q|| * max||row|| + 1e-8: two fp16 roundings per product (2u + u^2, u = 2^-11),
     // fp32 accumulation inside the tensor core (d * 2^-22, generous) and the exact kernel's own rounding (d * 2^-23)
     P.eps_coef = 9.765625e-4f + 2.384185791015625e-7f + (float)g->d * (2.384185791015625e-7f + 1.1920928955078125e-7f);
@@ -917,10 +1000,11 @@ static int batch_ws_get(svsb_engine* e, BatchWs*& out) {
 
 static int batch_ws_ensure(BatchWs* w, const BatchPlan& P, int b_pad) {
     CU(cudaSetDevice(w->dev));
-    if (b_pad > w->cap_b || P.ld > w->cap_ld || P.k > w->cap_k || P.sample_rows > w->cap_sample || P.cand_cap != w->cand_cap) {
+    const int64_t need_sample = std::max(P.sample_rows, P.sample_alloc_rows);
+    if (b_pad > w->cap_b || P.ld > w->cap_ld || P.k > w->cap_k || need_sample > w->cap_sample || P.cand_cap != w->cand_cap) {
         CU(cudaStreamSynchronize(w->st));
         const int nb = std::max(b_pad, w->cap_b), nld = std::max(P.ld, w->cap_ld), nk = std::max(P.k, w->cap_k);
-        const int64_t ns = std::max(P.sample_rows, w->cap_sample);
+        const int64_t ns = std::max(need_sample, w->cap_sample);
         w->release_device();
         const int ld16 = (nld + 7) & ~7;
         CU(cudaMalloc(&w->dQ, (size_t)nb * nld * 4));
@@ -968,7 +1052,7 @@ static int batch_enqueue(BatchWs* w, const Generation* g, const BatchPlan& P, co
     CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, st));
     CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
                           nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
-    CU(launch_sample_threshold(st, w->sample, P.sample_rows, b, P.kk, w->eps, w->thr));
+    CU(launch_sample_threshold(st, w->sample, P.sample_rows, b, P.sample_rank, w->eps, w->thr));
     if (env_int("SVSB_DEBUG_NO_SURVIVORS", 0)) {          // measurement aid: thresholds +inf -> the filter pass keeps nothing
         std::vector<uint32_t> inf((size_t)b_pad, 0x7f800000u);
         CU(cudaMemcpyAsync(w->thr, inf.data(), (size_t)b_pad * 4, cudaMemcpyHostToDevice, st));
@@ -980,9 +1064,21 @@ static int batch_enqueue(BatchWs* w, const Generation* g, const BatchPlan& P, co
     if (time_coarse) CU(cudaEventRecord(w->ev[3], st));
     RefineOut o{w->o_scores, nullptr, w->o_ids, (int64_t)P.k, w->o_counts, 1};
     if (out) o = *out;
-    CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, dQ, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->flags,
+    CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, dQ, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->thr, w->flags,
                      o, w->stats));
     return SVSB_OK;
+}
+
+// Did enough statistical thresholds fail verification (flag 16) that the chunk should be redone with guaranteed ones?
+// A handful of failures is cheaper to hand to the single-query kernels; many mean the sample is not representative
+// (rows stored in an order correlated with the queries), so the generation switches modes for good.
+static bool batch_thresholds_failed(Generation* g, const BatchPlan& P, const int32_t* h_flags, int b) {
+    if (P.sample_rank >= P.kk) return false;
+    int bad = 0;
+    for (int i = 0; i < b; ++i) bad += (h_flags[i] & (REFINE_FLAG_THRESHOLD_HIGH | 4)) ? 1 : 0;   // 4 = fewer than kk candidates: threshold far too high
+    if (bad <= std::max(2, b / 256)) return false;
+    g->batch_guaranteed.store(true, std::memory_order_relaxed);
+    return true;
 }
 
 static int query_batch_loop(svsb_engine* e, const std::shared_ptr<Generation>& g, const float* Q, int32_t b, int32_t d, int32_t k,
@@ -1028,12 +1124,16 @@ static int query_batch_gen(svsb_engine* e, const std::shared_ptr<Generation>& g,
         }
         CU(cudaSetDevice(w->dev));
         CU(cudaMemcpyAsync(w->dQ, w->h_Q, (size_t)bc * P.ld * 4, cudaMemcpyHostToDevice, w->st));
-        if ((rc = batch_enqueue(w, g.get(), P, w->dQ, bc, false, w->st)) != SVSB_OK) return rc;
-        CU(cudaMemcpyAsync(w->h_scores, w->o_scores, (size_t)bc * k * 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(w->h_ids, w->o_ids, (size_t)bc * k * 8, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(w->h_counts, w->o_counts, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaMemcpyAsync(w->h_flags, w->flags, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
-        CU(cudaStreamSynchronize(w->st));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if ((rc = batch_enqueue(w, g.get(), P, w->dQ, bc, false, w->st)) != SVSB_OK) return rc;
+            CU(cudaMemcpyAsync(w->h_scores, w->o_scores, (size_t)bc * k * 4, cudaMemcpyDeviceToHost, w->st));
+            CU(cudaMemcpyAsync(w->h_ids, w->o_ids, (size_t)bc * k * 8, cudaMemcpyDeviceToHost, w->st));
+            CU(cudaMemcpyAsync(w->h_counts, w->o_counts, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
+            CU(cudaMemcpyAsync(w->h_flags, w->flags, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
+            CU(cudaStreamSynchronize(w->st));
+            if (!batch_thresholds_failed(g.get(), P, w->h_flags, bc)) break;
+            batch_plan(e, g.get(), k, P, true);       // redo the chunk with guaranteed thresholds (same buffers)
+        }
         for (int i = 0; i < bc; ++i) {
             const int64_t o = (int64_t)(c0 + i) * k;
             if (w->h_flags[i] == 0 && w->h_counts[i] == P.kk) {
@@ -1205,6 +1305,13 @@ extern "C" int svsb_batch_stats(svsb_t* e, int32_t b, int32_t* candidates, int32
     if (rescored) CU(cudaMemcpy(rescored, w->stats, (size_t)b * 4, cudaMemcpyDeviceToHost));
     if (flags) CU(cudaMemcpy(flags, w->flags, (size_t)b * 4, cudaMemcpyDeviceToHost));
     return SVSB_OK;
+}
+
+extern "C" int svsb_batch_threshold_mode(svsb_t* e) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    return (g->batch_guaranteed.load(std::memory_order_relaxed) || env_int("SVSB_BATCH_GUARANTEED", 0) != 0) ? 1 : 0;
 }
 
 extern "C" int svsb_topk_scores(svsb_t* e, const float* scores, int64_t n, int32_t k,
@@ -1576,9 +1683,13 @@ extern "C" int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_
             if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
             int64_t* r0 = d_records + (int64_t)c0 * rec;
             RefineOut o{nullptr, reinterpret_cast<u64*>(r0), r0 + k, rec, reinterpret_cast<int32_t*>(r0 + 2 * (int64_t)k), 2 * rec};
-            if ((rc = batch_enqueue(w, g.get(), P, d_Q + (int64_t)c0 * P.ld, bc, false, st, &o)) != SVSB_OK) return rc;
-            CU(cudaMemcpyAsync(w->h_flags, w->flags, (size_t)bc * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if ((rc = batch_enqueue(w, g.get(), P, d_Q + (int64_t)c0 * P.ld, bc, false, st, &o)) != SVSB_OK) return rc;
+                CU(cudaMemcpyAsync(w->h_flags, w->flags, (size_t)bc * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (!batch_thresholds_failed(g.get(), P, w->h_flags, bc)) break;
+                batch_plan(e, g.get(), k, P, true);   // redo the chunk with guaranteed thresholds
+            }
             for (int i = 0; i < bc; ++i) if (w->h_flags[i] != 0) todo[c0 + i] = 1;
         }
     }
@@ -1589,6 +1700,220 @@ extern "C" int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_
         if (rc != SVSB_OK) return rc;
     }
     if (n_fallback) *n_fallback = fallbacks;
+    return SVSB_OK;
+}
+
+// ---- peer exchange: the fused selection + exchange step and the waiting merge (kernels.cuh, select.cu) -------------
+static int xchg_prepare(svsb_engine* e, const Generation* g);
+extern "C" int svsb_xchg_create(svsb_t* e, int32_t world, int32_t rank, int32_t k_max, void* handle_out) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (e->devs.size() != 1) return fail(SVSB_E_INVALID, "svsb_xchg_create: a sharded engine owns exactly one device");
+    if (world < 1 || world > XCHG_MAX_RANKS || rank < 0 || rank >= world) return fail(SVSB_E_INVALID, "svsb_xchg_create: bad world / rank (<= 16 ranks)");
+    if (k_max < 1 || k_max > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_xchg_create: 1 <= k_max <= 2048");
+    xchg_release(e);
+    std::unique_ptr<Xchg> x(new Xchg());
+    x->world = world; x->rank = rank; x->cap = k_max; x->rec_words = 2 * (int64_t)k_max + 2;
+    x->flags_bytes = ((size_t)x->slots * world * 8 + 255) & ~(size_t)255;
+    const size_t bytes = x->flags_bytes + (size_t)x->slots * world * x->rec_words * 8;
+    CU(cudaSetDevice(e->devs[0]));
+    CU(preload_gemv_kernels());
+    CU(preload_peer_kernels());
+    CU(cudaMalloc(&x->block, bytes));
+    CU(cudaMemset(x->block, 0, bytes));
+    CU(cudaDeviceSynchronize());
+    CU(cudaStreamCreateWithFlags(&x->st, cudaStreamNonBlocking));
+    x->ws.dev = e->devs[0]; x->ws.st = x->st;
+    if (const char* v = getenv("SVSB_XCHG_TIMEOUT_MS")) { const long long ms = atoll(v); if (ms > 0) x->timeout_ns = (unsigned long long)ms * 1000000ull; }
+    CU(cudaMallocHost(&x->h_scores, (size_t)k_max * 4));
+    CU(cudaMallocHost(&x->h_ids, (size_t)k_max * 8));
+    CU(cudaMallocHost(&x->h_count, 64));
+    x->h_cap = k_max;
+    x->peer_block.assign(world, nullptr);
+    x->peer_block[rank] = x->block;
+    if (handle_out) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, x->block));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handle_out, &h, 64);
+    }
+    x->connected = world == 1;
+    e->xchg = std::move(x);
+    return SVSB_OK;
+}
+
+extern "C" int svsb_xchg_connect(svsb_t* e, const void* handles) {
+    if (!e || !e->xchg) return fail(SVSB_E_STATE, "svsb_xchg_connect: svsb_xchg_create first");
+    if (!handles) return fail(SVSB_E_INVALID, "svsb_xchg_connect: NULL handles");
+    Xchg* x = e->xchg.get();
+    CU(cudaSetDevice(e->devs[0]));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * 64, 64);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->ipc_opened.push_back(p);
+        x->peer_block[r] = static_cast<unsigned char*>(p);
+    }
+    x->connected = true;
+    if (auto g = pin(e)) { int rc = xchg_prepare(e, g.get()); if (rc != SVSB_OK) return rc; }
+    return SVSB_OK;
+}
+
+extern "C" int svsb_xchg_connect_local(svsb_t* e, svsb_t* const* engines) {
+    if (!e || !e->xchg) return fail(SVSB_E_STATE, "svsb_xchg_connect_local: svsb_xchg_create first");
+    if (!engines) return fail(SVSB_E_INVALID, "svsb_xchg_connect_local: NULL engines");
+    Xchg* x = e->xchg.get();
+    CU(cudaSetDevice(e->devs[0]));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        svsb_engine* o = engines[r];
+        if (!o || !o->xchg || o->xchg->world != x->world || o->xchg->rank != r || o->xchg->cap != x->cap)
+            return fail(SVSB_E_INVALID, "svsb_xchg_connect_local: peer engine has no matching exchange window");
+        if (o->devs[0] != e->devs[0]) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, e->devs[0], o->devs[0]));
+            if (!can) return fail(SVSB_E_CUDA, "svsb_xchg_connect_local: no peer access between the devices");
+            cudaError_t pe = cudaDeviceEnablePeerAccess(o->devs[0], 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CU(pe);
+            (void)cudaGetLastError();
+        }
+        x->peer_block[r] = o->xchg->block;
+    }
+    x->connected = true;
+    if (auto g = pin(e)) { int rc = xchg_prepare(e, g.get()); if (rc != SVSB_OK) return rc; }
+    return SVSB_OK;
+}
+
+// Size every buffer the peer paths use for the resident generation.  Allocations, memsets and pinned allocations are
+// implicit synchronisation points of the CUDA runtime: issued while another engine OF THIS PROCESS has a merge kernel
+// spinning on a flag they can deadlock, so they all happen here -- at connect time and (a no-op once sized) at the
+// top of each call, before anything of that call is enqueued.
+static int xchg_prepare(svsb_engine* e, const Generation* g) {
+    Xchg* x = e->xchg.get();
+    const Shard& s = g->shards[0];
+    CU(cudaSetDevice(s.dev));
+    if (e->shard_ws.size() < 2) e->shard_ws.resize(2);
+    if (e->sel_pending.size() < e->shard_ws.size()) e->sel_pending.resize(e->shard_ws.size(), 0);
+    if (!e->side_st) CU(cudaStreamCreateWithFlags(&e->side_st, cudaStreamNonBlocking));
+    DevWs* sets[3] = {&x->ws, nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        if (!e->shard_ws[i]) { e->shard_ws[i].reset(new DevWs()); e->shard_ws[i]->dev = s.dev; }
+        sets[1 + i] = e->shard_ws[i].get();
+    }
+    for (DevWs* w : sets) {
+        int rc;
+        if (s.n > 0 && (rc = w->ensure_rows(s.n)) != SVSB_OK) return rc;
+        if ((rc = w->ensure_out(K_FAST_MAX)) != SVSB_OK) return rc;
+        if ((int64_t)x->world * x->cap > K_FAST_MAX && (rc = w->ensure_merge_scratch((int64_t)x->world * x->cap)) != SVSB_OK) return rc;
+        if (!w->ev) CU(cudaEventCreateWithFlags(&w->ev, cudaEventDisableTiming));
+        if (!w->ev_sel) CU(cudaEventCreateWithFlags(&w->ev_sel, cudaEventDisableTiming));
+    }
+    int rc;
+    if ((rc = x->ws.ensure_q(g->ld)) != SVSB_OK) return rc;
+    if (g->ld > x->h_q_cap) {
+        if (x->h_q) cudaFreeHost(x->h_q);
+        x->h_q = nullptr; x->h_q_cap = 0;
+        CU(cudaMallocHost(&x->h_q, (size_t)g->ld * 4));
+        x->h_q_cap = g->ld;
+    }
+    while (e->kev.size() < e->kev_used + 2) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
+    return SVSB_OK;
+}
+
+// Fill the push descriptor for the next query and return its window slot.
+static int xchg_next(Xchg* x, PeerPush& push) {
+    const unsigned long long seq = ++x->seq;
+    const int slot = (int)(seq % (unsigned long long)x->slots);
+    push.world = x->world; push.cap = x->cap; push.seq = seq;
+    for (int p = 0; p < x->world; ++p) {
+        push.rec[p] = x->rec_of(x->peer_block[p], slot, x->rank);
+        push.flag[p] = x->flags_of(x->peer_block[p], slot) + x->rank;
+    }
+    return slot;
+}
+
+// similarity on st_main, then (on st_sel) selection with the fused push and the waiting merge into out_*.
+static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStream_t st_main, cudaStream_t st_sel, cudaEvent_t ev_main_done,
+                        const float* d_query, int32_t k, float* out_scores, int64_t* out_ids, int32_t* out_count,
+                        bool time_kernel, int reserve_sms) {
+    Xchg* x = e->xchg.get();
+    const Shard& s = g->shards[0];
+    PeerPush push;
+    const int slot = xchg_next(x, push);
+    if (s.n == 0) {
+        CU(launch_push_empty(st_sel, push));
+    } else {
+        const int shift = group_shift_for(s.n);
+        if (time_kernel) CU(cudaEventRecord(e->kev[e->kev_used], st_main));
+        CU(launch_gemv(st_main, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, reserve_sms));
+        if (time_kernel) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st_main)); e->kev_used += 2; }
+        if (st_sel != st_main) { CU(cudaEventRecord(ev_main_done, st_main)); CU(cudaStreamWaitEvent(st_sel, ev_main_done, 0)); }
+        CU(launch_select(st_sel, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
+                         w.out_keys, w.out_scores, w.out_ids, w.out_count, nullptr, &push));
+    }
+    u64* sk = nullptr; int64_t* sp = nullptr;
+    if ((int64_t)x->world * k > K_FAST_MAX) { sk = w.mscr_keys; sp = w.mscr_ids; }
+    CU(launch_merge_window(st_sel, x->rec_of(x->block, slot, 0), x->flags_of(x->block, slot), push.seq, x->world, x->cap, k,
+                           x->timeout_ns, sk, sp, out_scores, out_ids, out_count));
+    return SVSB_OK;
+}
+
+extern "C" int svsb_enqueue_query_peer(svsb_t* e, void* stream, const float* d_query, int32_t k,
+                                       float* out_scores, int64_t* out_ids, int32_t* out_count, int32_t flags) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (!e->xchg || !e->xchg->connected) return fail(SVSB_E_STATE, "svsb_enqueue_query_peer: exchange not connected");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (k < 1 || k > e->xchg->cap) return fail(SVSB_E_INVALID, "svsb_enqueue_query_peer: 1 <= k <= k_max of the exchange");
+    if (!d_query || !out_scores || !out_ids || !out_count) return fail(SVSB_E_INVALID, "svsb_enqueue_query_peer: NULL pointer");
+    const bool time_kernel = (flags & 1) != 0, pipelined = (flags & 2) != 0;
+    const Shard& s = g->shards[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s.dev));
+    int rc = xchg_prepare(e, g.get());
+    if (rc != SVSB_OK) return rc;
+    const int slot = (int)(e->xchg->seq & 1);              // workspace set: alternates so that query i+1's similarity pass
+    DevWs& w = *e->shard_ws[slot];                         // overlaps query i's selection
+    cudaStream_t sel_st = st;
+    if (pipelined) {
+        if (e->sel_pending[slot]) CU(cudaStreamWaitEvent(st, w.ev_sel, 0));   // the slot's scores are free again
+        sel_st = e->side_st;
+    }
+    rc = xchg_enqueue(e, g.get(), w, st, sel_st, w.ev, d_query, k, out_scores, out_ids, out_count, time_kernel, pipelined ? 1 : 0);
+    if (rc != SVSB_OK) return rc;
+    if (pipelined) { CU(cudaEventRecord(w.ev_sel, e->side_st)); e->sel_pending[slot] = 1; }
+    return SVSB_OK;
+}
+
+extern "C" int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
+                               float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (!out_count) return fail(SVSB_E_INVALID, "svsb_query_peer: out_count is NULL");
+    *out_count = 0;
+    if (!e->xchg || !e->xchg->connected) return fail(SVSB_E_STATE, "svsb_query_peer: exchange not connected");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (d != g->d) return fail(SVSB_E_SHAPE, "svsb_query_peer: query dimension does not match the matrix");
+    Xchg* x = e->xchg.get();
+    if (k < 1 || k > x->cap) return fail(SVSB_E_INVALID, "svsb_query_peer: 1 <= k <= k_max of the exchange");
+    if (!q || !out_scores || !out_emb_ids) return fail(SVSB_E_INVALID, "svsb_query_peer: NULL buffer");
+    int rc = xchg_prepare(e, g.get());
+    if (rc != SVSB_OK) return rc;
+    memcpy(x->h_q, q, (size_t)d * 4);
+    for (int i = d; i < g->ld; ++i) x->h_q[i] = 0.f;
+    CU(launch_stage_query(x->st, x->h_q, x->ws.d_q, g->ld));     // a kernel reads the pinned query: no copy-engine hop
+    *x->h_count = -1;
+    // the merge kernel writes the result into pinned (mapped) host memory: no copy back, one synchronize
+    if ((rc = xchg_enqueue(e, g.get(), x->ws, x->st, x->st, nullptr, x->ws.d_q, k, x->h_scores, x->h_ids, x->h_count, false, 0)) != SVSB_OK) return rc;
+    CU(cudaStreamSynchronize(x->st));
+    const int32_t cnt = *x->h_count;
+    if (cnt == MERGE_WINDOW_TIMED_OUT)
+        return fail(SVSB_E_STATE, "svsb_query_peer: a peer's record did not arrive in time (a rank died or left the call sequence)");
+    if (cnt < 0 || cnt > k) return fail(SVSB_E_CUDA, "svsb_query_peer: internal: merge returned a bad count");
+    memcpy(out_scores, x->h_scores, (size_t)cnt * 4);
+    memcpy(out_emb_ids, x->h_ids, (size_t)cnt * 8);
+    *out_count = cnt;
     return SVSB_OK;
 }
 

@@ -300,6 +300,23 @@ static cudaError_t run_tma(cudaStream_t st, int device, const float* M, int64_t 
 #undef SVSB_TMA_CASE
 }
 
+// Force the (lazily loaded) similarity kernels onto the device now.  With CUDA's lazy module loading the FIRST launch
+// of a kernel synchronises the context; issued while another engine of this process has a merge kernel spinning on a
+// peer flag, that first launch would wait for the spin to end -- which may be waiting for this very launch.
+cudaError_t preload_gemv_kernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+#define SVSB_PRE(K) do { if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, K); } while (0)
+    SVSB_PRE((gemv_tma_kernel<8, 2>)); SVSB_PRE((gemv_tma_kernel<8, 6>)); SVSB_PRE((gemv_tma_kernel<8, 12>));
+    SVSB_PRE((gemv_tma_kernel<8, 24>)); SVSB_PRE((gemv_tma_kernel<8, 0>));
+    SVSB_PRE((gemv_tma_kernel<16, 2>)); SVSB_PRE((gemv_tma_kernel<16, 6>)); SVSB_PRE((gemv_tma_kernel<16, 12>));
+    SVSB_PRE((gemv_tma_kernel<16, 24>)); SVSB_PRE((gemv_tma_kernel<16, 0>));
+    SVSB_PRE((gemv_ldg_kernel<4, 3, 256>));
+#undef SVSB_PRE
+    return e;
+}
+
 cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld,
                         const float* q, float* scores, u64* gmax, int group_shift,
                         int variant, int tune_a, int tune_b, int reserve_sms)

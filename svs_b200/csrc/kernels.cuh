@@ -23,10 +23,15 @@ cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, 
 // Outputs (device): out_keys[k] (key with GLOBAL row = row0 + local row), out_scores[k], out_ids[k],
 // *out_count = min(k, n).  cand is scratch of cand_cap entries, cand_cap >= min(n, K_FAST_MAX << shift) + K_FAST_MAX.
 // Requires 1 <= k <= K_FAST_MAX.
+// push (optional): the fused exchange step of the one-process-per-GPU deployment -- the epilogue also stores the
+// record (keys, ids, count) into every rank's gather window over peer memory (NVLink / NVSwitch P2P stores) and then
+// publishes it there with a system-scope release store of the query's sequence number (see PeerPush).
+struct PeerPush;
 cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
                           int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
                           u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count,
-                          u64* dbg = nullptr);   // dbg: optional 16 x u64 of %globaltimer phase stamps
+                          u64* dbg = nullptr,    // dbg: optional 16 x u64 of %globaltimer phase stamps
+                          const PeerPush* push = nullptr);
 
 // Large-k path (k > K_FAST_MAX): sort all n keys.  sortbuf has next_pow2(n) entries.  Also zeroes gmax.
 cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
@@ -49,6 +54,34 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
                             int64_t count_list_stride, int64_t count_batch_stride,
                             u64* scratch_keys, int64_t* scratch_ids,
                             float* out_scores, int64_t* out_ids, int32_t* out_count);
+
+// ---- peer exchange (select.cu): candidate records pushed into every rank's window, merged after a flag wait ----
+// A window holds `slots` x `world` records of rec_words = 2*cap + 2 u64 words: [keys(cap) | ids(cap) | count | pad],
+// plus slots x world u64 flags.  Query number seq (1, 2, ...) uses slot seq % slots; flag (slot, r) == seq means
+// rank r's record for that query is complete in THIS window.
+constexpr int XCHG_MAX_RANKS = 16;
+struct PeerPush {
+    int world = 0, cap = 0;
+    unsigned long long seq = 0;
+    u64* rec[XCHG_MAX_RANKS];       // rec[p]: where THIS rank's record goes in rank p's window (slot already applied)
+    u64* flag[XCHG_MAX_RANKS];      // flag[p]: rank p's flag word for (slot, this rank)
+};
+// Load every kernel of the peer paths onto the current device now (lazy module loading would otherwise synchronise
+// the context at a kernel's first launch -- while a merge kernel of the same process may be spinning on a flag).
+cudaError_t preload_gemv_kernels();
+cudaError_t preload_peer_kernels();
+// d_q[0..ld) = host_q_mapped[0..ld) (pinned host memory, read by a kernel: no copy-engine operation).  ld % 4 == 0.
+cudaError_t launch_stage_query(cudaStream_t st, const float* host_q_mapped, float* d_q, int ld);
+// Record with count 0 (this rank owns no rows): same publication protocol, one small CTA.
+cudaError_t launch_push_empty(cudaStream_t st, const PeerPush& push);
+// One CTA: wait until flags[0..world) >= seq (ld.acquire.sys), then merge the world lists of the window slot
+// (coherent loads: the data was written by remote GPUs) into the top-k.  scratch as launch_merge (world*cap > 2048).
+// A flag that does not arrive within timeout_ns (a peer died or left the SPMD call sequence) ends the kernel with
+// *out_count = MERGE_WINDOW_TIMED_OUT instead of hanging the GPU.
+constexpr int MERGE_WINDOW_TIMED_OUT = -2;
+cudaError_t launch_merge_window(cudaStream_t st, const u64* slot_base, const u64* flags, unsigned long long seq,
+                                int world, int cap, int k, unsigned long long timeout_ns, u64* scratch_keys, int64_t* scratch_ids,
+                                float* out_scores, int64_t* out_ids, int32_t* out_count);
 
 // ---- K0: load path ---------------------------------------------------------------------------
 // Row L2 norms; optionally divide rows by their norm.  stats[0] = float bits of max | ||row|| - 1 |
@@ -83,14 +116,17 @@ cudaError_t launch_queries_to_f16(cudaStream_t st, const float* Q, int b, int b_
 cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void* M16, int64_t n, const void* Q16, int b_pad,
                                int ld16, int n_tiles, int tile_stride, const float* thr, u64* cand, int32_t* cand_cnt,
                                int cand_cap, void* sample, int64_t sample_rows, int64_t q_rows = 0, int64_t tri_q0 = -1);
-// thr[q] = (kk-th largest of sample[q][0..sample_rows)) - 2 eps[q] for q < b (one CTA per query).
+// thr[q] = (rank-th largest of sample[q][0..sample_rows)) - 2 eps[q] for q < b (one CTA per query).
 // sample: fp16 (coarse scores rounded down), as the coarse kernel's mode 1 writes it.
-cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t sample_rows, int b, int kk, const float* eps,
+// rank == kk: a guaranteed lower bound of (kk-th largest coarse score of all rows) - 2 eps.  rank < kk: an order
+// statistic that is such a bound with overwhelming probability only -- the refine kernel VERIFIES it (flag 16).
+cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t sample_rows, int b, int rank, const float* eps,
                                     float* thr);
 // One CTA per query: tau~ = kk-th largest coarse candidate; keep candidates with coarse >= tau~ - 2*eps[q]; re-score
 // them exactly (fp32, the similarity kernel's summation order); sort; write (score, embeddings.id) x kk.
-// flags[q] |= 2 candidate list overflowed, 4 fewer than kk candidates, 8 survivor list overflowed: such queries
-// are left to the caller's exact single-query path.  stats[q] (optional) = survivors re-scored.
+// flags[q] |= 2 candidate list overflowed, 4 fewer than kk candidates, 8 survivor list overflowed, 16 the filter
+// threshold thr[q] turned out ABOVE tau~ - 2*eps[q] (the candidate list may miss rows: only possible with a
+// statistical threshold): such queries are left to the caller's exact path.  stats[q] (optional) = survivors re-scored.
 // Output layout: entry i of query q goes to scores / keys / ids [q * stride + i] (scores, keys optional), its count
 // to counts[q * count_stride].  Two users: plain (b, k) arrays, and the packed per-query records of the sharded
 // path ([keys(k) | ids(k) | count], 2k+1 int64 words) whose keys carry GLOBAL rows (row0 + local row).
@@ -100,7 +136,8 @@ struct RefineOut {
 };
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
-                          const float* eps, int32_t* flags, RefineOut out, int32_t* stats);
+                          const float* eps, const float* thr, int32_t* flags, RefineOut out, int32_t* stats);
+constexpr int REFINE_FLAG_THRESHOLD_HIGH = 16;
 
 // ---- pairwise top pairs (pairs.cu): global candidate list on top of the coarse pass's pairwise mode --------
 // Sort keys[0..np2) descending; np2 a power of two >= 2048 (pad with 0).

@@ -126,6 +126,58 @@ __device__ u64 block_kth_largest(const u64* keys, int64_t count, int kk, SelectS
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peer exchange helpers.  Publication: every thread has stored its part of the record into the peers' windows;
+// after the CTA barrier thread p stores the count, fences at system scope (cumulative over the barrier) and
+// release-stores the sequence number into rank p's flag.  The consumer acquires the flag before reading.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void peer_publish(const PeerPush& push, int count) {
+    __syncthreads();
+    const int p = threadIdx.x;
+    if (p < push.world) {
+        push.rec[p][2 * push.cap] = (u64)(uint32_t)count;
+        __threadfence_system();
+        st_release_sys(push.flag[p], push.seq);
+    }
+}
+
+// Query upload without the copy engine: one small CTA reads the query from pinned (mapped) host memory over PCIe and
+// writes it to HBM, so the synchronous peer path is kernels only (no copy-engine -> compute hand-off before the
+// similarity pass).  ld.cv: never serve host memory the CPU rewrites per query from a stale cache line.
+__global__ void __launch_bounds__(256) stage_query_kernel(const float4* __restrict__ host_q, float4* __restrict__ d_q, int ld4) {
+    for (int c = threadIdx.x; c < ld4; c += blockDim.x) {
+        float4 v;
+        asm volatile("ld.global.cv.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(host_q + c));
+        d_q[c] = v;
+    }
+}
+
+cudaError_t launch_stage_query(cudaStream_t st, const float* host_q_mapped, float* d_q, int ld)
+{
+    if (ld <= 0 || (ld & 3)) return cudaErrorInvalidValue;
+    stage_query_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float4*>(host_q_mapped), reinterpret_cast<float4*>(d_q), ld / 4);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(32) push_empty_kernel(const __grid_constant__ PeerPush push) { peer_publish(push, 0); }
+
+cudaError_t launch_push_empty(cudaStream_t st, const PeerPush& push)
+{
+    if (push.world < 1 || push.world > XCHG_MAX_RANKS) return cudaErrorInvalidValue;
+    push_empty_kernel<<<1, 32, 0, st>>>(push);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // The selection kernel (one CTA).
 // ---------------------------------------------------------------------------------------------
 constexpr int SEL_KEYS_CAP = (int)GROUPS_TARGET;     // group maxima staged in shared memory
@@ -141,7 +193,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1)
 select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int group_shift,
                    int k, const int64_t* __restrict__ ids, int64_t row0, u64* cand, int64_t cand_cap,
                    u64* __restrict__ out_keys, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                   int32_t* __restrict__ out_count, u64* __restrict__ dbg)
+                   int32_t* __restrict__ out_count, u64* __restrict__ dbg, const __grid_constant__ PeerPush push)
 {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelectKeysSmem& big = *reinterpret_cast<SelectKeysSmem*>(sel_smem_raw);
@@ -265,20 +317,28 @@ select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int g
         const u64 key = sorted[i];
         const uint32_t row = key_row(key);
         const int64_t grow = row0 + (int64_t)row;
-        out_keys[i] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
+        const u64 gkey = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
+        const int64_t id = ids ? ids[row] : grow;
+        out_keys[i] = gkey;
         out_scores[i] = key_score(key);
-        out_ids[i] = ids ? ids[row] : grow;
+        out_ids[i] = id;
+        // the exchange step, fused: the record goes straight into every rank's gather window (peer stores)
+        for (int p = 0; p < push.world; ++p) { push.rec[p][i] = gkey; push.rec[p][push.cap + i] = (u64)id; }
     }
     if (tid == 0) *out_count = kk;
+    if (push.world > 0) peer_publish(push, kk);
     SEL_STAMP(6);
 #undef SEL_STAMP
 }
 
 cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,
                           int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
-                          u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count, u64* dbg)
+                          u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count, u64* dbg,
+                          const PeerPush* push)
 {
     if (k < 1 || k > K_FAST_MAX || n < 1) return cudaErrorInvalidValue;
+    PeerPush pp;
+    if (push) { pp = *push; if (pp.world < 1 || pp.world > XCHG_MAX_RANKS || pp.cap < k) return cudaErrorInvalidValue; }
     static bool attr_set[64] = {false};
     int dev = 0; cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
@@ -288,7 +348,7 @@ cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* 
     }
     if (((n + ((int64_t)1 << group_shift) - 1) >> group_shift) > SEL_KEYS_CAP) return cudaErrorInvalidValue;
     select_topk_kernel<<<1, SEL_THREADS, sizeof(SelectKeysSmem), st>>>(scores, n, gmax, group_shift, k, ids, row0,
-                                                                  cand, cand_cap, out_keys, out_scores, out_ids, out_count, dbg);
+                                                                  cand, cand_cap, out_keys, out_scores, out_ids, out_count, dbg, pp);
     count_launch();
     return cudaGetLastError();
 }
@@ -562,6 +622,111 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
     }
     count_launch();
     return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merge of a gather-window slot (peer exchange): the lists were stored by the other ranks' selection kernels over
+// peer memory.  Thread r waits for rank r's flag (acquire, system scope), then the CTA merges exactly like
+// merge_lists_kernel / merge_lists_big_kernel -- with L1-bypassing loads, since this SM may hold stale lines of
+// the slot from its previous use.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+merge_window_kernel(const u64* slot_base, const u64* flags, u64 seq, int world, int cap, int k, u64 timeout_ns,
+                    u64* sk, int64_t* sp, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                    int32_t* __restrict__ out_count)
+{
+    extern __shared__ __align__(16) unsigned char sel_smem_raw[];
+    SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t rec_words = 2 * (int64_t)cap + 2;
+    if (tid == 0) sm.counter = 0;
+    __syncthreads();
+    if (tid < world) {
+        // A peer that died or left the SPMD sequence must not hang this GPU: give up after timeout_ns and report it.
+        unsigned ns = 32;
+        u64 t0 = 0;
+        while (ld_acquire_sys(flags + tid) < seq) {
+            __nanosleep(ns);
+            if (ns < 1024) ns <<= 1;
+            else {
+                u64 now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > timeout_ns) { atomicAdd(&sm.counter, 1u); break; }
+            }
+        }
+    }
+    __syncthreads();
+    if (sm.counter != 0) { if (tid == 0) *out_count = MERGE_WINDOW_TIMED_OUT; return; }
+    __syncthreads();
+    const bool big = sk != nullptr;                            // world * k > SORT_CAP: compact into global scratch
+    const int span = world * k;
+    for (int i = tid; i < span; i += blockDim.x) {
+        const int l = i / k, p = i - l * k;
+        const u64* rec = slot_base + (int64_t)l * rec_words;
+        if (p < (int)min((u64)k, __ldcg(rec + 2 * cap))) {
+            const uint32_t slot = atomicAdd(&sm.counter, 1u);
+            const u64 key = __ldcg(rec + p);
+            const int64_t id = (int64_t)__ldcg(rec + cap + p);
+            if (big) { sk[slot] = key; sp[slot] = id; } else { sm.sortbuf[slot] = key; sm.payload[slot] = id; }
+        }
+    }
+    __syncthreads();
+    const int total = (int)sm.counter;
+    const int kk = min(k, total);
+    __syncthreads();
+    if (kk == 0) { if (tid == 0) *out_count = 0; return; }
+    int c = total;
+    if (big) {
+        u64 tau = 0;
+        if (total > kk) tau = block_kth_largest(sk, total, kk, sm);
+        if (tid == 0) sm.counter = 0;
+        __syncthreads();
+        for (int i = tid; i < total; i += blockDim.x) {
+            const u64 v = sk[i];
+            if (v >= tau) { const uint32_t slot = atomicAdd(&sm.counter, 1u); if (slot < (uint32_t)SORT_CAP) { sm.sortbuf[slot] = v; sm.payload[slot] = sp[i]; } }
+        }
+        __syncthreads();
+        c = (int)min(sm.counter, (uint32_t)SORT_CAP);
+    }
+    int np2 = 1; while (np2 < c) np2 <<= 1;
+    for (int i = c + tid; i < np2; i += blockDim.x) { sm.sortbuf[i] = 0ull; sm.payload[i] = -1; }
+    __syncthreads();
+    block_bitonic_desc<true>(sm.sortbuf, sm.payload, np2);
+    for (int i = tid; i < kk; i += blockDim.x) { out_scores[i] = key_score(sm.sortbuf[i]); out_ids[i] = sm.payload[i]; }
+    if (tid == 0) *out_count = kk;
+}
+
+cudaError_t launch_merge_window(cudaStream_t st, const u64* slot_base, const u64* flags, unsigned long long seq,
+                                int world, int cap, int k, unsigned long long timeout_ns, u64* scratch_keys, int64_t* scratch_ids,
+                                float* out_scores, int64_t* out_ids, int32_t* out_count)
+{
+    if (world < 1 || world > XCHG_MAX_RANKS || k < 1 || k > K_FAST_MAX || cap < k) return cudaErrorInvalidValue;
+    static bool attr_set[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(merge_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem));
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    const bool big = (int64_t)world * k > SORT_CAP;
+    if (big && (!scratch_keys || !scratch_ids)) return cudaErrorInvalidValue;
+    merge_window_kernel<<<1, SEL_THREADS, sizeof(SelectSmem), st>>>(slot_base, flags, seq, world, cap, k, timeout_ns,
+                                                                   big ? scratch_keys : nullptr, big ? scratch_ids : nullptr,
+                                                                   out_scores, out_ids, out_count);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t preload_peer_kernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, select_topk_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, merge_window_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, push_empty_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, stage_query_kernel);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectKeysSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(merge_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem));
+    return e;
 }
 
 cudaError_t launch_merge(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,

@@ -231,6 +231,13 @@ class Engine:
         check(self._lib.svsb_batch_stats(self._h, b, cand.ctypes.data, resc.ctypes.data, flags.ctypes.data))
         return cand, resc, flags
 
+    def batch_threshold_mode(self) -> int:
+        """0 = verified statistical filter thresholds (default), 1 = proven-bound thresholds (see svsb200.h)."""
+        rc = self._lib.svsb_batch_threshold_mode(self._h)
+        if rc < 0:
+            check(rc)
+        return rc
+
     def bench_last_result(self, k: int) -> List[Tuple[float, int]]:
         s = np.empty(k, dtype=np.float32)
         i = np.empty(k, dtype=np.int64)

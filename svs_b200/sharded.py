@@ -11,6 +11,13 @@ their embeddings.ids.  A query is answered by
 No reduction over scores is needed: rows are independent (splitting D instead would need an all-reduce
 of N floats).
 
+Single queries do not call a collective at all by default (`exchange="peer"`): steps 2 and 3 are fused into the
+kernels over NVLink / NVSwitch peer memory -- the selection kernel's epilogue stores its record into every rank's
+gather window and publishes it with a release store, and each rank's merge kernel waits for the `world` flags of
+its own window (include/svsb200.h "peer exchange").  The windows are exchanged once, as CUDA IPC handles, through
+torch.distributed.  `exchange="collective"` keeps the NCCL all-gather (the baseline the fused path is measured
+against; also what batches use: one all-gather per batch is already amortised).
+
 The collective / packing / batching logic is backend-agnostic so that it can be exercised on CPU with
 `gloo` (tests/test_sharded_gloo.py injects a NumPy backend); the product backend is `CudaShardBackend`.
 """
@@ -95,6 +102,42 @@ class CudaShardBackend:
                                                        queries.shape[0], k, C.c_void_p(records.data_ptr()), C.byref(nfb)))
         return nfb.value
 
+    # -- peer exchange (fused selection + exchange over NVLink peer memory) -------------------------
+    def exchange_handle(self, world: int, rank: int, k_max: int = 2048) -> bytes:
+        """Allocate this rank's gather window; returns its CUDA IPC handle (64 bytes) for the other ranks."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.svsb_xchg_create(self.engine._h, world, rank, k_max, buf))
+        return buf.raw
+
+    def exchange_connect(self, handles: List[bytes]) -> None:
+        blob = b"".join(handles)
+        self._check(self._lib.svsb_xchg_connect(self.engine._h, C.c_char_p(blob)))
+
+    def exchange_connect_local(self, backends: List["CudaShardBackend"]) -> None:
+        """All ranks live in this process (tests; one process driving several GPUs): plain pointers, no IPC."""
+        arr = (C.c_void_p * len(backends))(*[b.engine._h for b in backends])
+        self._check(self._lib.svsb_xchg_connect_local(self.engine._h, arr))
+
+    def enqueue_query_peer(self, query_row, k: int, out_scores, out_ids, out_count, time_kernel: bool = False,
+                           pipelined: bool = True) -> None:
+        """Similarity + selection with the fused push + waiting merge for one device-resident query; the GLOBAL top-k
+        lands in the output rows (identical on every rank).  pipelined: call join() before consuming them."""
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_enqueue_query_peer(self.engine._h, C.c_void_p(st), C.c_void_p(query_row.data_ptr()), k,
+                                                      C.c_void_p(out_scores.data_ptr()), C.c_void_p(out_ids.data_ptr()),
+                                                      C.c_void_p(out_count.data_ptr()),
+                                                      (1 if time_kernel else 0) | (2 if pipelined else 0)))
+
+    def query_peer(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Host query in, host (scores, ids) out, one synchronous C call (svsb_query_peer)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        s = np.empty(k, dtype=np.float32)
+        i = np.empty(k, dtype=np.int64)
+        cnt = C.c_int32()
+        self._check(self._lib.svsb_query_peer(self.engine._h, q.ctypes.data, q.shape[0], k, s.ctypes.data, i.ctypes.data,
+                                              C.byref(cnt)))
+        return s[:cnt.value], i[:cnt.value]
+
     def join(self) -> None:
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.svsb_enqueue_join(self.engine._h, C.c_void_p(st)))
@@ -120,11 +163,16 @@ class CudaShardBackend:
 class ShardedRetriever:
     """All ranks construct one and call the same methods in the same order (SPMD)."""
 
-    def __init__(self, rank: int, world: int, device_index: int = 0, backend=None, group=None):
+    def __init__(self, rank: int, world: int, device_index: int = 0, backend=None, group=None, exchange: str = "peer"):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world, self.group = rank, world, group
         self.backend = backend if backend is not None else CudaShardBackend(device_index)
+        if exchange not in ("peer", "collective"):
+            raise ValueError("exchange must be 'peer' or 'collective'")
+        # the fused peer exchange needs a backend that owns device windows; injected CPU backends use the collective
+        self.exchange = exchange if hasattr(self.backend, "exchange_handle") and world <= 16 else "collective"
+        self._peer_ready = False
         self.n = 0
         self.d = 0
         self.row0 = 0
@@ -148,6 +196,21 @@ class ShardedRetriever:
         sl = slice(self.row0, self.row0 + self.local_rows)
         self.backend.load_rows(np.ascontiguousarray(rows[sl]), np.ascontiguousarray(emb_ids[sl]))
 
+    def _ensure_peer(self) -> None:
+        """One-time window exchange: every rank allocates its gather window and all-gathers the IPC handles."""
+        if self._peer_ready:
+            return
+        handle = self.backend.exchange_handle(self.world, self.rank)
+        handles: List[Optional[bytes]] = [None] * self.world
+        if self.world > 1:
+            self.dist.all_gather_object(handles, handle, group=self.group)
+        else:
+            handles[0] = handle
+        self.backend.exchange_connect(handles)
+        if self.world > 1:
+            self.dist.barrier(group=self.group)                    # every window is open before the first push
+        self._peer_ready = True
+
     # -- queries ---------------------------------------------------------------------------------
     def set_queries(self, Q: np.ndarray) -> None:
         self._queries = self.backend.device_queries(Q)
@@ -164,6 +227,12 @@ class ShardedRetriever:
         """Local top-k for len(qrows) device queries, one all-gather, one merge.  Returns output views."""
         rec, gath, (o_s, o_i, o_c) = self._buffers(k)
         nb = len(qrows)
+        if self.exchange == "peer":
+            self._ensure_peer()
+            for j, q in enumerate(qrows):                          # no collective, no separate merge launch per batch
+                self.backend.enqueue_query_peer(q, k, o_s[j], o_i[j], o_c[j], time_gemv, pipelined=True)
+            self.backend.join()
+            return o_s[:nb], o_i[:nb], o_c[:nb]
         for j, q in enumerate(qrows):
             self.backend.enqueue_local(q, k, rec[j], time_gemv, seq=j)
         self.backend.join()                                        # records complete before the exchange
@@ -229,6 +298,10 @@ class ShardedRetriever:
         k = min(int(n), 2048)
         if n > 2048 and self.n > 2048:
             raise NotImplementedError("n > 2048 is not supported by the sharded path")
+        if self.exchange == "peer":
+            self._ensure_peer()
+            s, i = self.backend.query_peer(q, k)                   # one synchronous C call, result written to host
+            return [(float(a), int(b)) for a, b in zip(s, i)]
         dq = self.backend.device_queries(q[None, :])
         o_s, o_i, o_c = self._micro_batch([dq[0]], k, False)
         cnt = int(o_c[0].item())                                   # synchronises the stream

@@ -41,6 +41,8 @@ def _assert_same_as_single(engine, q, k, s, i, c, check=None):
     (30_000, 100, 7, 33, "normal"),            # d not a multiple of 8
     (12_345, 3072, 1000, 20, "uniform"),       # large k
     (40_000, 256, 1, 513, "normal"),           # k = 1, three query tiles
+    (300_000, 128, 10, 64, "normal"),          # sample = 1.4 % of the rows: statistical threshold (7th largest of the sample)
+    (400_000, 64, 100, 40, "uniform"),         # sample = 8 % of the rows: statistical threshold (29th largest)
 ])
 def test_batch_equals_single_query_bits(engine, n, d, k, b, dist):
     rng = np.random.default_rng(n + d + k)
@@ -83,6 +85,32 @@ def test_batch_with_massive_ties_falls_back_and_stays_exact(engine):
     assert (flags != 0).all()
     assert (i == np.arange(k)[None, :]).all()                     # ties: ascending row / id
     _assert_same_as_single(engine, q, k, s, i, c)
+
+
+def test_statistical_thresholds_fail_verification_on_sorted_rows_and_stay_exact(engine):
+    """Rows stored in descending similarity to the queries' common direction: the strided row sample then holds the
+    overall top rows, the sample's order statistic lands ABOVE the true cut-off, the refine kernel's verification
+    (flag 16 / 4) catches it, the chunk is redone with proven-bound thresholds and the generation stays in that mode.
+    Results must still be the single-query path's bits."""
+    rng = np.random.default_rng(21)
+    n, d, k, b = 300_000, 64, 20, 64
+    base = _unit(rng, (1, d), "normal")[0]
+    m = _unit(rng, (n, d), "normal")
+    m = m[np.argsort(-(m @ base), kind="stable")]                 # best rows first: row tile 0 is always sampled
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    q = base[None, :] + 0.05 * rng.standard_normal((b, d)).astype(np.float32)
+    q /= np.sqrt((q * q).sum(axis=1))[:, None]
+    engine.load(m, ids)
+    assert engine.batch_threshold_mode() == 0
+    s, i, c = engine.query_batch(q, k)
+    assert engine.batch_threshold_mode() == 1, "verification should have failed for most queries"
+    cand, resc, flags = engine.batch_stats(b)
+    assert (flags == 0).all()                                      # answered by the redone coarse pass, not one by one
+    _assert_same_as_single(engine, q, k, s, i, c, check=range(0, b, 4))
+    s2, i2, c2 = engine.query_batch(q, k)                          # later batches go straight to the proven bound
+    assert np.array_equal(s.view(np.uint32), s2.view(np.uint32)) and np.array_equal(i, i2)
+    engine.load(m[::-1].copy(), ids)                               # a new generation starts statistical again
+    assert engine.batch_threshold_mode() == 0
 
 
 def test_batch_edge_cases(engine):

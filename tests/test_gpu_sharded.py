@@ -102,17 +102,118 @@ def test_two_shard_engines_batched_records_equal_the_single_query_records():
             b.close()
 
 
-def test_world_size_one_process_group_runs_the_real_collective():
+def _two_backends(m, ids, world=2):
+    import os
+    from svs_b200.sharded import CudaShardBackend, partition
+    os.environ["SVSB_XCHG_TIMEOUT_MS"] = "5000"                 # a protocol bug must fail the test, not hang the GPU
+    backs = []
+    for r in range(world):
+        b = CudaShardBackend(0)
+        row0, cnt = partition(len(m), world, r)
+        b.set_shard(row0)
+        b.load_rows(np.ascontiguousarray(m[row0:row0 + cnt]), np.ascontiguousarray(ids[row0:row0 + cnt]))
+        backs.append(b)
+    for r, b in enumerate(backs):
+        assert len(b.exchange_handle(world, r)) == 64
+    for b in backs:
+        b.exchange_connect_local(backs)
+    return backs
+
+
+def test_peer_exchange_pipelined_two_virtual_ranks_match_the_oracle():
+    """The fused exchange (selection epilogue pushes the record into every rank's window; the merge kernel waits
+    for the flags) with two shard engines on ONE device: windows connected by plain pointers, similarity passes on
+    the shared stream, selection + push + waiting merge on each engine's side stream.  40 queries per k cycle
+    through the 4 window slots ten times; every rank must hold the identical, oracle-matching answer."""
+    torch = pytest.importorskip("torch")
+    n, d = 30_001, 256
+    m = oracle.synth_matrix_uniform(n, d, 15)
+    m[7] = m[n - 3]                                            # exact tie across shards
+    ids = np.cumsum(np.random.default_rng(12).integers(1, 4, size=n)).astype(np.int64)
+    backs = _two_backends(m, ids)
+    qs = oracle.synth_queries(40, d, 16)
+    qs[1] = m[7]
+    try:
+        dq = backs[0].device_queries(qs)
+        for k in (1, 100, 1500, 2048):                         # 2 * 1500 > 2048: the merge's scratch path
+            outs = [b.new_outputs(len(qs), k) for b in backs]
+            for j in range(len(qs)):
+                for b, (o_s, o_i, o_c) in zip(backs, outs):
+                    b.enqueue_query_peer(dq[j], k, o_s[j], o_i[j], o_c[j], time_kernel=(k == 100), pipelined=True)
+            for b in backs:
+                b.join()
+            torch.cuda.synchronize()
+            res = [(o_s.cpu().numpy(), o_i.cpu().numpy(), o_c.cpu().numpy()) for o_s, o_i, o_c in outs]
+            assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32))      # same bits on both ranks
+            assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+            s, i, c = res[0]
+            assert (c == min(k, n)).all()
+            for j in range(0, len(qs), 3):
+                got = list(zip(s[j, :c[j]].tolist(), i[j, :c[j]].tolist()))
+                oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+            if k >= 2:
+                assert i[1, :2].tolist() == [int(ids[7]), int(ids[n - 3])]                   # tie: ascending id
+            if k == 100:
+                assert backs[0].collect_kernel_ms() > 0 and backs[1].collect_kernel_ms() > 0
+    finally:
+        for b in backs:
+            b.close()
+
+
+def test_peer_exchange_synchronous_query_from_two_threads_and_an_empty_shard():
+    """svsb_query_peer (host buffers, result written into pinned host memory by the merge kernel) called SPMD from
+    one thread per virtual rank; 3 ranks over 2 rows leave the last shard empty (count-0 record)."""
+    pytest.importorskip("torch")
+    import threading
+    n, d, k = 20_000, 128, 50
+    m = oracle.synth_matrix_uniform(n, d, 25)
+    ids = np.arange(10, 10 + n, dtype=np.int64)
+    qs = oracle.synth_queries(12, d, 26)
+    for rows, world in ((n, 2), (2, 3)):
+        backs = _two_backends(m[:rows], ids[:rows], world)
+        results = [[None] * len(qs) for _ in range(world)]
+        errors = []
+
+        def work(r):
+            try:
+                for j, q in enumerate(qs):
+                    results[r][j] = backs[r].query_peer(q, k)
+            except Exception as ex:                            # pragma: no cover - reported below
+                errors.append(ex)
+
+        try:
+            threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join(timeout=120)
+            assert not errors, errors
+            assert all(not t.is_alive() for t in threads), "a rank is stuck waiting for a peer's record"
+            for j, q in enumerate(qs):
+                s0, i0 = results[0][j]
+                for r in range(1, world):
+                    assert np.array_equal(s0.view(np.uint32), results[r][j][0].view(np.uint32))
+                    assert np.array_equal(i0, results[r][j][1])
+                got = list(zip(s0.tolist(), i0.tolist()))
+                oracle.compare_retrieval(got, oracle.superheavy(m[:rows], ids[:rows], q, k), oracle.scores_of(m[:rows], q), ids[:rows])
+        finally:
+            for b in backs:
+                b.close()
+
+
+@pytest.mark.parametrize("exchange", ["peer", "collective"])
+def test_world_size_one_process_group_runs_the_real_collective(exchange):
     torch = pytest.importorskip("torch")
     import os
     import torch.distributed as dist
     from svs_b200.sharded import ShardedRetriever
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29581")
+    os.environ["MASTER_PORT"] = "29581" if exchange == "peer" else "29582"
     torch.cuda.set_device(0)
     dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
     try:
-        sr = ShardedRetriever(0, 1, 0)
+        sr = ShardedRetriever(0, 1, 0, exchange=exchange)
+        assert sr.exchange == exchange
         sr.load_synthetic(50_000, 1536, seed=3, id0=1, id_step=1)
         rows, ids = sr.backend.engine.read_rows(0, 50_000)
         qs = oracle.synth_queries(11, 1536, 7)
