@@ -1400,7 +1400,11 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
         if ((int64_t)nd * c->g_stride > K_FAST_MAX && (rc = c->ws[0].ensure_merge_scratch((int64_t)nd * c->g_stride)) != SVSB_OK) return rc;
     }
     // gemv_ms requested: bracket every similarity-kernel launch on device 0 with events INSIDE the timed loop
+    // (one launch in KTIME_EVERY: the two event records cost ~5 us of stream time per bracketed launch, 4 % of a
+    // 125 k-row shard's query -- profiles/r01_shard_probe.txt -- and the loop being timed should be the product's)
     const bool ktime = gemv_ms != nullptr && g->shards[0].n > 0;
+    constexpr int KTIME_EVERY = 8;
+    auto timed_it = [&](int it) { return ktime && it % KTIME_EVERY == 0; };
     if (ktime && (rc = ensure_kernel_events(c->ws[0].dev, (size_t)iters * 2)) != SVSB_OK) return rc;
     // Single device, k <= 2048: software pipeline.  The similarity kernel of query i+1 (stream A, all SMs but one)
     // runs while the one-CTA selection kernel of query i (stream B) finishes on the SM left free; two buffer sets.
@@ -1431,9 +1435,9 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
             DevWs& W = (it & 1) ? w1 : w0;
             const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
             if (it >= 2) CU(cudaStreamWaitEvent(sa, W.ev_sel, 0));           // selection of query it-2 is done with W
-            if (ktime) CU(cudaEventRecord(g_kev[2 * it], sa));
+            if (timed_it(it)) CU(cudaEventRecord(g_kev[2 * it], sa));
             CU(launch_gemv(sa, W.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, W.scores, W.gmax, shift, 0, 0, 0, /*reserve_sms=*/1));
-            if (ktime) CU(cudaEventRecord(g_kev[2 * it + 1], sa));
+            if (timed_it(it)) CU(cudaEventRecord(g_kev[2 * it + 1], sa));
             CU(cudaEventRecord(W.ev, sa));
             CU(cudaStreamWaitEvent(sb, W.ev, 0));
             CU(launch_select(sb, W.scores, s.n, W.gmax, shift, (int)kk, s.ids, s.row0, W.cand, W.cand_cap,
@@ -1449,7 +1453,7 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
             for (int i = 0; i < nd; ++i) {
                 if (!g->shards[i].n) continue;
                 CU(cudaSetDevice(c->ws[i].dev));
-                if (ktime && i == 0) {
+                if (timed_it(it) && i == 0) {
                     DevWs& w = c->ws[0]; const Shard& s = g->shards[0];
                     const int shift = group_shift_for(s.n);
                     CU(cudaEventRecord(g_kev[2 * it], w.st));
@@ -1482,9 +1486,10 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
     if (launches) *launches = g_launches.load() - l0;
     if (ktime) {
         CU(cudaSetDevice(c->ws[0].dev));
-        float sum = 0.f;
-        for (int it = 0; it < iters; ++it) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, g_kev[2 * it], g_kev[2 * it + 1])); sum += ms; }
-        *gemv_ms = sum;
+        float sum = 0.f; int cnt = 0;
+        for (int it = 0; it < iters; ++it)
+            if (timed_it(it)) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, g_kev[2 * it], g_kev[2 * it + 1])); sum += ms; ++cnt; }
+        *gemv_ms = sum * (float)iters / (float)cnt;            // mean bracketed launch x launches
     } else if (gemv_ms) *gemv_ms = 0.f;
     return SVSB_OK;
 }

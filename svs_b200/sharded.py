@@ -29,6 +29,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 MICRO_BATCH = 16
+TIME_EVERY = 8        # bracket one similarity launch in 8 with timing events (two records cost ~5 us of stream time)
 
 
 def partition(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -68,12 +69,21 @@ class CudaShardBackend:
         self.ld = (d + 3) & ~3
 
     def device_queries(self, Q: np.ndarray):
-        """(nq, d) host float32 -> (nq, ld) device tensor, zero padded."""
+        """(nq, d) host float32 -> (nq, ld) device tensor, zero padded, staged through a cached pinned buffer."""
         t = self.torch
         Q = np.ascontiguousarray(Q, dtype=np.float32)
-        host = t.zeros((Q.shape[0], self.ld), dtype=t.float32).pin_memory()
+        key = (Q.shape[0], self.ld)
+        stage = getattr(self, "_stage", None)
+        if stage is None or stage[0] != key:                       # pinning is slow (ms): once per shape, not per call
+            stage = (key, t.zeros(key, dtype=t.float32).pin_memory(), t.cuda.Event())
+            self._stage = stage
+        else:
+            stage[2].synchronize()                                 # the previous upload out of this buffer has finished
+        host = stage[1]
         host[:, :Q.shape[1]] = t.from_numpy(Q)
-        return host.to(self.device, non_blocking=True)
+        dev = host.to(self.device, non_blocking=True)
+        stage[2].record(t.cuda.current_stream(self.device))
+        return dev
 
     def new_records(self, count: int, k: int):
         return self.torch.zeros((count, 2 * k + 1), dtype=self.torch.int64, device=self.device)
@@ -230,11 +240,11 @@ class ShardedRetriever:
         if self.exchange == "peer":
             self._ensure_peer()
             for j, q in enumerate(qrows):                          # no collective, no separate merge launch per batch
-                self.backend.enqueue_query_peer(q, k, o_s[j], o_i[j], o_c[j], time_gemv, pipelined=True)
+                self.backend.enqueue_query_peer(q, k, o_s[j], o_i[j], o_c[j], time_gemv and j % TIME_EVERY == 0, pipelined=True)
             self.backend.join()
             return o_s[:nb], o_i[:nb], o_c[:nb]
         for j, q in enumerate(qrows):
-            self.backend.enqueue_local(q, k, rec[j], time_gemv, seq=j)
+            self.backend.enqueue_local(q, k, rec[j], time_gemv and j % TIME_EVERY == 0, seq=j)
         self.backend.join()                                        # records complete before the exchange
         recw = 2 * k + 1
         g = gath.view(-1)[: self.world * nb * recw]
@@ -246,12 +256,14 @@ class ShardedRetriever:
         """`count` retrieves over the uploaded queries, device-resident end to end (bench path)."""
         assert self._queries is not None, "set_queries first"
         nq = self._queries.shape[0]
-        done = 0
+        done = timed = 0
         while done < count:
             nb = min(MICRO_BATCH, count - done)
             self._micro_batch([self._queries[(done + j) % nq] for j in range(nb)], k, time_gemv)
             done += nb
-        return self.backend.collect_kernel_ms() if time_gemv else 0.0
+            timed += (nb + TIME_EVERY - 1) // TIME_EVERY
+        # similarity-kernel time of the run, estimated as (mean bracketed launch) x launches
+        return self.backend.collect_kernel_ms() * count / timed if time_gemv else 0.0
 
     # -- batches ---------------------------------------------------------------------------------
     def _batch(self, dq, k: int):
@@ -273,20 +285,25 @@ class ShardedRetriever:
         assert self._queries is not None, "set_queries first"
         self._batch(self._queries, k)
 
-    def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
-        """superheavy() for every row of query_vecs on every rank: host queries in, host lists out."""
+    def retrieve_many_arrays(self, query_vecs: np.ndarray, n: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """superheavy() for every row of query_vecs on every rank, as arrays: host queries in; host
+        (scores (b, k) float32, embeddings.id (b, k) int64, counts (b,) int32) out, row j valid up to counts[j]."""
         Q = np.ascontiguousarray(query_vecs, dtype=np.float32)
         if Q.ndim != 2 or Q.shape[1] != self.d or self.n == 0:
             raise ValueError(f"shapes ({self.n},{self.d if self.n else 0}) and {Q.shape} not aligned")
         if n <= 0 or Q.shape[0] == 0:
-            return [[] for _ in range(Q.shape[0])]
+            return (np.zeros((Q.shape[0], 0), np.float32), np.zeros((Q.shape[0], 0), np.int64), np.zeros(Q.shape[0], np.int32))
         if n > 2048 and self.n > 2048:
             raise NotImplementedError("n > 2048 is not supported by the sharded path")
         k = min(int(n), 2048)
         o_s, o_i, o_c = self._batch(self.backend.device_queries(Q), k)
         cnt = o_c.cpu().numpy()                                     # synchronises the stream
-        s, i = o_s.cpu().numpy(), o_i.cpu().numpy()
-        return [[(float(a), int(x)) for a, x in zip(s[j, :cnt[j]], i[j, :cnt[j]])] for j in range(Q.shape[0])]
+        return o_s.cpu().numpy(), o_i.cpu().numpy(), cnt
+
+    def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
+        """superheavy() for every row of query_vecs on every rank: host queries in, host lists out."""
+        s, i, cnt = self.retrieve_many_arrays(query_vecs, n)
+        return [[(float(a), int(x)) for a, x in zip(s[j, :cnt[j]], i[j, :cnt[j]])] for j in range(s.shape[0])]
 
     def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
         """The reference's superheavy() result, on every rank: host query in, host list out."""

@@ -87,6 +87,134 @@ class NumpyShardBackend:
         pass
 
 
+class NumpyPeerBackend(NumpyShardBackend):
+    """CPU restatement of the fused peer exchange (include/svsb200.h "peer exchange"; csrc/select.cu peer_publish /
+    merge_window_kernel): every rank owns a gather window -- here a POSIX shared-memory block instead of HBM opened
+    over CUDA IPC -- of SLOTS x world records [keys(cap) | ids(cap) | count | pad] plus SLOTS x world flag words.
+    Query number seq uses slot seq % SLOTS; a rank stores its record into EVERY rank's window, then the flag = seq;
+    the merge spins on its own window's flags.  Test infrastructure for ShardedRetriever's exchange="peer" host
+    logic (handle all-gather, connect, SPMD sequence numbers, slot reuse)."""
+    SLOTS = 4
+
+    def exchange_handle(self, world, rank, k_max=64):
+        from multiprocessing import shared_memory
+        self.world, self.rank, self.cap, self.seq = world, rank, k_max, 0
+        self.rec_words = 2 * k_max + 2
+        words = self.SLOTS * world + self.SLOTS * world * self.rec_words
+        self._own = shared_memory.SharedMemory(create=True, size=words * 8)
+        np.ndarray((words,), dtype=np.uint64, buffer=self._own.buf)[:] = 0
+        return self._own.name.encode().ljust(64, b"\0")            # 64 bytes, like a cudaIpcMemHandle_t
+
+    def exchange_connect(self, handles):
+        from multiprocessing import shared_memory
+        assert len(handles) == self.world and all(len(h) == 64 for h in handles)
+        self._shm, self._win = [], []
+        for r, h in enumerate(handles):
+            shm = self._own if r == self.rank else shared_memory.SharedMemory(name=h.rstrip(b"\0").decode())
+            self._shm.append(shm)
+            self._win.append(np.ndarray((shm.size // 8,), dtype=np.uint64, buffer=shm.buf))
+
+    def _rec(self, win, slot, src):
+        base = self.SLOTS * self.world + (slot * self.world + src) * self.rec_words
+        return win[base:base + self.rec_words]
+
+    def _query(self, q, k):
+        import time
+        self.seq += 1
+        slot = self.seq % self.SLOTS
+        tmp = torch.zeros(2 * k + 1, dtype=torch.int64)
+        self.enqueue_local(q, k, tmp)                              # local record, the collective path's layout
+        t = tmp.numpy().view(np.uint64)
+        cnt = int(t[2 * k])
+        for p in range(self.world):                                # the "epilogue": push into every window, then publish
+            rec = self._rec(self._win[p], slot, self.rank)
+            rec[:cnt] = t[:cnt]
+            rec[self.cap:self.cap + cnt] = t[k:k + cnt]
+            rec[2 * self.cap] = cnt
+            self._win[p][slot * self.world + self.rank] = self.seq
+        own = self._win[self.rank]
+        deadline = time.time() + 30
+        while not all(int(own[slot * self.world + r]) >= self.seq for r in range(self.world)):   # the waiting merge
+            assert time.time() < deadline, "a peer's record did not arrive"
+            time.sleep(0.0002)
+        keys, ids = [], []
+        for r in range(self.world):
+            rec = self._rec(own, slot, r)
+            c = int(rec[2 * self.cap])
+            keys.append(rec[:c].copy()); ids.append(rec[self.cap:self.cap + c].copy().view(np.int64))
+        keys, ids = np.concatenate(keys), np.concatenate(ids)
+        order = np.argsort(keys)[::-1][:k]
+        return key_score(keys[order]), ids[order]
+
+    def query_peer(self, q, k):
+        return self._query(torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)), k)
+
+    def enqueue_query_peer(self, q, k, out_scores, out_ids, out_count, time_kernel=False, pipelined=True):
+        s, i = self._query(q, k)
+        out_scores.numpy()[:len(s)] = s
+        out_ids.numpy()[:len(i)] = i
+        out_count.numpy()[...] = len(s)
+
+    def close(self):
+        for r, shm in enumerate(getattr(self, "_shm", [])):
+            self._win[r] = None
+        self._win = []
+        for r, shm in enumerate(getattr(self, "_shm", [])):
+            shm.close()
+        if getattr(self, "_own", None) is not None:
+            self._own.unlink()
+            self._own = None
+
+
+def _peer_worker(rank, world, port, n, d, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = oracle.synth_matrix_normal(n, d, 13)
+        if n > 10:
+            m[5] = m[n - 2]
+        ids = np.cumsum(np.random.default_rng(1).integers(1, 4, size=n)).astype(np.int64)
+        sr = ShardedRetriever(rank, world, backend=NumpyPeerBackend())
+        assert sr.exchange == "peer"
+        sr.load_global(m, ids)
+        qs = oracle.synth_queries(MICRO_BATCH + 5, d, 14, "normal")
+        if n > 10:
+            qs[1] = m[5]
+        out = []
+        for k in (1, 10, 64):
+            for q in qs[:6]:                                       # 18 queries: every window slot is reused 4 times
+                got = sr.retrieve(q, k)
+                oracle.compare_retrieval(got, oracle.superheavy(m, ids, q, k), oracle.scores_of(m, q), ids)
+                out.append(got)
+        if n > 10:
+            assert [i for _, i in sr.retrieve(qs[1], 2)] == [int(ids[5]), int(ids[n - 2])]
+        sr.set_queries(qs)
+        assert sr.run_queries(10, len(qs)) == 0.0                 # device-resident loop: no collective inside
+        s_, i_, c_ = sr._micro_batch([sr._queries[j] for j in range(3)], 10, False)
+        for j in range(3):
+            got = [(float(a), int(b)) for a, b in zip(s_[j].numpy(), i_[j].numpy())][:int(c_[j])]
+            oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], 10), oracle.scores_of(m, qs[j]), ids)
+            out.append(got)
+        ret[rank] = out
+        dist.barrier()
+        sr.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1001), (3, 2)])
+def test_peer_exchange_protocol_on_cpu_matches_the_oracle_on_every_rank(world, n):
+    """exchange="peer" end to end on CPU: handles all-gathered over gloo, windows connected, records pushed and
+    flags awaited across PROCESSES (shared memory standing in for NVLink peer memory)."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_peer_worker, args=(world, _free_port(), n, 24, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(1, world):
+        assert ret[r] == ret[0]
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
