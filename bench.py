@@ -224,12 +224,19 @@ def run_batch_arm(args, n, d, k, desc):
     for qi in (0, BATCH // 2, BATCH - 1):
         got, flag = eng.bench_batch_result(qi, k)
         agree = agree and flag == 0 and got == eng.retrieve(queries[qi], k)
-    # e2e: the public C-ABI call with host buffers (H2D of the batch, D2H of the results inside every call)
-    eng.query_batch(queries, k)
+    # e2e: the public C-ABI call with host buffers (H2D of the batch from pinned host memory, D2H of the results
+    # into pinned host memory, inside every call)
+    from svs_b200 import pinned_empty
+    hq = pinned_empty((BATCH, d), np.float32)
+    hq[:] = queries
+    out = (pinned_empty((BATCH, k), np.float32), pinned_empty((BATCH, k), np.int64), np.zeros(BATCH, dtype=np.int32))
+    eng.query_batch(hq, k, out=out)
     t0 = time.perf_counter()
     for s in range(args.steps):
-        eng.query_batch(queries, k)
+        eng.query_batch(hq, k, out=out)
     e2e_qps = args.steps * BATCH / (time.perf_counter() - t0)
+    ref_s, ref_i, _ = eng.query_batch(queries, k)               # pageable buffers take the staged path: same answer
+    agree = agree and np.array_equal(out[0].view(np.uint32), ref_s.view(np.uint32)) and np.array_equal(out[1], ref_i)
     nq = args.steps * BATCH
     flop = 2.0 * n * d * BATCH
     achieved = flop * args.steps / (coarse_ms / 1e3) / 1e12

@@ -115,6 +115,11 @@ int svsb_query_batch(svsb_t* e, const float* Q, int32_t b, int32_t d, int32_t k,
                      float* out_scores, int64_t* out_emb_ids, int32_t* out_counts);
 int svsb_snapshot_query_batch(svsb_t* e, svsb_snap_t* s, const float* Q, int32_t b, int32_t d, int32_t k,
                               float* out_scores, int64_t* out_emb_ids, int32_t* out_counts);
+/* Page-locked host buffers for callers without a CUDA binding of their own.  svsb_query_batch copies straight from /
+ * into caller buffers that are page-locked (these, cudaHostRegister'ed memory, torch pin_memory tensors) and stages
+ * pageable ones through its own pinned buffers. */
+int svsb_host_alloc(size_t bytes, void** out);
+int svsb_host_free(void* p);
 /* Diagnostics of the last batch chunk (<= 2048 queries): coarse candidates per query, rows re-scored exactly per
  * query, flag word per query (0 = answered by the coarse path; otherwise it took the single-query kernels). */
 int svsb_batch_stats(svsb_t* e, int32_t b, int32_t* candidates, int32_t* rescored, int32_t* flags);

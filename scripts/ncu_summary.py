@@ -97,7 +97,10 @@ if __name__ == "__main__":
             ("prof_gemv.ncu-rep", "similarity kernel (gemv_tma_kernel), workload c2 = 1M x 1536 fp32", "c2", None),
             ("prof_select.ncu-rep", "selection kernel (select_topk_kernel), workload c2, k = 100", None, None),
             ("prof_coarse.ncu-rep", "batched coarse contraction (coarse_gemm_kernel<1> sample pass, <0> filter pass), workload c3",
-             "c3", "coarse_gemm_kernel<0>")):
+             "c3", "coarse_gemm_kernel<0"),
+            ("prof_refine.ncu-rep", "batched path: sample_threshold_kernel and refine_kernel, workload c3", None, None),
+            ("prof_peer.ncu-rep", "peer exchange at world size 1 (scripts/peer_profile.py): select_topk_kernel with the fused push, "
+             "merge_window_kernel; 1M x 1536 shard, k = 100", None, None)):
         p = os.path.join(OUT, rep)
         if os.path.exists(p):
             t = summarise(p, title, f"{rtag}_{rep.split('.')[0][5:]}_ncu", only)

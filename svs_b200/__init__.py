@@ -10,7 +10,7 @@ There is no CPU fallback: importing works anywhere, but creating an Engine witho
 library or without a B200 raises.
 """
 from ._lib import EngineError, LIB_PATH
-from .engine import Engine, Snapshot, launch_count
+from .engine import Engine, Snapshot, launch_count, pinned_empty
 from .matrix import DeviceEmbeddingsMatrix, DeviceMatrix, load_from_connection
 from .dropin import install, uninstall
 
@@ -18,5 +18,5 @@ __version__ = "0.1.0"
 
 __all__ = [
     "Engine", "Snapshot", "EngineError", "DeviceEmbeddingsMatrix", "DeviceMatrix",
-    "load_from_connection", "install", "uninstall", "launch_count", "LIB_PATH",
+    "load_from_connection", "install", "uninstall", "launch_count", "pinned_empty", "LIB_PATH",
 ]

@@ -1081,6 +1081,26 @@ static bool batch_thresholds_failed(Generation* g, const BatchPlan& P, const int
     return true;
 }
 
+static bool is_pinned_host(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int svsb_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(SVSB_E_INVALID, "svsb_host_alloc: NULL argument");
+    *out = nullptr;
+    if (bytes == 0) bytes = 1;
+    cudaError_t ce = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (ce != cudaSuccess) { (void)cudaGetLastError(); return fail(ce == cudaErrorMemoryAllocation ? SVSB_E_NOMEM : SVSB_E_CUDA, std::string("svsb_host_alloc: ") + cudaGetErrorString(ce)); }
+    return SVSB_OK;
+}
+extern "C" int svsb_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return SVSB_OK;
+}
+
 static int query_batch_loop(svsb_engine* e, const std::shared_ptr<Generation>& g, const float* Q, int32_t b, int32_t d, int32_t k,
                             float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
     const int64_t kstride = k > 0 ? k : 0;
@@ -1113,21 +1133,31 @@ static int query_batch_gen(svsb_engine* e, const std::shared_ptr<Generation>& g,
         if (rc == SVSB_E_NOMEM) return query_batch_loop(e, g, Q, b, d, k, out_scores, out_emb_ids, out_counts);
         return rc;
     }
+    // Page-locked caller buffers (svsb_host_alloc, cudaHostRegister, torch pin_memory) are DMA'd from / into directly;
+    // pageable ones are staged through the workspace's pinned buffers.
+    const bool q_direct = is_pinned_host(Q) && d == P.ld;
+    const bool out_direct = is_pinned_host(out_scores) && is_pinned_host(out_emb_ids);
     for (int32_t c0 = 0; c0 < b; c0 += COARSE_MAX_BATCH) {
         const int bc = std::min<int32_t>(COARSE_MAX_BATCH, b - c0);
         const int b_pad = (bc + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
         if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
-        for (int i = 0; i < bc; ++i) {
-            float* dst = w->h_Q + (size_t)i * P.ld;
-            memcpy(dst, Q + (size_t)(c0 + i) * d, (size_t)d * 4);
-            for (int c = d; c < P.ld; ++c) dst[c] = 0.f;
+        const float* src = Q + (size_t)c0 * d;
+        if (!q_direct) {
+            for (int i = 0; i < bc; ++i) {
+                float* dst = w->h_Q + (size_t)i * P.ld;
+                memcpy(dst, Q + (size_t)(c0 + i) * d, (size_t)d * 4);
+                for (int c = d; c < P.ld; ++c) dst[c] = 0.f;
+            }
+            src = w->h_Q;
         }
+        float* dst_scores = out_direct ? out_scores + (int64_t)c0 * k : w->h_scores;
+        int64_t* dst_ids = out_direct ? out_emb_ids + (int64_t)c0 * k : w->h_ids;
         CU(cudaSetDevice(w->dev));
-        CU(cudaMemcpyAsync(w->dQ, w->h_Q, (size_t)bc * P.ld * 4, cudaMemcpyHostToDevice, w->st));
+        CU(cudaMemcpyAsync(w->dQ, src, (size_t)bc * P.ld * 4, cudaMemcpyHostToDevice, w->st));
         for (int attempt = 0; attempt < 2; ++attempt) {
             if ((rc = batch_enqueue(w, g.get(), P, w->dQ, bc, false, w->st)) != SVSB_OK) return rc;
-            CU(cudaMemcpyAsync(w->h_scores, w->o_scores, (size_t)bc * k * 4, cudaMemcpyDeviceToHost, w->st));
-            CU(cudaMemcpyAsync(w->h_ids, w->o_ids, (size_t)bc * k * 8, cudaMemcpyDeviceToHost, w->st));
+            CU(cudaMemcpyAsync(dst_scores, w->o_scores, (size_t)bc * k * 4, cudaMemcpyDeviceToHost, w->st));
+            CU(cudaMemcpyAsync(dst_ids, w->o_ids, (size_t)bc * k * 8, cudaMemcpyDeviceToHost, w->st));
             CU(cudaMemcpyAsync(w->h_counts, w->o_counts, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
             CU(cudaMemcpyAsync(w->h_flags, w->flags, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
             CU(cudaStreamSynchronize(w->st));
@@ -1137,8 +1167,10 @@ static int query_batch_gen(svsb_engine* e, const std::shared_ptr<Generation>& g,
         for (int i = 0; i < bc; ++i) {
             const int64_t o = (int64_t)(c0 + i) * k;
             if (w->h_flags[i] == 0 && w->h_counts[i] == P.kk) {
-                memcpy(out_scores + o, w->h_scores + (size_t)i * k, (size_t)P.kk * 4);
-                memcpy(out_emb_ids + o, w->h_ids + (size_t)i * k, (size_t)P.kk * 8);
+                if (!out_direct) {
+                    memcpy(out_scores + o, w->h_scores + (size_t)i * k, (size_t)P.kk * 4);
+                    memcpy(out_emb_ids + o, w->h_ids + (size_t)i * k, (size_t)P.kk * 8);
+                }
                 out_counts[c0 + i] = P.kk;
             } else {                                   // overflowed / untrusted query: exact single-query kernels
                 rc = query_gen(e, g, Q + (size_t)(c0 + i) * d, d, k, out_scores + o, out_emb_ids + o, out_counts + c0 + i);

@@ -152,17 +152,27 @@ class Engine:
         """Pin the resident generation (the reference's `embeddings_matrix, emb_id_lookup` references)."""
         return Snapshot(self)
 
-    def query_batch(self, Q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    def query_batch(self, Q: np.ndarray, k: int, out=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """b queries at once: (scores (b, k), emb_ids (b, k), counts (b,)).  Bit-identical to b calls of query();
-        large batches run as one tensor-core contraction + exact refine (include/svsb200.h: svsb_query_batch)."""
+        large batches run as one tensor-core contraction + exact refine (include/svsb200.h: svsb_query_batch).
+        out: optional (scores, ids, counts) arrays to fill (C-contiguous, shapes as returned); with page-locked
+        arrays (pinned_empty) for Q and out the library copies straight from / into them."""
         Q = _f32c(Q)
         if Q.ndim != 2:
             raise ValueError("Q must be (b, d)")
         b, d = Q.shape
         cap = max(int(k), 0)
-        scores = np.zeros((b, cap), dtype=np.float32)
-        ids = np.full((b, cap), -1, dtype=np.int64)
-        counts = np.zeros(b, dtype=np.int32)
+        if out is None:
+            scores = np.zeros((b, cap), dtype=np.float32)
+            ids = np.full((b, cap), -1, dtype=np.int64)
+            counts = np.zeros(b, dtype=np.int32)
+        else:
+            scores, ids, counts = out
+            ok = (scores.shape == (b, cap) and ids.shape == (b, cap) and counts.shape == (b,) and scores.dtype == np.float32
+                  and ids.dtype == np.int64 and counts.dtype == np.int32
+                  and scores.flags.c_contiguous and ids.flags.c_contiguous and counts.flags.c_contiguous)
+            if not ok:
+                raise ValueError("out must be C-contiguous (float32 (b, k), int64 (b, k), int32 (b,)) arrays")
         check(self._lib.svsb_query_batch(self._h, Q.ctypes.data, b, d, int(k), scores.ctypes.data, ids.ctypes.data, counts.ctypes.data))
         return scores, ids, counts
 
@@ -244,6 +254,34 @@ class Engine:
         cnt = C.c_int32()
         check(self._lib.svsb_bench_last_result(self._h, k, s.ctypes.data, i.ctypes.data, C.byref(cnt)))
         return [(float(a), int(b)) for a, b in zip(s[:cnt.value], i[:cnt.value])]
+
+
+class _PinnedBlock:
+    """Owner of one svsb_host_alloc allocation; arrays made over it keep it alive through their .base chain."""
+
+    def __init__(self, nbytes: int):
+        self._lib = _lib.load()
+        self._p = C.c_void_p()
+        check(self._lib.svsb_host_alloc(nbytes, C.byref(self._p)))
+        self.buf = (C.c_uint8 * max(nbytes, 1)).from_address(self._p.value)
+
+    def __del__(self):
+        try:
+            if self._p.value:
+                self._lib.svsb_host_free(self._p)
+                self._p = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """A page-locked (cudaHostAlloc) NumPy array: query batches / result buffers the engine can DMA without staging."""
+    dtype = np.dtype(dtype)
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    n = int(np.prod(shape)) if shape else 1
+    block = _PinnedBlock(n * dtype.itemsize)
+    block.buf._owner = block          # the array's buffer exporter keeps the block alive (a cycle the GC frees later)
+    return np.frombuffer(block.buf, dtype=dtype, count=n).reshape(shape)
 
 
 class Snapshot:

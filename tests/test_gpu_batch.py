@@ -134,6 +134,28 @@ def test_batch_edge_cases(engine):
     _assert_same_as_single(engine, big, 5, s, i, c)
 
 
+def test_batch_with_page_locked_buffers_matches_the_staged_path(engine):
+    """Page-locked query / result arrays (svsb_host_alloc) are DMA'd directly; pageable ones are staged: same bits.
+    Covers two chunks (b > 2048) and a flagged query whose row is rewritten by the exact path in place."""
+    from svs_b200 import pinned_empty
+    rng = np.random.default_rng(17)
+    n, d, k, b = 30_000, 256, 20, 2100
+    m = _unit(rng, (n, d), "normal")
+    engine.load(m, np.arange(5, 5 + n, dtype=np.int64))
+    q = _unit(rng, (b, d), "normal")
+    q[7] *= 50.0                                                   # far from unit norm: exact path for this query
+    hq = pinned_empty((b, d), np.float32)
+    hq[:] = q
+    out = (pinned_empty((b, k), np.float32), pinned_empty((b, k), np.int64), np.zeros(b, dtype=np.int32))
+    s1, i1, c1 = engine.query_batch(hq, k, out=out)
+    assert s1 is out[0] and i1 is out[1]
+    s2, i2, c2 = engine.query_batch(q, k)
+    assert np.array_equal(s1.view(np.uint32), s2.view(np.uint32)) and np.array_equal(i1, i2) and np.array_equal(c1, c2)
+    _assert_same_as_single(engine, q, k, s1, i1, c1, check=[0, 7, 2047, 2048, 2099])
+    with pytest.raises(ValueError):
+        engine.query_batch(q, k, out=(out[0][:10], out[1], out[2]))
+
+
 def test_batch_after_reload_uses_the_new_generation(engine):
     rng = np.random.default_rng(13)
     d, k, b = 128, 10, 16
