@@ -198,6 +198,9 @@ int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_Q, int32_t 
 int svsb_xchg_create(svsb_t* e, int32_t world, int32_t rank, int32_t k_max, void* ipc_handle_out);
 int svsb_xchg_connect(svsb_t* e, const void* ipc_handles);
 int svsb_xchg_connect_local(svsb_t* e, svsb_t* const* engines);
+/* Orderly shutdown: every rank disconnects (waits for its own queries, unmaps the peers' windows), the launcher
+ * barriers, then the engines are destroyed -- no rank frees a window another rank still has mapped. */
+int svsb_xchg_disconnect(svsb_t* e);
 /* One query, device resident: similarity on `stream`, selection + push + waiting merge on `stream` (flags bit 1 clear)
  * or on the engine's side stream with one SM reserved for them (bit 1 set: overlaps the next query's similarity
  * pass; outputs are complete after svsb_enqueue_join).  Bit 0: time the similarity kernel (svsb_kernel_time_collect).

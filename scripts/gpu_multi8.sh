@@ -16,10 +16,11 @@ except Exception as ex:
     print(sys.argv[1], "no result", ex)
 PY
 }
-for ex in peer collective; do
+for ex in ${EXCHANGES:-peer collective}; do
   timeout 300 $TR --master-port 29612 bench.py --gpus $N --steps 20 --warmup 3 --exchange $ex > gpurun_out/bench_c2_n${N}_$ex.json 2> gpurun_out/bench_c2_n${N}_$ex.err; echo "c2 n$N $ex rc=$?"
   show gpurun_out/bench_c2_n${N}_$ex.json
 done
+[ "${LIGHT:-0}" = "1" ] && exit 0
 timeout 400 $TR --master-port 29613 bench.py --gpus $N --workload c4 --steps 10 --warmup 3 > gpurun_out/bench_c4_n${N}_peer.json 2> gpurun_out/bench_c4_n${N}_peer.err; echo "c4 rc=$?"
 show gpurun_out/bench_c4_n${N}_peer.json
 timeout 300 $TR --master-port 29614 bench.py --gpus $N --workload c3 --steps 10 --warmup 3 > gpurun_out/bench_c3_n${N}.json 2> gpurun_out/bench_c3_n${N}.err; echo "c3 rc=$?"

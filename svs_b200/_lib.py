@@ -68,6 +68,7 @@ SIGNATURES = {
     "svsb_xchg_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "svsb_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "svsb_xchg_connect_local": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "svsb_xchg_disconnect": (C.c_int, [C.c_void_p]),
     "svsb_enqueue_query_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "svsb_query_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_enqueue_local_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),

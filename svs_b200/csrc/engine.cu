@@ -228,6 +228,15 @@ struct Xchg {
     bool connected = false;
     unsigned long long seq = 0;
     unsigned long long timeout_ns = 30ull * 1000000000ull;   // merge kernel gives up waiting for a peer (SVSB_XCHG_TIMEOUT_MS)
+    // Pipelined path: the merge of query j is enqueued on the side stream BEHIND the selection of query j+1, so a
+    // peer has a whole query time to deliver its record before this rank's side stream would wait for it.
+    struct DeferredMerge {
+        bool pending = false;
+        int slot = 0, k = 0; unsigned long long seq = 0;
+        u64* sk = nullptr; int64_t* sp = nullptr;
+        float* out_scores = nullptr; int64_t* out_ids = nullptr; int32_t* out_count = nullptr;
+    } deferred;
+    cudaEvent_t ev_join = nullptr;
     // synchronous path (svsb_query_peer): own stream, device query, pinned staging; results land in pinned
     // host memory straight from the merge kernel (mapped, no copy back)
     cudaStream_t st = nullptr;
@@ -431,6 +440,7 @@ static void xchg_release(svsb_engine* e) {
     if (x->block) cudaFree(x->block);
     x->ws.release();
     if (x->st) cudaStreamDestroy(x->st);
+    if (x->ev_join) cudaEventDestroy(x->ev_join);
     if (x->h_q) cudaFreeHost(x->h_q);
     if (x->h_scores) cudaFreeHost(x->h_scores);
     if (x->h_ids) cudaFreeHost(x->h_ids);
@@ -1742,13 +1752,15 @@ extern "C" int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_
 
 // ---- peer exchange: the fused selection + exchange step and the waiting merge (kernels.cuh, select.cu) -------------
 static int xchg_prepare(svsb_engine* e, const Generation* g);
+static int xchg_flush_merge(svsb_engine* e, cudaStream_t st_sel);
 extern "C" int svsb_xchg_create(svsb_t* e, int32_t world, int32_t rank, int32_t k_max, void* handle_out) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     if (e->devs.size() != 1) return fail(SVSB_E_INVALID, "svsb_xchg_create: a sharded engine owns exactly one device");
     if (world < 1 || world > XCHG_MAX_RANKS || rank < 0 || rank >= world) return fail(SVSB_E_INVALID, "svsb_xchg_create: bad world / rank (<= 16 ranks)");
     if (k_max < 1 || k_max > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_xchg_create: 1 <= k_max <= 2048");
     xchg_release(e);
-    std::unique_ptr<Xchg> x(new Xchg());
+    e->xchg.reset(new Xchg());                 // owned by the engine from the start: a failure below leaves a window that
+    Xchg* x = e->xchg.get();                   // is not `connected`; the next create / svsb_destroy releases what exists
     x->world = world; x->rank = rank; x->cap = k_max; x->rec_words = 2 * (int64_t)k_max + 2;
     x->flags_bytes = ((size_t)x->slots * world * 8 + 255) & ~(size_t)255;
     const size_t bytes = x->flags_bytes + (size_t)x->slots * world * x->rec_words * 8;
@@ -1774,7 +1786,23 @@ extern "C" int svsb_xchg_create(svsb_t* e, int32_t world, int32_t rank, int32_t 
         memcpy(handle_out, &h, 64);
     }
     x->connected = world == 1;
-    e->xchg = std::move(x);
+    return SVSB_OK;
+}
+
+// Close the peers' windows (this rank stops pushing) but keep the own one alive: peers may still have it mapped.
+// Shutdown order across ranks: disconnect everywhere, barrier, then svsb_destroy.
+extern "C" int svsb_xchg_disconnect(svsb_t* e) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    Xchg* x = e->xchg.get();
+    if (!x) return SVSB_OK;
+    CU(cudaSetDevice(e->devs[0]));
+    if (x->deferred.pending && e->side_st) { int rc = xchg_flush_merge(e, e->side_st); if (rc != SVSB_OK) return rc; }
+    if (x->st) CU(cudaStreamSynchronize(x->st));
+    if (e->side_st) CU(cudaStreamSynchronize(e->side_st));
+    for (void* p : x->ipc_opened) cudaIpcCloseMemHandle(p);
+    x->ipc_opened.clear();
+    for (int r = 0; r < x->world; ++r) if (r != x->rank) x->peer_block[r] = nullptr;
+    x->connected = false;
     return SVSB_OK;
 }
 
@@ -1855,6 +1883,7 @@ static int xchg_prepare(svsb_engine* e, const Generation* g) {
         x->h_q_cap = g->ld;
     }
     while (e->kev.size() < e->kev_used + 2) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
+    if (!x->ev_join) CU(cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming));
     return SVSB_OK;
 }
 
@@ -1870,10 +1899,23 @@ static int xchg_next(Xchg* x, PeerPush& push) {
     return slot;
 }
 
+static int xchg_flush_merge(svsb_engine* e, cudaStream_t st_sel) {
+    Xchg* x = e->xchg.get();
+    Xchg::DeferredMerge& m = x->deferred;
+    if (!m.pending) return SVSB_OK;
+    m.pending = false;
+    CU(launch_merge_window(st_sel, x->rec_of(x->block, m.slot, 0), x->flags_of(x->block, m.slot), m.seq, x->world, x->cap, m.k,
+                           x->timeout_ns, m.sk, m.sp, m.out_scores, m.out_ids, m.out_count));
+    return SVSB_OK;
+}
+
 // similarity on st_main, then (on st_sel) selection with the fused push and the waiting merge into out_*.
+// defer_merge: the merge is enqueued by the NEXT call (or by svsb_enqueue_join), behind that call's selection.
+// Window slots stay safe with 4 of them: a rank pushes query j+4 after its merge(j+2), i.e. after every peer pushed
+// j+2, and each peer enqueues merge(j) before its selection j+2.
 static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStream_t st_main, cudaStream_t st_sel, cudaEvent_t ev_main_done,
                         const float* d_query, int32_t k, float* out_scores, int64_t* out_ids, int32_t* out_count,
-                        bool time_kernel, int reserve_sms) {
+                        bool time_kernel, int reserve_sms, bool defer_merge = false, cudaEvent_t ev_sel_done = nullptr) {
     Xchg* x = e->xchg.get();
     const Shard& s = g->shards[0];
     PeerPush push;
@@ -1889,8 +1931,17 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
         CU(launch_select(st_sel, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
                          w.out_keys, w.out_scores, w.out_ids, w.out_count, nullptr, &push));
     }
+    if (ev_sel_done) CU(cudaEventRecord(ev_sel_done, st_sel));   // the workspace's scores are free from here on
     u64* sk = nullptr; int64_t* sp = nullptr;
     if ((int64_t)x->world * k > K_FAST_MAX) { sk = w.mscr_keys; sp = w.mscr_ids; }
+    if (defer_merge) {
+        int rc = xchg_flush_merge(e, st_sel);                    // the previous query's merge goes behind this selection
+        if (rc != SVSB_OK) return rc;
+        Xchg::DeferredMerge& m = x->deferred;
+        m.pending = true; m.slot = slot; m.k = k; m.seq = push.seq; m.sk = sk; m.sp = sp;
+        m.out_scores = out_scores; m.out_ids = out_ids; m.out_count = out_count;
+        return SVSB_OK;
+    }
     CU(launch_merge_window(st_sel, x->rec_of(x->block, slot, 0), x->flags_of(x->block, slot), push.seq, x->world, x->cap, k,
                            x->timeout_ns, sk, sp, out_scores, out_ids, out_count));
     return SVSB_OK;
@@ -1916,10 +1967,12 @@ extern "C" int svsb_enqueue_query_peer(svsb_t* e, void* stream, const float* d_q
     if (pipelined) {
         if (e->sel_pending[slot]) CU(cudaStreamWaitEvent(st, w.ev_sel, 0));   // the slot's scores are free again
         sel_st = e->side_st;
-    }
-    rc = xchg_enqueue(e, g.get(), w, st, sel_st, w.ev, d_query, k, out_scores, out_ids, out_count, time_kernel, pipelined ? 1 : 0);
+    } else if (e->xchg->deferred.pending && (rc = xchg_flush_merge(e, e->side_st)) != SVSB_OK) return rc;
+    // pipelined: ev_sel marks "selection done" (scores reusable by the similarity pass two queries on); the merge is deferred
+    rc = xchg_enqueue(e, g.get(), w, st, sel_st, w.ev, d_query, k, out_scores, out_ids, out_count, time_kernel, pipelined ? 1 : 0,
+                      /*defer_merge=*/pipelined, pipelined ? w.ev_sel : nullptr);
     if (rc != SVSB_OK) return rc;
-    if (pipelined) { CU(cudaEventRecord(w.ev_sel, e->side_st)); e->sel_pending[slot] = 1; }
+    if (pipelined) e->sel_pending[slot] = 1;
     return SVSB_OK;
 }
 
@@ -1937,6 +1990,7 @@ extern "C" int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
     if (!q || !out_scores || !out_emb_ids) return fail(SVSB_E_INVALID, "svsb_query_peer: NULL buffer");
     int rc = xchg_prepare(e, g.get());
     if (rc != SVSB_OK) return rc;
+    if (x->deferred.pending && (rc = xchg_flush_merge(e, e->side_st)) != SVSB_OK) return rc;   // keep merges in sequence order
     memcpy(x->h_q, q, (size_t)d * 4);
     for (int i = d; i < g->ld; ++i) x->h_q[i] = 0.f;
     CU(launch_stage_query(x->st, x->h_q, x->ws.d_q, g->ld));     // a kernel reads the pinned query: no copy-engine hop
@@ -1957,6 +2011,14 @@ extern "C" int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
 extern "C" int svsb_enqueue_join(svsb_t* e, void* stream) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     CU(cudaSetDevice(e->devs[0]));
+    if (e->xchg && e->xchg->deferred.pending && e->side_st) {       // the last peer query's merge, then everything on the side stream
+        int rc = xchg_flush_merge(e, e->side_st);
+        if (rc != SVSB_OK) return rc;
+    }
+    if (e->xchg && e->xchg->ev_join && e->side_st) {
+        CU(cudaEventRecord(e->xchg->ev_join, e->side_st));
+        CU(cudaStreamWaitEvent((cudaStream_t)stream, e->xchg->ev_join, 0));
+    }
     for (size_t i = 0; i < e->sel_pending.size(); ++i)
         if (e->sel_pending[i] && e->shard_ws[i] && e->shard_ws[i]->ev_sel)
             CU(cudaStreamWaitEvent((cudaStream_t)stream, e->shard_ws[i]->ev_sel, 0));

@@ -128,6 +128,9 @@ class CudaShardBackend:
         arr = (C.c_void_p * len(backends))(*[b.engine._h for b in backends])
         self._check(self._lib.svsb_xchg_connect_local(self.engine._h, arr))
 
+    def exchange_disconnect(self) -> None:
+        self._check(self._lib.svsb_xchg_disconnect(self.engine._h))
+
     def enqueue_query_peer(self, query_row, k: int, out_scores, out_ids, out_count, time_kernel: bool = False,
                            pipelined: bool = True) -> None:
         """Similarity + selection with the fused push + waiting merge for one device-resident query; the GLOBAL top-k
@@ -257,6 +260,18 @@ class ShardedRetriever:
         assert self._queries is not None, "set_queries first"
         nq = self._queries.shape[0]
         done = timed = 0
+        if self.exchange == "peer":
+            # no collective and nothing consumed on the host: enqueue every query back to back (outputs cycle through the
+            # micro-batch buffers in stream order) and join once -- ranks couple only through the window flags
+            self._ensure_peer()
+            _rec, _gath, (o_s, o_i, o_c) = self._buffers(k)
+            for done in range(count):
+                j = done % MICRO_BATCH
+                t = time_gemv and done % TIME_EVERY == 0
+                timed += 1 if t else 0
+                self.backend.enqueue_query_peer(self._queries[done % nq], k, o_s[j], o_i[j], o_c[j], t, pipelined=True)
+            self.backend.join()
+            return self.backend.collect_kernel_ms() * count / timed if time_gemv else 0.0
         while done < count:
             nb = min(MICRO_BATCH, count - done)
             self._micro_batch([self._queries[(done + j) % nq] for j in range(nb)], k, time_gemv)
@@ -327,4 +342,11 @@ class ShardedRetriever:
         return [(float(a), int(b)) for a, b in zip(s, i)]
 
     def close(self) -> None:
+        """Collective when the peer exchange is up: unmap the peers' windows everywhere before any rank frees its own."""
+        if self._peer_ready:
+            if hasattr(self.backend, "exchange_disconnect"):
+                self.backend.exchange_disconnect()
+            if self.world > 1:
+                self.dist.barrier(group=self.group)
+            self._peer_ready = False
         self.backend.close()
