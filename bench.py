@@ -26,6 +26,12 @@ import sys
 import threading
 import time
 
+# The reference arm must run on all the host threads OpenBLAS can use, but torchrun exports OMP_NUM_THREADS=1 to
+# every rank: undo that BEFORE NumPy loads its BLAS (rank 0 alone runs the arm).
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"]:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -129,6 +135,18 @@ def _reference_get_top_k():
     return get_top_k, "port"
 
 
+def blas_threads() -> int:
+    """Threads the BLAS behind np.dot actually uses (what `cores` must report)."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(p.get("num_threads", 0)) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if n and max(n) > 0:
+            return max(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
 def cpu_matrix(n: int, d: int, seed: int = 0) -> np.ndarray:
     """The notebook's recipe (uniform [0,1) rows / L2 norm) in chunks, float32."""
     rng = np.random.default_rng(seed)
@@ -186,7 +204,7 @@ def run_reference_arm(args, n, d, k, desc):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "rows": n, "dims": d, "k": k},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": blas_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -273,7 +291,7 @@ def run_batch_arm(args, n, d, k, desc):
             one_query(queries[cnt % len(queries)]); cnt += 1
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {
-            "value": cnt / dt * (rows / n), "unit": "queries/s", "cores": os.cpu_count(), "kind": kind,
+            "value": cnt / dt * (rows / n), "unit": "queries/s", "cores": blas_threads(), "kind": kind,
             "sample": f"{cnt} of the {BATCH} queries, each np.dot + get_top_k on {rows} x {d} host rows (the reference has no batched API)"}
     eng.close()
     print(json.dumps(line), flush=True)
@@ -442,7 +460,7 @@ def main():
             dt = time.perf_counter() - t0
             scale = rows / n
             line["cpu_baseline"] = {
-                "value": cnt / dt * scale, "unit": "queries/s", "cores": os.cpu_count(), "kind": kind,
+                "value": cnt / dt * scale, "unit": "queries/s", "cores": blas_threads(), "kind": kind,
                 "sample": f"{cnt} queries of np.dot + get_top_k on {rows} x {d} host rows"
                           + ("" if rows == n else f", scaled x{scale:.3f}")}
         eng.close()
