@@ -31,6 +31,9 @@ using namespace svsb;
 // errors, launch counter
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static thread_local bool g_pdl = false;
+namespace svsb { void set_pdl(bool on) { g_pdl = on; } bool pdl_enabled() { return g_pdl; } }
+static int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
 static std::atomic<int64_t> g_launches{0};
 namespace svsb { void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); } }
 
@@ -105,6 +108,9 @@ struct svsb_workspace {
             CU(cudaMalloc(&scores, (size_t)n * 4));
             CU(cudaMalloc(&gmax, (size_t)G * 8));
             CU(cudaMemset(gmax, 0, (size_t)G * 8));
+            // cudaMemset runs on the legacy default stream, asynchronously to the host, and the engine's streams are
+            // non-blocking: without this wait a similarity kernel could write group maxima BEFORE the zeroing lands
+            CU(cudaStreamSynchronize(cudaStreamLegacy));
             CU(cudaMalloc(&cand, (size_t)cc * 8));
             n_cap = n; g_cap = G; cand_cap = cc;
         }
@@ -533,7 +539,11 @@ extern "C" int svsb_load_begin(svsb_t* e, int64_t n, int32_t d, int32_t norm_mod
         L->slab_rows = e->slab_bytes_rows / ((int64_t)d * 4);
         if (L->slab_rows > e->slab_ids_cap) L->slab_rows = e->slab_ids_cap;
         if (L->gen->ld != d)                       // zero the padding columns once
-            for (auto& s : L->gen->shards) if (s.n) { CU(cudaSetDevice(s.dev)); CU(cudaMemset(s.M, 0, (size_t)s.n * L->gen->ld * 4)); }
+            for (auto& s : L->gen->shards) if (s.n) {
+                CU(cudaSetDevice(s.dev));
+                CU(cudaMemset(s.M, 0, (size_t)s.n * L->gen->ld * 4));
+                CU(cudaStreamSynchronize(cudaStreamLegacy));     // before the row copies on the (non-blocking) copy streams
+            }
     }
     e->loading = std::move(L);
     return SVSB_OK;
@@ -865,7 +875,10 @@ static int query_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, const
             const int shift = group_shift_for(s.n);
             *c->h_count = -1;
             CU(launch_stage_query(w.st, c->h_q, w.d_q, g->ld));
-            CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift));
+            {   // programmatic dependent launch: the similarity kernel streams its first tiles under the staging kernel
+                PdlScope pdl(env_int("SVSB_PDL", 1) != 0);
+                CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift));
+            }
             CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
                              w.out_keys, c->h_scores, c->h_ids, c->h_count));
             continue;
@@ -935,7 +948,6 @@ extern "C" int svsb_snapshot_query(svsb_t* e, svsb_snap_t* s, const float* q, in
 // ------------------------------------------------------------------------------------------------
 // batched queries: coarse tensor-core contraction + exact refine (coarse.cu, batch.cu)
 // ------------------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
 
 struct BatchPlan {
     int64_t n = 0; int d = 0, ld = 0, ld16 = 0, kk = 0, k = 0;
@@ -1915,7 +1927,8 @@ static int xchg_flush_merge(svsb_engine* e, cudaStream_t st_sel) {
 // j+2, and each peer enqueues merge(j) before its selection j+2.
 static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStream_t st_main, cudaStream_t st_sel, cudaEvent_t ev_main_done,
                         const float* d_query, int32_t k, float* out_scores, int64_t* out_ids, int32_t* out_count,
-                        bool time_kernel, int reserve_sms, bool defer_merge = false, cudaEvent_t ev_sel_done = nullptr) {
+                        bool time_kernel, int reserve_sms, bool defer_merge = false, cudaEvent_t ev_sel_done = nullptr,
+                        bool pdl_gemv = false) {
     Xchg* x = e->xchg.get();
     const Shard& s = g->shards[0];
     PeerPush push;
@@ -1925,7 +1938,10 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
     } else {
         const int shift = group_shift_for(s.n);
         if (time_kernel) CU(cudaEventRecord(e->kev[e->kev_used], st_main));
-        CU(launch_gemv(st_main, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, reserve_sms));
+        {
+            PdlScope pdl(pdl_gemv);                               // only after the staging kernel of the synchronous path
+            CU(launch_gemv(st_main, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, reserve_sms));
+        }
         if (time_kernel) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st_main)); e->kev_used += 2; }
         if (st_sel != st_main) { CU(cudaEventRecord(ev_main_done, st_main)); CU(cudaStreamWaitEvent(st_sel, ev_main_done, 0)); }
         CU(launch_select(st_sel, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
@@ -1996,7 +2012,8 @@ extern "C" int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
     CU(launch_stage_query(x->st, x->h_q, x->ws.d_q, g->ld));     // a kernel reads the pinned query: no copy-engine hop
     *x->h_count = -1;
     // the merge kernel writes the result into pinned (mapped) host memory: no copy back, one synchronize
-    if ((rc = xchg_enqueue(e, g.get(), x->ws, x->st, x->st, nullptr, x->ws.d_q, k, x->h_scores, x->h_ids, x->h_count, false, 0)) != SVSB_OK) return rc;
+    if ((rc = xchg_enqueue(e, g.get(), x->ws, x->st, x->st, nullptr, x->ws.d_q, k, x->h_scores, x->h_ids, x->h_count, false, 0,
+                           false, nullptr, /*pdl_gemv=*/env_int("SVSB_PDL", 1) != 0)) != SVSB_OK) return rc;
     CU(cudaStreamSynchronize(x->st));
     const int32_t cnt = *x->h_count;
     if (cnt == MERGE_WINDOW_TIMED_OUT)

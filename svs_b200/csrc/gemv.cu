@@ -27,7 +27,9 @@ gemv_ldg_kernel(const float4* __restrict__ M, int64_t n, int d4, const float4* _
                 float* __restrict__ scores, u64* __restrict__ gmax, int group_shift)
 {
     extern __shared__ float4 sq[];
-    for (int c = threadIdx.x; c < d4; c += THREADS) sq[c] = q[c];
+    pdl_wait();                                   // the query (and the scores buffer) belong to the previous kernels
+    pdl_trigger();
+    for (int c = threadIdx.x; c < d4; c += THREADS) sq[c] = __ldcg(q + c);   // L2 only: see gemv_tma_kernel
     __syncthreads();
 
     constexpr int WARPS = THREADS / 32;
@@ -131,9 +133,14 @@ gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, i
     uint64_t* empty = full + stages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (NQ == 0)
-        for (int c = threadIdx.x; c < d4; c += blockDim.x) sq[c] = reinterpret_cast<const float4*>(q)[c];
+    // Programmatic dependent launch (one-query-in-flight chains): the matrix does not depend on the previous kernel, so
+    // the producer starts streaming tiles at once; whoever reads the query or writes scores / group maxima waits first.
+    if (NQ == 0) {
+        pdl_wait();
+        for (int c = threadIdx.x; c < d4; c += blockDim.x) sq[c] = __ldcg(reinterpret_cast<const float4*>(q) + c);
+    }
     if (threadIdx.x == 0) {
+        pdl_trigger();
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -161,10 +168,14 @@ gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, i
         // ---- consumers: warp w takes rows w, w+CW, ... of each tile
         float4 qr[NQ > 0 ? NQ : 1];
         if (NQ > 0) {
+            pdl_wait();
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
                 const int c = lane + 32 * j;
-                qr[j] = c < d4 ? reinterpret_cast<const float4*>(q)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                // ld.global.cg, not the read-only (.nc) path: under programmatic dependent launch this grid is resident
+                // while the previous kernel WRITES q, which the read-only path is not allowed to observe (measured:
+                // 1 query in ~1000 came out with a mixture of old and new q, scripts/pdl_stress.py)
+                qr[j] = c < d4 ? __ldcg(reinterpret_cast<const float4*>(q) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         int s = 0; uint32_t phase = 0;
@@ -246,10 +257,10 @@ static cudaError_t run_ldg(cudaStream_t st, int device, const float* M, int64_t 
     const int64_t need = (ngroups + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, THREADS, smem, st>>>(reinterpret_cast<const float4*>(M), n, d4,
-                                                reinterpret_cast<const float4*>(q), scores, gmax, group_shift);
+    e = launch_kernel(kern, dim3((unsigned)grid), dim3(THREADS), smem, st, reinterpret_cast<const float4*>(M), n, d4,
+                      reinterpret_cast<const float4*>(q), scores, gmax, group_shift);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <int CW, int NQ>
@@ -259,9 +270,9 @@ static cudaError_t run_tma_inst(cudaStream_t st, int64_t grid, size_t smem, cons
     auto kern = gemv_tma_kernel<CW, NQ>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)grid, (CW + 1) * 32, smem, st>>>(M, n, d4, tile_rows, stages, q, scores, gmax, group_shift);
+    e = launch_kernel(kern, dim3((unsigned)grid), dim3((CW + 1) * 32), smem, st, M, n, d4, tile_rows, stages, q, scores, gmax, group_shift);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // tile_rows / stages: 0 = default.  cw: consumer warps (8 or 16; 0 = default).

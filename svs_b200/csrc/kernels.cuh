@@ -7,6 +7,33 @@ namespace svsb {
 // Launch counter (svsb_launch_count): every kernel launch of the library goes through count_launch().
 void count_launch(int n = 1);
 
+// Programmatic dependent launch for the one-query-in-flight chains (stage query -> similarity -> selection -> merge):
+// while set (per host thread), the launchers below mark their kernel "programmatic stream serialization allowed", so
+// it may start while the previous kernel of the stream is still running; the kernels call pdl_wait() before they
+// touch anything the previous kernel produces and pdl_trigger() as early as their successor may be scheduled.
+// Without the attribute both are no-ops, so every other path is unchanged.
+void set_pdl(bool on);
+bool pdl_enabled();
+struct PdlScope { bool prev; explicit PdlScope(bool on) : prev(pdl_enabled()) { set_pdl(on); } ~PdlScope() { set_pdl(prev); } };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- K1: similarity (fp32 GEMV) -------------------------------------------------------------
 // scores[r] = dot(M[r, :], q) for r < n, and gmax[r >> group_shift] = max(key(score, r)) via atomics.
 // M is row-major with leading dimension ld floats (ld % 4 == 0, rows 16-byte aligned, padding zero);

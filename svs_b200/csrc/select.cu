@@ -152,6 +152,7 @@ __device__ __forceinline__ void peer_publish(const PeerPush& push, int count) {
 // writes it to HBM, so the synchronous peer path is kernels only (no copy-engine -> compute hand-off before the
 // similarity pass).  ld.cv: never serve host memory the CPU rewrites per query from a stale cache line.
 __global__ void __launch_bounds__(256) stage_query_kernel(const float4* __restrict__ host_q, float4* __restrict__ d_q, int ld4) {
+    pdl_trigger();                                 // the similarity kernel may start streaming the matrix right away
     for (int c = threadIdx.x; c < ld4; c += blockDim.x) {
         float4 v;
         asm volatile("ld.global.cv.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(host_q + c));
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(256) stage_query_kernel(const float4* __restri
 cudaError_t launch_stage_query(cudaStream_t st, const float* host_q_mapped, float* d_q, int ld)
 {
     if (ld <= 0 || (ld & 3)) return cudaErrorInvalidValue;
+    // never itself a programmatic dependent: it overwrites the query buffer the previous call's kernels read
     stage_query_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float4*>(host_q_mapped), reinterpret_cast<float4*>(d_q), ld / 4);
     count_launch();
     return cudaGetLastError();
@@ -198,6 +200,8 @@ select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int g
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelectKeysSmem& big = *reinterpret_cast<SelectKeysSmem*>(sel_smem_raw);
 #define SEL_STAMP(i) do { if (dbg && threadIdx.x == 0) { u64 t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[i] = t_; } } while (0)
+    pdl_wait();                                    // scores and group maxima come from the similarity kernel
+    pdl_trigger();
     SEL_STAMP(0);
     SelectSmem& sm = big.base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -347,10 +351,10 @@ cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* 
         attr_set[dev] = true;
     }
     if (((n + ((int64_t)1 << group_shift) - 1) >> group_shift) > SEL_KEYS_CAP) return cudaErrorInvalidValue;
-    select_topk_kernel<<<1, SEL_THREADS, sizeof(SelectKeysSmem), st>>>(scores, n, gmax, group_shift, k, ids, row0,
-                                                                  cand, cand_cap, out_keys, out_scores, out_ids, out_count, dbg, pp);
+    cudaError_t le = launch_kernel(select_topk_kernel, dim3(1), dim3(SEL_THREADS), sizeof(SelectKeysSmem), st, scores, n, gmax, group_shift, k,
+                                   ids, row0, cand, cand_cap, out_keys, out_scores, out_ids, out_count, dbg, pp);
     count_launch();
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -639,6 +643,7 @@ merge_window_kernel(const u64* slot_base, const u64* flags, u64 seq, int world, 
     SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
     const int tid = threadIdx.x;
     const int64_t rec_words = 2 * (int64_t)cap + 2;
+    pdl_wait();                                    // scratch / outputs may still be in use by the previous kernel
     if (tid == 0) sm.counter = 0;
     __syncthreads();
     if (tid < world) {
@@ -710,11 +715,11 @@ cudaError_t launch_merge_window(cudaStream_t st, const u64* slot_base, const u64
     }
     const bool big = (int64_t)world * k > SORT_CAP;
     if (big && (!scratch_keys || !scratch_ids)) return cudaErrorInvalidValue;
-    merge_window_kernel<<<1, SEL_THREADS, sizeof(SelectSmem), st>>>(slot_base, flags, seq, world, cap, k, timeout_ns,
-                                                                   big ? scratch_keys : nullptr, big ? scratch_ids : nullptr,
-                                                                   out_scores, out_ids, out_count);
+    cudaError_t le = launch_kernel(merge_window_kernel, dim3(1), dim3(SEL_THREADS), sizeof(SelectSmem), st, slot_base, flags, (u64)seq, world, cap, k,
+                                   (u64)timeout_ns, big ? scratch_keys : (u64*)nullptr, big ? scratch_ids : (int64_t*)nullptr,
+                                   out_scores, out_ids, out_count);
     count_launch();
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t preload_peer_kernels()

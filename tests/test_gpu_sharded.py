@@ -102,10 +102,10 @@ def test_two_shard_engines_batched_records_equal_the_single_query_records():
             b.close()
 
 
-def _two_backends(m, ids, world=2):
+def _two_backends(m, ids, world=2, timeout_ms=5000):
     import os
     from svs_b200.sharded import CudaShardBackend, partition
-    os.environ["SVSB_XCHG_TIMEOUT_MS"] = "5000"                 # a protocol bug must fail the test, not hang the GPU
+    os.environ["SVSB_XCHG_TIMEOUT_MS"] = str(timeout_ms)        # a protocol bug must fail the test, not hang the GPU
     backs = []
     for r in range(world):
         b = CudaShardBackend(0)
@@ -199,6 +199,25 @@ def test_peer_exchange_synchronous_query_from_two_threads_and_an_empty_shard():
         finally:
             for b in backs:
                 b.close()
+
+
+def test_peer_exchange_missing_peer_times_out_instead_of_hanging():
+    """A rank whose peer never issues the query must get an error after SVSB_XCHG_TIMEOUT_MS, not a hung GPU."""
+    pytest.importorskip("torch")
+    import time
+    import svs_b200
+    n, d = 4_000, 64
+    m = oracle.synth_matrix_uniform(n, d, 35)
+    ids = np.arange(n, dtype=np.int64)
+    backs = _two_backends(m, ids, timeout_ms=300)
+    try:
+        t0 = time.time()
+        with pytest.raises(svs_b200.EngineError, match="did not arrive"):
+            backs[0].query_peer(oracle.synth_queries(1, d, 36)[0], 10)      # rank 1 never calls
+        assert 0.25 < time.time() - t0 < 5.0
+    finally:
+        for b in backs:
+            b.close()
 
 
 @pytest.mark.parametrize("exchange", ["peer", "collective"])
