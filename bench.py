@@ -501,12 +501,12 @@ def main():
     nq = args.steps * QUERIES_PER_STEP
     # e2e: host query in, host result out, every call
     for i in range(4):
-        sr.retrieve(queries[i], k)
+        sr.retrieve_arrays(queries[i], k)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        for j in range(QUERIES_PER_STEP):
-            sr.retrieve(queries[(s * QUERIES_PER_STEP + j) % len(queries)], k)
+        for j in range(QUERIES_PER_STEP):                       # host query in, host (scores, ids) arrays out, as Engine.query at N=1
+            sr.retrieve_arrays(queries[(s * QUERIES_PER_STEP + j) % len(queries)], k)
     torch.cuda.synchronize(); dist.barrier()
     e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)

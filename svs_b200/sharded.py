@@ -320,25 +320,28 @@ class ShardedRetriever:
         s, i, cnt = self.retrieve_many_arrays(query_vecs, n)
         return [[(float(a), int(x)) for a, x in zip(s[j, :cnt[j]], i[j, :cnt[j]])] for j in range(s.shape[0])]
 
-    def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
-        """The reference's superheavy() result, on every rank: host query in, host list out."""
+    def retrieve_arrays(self, query_vec: np.ndarray, n: int) -> Tuple[np.ndarray, np.ndarray]:
+        """superheavy() on every rank as host arrays: (scores float32[c], embeddings.id int64[c]), c = min(n, N)
+        (the sharded counterpart of Engine.query: host query in, host buffers out, one synchronous call)."""
         q = np.ascontiguousarray(query_vec, dtype=np.float32)
         if q.ndim != 1 or q.shape[0] != self.d or self.n == 0:
             raise ValueError(f"shapes ({self.n},{self.d if self.n else 0}) and ({q.shape[0]},) not aligned")
         if n <= 0:
-            return []
+            return np.zeros(0, np.float32), np.zeros(0, np.int64)
         k = min(int(n), 2048)
         if n > 2048 and self.n > 2048:
             raise NotImplementedError("n > 2048 is not supported by the sharded path")
         if self.exchange == "peer":
             self._ensure_peer()
-            s, i = self.backend.query_peer(q, k)                   # one synchronous C call, result written to host
-            return [(float(a), int(b)) for a, b in zip(s, i)]
+            return self.backend.query_peer(q, k)                   # one synchronous C call, result written to host
         dq = self.backend.device_queries(q[None, :])
         o_s, o_i, o_c = self._micro_batch([dq[0]], k, False)
         cnt = int(o_c[0].item())                                   # synchronises the stream
-        s = o_s[0, :cnt].cpu().numpy()
-        i = o_i[0, :cnt].cpu().numpy()
+        return o_s[0, :cnt].cpu().numpy(), o_i[0, :cnt].cpu().numpy()
+
+    def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
+        """The reference's superheavy() result, on every rank: host query in, host list out."""
+        s, i = self.retrieve_arrays(query_vec, n)
         return [(float(a), int(b)) for a, b in zip(s, i)]
 
     def close(self) -> None:
