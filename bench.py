@@ -472,6 +472,8 @@ def main():
     import torch.distributed as dist
     from svs_b200.sharded import ShardedRetriever
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"                       # keep NCCL's version banner off stdout: one JSON line only
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sr = ShardedRetriever(rank, world, local_rank, exchange=args.exchange)
     sr.load_synthetic(n, d, seed=0, id0=1, id_step=1)

@@ -11,6 +11,9 @@ timeout 600 python bench.py --workload c3 > gpurun_out/bench_c3.json 2> gpurun_o
 for w in c1 c5 c4; do
   timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; echo "$w rc=$?"
 done
+timeout 300 python scripts/c1_dropin_bench.py > gpurun_out/c1_dropin.json 2> gpurun_out/c1_dropin.err; echo "c1 dropin rc=$?"
+timeout 120 python scripts/latency_ab.py > gpurun_out/latency_ab.txt 2>&1; tail -2 gpurun_out/latency_ab.txt
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 timeout 120 python scripts/select_phases.py > gpurun_out/select_phases.log 2>&1; tail -2 gpurun_out/select_phases.log
 timeout 200 python scripts/shard_probe.py > gpurun_out/shard_probe.txt 2>&1; tail -3 gpurun_out/shard_probe.txt
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
