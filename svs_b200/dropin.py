@@ -89,11 +89,14 @@ class _Coalescer:
 
 
 def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, normalize: bool = False,
-            pairwise: Optional[bool] = None, coalesce: bool = True) -> None:
+            pairwise: Optional[bool] = None, coalesce: bool = True, prewarm: bool = False) -> None:
     """Patch `svs` in place.  Idempotent.  `devices`: CUDA devices to row-shard the matrix over.
     `pairwise`: also route document_top_pairwise_scores to the engine (default: yes on a single device; the
     multi-device engine keeps the reference's host NumPy path for it).
-    `coalesce`: batch concurrent AsyncKB.retrieve calls into one engine call (see _Coalescer)."""
+    `coalesce`: batch concurrent AsyncKB.retrieve calls into one engine call (see _Coalescer).
+    `prewarm`: create the engine (= the CUDA context, ~2 s once per process on a B200 box,
+    profiles/r01_first_query_probe.txt) on a background thread as soon as a KB object exists, instead of inside the
+    first retrieve."""
     if pairwise is None:
         pairwise = devices is None or len(devices) <= 1
     if svs_module is None:
@@ -111,6 +114,8 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
             super().__init__()
             self.device = DeviceEmbeddingsMatrix(devices, normalize)
             self.coalescer = _Coalescer() if coalesce else None
+            if prewarm:
+                self.device.prewarm()
 
         def invalidate(self) -> None:
             super().invalidate()

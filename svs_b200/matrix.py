@@ -126,6 +126,18 @@ class DeviceEmbeddingsMatrix:
             self._engine = Engine(self._devices)
         return self._engine
 
+    def prewarm(self) -> threading.Thread:
+        """Create the engine (CUDA context, streams) on a daemon thread; a load that arrives first simply waits for it."""
+        def work() -> None:
+            try:
+                with self._mu:
+                    self._get_engine()
+            except Exception as ex:                      # reported again, loudly, by the first load
+                _LOG.warning("engine pre-warm failed: %s", ex)
+        t = threading.Thread(target=work, name="svs_b200-prewarm", daemon=True)
+        t.start()
+        return t
+
     def invalidate(self) -> None:
         """kb.py:861-864.  In-flight queries keep the generation they started on."""
         _LOG.info("invalidating cached device vectors; they'll be re-built next time you `retrieve()`")

@@ -184,6 +184,16 @@ def test_device_embeddings_matrix_cache_protocol(tmp_path, fake_engine):
     assert ("close",) in fake_engine[0].calls
 
 
+def test_prewarm_creates_the_engine_in_the_background_and_loads_wait_for_it(tmp_path, fake_engine):
+    db = _FakeDB(_kb_copy(tmp_path))
+    cache = svs_b200.DeviceEmbeddingsMatrix()
+    t = cache.prewarm()
+    m = cache.get_sync(db)                                        # may race with the pre-warm thread: one engine either way
+    t.join(timeout=10)
+    assert not t.is_alive() and len(fake_engine) == 1 and m.shape == (415, 64)
+    cache.close()
+
+
 def _fake_svs_module():
     """A stand-in with the seam of svs.kb (reference src/svs/kb.py:856-893, 925+, 1407+)."""
     kb = types.ModuleType("fakesvs.kb")
