@@ -149,9 +149,9 @@ int svsb_topk_scores(svsb_t* e, const float* scores, int64_t n, int32_t k,
 int svsb_bench_set_queries(svsb_t* e, const float* Q, int32_t nq, int32_t d);
 /* Run `iters` single-query retrieves back to back, cycling through the uploaded queries, everything
  * device-resident, timed with CUDA events on the launching stream(s).  Returns total milliseconds
- * (max over devices), the number of kernel launches issued and, when gemv_ms != NULL, the summed
- * duration of the similarity-kernel launches on device 0, each bracketed by its own pair of events
- * inside the same timed loop (the roofline numerator's denominator). */
+ * (max over devices), the number of kernel launches issued and, when gemv_ms != NULL, the duration of the
+ * similarity-kernel launches on device 0: one launch in 8 is bracketed by its own pair of events inside the same
+ * timed loop and *gemv_ms = (mean bracketed launch) x iters (the roofline numerator's denominator). */
 int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_ms, float* gemv_ms, int64_t* launches);
 /* Same through the batched path: per iteration ONE batch of all uploaded queries (<= 2048), device-resident.
  * coarse_ms (optional): summed duration of the tensor-core filter pass, bracketed by its own events. */
@@ -166,8 +166,11 @@ int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, int64_t* out
 
 /* ---- sharded deployment: one process per GPU -----------------------------
  * Each process owns ONE device and the rows [global_row0, global_row0 + n) of the matrix, in scan order.
- * The library does the compute on the caller's stream; the caller (torch.distributed / NCCL) does the one
- * exchange step: an all-gather of one packed record per query per rank.
+ * Two ways to do the one exchange step.  (1) Collective: the library does the compute on the caller's stream and
+ * the caller (torch.distributed / NCCL) all-gathers one packed record per query per rank, then
+ * svsb_enqueue_merge_records.  (2) Fused ("peer exchange", below): the kernels themselves move the records over
+ * NVLink peer memory; the caller only exchanges 64-byte IPC handles once.  None of the svsb_enqueue_* / svsb_xchg_* /
+ * svsb_*_peer entry points is re-entrant: one host thread drives a shard engine.
  * Record layout: 2*k+1 int64 words = [ keys (k, uint64: ordered score << 32 | ~global_row) |
  *                                      embeddings.id (k) | count (int32 in the low half of the last word) ]. */
 int svsb_set_shard(svsb_t* e, int64_t global_row0);           /* call before svsb_load_*          */
@@ -208,11 +211,14 @@ int svsb_xchg_disconnect(svsb_t* e);
 int svsb_enqueue_query_peer(svsb_t* e, void* stream, const float* d_query, int32_t k,
                             float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_count, int32_t flags);
 /* One query, host buffers in and out, synchronous (the sharded counterpart of svsb_query; replaces a6 + a7 of
- * SURVEY.md section 8 on a row-sharded matrix): H2D of the query, similarity, selection + push, waiting merge that
- * writes the result straight into pinned host memory, one stream synchronize. */
+ * SURVEY.md section 8 on a row-sharded matrix): a staging kernel reads the query from pinned host memory, similarity,
+ * selection + push, waiting merge that writes the result straight into pinned host memory, one stream synchronize.
+ * SVSB_E_STATE if a peer's record does not arrive within SVSB_XCHG_TIMEOUT_MS (default 30 000): the sequence is then
+ * broken and the exchange must be re-created on every rank. */
 int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
                     float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
-/* Make `stream` wait for every selection kernel the pipelined svsb_enqueue_local_topk calls have issued. */
+/* Make `stream` wait for everything the pipelined svsb_enqueue_local_topk / svsb_enqueue_query_peer calls have issued
+ * on the side stream (it also enqueues the last peer query's deferred merge). */
 int svsb_enqueue_join(svsb_t* e, void* stream);
 /* d_records: all-gathered records, [n_lists][batch][2k+1].  Outputs [batch][k], [batch][k], [batch]. */
 int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
