@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 
 typedef unsigned long long u64;
 
@@ -56,6 +57,13 @@ constexpr int GROUP_SHIFT_MIN = 6;     // 64 rows per group at least
 // rows per group = 1 << shift, chosen so that ceil(n / rows) <= GROUPS_TARGET
 __host__ __device__ inline int group_shift_for(int64_t n) {
     int s = GROUP_SHIFT_MIN;
+#ifndef __CUDA_ARCH__
+    // measurement knob: SVSB_GROUP_SHIFT_MIN = 4..12 (rows per group = 1 << shift); fewer, larger groups make the
+    // selection kernel's key staging / threshold phases cheaper and its candidate rescan dearer
+    static const int env_min = [] { const char* v = getenv("SVSB_GROUP_SHIFT_MIN"); const int x = v ? atoi(v) : 0;
+                                    return (x >= 4 && x <= 12) ? x : GROUP_SHIFT_MIN; }();
+    s = env_min;
+#endif
     while (((n + ((int64_t)1 << s) - 1) >> s) > GROUPS_TARGET) ++s;
     return s;
 }
