@@ -519,6 +519,41 @@ struct MergeLayout {
     int64_t list_stride, batch_stride, count_list_stride, count_batch_stride;
 };
 
+// Rank merge of n_lists lists that are each sorted descending (what the selection / refine kernels emit): list l sits at
+// sm.sortbuf[off[l] .. off[l] + cnt[l]) with its payload beside it; keys are unique (the row is in the low word), so the
+// global rank of an element is its index in its own list plus, for every other list, the number of keys greater than
+// it (one binary search each).  Elements of rank < kk go straight to the output: no sort, no second buffer.
+// Returns false (nothing written) if some list is not sorted; the caller then takes the bitonic path.
+__device__ bool rank_merge_emit(SelectSmem& sm, int n_lists, const uint32_t* cnt, const uint32_t* off, int total, int kk,
+                                float* __restrict__ out_scores, int64_t* __restrict__ out_ids)
+{
+    const int tid = threadIdx.x;
+    __shared__ int unsorted;
+    if (tid == 0) unsorted = 0;
+    __syncthreads();
+    for (int i = tid; i < total; i += blockDim.x) {
+        int l = 0;
+        while (l + 1 < n_lists && (uint32_t)i >= off[l + 1]) ++l;
+        if ((uint32_t)i > off[l] && sm.sortbuf[i] >= sm.sortbuf[i - 1]) unsorted = 1;
+    }
+    __syncthreads();
+    if (unsorted) return false;
+    for (int i = tid; i < total; i += blockDim.x) {
+        int l = 0;
+        while (l + 1 < n_lists && (uint32_t)i >= off[l + 1]) ++l;
+        const u64 key = sm.sortbuf[i];
+        int rank = i - (int)off[l];
+        for (int m = 0; m < n_lists; ++m) {
+            if (m == l) continue;
+            int lo = (int)off[m], hi = lo + (int)cnt[m];               // first position in list m whose key is < mine
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.sortbuf[mid] > key) lo = mid + 1; else hi = mid; }
+            rank += lo - (int)off[m];
+        }
+        if (rank < kk) { out_scores[rank] = key_score(key); out_ids[rank] = sm.payload[i]; }
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
                    MergeLayout L, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
@@ -530,20 +565,27 @@ merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids
     keys += (int64_t)b * L.batch_stride; ids += (int64_t)b * L.batch_stride;
     counts += (int64_t)b * L.count_batch_stride;
     out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
-    if (tid == 0) sm.counter = 0;
+    uint32_t* cnt = sm.hist;                                  // per-list counts and offsets (list order is kept);
+    uint32_t* off = sm.hist + 1024;                           // n_lists <= 1023 (launcher)
+    if (tid < L.n_lists) cnt[tid] = (uint32_t)max(0, min(counts[(int64_t)tid * L.count_list_stride], L.cap));
+    __syncthreads();
+    if (tid == 0) { uint32_t o = 0; for (int l = 0; l < L.n_lists; ++l) { off[l] = o; o += cnt[l]; } off[L.n_lists] = o; }
     __syncthreads();
     const int span = L.n_lists * L.cap;                       // <= SORT_CAP (host guarantees)
     for (int i = tid; i < span; i += blockDim.x) {
         const int l = i / L.cap, p = i - l * L.cap;
-        if (p < min(counts[(int64_t)l * L.count_list_stride], L.cap)) {
-            const uint32_t slot = atomicAdd(&sm.counter, 1u);
-            sm.sortbuf[slot] = keys[(int64_t)l * L.list_stride + p];
-            sm.payload[slot] = ids[(int64_t)l * L.list_stride + p];
+        if ((uint32_t)p < cnt[l]) {
+            sm.sortbuf[off[l] + p] = keys[(int64_t)l * L.list_stride + p];
+            sm.payload[off[l] + p] = ids[(int64_t)l * L.list_stride + p];
         }
     }
     __syncthreads();
-    const int total = (int)sm.counter;
+    const int total = (int)off[L.n_lists];
     const int kk = min(L.k, total);
+    if (rank_merge_emit(sm, L.n_lists, cnt, off, total, kk, out_scores, out_ids)) {
+        if (tid == 0) out_count[b] = kk;
+        return;
+    }
     int np2 = 1; while (np2 < total) np2 <<= 1;
     for (int i = total + tid; i < np2; i += blockDim.x) { sm.sortbuf[i] = 0ull; sm.payload[i] = -1; }
     __syncthreads();
@@ -605,7 +647,7 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
                             u64* scratch_keys, int64_t* scratch_ids,
                             float* out_scores, int64_t* out_ids, int32_t* out_count)
 {
-    if (n_lists < 1 || cap < 1 || k < 1 || k > K_FAST_MAX || batch < 1) return cudaErrorInvalidValue;
+    if (n_lists < 1 || n_lists > 1023 || cap < 1 || k < 1 || k > K_FAST_MAX || batch < 1) return cudaErrorInvalidValue;
     static bool attr_set[64][2] = {{false}};
     int dev = 0; cudaGetDevice(&dev);
     const bool big = (int64_t)n_lists * cap > SORT_CAP;
@@ -665,17 +707,42 @@ merge_window_kernel(const u64* slot_base, const u64* flags, u64 seq, int world, 
     __syncthreads();
     const bool big = sk != nullptr;                            // world * k > SORT_CAP: compact into global scratch
     const int span = world * k;
-    for (int i = tid; i < span; i += blockDim.x) {
-        const int l = i / k, p = i - l * k;
-        const u64* rec = slot_base + (int64_t)l * rec_words;
-        if (p < (int)min((u64)k, __ldcg(rec + 2 * cap))) {
-            const uint32_t slot = atomicAdd(&sm.counter, 1u);
-            const u64 key = __ldcg(rec + p);
-            const int64_t id = (int64_t)__ldcg(rec + cap + p);
-            if (big) { sk[slot] = key; sp[slot] = id; } else { sm.sortbuf[slot] = key; sm.payload[slot] = id; }
+    if (!big) {
+        // lists kept in order in shared memory, then the rank merge (each rank's record is sorted descending)
+        uint32_t* cnt = sm.hist;
+        uint32_t* off = sm.hist + 64;
+        if (tid < world) cnt[tid] = (uint32_t)min((u64)k, __ldcg(slot_base + (int64_t)tid * rec_words + 2 * cap));
+        __syncthreads();
+        if (tid == 0) { uint32_t o = 0; for (int l = 0; l < world; ++l) { off[l] = o; o += cnt[l]; } off[world] = o; }
+        __syncthreads();
+        for (int i = tid; i < span; i += blockDim.x) {
+            const int l = i / k, p = i - l * k;
+            const u64* rec = slot_base + (int64_t)l * rec_words;
+            if ((uint32_t)p < cnt[l]) {
+                sm.sortbuf[off[l] + p] = __ldcg(rec + p);
+                sm.payload[off[l] + p] = (int64_t)__ldcg(rec + cap + p);
+            }
         }
+        __syncthreads();
+        const int total_s = (int)off[world];
+        const int kk_s = min(k, total_s);
+        if (rank_merge_emit(sm, world, cnt, off, total_s, kk_s, out_scores, out_ids)) {
+            if (tid == 0) *out_count = kk_s;
+            return;
+        }
+        if (tid == 0) sm.counter = (uint32_t)total_s;         // unsorted input: fall through to the bitonic sort
+        __syncthreads();
+    } else {
+        for (int i = tid; i < span; i += blockDim.x) {
+            const int l = i / k, p = i - l * k;
+            const u64* rec = slot_base + (int64_t)l * rec_words;
+            if (p < (int)min((u64)k, __ldcg(rec + 2 * cap))) {
+                const uint32_t slot = atomicAdd(&sm.counter, 1u);
+                sk[slot] = __ldcg(rec + p); sp[slot] = (int64_t)__ldcg(rec + cap + p);
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const int total = (int)sm.counter;
     const int kk = min(k, total);
     __syncthreads();

@@ -102,6 +102,45 @@ def test_two_shard_engines_batched_records_equal_the_single_query_records():
             b.close()
 
 
+def test_merge_records_rank_merge_and_unsorted_fallback():
+    """svsb_enqueue_merge_records on crafted records: lists sorted descending take the rank merge (one binary search per
+    other list, no sort); a list that is NOT sorted makes the kernel fall back to the bitonic sort.  Both must return
+    the k largest keys in order, with ragged counts and an empty list."""
+    torch = pytest.importorskip("torch")
+    from svs_b200.sharded import CudaShardBackend
+    rng = np.random.default_rng(77)
+    b = CudaShardBackend(0)
+    b.load_rows(np.ones((4, 4), np.float32), np.arange(4, dtype=np.int64))      # the merge only needs an engine
+    try:
+        for world, batch, k, shuffle in ((3, 2, 50, False), (3, 2, 50, True), (8, 5, 100, False), (16, 1, 128, False), (2, 3, 1, True)):
+            rec = np.zeros((world, batch, 2 * k + 1), dtype=np.int64)
+            want = []
+            for q in range(batch):
+                pool = []
+                for l in range(world):
+                    c = 0 if (l == 1 and world > 2) else int(rng.integers(1, k + 1))
+                    keys = np.unique(rng.integers(1, 2 ** 62, size=c, dtype=np.int64))[::-1].copy()   # unique, descending
+                    c = len(keys)
+                    if shuffle:
+                        rng.shuffle(keys)
+                    ids = rng.integers(0, 2 ** 40, size=c, dtype=np.int64)
+                    rec[l, q, :c] = keys
+                    rec[l, q, k:k + c] = ids
+                    rec[l, q, 2 * k] = c
+                    pool += list(zip(keys.tolist(), ids.tolist()))
+                pool.sort(reverse=True)
+                want.append(pool[:k])
+            o_s, o_i, o_c = b.new_outputs(batch, k)
+            b.enqueue_merge(torch.from_numpy(rec).cuda(), world, batch, k, o_s, o_i, o_c)
+            torch.cuda.synchronize()
+            for q in range(batch):
+                c = int(o_c[q])
+                assert c == len(want[q])
+                assert o_i[q, :c].cpu().numpy().tolist() == [i for _, i in want[q]], (world, batch, k, shuffle, q)
+    finally:
+        b.close()
+
+
 def _two_backends(m, ids, world=2, timeout_ms=5000):
     import os
     from svs_b200.sharded import CudaShardBackend, partition
