@@ -63,6 +63,31 @@ def test_shapes_including_d_not_multiple_of_four(engine, n, d, k, variant, monke
         _check(engine, m, ids, q, k)
 
 
+def test_the_plain_c_oracle_accepts_the_engine_too(engine):
+    """Second checker: oracle/svs_oracle_c.c (its own dot product, its own selection) judges the CUDA path through the
+    same tolerance-aware comparator as the NumPy oracle does."""
+    import shutil
+    import sys
+    if shutil.which("gcc") is None and shutil.which("cc") is None and not os.path.exists(
+            os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libsvs_oracle_c.so")):
+        pytest.skip("no C compiler and no prebuilt C oracle")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import build_oracle_c
+    oc = build_oracle_c.OracleC()
+    rng = np.random.default_rng(123)
+    for n, d, k in ((3000, 96, 10), (20_000, 1536, 100), (5000, 257, 1000)):
+        m = rng.standard_normal((n, d)).astype(np.float32)
+        m /= np.sqrt((m * m).sum(axis=1))[:, None]
+        ids = np.cumsum(rng.integers(1, 4, size=n)).astype(np.int64)
+        engine.load(m, ids)
+        for _ in range(2):
+            q = rng.standard_normal(d).astype(np.float32)
+            q /= np.sqrt((q * q).sum())
+            want = oc.superheavy(m, ids, q, k)
+            rep = oracle.compare_retrieval(engine.retrieve(q, k), want, oc.scores(m, q), ids)
+            assert rep["max_rel_score_err"] <= 1e-5
+
+
 @pytest.mark.parametrize("tune_a", ["1", "2", "3", "4", "5", "6", "7", "8", "9"])
 def test_every_ldg_instantiation_is_correct(engine, tune_a, monkeypatch):
     monkeypatch.setenv("SVSB_GEMV_VARIANT", "1")
