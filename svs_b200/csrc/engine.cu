@@ -1931,7 +1931,7 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
                         bool pdl_gemv = false) {
     Xchg* x = e->xchg.get();
     const Shard& s = g->shards[0];
-    PeerPush push;
+    PeerPush push{};
     const int slot = xchg_next(x, push);
     if (s.n == 0) {
         CU(launch_push_empty(st_sel, push));

@@ -341,7 +341,7 @@ cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* 
                           const PeerPush* push)
 {
     if (k < 1 || k > K_FAST_MAX || n < 1) return cudaErrorInvalidValue;
-    PeerPush pp;
+    PeerPush pp{};
     if (push) { pp = *push; if (pp.world < 1 || pp.world > XCHG_MAX_RANKS || pp.cap < k) return cudaErrorInvalidValue; }
     static bool attr_set[64] = {false};
     int dev = 0; cudaGetDevice(&dev);
