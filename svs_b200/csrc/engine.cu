@@ -95,9 +95,18 @@ struct svsb_workspace {
     int32_t* out_count = nullptr;
     u64* mscr_keys = nullptr; int64_t* mscr_ids = nullptr; int64_t mscr_cap = 0;   // merge scratch
     cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr, ev_sel = nullptr;
+    // The similarity kernel leaves group maxima in gmax and only a SUCCESSFUL selection kernel re-zeroes them
+    // (select.cu).  Set before the similarity launch, cleared once the selection is enqueued: a call that failed in
+    // between leaves it set and the next user of this (pooled) workspace re-zeroes gmax first.
+    bool gmax_dirty = false;
 
     int ensure_rows(int64_t n) {
         cudaSetDevice(dev);
+        if (gmax_dirty && gmax && n <= n_cap) {
+            CU(cudaMemset(gmax, 0, (size_t)g_cap * 8));
+            CU(cudaStreamSynchronize(cudaStreamLegacy));
+            gmax_dirty = false;
+        }
         if (n > n_cap) {
             if (scores) cudaFree(scores); if (gmax) cudaFree(gmax); if (cand) cudaFree(cand);
             scores = nullptr; gmax = nullptr; cand = nullptr; n_cap = 0;
@@ -112,7 +121,7 @@ struct svsb_workspace {
             // non-blocking: without this wait a similarity kernel could write group maxima BEFORE the zeroing lands
             CU(cudaStreamSynchronize(cudaStreamLegacy));
             CU(cudaMalloc(&cand, (size_t)cc * 8));
-            n_cap = n; g_cap = G; cand_cap = cc;
+            n_cap = n; g_cap = G; cand_cap = cc; gmax_dirty = false;
         }
         return SVSB_OK;
     }
@@ -272,6 +281,7 @@ struct svsb_engine {
     // bench state
     std::vector<float*> bench_q; int bench_nq = 0, bench_d = 0, bench_ld = 0;
     std::unique_ptr<QueryCtx> bench_ctx;
+    std::vector<cudaEvent_t> bench_kev;                  // similarity-kernel timing events of svsb_bench_run (device 0)
     // sharded deployment (one process per GPU)
     int64_t shard_row0 = 0;                              // global row of this engine's first row
     std::vector<std::unique_ptr<DevWs>> shard_ws;        // workspaces for svsb_enqueue_local_topk (by slot)
@@ -467,6 +477,7 @@ extern "C" void svsb_destroy(svsb_t* e) {
     xchg_release(e);
     if (e->side_st) { cudaSetDevice(e->devs[0]); cudaStreamDestroy(e->side_st); }
     for (auto ev : e->kev) cudaEventDestroy(ev);
+    if (!e->bench_kev.empty()) { cudaSetDevice(e->devs[0]); for (auto ev : e->bench_kev) cudaEventDestroy(ev); }
     for (size_t i = 0; i < e->bench_q.size(); ++i) if (e->bench_q[i]) { cudaSetDevice(e->devs[i]); cudaFree(e->bench_q[i]); }
     free_slabs(e);
     for (size_t i = 0; i < e->copy_st.size(); ++i) { cudaSetDevice(e->devs[i]); cudaStreamDestroy(e->copy_st[i]); }
@@ -778,6 +789,7 @@ extern "C" int svsb_read_rows(svsb_t* e, int64_t row0, int64_t count, float* row
 // Enqueue GEMV + local top-k for one shard on its workspace stream.  d_q: device query (ld floats).
 static int enqueue_local(DevWs& w, const Generation* g, const Shard& s, const float* d_q, int64_t kk) {
     const int shift = group_shift_for(s.n);
+    w.gmax_dirty = true;
     CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, d_q, w.scores, w.gmax, shift));
     if (kk <= K_FAST_MAX)
         CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
@@ -785,6 +797,7 @@ static int enqueue_local(DevWs& w, const Generation* g, const Shard& s, const fl
     else
         CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
                                 w.out_keys, w.out_scores, w.out_ids, w.out_count));
+    w.gmax_dirty = false;
     return SVSB_OK;
 }
 
@@ -875,12 +888,14 @@ static int query_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, const
             const int shift = group_shift_for(s.n);
             *c->h_count = -1;
             CU(launch_stage_query(w.st, c->h_q, w.d_q, g->ld));
+            w.gmax_dirty = true;
             {   // programmatic dependent launch: the similarity kernel streams its first tiles under the staging kernel
                 PdlScope pdl(env_int("SVSB_PDL", 1) != 0);
                 CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift));
             }
             CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
                              w.out_keys, c->h_scores, c->h_ids, c->h_count));
+            w.gmax_dirty = false;
             continue;
         }
         CU(cudaMemcpyAsync(w.d_q, c->h_q, (size_t)g->ld * 4, cudaMemcpyHostToDevice, w.st));
@@ -1428,11 +1443,10 @@ extern "C" int svsb_bench_set_queries(svsb_t* e, const float* Q, int32_t nq, int
     return SVSB_OK;
 }
 
-// Timing events for the similarity kernel inside the timed loop (device 0's stream).
-static std::vector<cudaEvent_t> g_kev;
-static int ensure_kernel_events(int dev, size_t n) {
+// Timing events for the similarity kernel inside the timed loop: owned by the engine, created on ITS device 0.
+static int ensure_kernel_events(svsb_engine* e, int dev, size_t n) {
     CU(cudaSetDevice(dev));
-    while (g_kev.size() < n) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); g_kev.push_back(ev); }
+    while (e->bench_kev.size() < n) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->bench_kev.push_back(ev); }
     return SVSB_OK;
 }
 
@@ -1459,7 +1473,7 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
     const bool ktime = gemv_ms != nullptr && g->shards[0].n > 0;
     constexpr int KTIME_EVERY = 8;
     auto timed_it = [&](int it) { return ktime && it % KTIME_EVERY == 0; };
-    if (ktime && (rc = ensure_kernel_events(c->ws[0].dev, (size_t)iters * 2)) != SVSB_OK) return rc;
+    if (ktime && (rc = ensure_kernel_events(e, c->ws[0].dev, (size_t)iters * 2)) != SVSB_OK) return rc;
     // Single device, k <= 2048: software pipeline.  The similarity kernel of query i+1 (stream A, all SMs but one)
     // runs while the one-CTA selection kernel of query i (stream B) finishes on the SM left free; two buffer sets.
     const bool pipelined = nd == 1 && kk <= K_FAST_MAX && env_int("SVSB_PIPELINE", 1) != 0 && sm_count(c->ws[0].dev) > 8;
@@ -1476,6 +1490,7 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
         }
         if ((rc = prepare_ws(*c->alt, g.get(), g->shards[0], kk)) != SVSB_OK) return rc;
     }
+    std::vector<cudaEvent_t>& g_kev = e->bench_kev;
     const int64_t l0 = g_launches.load();
     for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaStreamSynchronize(c->ws[i].st)); }
     if (pipelined) CU(cudaStreamSynchronize(c->alt->st));
@@ -1490,12 +1505,14 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
             const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
             if (it >= 2) CU(cudaStreamWaitEvent(sa, W.ev_sel, 0));           // selection of query it-2 is done with W
             if (timed_it(it)) CU(cudaEventRecord(g_kev[2 * it], sa));
+            W.gmax_dirty = true;
             CU(launch_gemv(sa, W.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, W.scores, W.gmax, shift, 0, 0, 0, /*reserve_sms=*/1));
             if (timed_it(it)) CU(cudaEventRecord(g_kev[2 * it + 1], sa));
             CU(cudaEventRecord(W.ev, sa));
             CU(cudaStreamWaitEvent(sb, W.ev, 0));
             CU(launch_select(sb, W.scores, s.n, W.gmax, shift, (int)kk, s.ids, s.row0, W.cand, W.cand_cap,
                              W.out_keys, W.out_scores, W.out_ids, W.out_count));
+            W.gmax_dirty = false;
             CU(cudaEventRecord(W.ev_sel, sb));
             c->last = &W;
         }
@@ -1511,6 +1528,7 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
                     DevWs& w = c->ws[0]; const Shard& s = g->shards[0];
                     const int shift = group_shift_for(s.n);
                     CU(cudaEventRecord(g_kev[2 * it], w.st));
+                    w.gmax_dirty = true;
                     CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, w.scores, w.gmax, shift));
                     CU(cudaEventRecord(g_kev[2 * it + 1], w.st));
                     if (kk <= K_FAST_MAX)
@@ -1519,6 +1537,7 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
                     else
                         CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
                                                 w.out_keys, w.out_scores, w.out_ids, w.out_count));
+                    w.gmax_dirty = false;
                 } else if ((rc = enqueue_local(c->ws[i], g.get(), g->shards[i], e->bench_q[i] + qoff, kk)) != SVSB_OK) return rc;
             }
             if (nd > 1 && (rc = enqueue_gather_merge(e, c, g.get(), kk)) != SVSB_OK) return rc;
@@ -1691,12 +1710,16 @@ extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, co
         if (!w.ev_sel) CU(cudaEventCreateWithFlags(&w.ev_sel, cudaEventDisableTiming));
         // the slot's previous selection must have finished reading scores / group maxima before they are overwritten
         if (e->sel_pending[slot]) CU(cudaStreamWaitEvent(st, w.ev_sel, 0));
+    } else if (e->sel_pending[slot] && w.ev_sel) {
+        CU(cudaStreamWaitEvent(st, w.ev_sel, 0));           // a caller mixing pipelined and plain calls on one slot
+        e->sel_pending[slot] = 0;
     }
     const int shift = group_shift_for(s.n);
     if (time_kernel) {
         while (e->kev.size() < e->kev_used + 2) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
         CU(cudaEventRecord(e->kev[e->kev_used], st));
     }
+    w.gmax_dirty = true;
     CU(launch_gemv(st, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, pipelined ? 1 : 0));
     if (time_kernel) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
     cudaStream_t sel_st = st;
@@ -1707,6 +1730,7 @@ extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, co
     }
     CU(launch_select(sel_st, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
                      reinterpret_cast<u64*>(d_record), w.out_scores, d_record + k, d_count));
+    w.gmax_dirty = false;
     if (pipelined) { CU(cudaEventRecord(w.ev_sel, e->side_st)); e->sel_pending[slot] = 1; }
     return SVSB_OK;
 }
@@ -1735,8 +1759,10 @@ extern "C" int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_
         BatchWs* w = nullptr;
         int rc = batch_ws_get(e, w);
         if (rc != SVSB_OK) return rc;
-        if ((rc = ensure_m16(g.get(), P, st)) != SVSB_OK) return rc;
-        for (int32_t c0 = 0; c0 < b; c0 += COARSE_MAX_BATCH) {
+        rc = ensure_m16(g.get(), P, st);
+        if (rc == SVSB_E_NOMEM) std::fill(todo.begin(), todo.end(), 1);    // no room for the fp16 shadow (+50 % of the shard):
+        else if (rc != SVSB_OK) return rc;                                 // the exact kernels answer, as in svsb_query_batch
+        for (int32_t c0 = 0; rc == SVSB_OK && c0 < b; c0 += COARSE_MAX_BATCH) {
             const int bc = std::min<int32_t>(COARSE_MAX_BATCH, b - c0);
             const int b_pad = (bc + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
             if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
@@ -1938,6 +1964,7 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
     } else {
         const int shift = group_shift_for(s.n);
         if (time_kernel) CU(cudaEventRecord(e->kev[e->kev_used], st_main));
+        w.gmax_dirty = true;
         {
             PdlScope pdl(pdl_gemv);                               // only after the staging kernel of the synchronous path
             CU(launch_gemv(st_main, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, reserve_sms));
@@ -1946,6 +1973,7 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
         if (st_sel != st_main) { CU(cudaEventRecord(ev_main_done, st_main)); CU(cudaStreamWaitEvent(st_sel, ev_main_done, 0)); }
         CU(launch_select(st_sel, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
                          w.out_keys, w.out_scores, w.out_ids, w.out_count, nullptr, &push));
+        w.gmax_dirty = false;
     }
     if (ev_sel_done) CU(cudaEventRecord(ev_sel_done, st_sel));   // the workspace's scores are free from here on
     u64* sk = nullptr; int64_t* sp = nullptr;
@@ -1983,7 +2011,13 @@ extern "C" int svsb_enqueue_query_peer(svsb_t* e, void* stream, const float* d_q
     if (pipelined) {
         if (e->sel_pending[slot]) CU(cudaStreamWaitEvent(st, w.ev_sel, 0));   // the slot's scores are free again
         sel_st = e->side_st;
-    } else if (e->xchg->deferred.pending && (rc = xchg_flush_merge(e, e->side_st)) != SVSB_OK) return rc;
+    } else {
+        if (e->xchg->deferred.pending && (rc = xchg_flush_merge(e, e->side_st)) != SVSB_OK) return rc;
+        if (e->sel_pending[slot]) {                               // a pipelined call used this slot before: its selection on
+            CU(cudaStreamWaitEvent(st, w.ev_sel, 0));             // the side stream may still be reading scores / group maxima
+            e->sel_pending[slot] = 0;
+        }
+    }
     // pipelined: ev_sel marks "selection done" (scores reusable by the similarity pass two queries on); the merge is deferred
     rc = xchg_enqueue(e, g.get(), w, st, sel_st, w.ev, d_query, k, out_scores, out_ids, out_count, time_kernel, pipelined ? 1 : 0,
                       /*defer_merge=*/pipelined, pipelined ? w.ev_sel : nullptr);
@@ -2120,6 +2154,7 @@ extern "C" int svsb_launch_local_topk(svsb_ws_t* ws, void* stream, const float* 
     CU(cudaSetDevice(ws->dev));
     cudaStream_t st = (cudaStream_t)stream;
     const int shift = group_shift_for(n);
+    ws->gmax_dirty = true;
     CU(launch_gemv(st, ws->dev, d_matrix, n, d, ld, d_query, ws->scores, ws->gmax, shift));
     if (kk <= K_FAST_MAX)
         CU(launch_select(st, ws->scores, n, ws->gmax, shift, (int)kk, d_emb_ids, global_row0, ws->cand, ws->cand_cap,
@@ -2127,6 +2162,7 @@ extern "C" int svsb_launch_local_topk(svsb_ws_t* ws, void* stream, const float* 
     else
         CU(launch_fullsort_topk(st, ws->scores, n, ws->gmax, shift, kk, d_emb_ids, global_row0, ws->sortbuf,
                                 (u64*)d_out_keys, ws->out_scores, d_out_ids, d_out_count));
+    ws->gmax_dirty = false;
     return SVSB_OK;
 }
 

@@ -28,9 +28,12 @@ from typing import Any, List, Optional, Sequence
 
 import numpy as np
 
+from . import _lib
 from .matrix import DeviceEmbeddingsMatrix
 
 _ORIGINALS: dict = {}
+# svsb_top_pairs refusals that the reference's np.dot(M, M.T) + get_top_pairs still answers (include/svsb200.h)
+_PAIRS_DELEGATE = (_lib.SVSB_E_NOMEM, _lib.SVSB_E_INVALID)
 
 
 class _Coalescer:
@@ -66,7 +69,10 @@ class _Coalescer:
                 dim = self._pending[0][1].shape
                 batch = [it for it in self._pending if it[0] is matrix and it[1].shape == dim]
                 self._pending = [it for it in self._pending if not (it[0] is matrix and it[1].shape == dim)]
-                k = max(it[2] for it in batch)
+                # every caller's n is clipped to the row count first (get_top_k, src/svs/util.py:198-199): one caller's
+                # oversized n must not size the whole batch's buffers
+                rows = int(matrix.shape[0])
+                k = max(min(max(int(it[2]), 0), rows) for it in batch)
                 try:
                     if len(batch) == 1:
                         res = [await loop.run_in_executor(None, matrix.retrieve, batch[0][1], batch[0][2])]
@@ -221,7 +227,16 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
         matrix = self.embeddings_matrix.device.get_sync(self.db)
         n_docs = matrix.shape[0]
         log.info(f"computing pairwise similarity over {n_docs} documents")
-        pairwise_scores = matrix.top_pairs(n)
+        try:
+            pairwise_scores = matrix.top_pairs(n)
+        except _lib.EngineError as ex:
+            if ex.code not in _PAIRS_DELEGATE:
+                raise
+            # The engine's pair list has fixed capacity (millions of near-tied pairs -- e.g. thousands of duplicate
+            # documents, the typical use of this API -- or n > 2^22 overflow it) and its fp16 coarse pass needs rows near
+            # unit norm.  The reference answers all of these: hand the call to its own host path (the host cache is kept).
+            log.info(f"engine declined the pairwise query ({ex}); using the reference's host path")
+            return _ORIGINALS["KB.pairs"](self, n)
         log.info(f"computed {n_docs * n_docs} pairwise cosine similarities")
         with self.db as q:
             return _pair_docs(q, pairwise_scores, n)
@@ -233,7 +248,13 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
             matrix = await self.embeddings_matrix.device.get(db)
         n_docs = matrix.shape[0]
         log.info(f"computing pairwise similarity over {n_docs} documents")
-        pairwise_scores = await loop.run_in_executor(None, matrix.top_pairs, n)
+        try:
+            pairwise_scores = await loop.run_in_executor(None, matrix.top_pairs, n)
+        except _lib.EngineError as ex:
+            if ex.code not in _PAIRS_DELEGATE:
+                raise
+            log.info(f"engine declined the pairwise query ({ex}); using the reference's host path")
+            return await _ORIGINALS["AsyncKB.pairs"](self, n)
         log.info(f"computed {n_docs * n_docs} pairwise cosine similarities")
         async with self._get_lock():
             db = await self._ensure_db()

@@ -17,6 +17,13 @@ def _f32c(a: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def clamp_k(k, n_rows: int) -> int:
+    """get_top_k clips top_k to len(scores) and answers [] for k <= 0 (src/svs/util.py:198-201).  Done HERE, before any
+    buffer is sized by k and before k passes through a 32-bit C argument: retrieve(q, n=10**12) must return all N rows,
+    not allocate terabytes or wrap around."""
+    return min(max(int(k), 0), max(int(n_rows), 0), 0x7fffffff)
+
+
 class Engine:
     """One engine == one cached device matrix (the replacement of `_EmbeddingsMatrix`' two arrays,
     reference src/svs/kb.py:856-893) plus the kernels that query it.
@@ -141,12 +148,18 @@ class Engine:
         q = _f32c(q)
         if q.ndim != 1:
             raise ValueError("query vector must be 1-D")
-        cap = max(int(k), 0)
+        cap = clamp_k(k, self._rows_or_zero())
+        k = cap if int(k) > 0 else int(max(k, -1))
         scores = np.empty(cap, dtype=np.float32)
         ids = np.empty(cap, dtype=np.int64)
         cnt = C.c_int32()
-        check(self._lib.svsb_query(self._h, q.ctypes.data, q.shape[0], int(k), scores.ctypes.data, ids.ctypes.data, C.byref(cnt)))
+        check(self._lib.svsb_query(self._h, q.ctypes.data, q.shape[0], k, scores.ctypes.data, ids.ctypes.data, C.byref(cnt)))
         return scores[:cnt.value], ids[:cnt.value]
+
+    def _rows_or_zero(self) -> int:
+        """Rows of the resident matrix, 0 when nothing is resident (the C call then reports SVSB_E_NOT_LOADED)."""
+        n = C.c_int64()
+        return n.value if self._lib.svsb_shape(self._h, C.byref(n), None) == _lib.SVSB_OK else 0
 
     def snapshot(self) -> "Snapshot":
         """Pin the resident generation (the reference's `embeddings_matrix, emb_id_lookup` references)."""
@@ -161,7 +174,8 @@ class Engine:
         if Q.ndim != 2:
             raise ValueError("Q must be (b, d)")
         b, d = Q.shape
-        cap = max(int(k), 0)
+        cap = clamp_k(k, self._rows_or_zero())
+        k = cap if int(k) > 0 else int(max(k, -1))
         if out is None:
             scores = np.zeros((b, cap), dtype=np.float32)
             ids = np.full((b, cap), -1, dtype=np.int64)
@@ -173,7 +187,7 @@ class Engine:
                   and scores.flags.c_contiguous and ids.flags.c_contiguous and counts.flags.c_contiguous)
             if not ok:
                 raise ValueError("out must be C-contiguous (float32 (b, k), int64 (b, k), int32 (b,)) arrays")
-        check(self._lib.svsb_query_batch(self._h, Q.ctypes.data, b, d, int(k), scores.ctypes.data, ids.ctypes.data, counts.ctypes.data))
+        check(self._lib.svsb_query_batch(self._h, Q.ctypes.data, b, d, k, scores.ctypes.data, ids.ctypes.data, counts.ctypes.data))
         return scores, ids, counts
 
     def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
@@ -304,11 +318,12 @@ class Snapshot:
             raise ValueError("query vector must be 1-D")
         if not self._engine._h.value:
             raise _lib.EngineError(_lib.SVSB_E_STATE, "engine is closed")
-        cap = max(int(k), 0)
+        cap = clamp_k(k, self.shape[0])
+        k = cap if int(k) > 0 else int(max(k, -1))
         scores = np.empty(cap, dtype=np.float32)
         ids = np.empty(cap, dtype=np.int64)
         cnt = C.c_int32()
-        check(self._lib.svsb_snapshot_query(self._engine._h, self._s, q.ctypes.data, q.shape[0], int(k),
+        check(self._lib.svsb_snapshot_query(self._engine._h, self._s, q.ctypes.data, q.shape[0], k,
                                             scores.ctypes.data, ids.ctypes.data, C.byref(cnt)))
         return scores[:cnt.value], ids[:cnt.value]
 
@@ -324,11 +339,12 @@ class Snapshot:
         if not self._engine._h.value:
             raise _lib.EngineError(_lib.SVSB_E_STATE, "engine is closed")
         b, d = Q.shape
-        cap = max(int(k), 0)
+        cap = clamp_k(k, self.shape[0])
+        k = cap if int(k) > 0 else int(max(k, -1))
         scores = np.zeros((b, cap), dtype=np.float32)
         ids = np.full((b, cap), -1, dtype=np.int64)
         counts = np.zeros(b, dtype=np.int32)
-        check(self._lib.svsb_snapshot_query_batch(self._engine._h, self._s, Q.ctypes.data, b, d, int(k),
+        check(self._lib.svsb_snapshot_query_batch(self._engine._h, self._s, Q.ctypes.data, b, d, k,
                                                   scores.ctypes.data, ids.ctypes.data, counts.ctypes.data))
         return scores, ids, counts
 

@@ -310,7 +310,7 @@ class ShardedRetriever:
             return (np.zeros((Q.shape[0], 0), np.float32), np.zeros((Q.shape[0], 0), np.int64), np.zeros(Q.shape[0], np.int32))
         if n > 2048 and self.n > 2048:
             raise NotImplementedError("n > 2048 is not supported by the sharded path")
-        k = min(int(n), 2048)
+        k = min(int(n), 2048, self.n)                               # get_top_k clips n to the row count (util.py:198-199)
         o_s, o_i, o_c = self._batch(self.backend.device_queries(Q), k)
         cnt = o_c.cpu().numpy()                                     # synchronises the stream
         return o_s.cpu().numpy(), o_i.cpu().numpy(), cnt
@@ -328,7 +328,7 @@ class ShardedRetriever:
             raise ValueError(f"shapes ({self.n},{self.d if self.n else 0}) and ({q.shape[0]},) not aligned")
         if n <= 0:
             return np.zeros(0, np.float32), np.zeros(0, np.int64)
-        k = min(int(n), 2048)
+        k = min(int(n), 2048, self.n)                               # get_top_k clips n to the row count (util.py:198-199)
         if n > 2048 and self.n > 2048:
             raise NotImplementedError("n > 2048 is not supported by the sharded path")
         if self.exchange == "peer":

@@ -171,3 +171,34 @@ def test_retrieve_many_equals_looping_retrieve(svs_patched, tmp_path):
             assert [(x['score'], x['doc']['id']) for x in r] == [(x['score'], x['doc']['id']) for x in s]
         await akb.close()
     asyncio.run(go())
+
+
+def test_pairwise_with_thousands_of_duplicates_is_handed_to_the_reference_path(svs_patched, tmp_path, caplog):
+    """Duplicate detection is the typical use of document_top_pairwise_scores: ~3000 identical documents are 4.5M pairs
+    at score 1.0, more than the engine's candidate list holds (SVSB_E_NOMEM).  The reference's np.dot(M, M.T) +
+    get_top_pairs answers it, so the patched call must too (it delegates), not raise."""
+    import logging
+    svs = svs_patched
+    d = 32
+
+    async def embed(texts):
+        return [stub_vector(t.split("#")[0], d) for t in texts]
+    kb = svs.KB(str(tmp_path / "dups.sqlite"), embed)
+    with kb.bulk_add_docs() as add_doc:
+        for i in range(3100):
+            add_doc(f"the same text#{i}")
+        for i in range(40):
+            add_doc(f"other {i}")
+    with caplog.at_level(logging.INFO):
+        res = kb.document_top_pairwise_scores(n=25)
+    assert len(res) == 25
+    for score, a, b in res:
+        assert score == pytest.approx(1.0, abs=1e-5) and a['text'].startswith("the same text") and b['text'].startswith("the same text")
+    assert any("engine declined the pairwise query" in r.getMessage() for r in caplog.records)
+    # a query the engine does answer still goes through it
+    with kb.bulk_del_docs() as del_doc:
+        for i in range(3, 3101):
+            del_doc(i)
+    res = kb.document_top_pairwise_scores(n=3)
+    assert res[0][0] == pytest.approx(1.0, abs=1e-5) and {res[0][1]['id'], res[0][2]['id']} == {1, 2}
+    kb.close()

@@ -248,3 +248,24 @@ def test_bench_path_computes_the_same_result(engine):
     got = engine.bench_last_result(100)                            # the 5th query (index 4)
     oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[4], 100), oracle.scores_of(m, qs[4]), ids)
     assert engine.retrieve(qs[4], 100) == got
+
+
+def test_oversized_n_returns_the_full_ranking(engine):
+    """get_top_k clips n to the row count (src/svs/util.py:198-199): n = 2**31, 2**32 + 3 or 10**12 must neither wrap
+    around in a 32-bit argument nor size a buffer -- every one of them is the full ranking."""
+    m = oracle.synth_matrix_normal(777, 48, 5)
+    ids = np.arange(10, 10 + 777, dtype=np.int64)
+    engine.load(m, ids)
+    q = oracle.synth_queries(1, 48, 6, dist="normal")[0]
+    full = engine.retrieve(q, 777)
+    oracle.compare_retrieval(full, oracle.superheavy(m, ids, q, 777), oracle.scores_of(m, q), ids)
+    for n in (778, 2**31 - 1, 2**31, 2**31 + 3, 2**32, 2**32 + 3, 10**12):
+        assert engine.retrieve(q, n) == full
+    snap = engine.snapshot()
+    assert snap.retrieve(q, 10**12) == full
+    s, i, c = engine.query_batch(np.stack([q, q]), 10**12)
+    assert s.shape == (2, 777) and c.tolist() == [777, 777] and [(float(a), int(b)) for a, b in zip(s[1], i[1])] == full
+    s, i, c = snap.query_batch(np.stack([q, q]), 2**31)
+    assert s.shape == (2, 777) and c.tolist() == [777, 777]
+    assert engine.retrieve(q, -(2**40)) == [] and engine.retrieve(q, 0) == []
+    snap.release()
