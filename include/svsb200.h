@@ -15,6 +15,10 @@
  *     the default thread pool without holding the KB lock, src/svs/kb.py:1180,1190);
  *     svsb_invalidate / svsb_load_* may race with in-flight queries: a query keeps the generation
  *     it started on alive until it returns (the reference relies on NumPy refcounts for the same).
+ *   - k is clipped to the row count (src/svs/util.py:198-199) for every k, on one device or several; callers with a
+ *     wider integer type clip BEFORE the int32 argument (svs_b200/engine.py: clamp_k);
+ *   - +0.0 and -0.0 are different keys: +0.0 sorts before -0.0 (the reference's float comparison treats them as equal
+ *     and orders them by index); harmless under the tolerance clause, stated here for completeness;
  *   - result order: score descending, ties by ascending row (== ascending embeddings.id for a rowid
  *     scan, src/svs/kb.py:603-609).  The reference's get_top_k orders exact ties by DEscending index
  *     (src/svs/util.py:203); BASELINE.json's north star prescribes ascending id.
@@ -77,6 +81,29 @@ int svsb_load_abort(svsb_t* e);
 int svsb_load_synthetic(svsb_t* e, int64_t n, int32_t d, uint64_t seed, int64_t id0, int64_t id_step,
                         uint64_t* generation);
 
+/* ---- incremental update: instead of the full invalidate + rebuild the reference does after every bulk add / delete
+ *      (src/svs/kb.py:1062, 1086, 1523, 1541) ------------------------------------------
+ * Applies ONE committed batch of mutations of the `embeddings` table to the resident generation and publishes the
+ * result as a new generation that SHARES the matrix buffers with the old one (queries in flight on the old generation,
+ * and snapshots, are undisturbed -- what NumPy refcounts give the reference):
+ *   del_ids[n_del]            embeddings.id of deleted rows (`DELETE FROM embeddings WHERE id = ?`, kb.py:403, 548): each
+ *                             must be a live row; it is tombstoned (its key sorts below every live row's);
+ *   add_rows[n_add][d], add_ids[n_add]
+ *                             inserted rows (`INSERT INTO embeddings`, kb.py:310, 557), in insertion order; ids must be
+ *                             ascending and greater than every live id -- what SQLite's rowid allocation guarantees --
+ *                             so that appending them keeps "row order == scan order of a fresh rebuild" (kb.py:603-609).
+ *                             Rows are appended behind the last row (the last shard of a multi-device engine); the
+ *                             buffer grows geometrically (one device-to-device copy) when it is full.
+ * Deletes are applied first (an id deleted and re-inserted in one transaction is a tombstone plus an append).
+ * SVSB_E_STATE: no generation resident, a del id that is not live, ids not ascending, or d mismatch -- nothing is
+ * published and the caller falls back to the full rebuild.  The result equals a fresh rebuild bit for bit: same ids,
+ * same scores (tests/test_gpu_mutate.py).  Generations with tombstones answer batches and large k through the exact
+ * kernels; svsb_top_pairs asks for a reload (SVSB_E_INVALID). */
+int svsb_apply_mutations(svsb_t* e, const int64_t* del_ids, int64_t n_del, const float* add_rows, const int64_t* add_ids,
+                         int64_t n_add, int32_t d, uint64_t* generation);
+/* Physical rows of the resident generation (tombstoned ones included) and live rows (== svsb_shape's n). */
+int svsb_generation_rows(svsb_t* e, int64_t* physical, int64_t* live);
+
 /* _EmbeddingsMatrix.invalidate (src/svs/kb.py:861-864; call sites kb.py:984,1062,1086,1455,1523,1541). */
 int svsb_invalidate(svsb_t* e);
 /* Cache-hit test of get_sync / get (src/svs/kb.py:867, 880).  Returns 1 / 0. */
@@ -86,7 +113,8 @@ int svsb_shape(svsb_t* e, int64_t* n, int32_t* d);
 /* Row-norm statistics computed by the load path's norm kernel: max | ||row|| - 1 | and the number of
  * rows outside the reference's tolerance 1e-3 (src/svs/kb.py:58, src/svs/embeddings/util.py:35-38). */
 int svsb_norm_stats(svsb_t* e, float* max_abs_dev, int64_t* n_out_of_tolerance);
-/* Verification accessor: copy rows [row0, row0+count) of the resident matrix (and ids) back to the host. */
+/* Verification accessor: copy LIVE rows [row0, row0+count) of the resident matrix (and ids), in row order, back to the
+ * host -- what a fresh rebuild's matrix holds at those positions. */
 int svsb_read_rows(svsb_t* e, int64_t row0, int64_t count, float* rows, int64_t* emb_ids);
 
 /* ---- the hot path: replaces superheavy() = np.dot + get_top_k + emb_id_lookup
@@ -96,6 +124,16 @@ int svsb_read_rows(svsb_t* e, int64_t row0, int64_t count, float* rows, int64_t*
  * capacity k.  *out_count = min(k, N); k <= 0 gives 0 results (util.py:198-201). */
 int svsb_query(svsb_t* e, const float* q, int32_t d, int32_t k,
                float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
+/* The same query with several in flight from ONE host thread: submit copies q, enqueues the whole chain (query staged
+ * from pinned host memory by a kernel, similarity, selection that writes the result into pinned host memory) and returns
+ * at once; wait blocks for that query's result and frees the handle (every submitted handle must be waited for, also
+ * after an error).  With >= 2 queries in flight the launch gaps, the serial selection and the host round trip of
+ * svsb_query overlap the next query's similarity pass (src/svs/kb.py:1190: AsyncKB runs concurrent retrieves the same
+ * way, one executor thread each).  At most 3 (multi-device) / SVSB_MAX_CONTEXTS (one device, default 4) can be pending;
+ * a further submit blocks until one is waited for.  Multi-device engines: k <= 2048. */
+typedef struct svsb_pending svsb_pending_t;
+int svsb_query_submit(svsb_t* e, const float* q, int32_t d, int32_t k, svsb_pending_t** out);
+int svsb_query_wait(svsb_t* e, svsb_pending_t* p, float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
 /* Snapshots.  The reference's retrieve keeps Python references to the (matrix, ids) pair it fetched
  * while the lock is released (src/svs/kb.py:1178-1190), so a concurrent bulk_add/bulk_del that
  * invalidates the cache (kb.py:1062, 1086) does not disturb it.  A snapshot is that pair of
@@ -104,6 +142,7 @@ typedef struct svsb_snapshot svsb_snap_t;
 int  svsb_snapshot_acquire(svsb_t* e, svsb_snap_t** out);
 void svsb_snapshot_release(svsb_snap_t* s);
 int  svsb_snapshot_shape(svsb_snap_t* s, int64_t* n, int32_t* d, uint64_t* generation);
+int  svsb_snapshot_rows(svsb_snap_t* s, int64_t* physical, int64_t* live);      /* as svsb_generation_rows */
 int  svsb_snapshot_query(svsb_t* e, svsb_snap_t* s, const float* q, int32_t d, int32_t k,
                          float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
 /* Batched queries (new; the reference has no batched API -- a batch is a Python loop over retrieve,
@@ -217,6 +256,12 @@ int svsb_enqueue_query_peer(svsb_t* e, void* stream, const float* d_query, int32
  * broken and the exchange must be re-created on every rank. */
 int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
                     float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
+/* The same with up to 3 queries in flight from the host thread that drives the shard engine (SPMD: every rank issues
+ * the same sequence of submits; waits are local, oldest first).  Query j+1's similarity pass overlaps query j's selection,
+ * exchange, merge and host round trip: selection + push and the waiting merge run on the engine's side stream with one
+ * SM reserved for them.  Do not interleave with svsb_enqueue_query_peer while tickets are pending. */
+int svsb_query_peer_submit(svsb_t* e, const float* q, int32_t d, int32_t k, int32_t* ticket);
+int svsb_query_peer_wait(svsb_t* e, int32_t ticket, float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
 /* Make `stream` wait for everything the pipelined svsb_enqueue_local_topk / svsb_enqueue_query_peer calls have issued
  * on the side stream (it also enqueues the last peer query's deferred merge). */
 int svsb_enqueue_join(svsb_t* e, void* stream);

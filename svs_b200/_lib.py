@@ -44,6 +44,11 @@ SIGNATURES = {
     "svsb_norm_stats": (C.c_int, [C.c_void_p, c_float_p, c_i64_p]),
     "svsb_read_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "svsb_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
+    "svsb_query_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "svsb_query_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i32_p]),
+    "svsb_apply_mutations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, c_u64_p]),
+    "svsb_generation_rows": (C.c_int, [C.c_void_p, c_i64_p, c_i64_p]),
+    "svsb_snapshot_rows": (C.c_int, [C.c_void_p, c_i64_p, c_i64_p]),
     "svsb_snapshot_acquire": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "svsb_snapshot_release": (None, [C.c_void_p]),
     "svsb_snapshot_shape": (C.c_int, [C.c_void_p, c_i64_p, c_i32_p, c_u64_p]),
@@ -71,6 +76,8 @@ SIGNATURES = {
     "svsb_xchg_disconnect": (C.c_int, [C.c_void_p]),
     "svsb_enqueue_query_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "svsb_query_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
+    "svsb_query_peer_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_i32_p]),
+    "svsb_query_peer_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_enqueue_local_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "svsb_batch_local_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, c_i32_p]),
     "svsb_enqueue_join": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsvsb200.so")
-SOURCES = ["gemv.cu", "select.cu", "rows.cu", "coarse.cu", "batch.cu", "pairs.cu", "engine.cu"]
+SOURCES = ["gemv.cu", "select.cu", "rows.cu", "coarse.cu", "batch.cu", "pairs.cu", "engine.cu", "multi.cu", "mutate.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

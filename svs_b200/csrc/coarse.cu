@@ -513,18 +513,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // initialised once, thread-safely (C++11 magic static): several host threads reach this concurrently on a multi-device
+    // engine, one worker per device
+    static const EncodeTiledFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            (void)cudaGetLastError();
-    }
+            return reinterpret_cast<EncodeTiledFn>(p);
+        (void)cudaGetLastError();
+        return (EncodeTiledFn) nullptr;
+    }();
     return fn;
 }
 

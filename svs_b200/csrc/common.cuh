@@ -48,6 +48,10 @@ __host__ __device__ __forceinline__ u64 make_key(float score, uint32_t row) {
 __host__ __device__ __forceinline__ uint32_t key_row(u64 key) { return ~(uint32_t)key; }
 __host__ __device__ __forceinline__ float key_score(u64 key) { return ordered_to_f32((uint32_t)(key >> 32)); }
 
+// Score stored for a tombstoned row: the bit pattern 0xffffffff orders below every other float under f32_to_ordered
+// (key high word 0), -inf and negative-sign NaNs included.
+__host__ __device__ __forceinline__ float dead_score() { return bits_f32(0xffffffffu); }
+
 // Largest k the single-CTA selection kernel handles; larger k takes the full-sort path.
 constexpr int K_FAST_MAX = 2048;
 // Target upper bound on the number of row groups whose maxima the selection kernel scans.

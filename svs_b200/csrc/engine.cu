@@ -11,287 +11,14 @@
 //     svsb_query is re-entrant from several OS threads;
 //   * multi-device: contiguous row shards, per-device GEMV + exact local top-k, candidate lists copied
 //     peer-to-peer to device 0 and merged there by one kernel.
-#include "../../include/svsb200.h"
-#include "kernels.cuh"
+#include "engine.cuh"
 
-#include <algorithm>
-#include <atomic>
-#include <cmath>
-#include <condition_variable>
-#include <cstdio>
-#include <cstdlib>
-#include <memory>
-#include <mutex>
-#include <string>
-#include <vector>
-
-using namespace svsb;
-
-// ------------------------------------------------------------------------------------------------
-// errors, launch counter
-// ------------------------------------------------------------------------------------------------
-static thread_local std::string g_err;
+thread_local std::string g_err;
 static thread_local bool g_pdl = false;
 namespace svsb { void set_pdl(bool on) { g_pdl = on; } bool pdl_enabled() { return g_pdl; } }
-static int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
-static std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_launches{0};
 namespace svsb { void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); } }
 
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t _e = (call);                                                                   \
-        if (_e != cudaSuccess) {                                                                   \
-            (void)cudaGetLastError();                                                              \
-            return fail(_e == cudaErrorMemoryAllocation ? SVSB_E_NOMEM : SVSB_E_CUDA,              \
-                        std::string(#call) + ": " + cudaGetErrorString(_e));                       \
-        }                                                                                          \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// data structures
-// ------------------------------------------------------------------------------------------------
-struct Shard {
-    int dev = 0;
-    int64_t row0 = 0, n = 0;
-    float* M = nullptr;          // n x ld floats
-    int64_t* ids = nullptr;      // n
-};
-
-struct Generation {
-    uint64_t id = 0;
-    int64_t n = 0;
-    int d = 0, ld = 0;
-    std::vector<Shard> shards;
-    float max_dev = 0.f;
-    int64_t n_out_of_tol = 0;
-    // fp16 shadow of shard 0 for the batched coarse contraction (built lazily by the first batch)
-    std::mutex m16_mu;
-    void* M16 = nullptr; int ld16 = 0;
-    // set once a batch saw its statistical filter thresholds fail verification (rows not in random order w.r.t. the
-    // queries): later batches of this generation use the guaranteed thresholds
-    std::atomic<bool> batch_guaranteed{false};
-    ~Generation() {
-        for (auto& s : shards) {
-            if (s.M || s.ids) cudaSetDevice(s.dev);
-            if (s.M) cudaFree(s.M);
-            if (s.ids) cudaFree(s.ids);
-        }
-        if (M16 && !shards.empty()) { cudaSetDevice(shards[0].dev); cudaFree(M16); }
-    }
-};
-
-// per-device scratch for one in-flight query
-struct svsb_workspace {
-    int dev = 0;
-    cudaStream_t st = nullptr;       // owned when created by the engine; null for the stateless API
-    bool own_stream = false;
-    float* d_q = nullptr;   int q_cap = 0;
-    float* scores = nullptr; int64_t n_cap = 0;
-    u64* gmax = nullptr;     int64_t g_cap = 0;
-    u64* cand = nullptr;     int64_t cand_cap = 0;
-    u64* sortbuf = nullptr;  int64_t sort_cap = 0;
-    u64* out_keys = nullptr; float* out_scores = nullptr; int64_t* out_ids = nullptr; int64_t out_cap = 0;
-    int32_t* out_count = nullptr;
-    u64* mscr_keys = nullptr; int64_t* mscr_ids = nullptr; int64_t mscr_cap = 0;   // merge scratch
-    cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr, ev_sel = nullptr;
-    // The similarity kernel leaves group maxima in gmax and only a SUCCESSFUL selection kernel re-zeroes them
-    // (select.cu).  Set before the similarity launch, cleared once the selection is enqueued: a call that failed in
-    // between leaves it set and the next user of this (pooled) workspace re-zeroes gmax first.
-    bool gmax_dirty = false;
-
-    int ensure_rows(int64_t n) {
-        cudaSetDevice(dev);
-        if (gmax_dirty && gmax && n <= n_cap) {
-            CU(cudaMemset(gmax, 0, (size_t)g_cap * 8));
-            CU(cudaStreamSynchronize(cudaStreamLegacy));
-            gmax_dirty = false;
-        }
-        if (n > n_cap) {
-            if (scores) cudaFree(scores); if (gmax) cudaFree(gmax); if (cand) cudaFree(cand);
-            scores = nullptr; gmax = nullptr; cand = nullptr; n_cap = 0;
-            const int shift = group_shift_for(n);
-            const int64_t G = (n + ((int64_t)1 << shift) - 1) >> shift;
-            int64_t cc = (int64_t)K_FAST_MAX << shift; if (cc > n) cc = n;
-            cc += K_FAST_MAX;                       // room for the overflow path to re-home the sort buffer
-            CU(cudaMalloc(&scores, (size_t)n * 4));
-            CU(cudaMalloc(&gmax, (size_t)G * 8));
-            CU(cudaMemset(gmax, 0, (size_t)G * 8));
-            // cudaMemset runs on the legacy default stream, asynchronously to the host, and the engine's streams are
-            // non-blocking: without this wait a similarity kernel could write group maxima BEFORE the zeroing lands
-            CU(cudaStreamSynchronize(cudaStreamLegacy));
-            CU(cudaMalloc(&cand, (size_t)cc * 8));
-            n_cap = n; g_cap = G; cand_cap = cc; gmax_dirty = false;
-        }
-        return SVSB_OK;
-    }
-    int ensure_q(int ld) {
-        cudaSetDevice(dev);
-        if (ld > q_cap) { if (d_q) cudaFree(d_q); d_q = nullptr; CU(cudaMalloc(&d_q, (size_t)ld * 4)); q_cap = ld; }
-        return SVSB_OK;
-    }
-    int ensure_out(int64_t k) {
-        cudaSetDevice(dev);
-        if (!out_count) CU(cudaMalloc(&out_count, 64));
-        if (k > out_cap) {
-            if (out_keys) cudaFree(out_keys); if (out_scores) cudaFree(out_scores); if (out_ids) cudaFree(out_ids);
-            out_keys = nullptr; out_scores = nullptr; out_ids = nullptr; out_cap = 0;
-            CU(cudaMalloc(&out_keys, (size_t)k * 8));
-            CU(cudaMalloc(&out_scores, (size_t)k * 4));
-            CU(cudaMalloc(&out_ids, (size_t)k * 8));
-            out_cap = k;
-        }
-        return SVSB_OK;
-    }
-    int ensure_sort(int64_t n) {
-        cudaSetDevice(dev);
-        int64_t need = next_pow2(n); if (need < 2048) need = 2048;
-        if (need > sort_cap) { if (sortbuf) cudaFree(sortbuf); sortbuf = nullptr; CU(cudaMalloc(&sortbuf, (size_t)need * 8)); sort_cap = need; }
-        return SVSB_OK;
-    }
-    int ensure_merge_scratch(int64_t entries) {
-        cudaSetDevice(dev);
-        if (entries > mscr_cap) {
-            if (mscr_keys) cudaFree(mscr_keys); if (mscr_ids) cudaFree(mscr_ids);
-            mscr_keys = nullptr; mscr_ids = nullptr; mscr_cap = 0;
-            CU(cudaMalloc(&mscr_keys, (size_t)entries * 8));
-            CU(cudaMalloc(&mscr_ids, (size_t)entries * 8));
-            mscr_cap = entries;
-        }
-        return SVSB_OK;
-    }
-    void release() {
-        cudaSetDevice(dev);
-        void* ptrs[] = {d_q, scores, gmax, cand, sortbuf, out_keys, out_scores, out_ids, out_count, mscr_keys, mscr_ids};
-        for (void* p : ptrs) if (p) cudaFree(p);
-        if (ev) cudaEventDestroy(ev); if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
-        if (ev_sel) cudaEventDestroy(ev_sel);
-        if (own_stream && st) cudaStreamDestroy(st);
-    }
-};
-typedef svsb_workspace DevWs;
-
-struct QueryCtx {
-    std::vector<DevWs> ws;                 // one per engine device
-    std::unique_ptr<DevWs> alt;            // second buffer set + the selection stream of the pipelined bench loop (device 0)
-    DevWs* last = nullptr;                 // workspace holding the last single-device bench result
-    // pinned host staging
-    float* h_q = nullptr; int h_q_cap = 0;
-    float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_count = nullptr; int64_t h_out_cap = 0;
-    // device-0 gather + merge outputs (multi-device)
-    u64* g_keys = nullptr; int64_t* g_ids = nullptr; int32_t* g_counts = nullptr; int64_t g_stride = 0;
-    float* m_scores = nullptr; int64_t* m_ids = nullptr; int32_t* m_count = nullptr; int64_t m_cap = 0;
-    cudaEvent_t ev_merge = nullptr; bool merge_recorded = false;   // last merge that read g_keys / g_ids
-};
-
-struct Slab {
-    float* rows = nullptr; int64_t* ids = nullptr;
-    std::vector<cudaEvent_t> ev;           // per device: last copy out of this slab
-    std::vector<char> pending;
-};
-
-struct Loading {
-    std::shared_ptr<Generation> gen;
-    int norm_mode = SVSB_NORM_CHECK;
-    int64_t loaded = 0;
-    int64_t slab_rows = 0;
-    int cur = 0;
-    bool borrowed = false;
-};
-
-// workspace of the batched path: coarse operands, thresholds, candidate lists, outputs (device) + pinned staging
-struct BatchWs {
-    int dev = 0;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    // capacities
-    int cap_b = 0, cap_ld = 0, cap_k = 0; int64_t cap_sample = 0; int cand_cap = 0;
-    float* dQ = nullptr; void* dQ16 = nullptr;
-    float* eps = nullptr; float* thr = nullptr; int32_t* flags = nullptr; int32_t* cand_cnt = nullptr; int32_t* stats = nullptr;
-    float* sample = nullptr; u64* cand = nullptr;
-    float* o_scores = nullptr; int64_t* o_ids = nullptr; int32_t* o_counts = nullptr;
-    float* h_Q = nullptr; float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_counts = nullptr;
-    int32_t* h_flags = nullptr; int32_t* h_stats = nullptr; int32_t* h_cnt = nullptr;
-
-    void release_device() {
-        cudaSetDevice(dev);
-        void* ptrs[] = {dQ, dQ16, eps, thr, flags, cand_cnt, stats, sample, cand, o_scores, o_ids, o_counts};
-        for (void* p : ptrs) if (p) cudaFree(p);
-        void* hp[] = {h_Q, h_scores, h_ids, h_counts, h_flags, h_stats, h_cnt};
-        for (void* p : hp) if (p) cudaFreeHost(p);
-        dQ = nullptr; dQ16 = nullptr; eps = thr = nullptr; flags = cand_cnt = stats = nullptr; sample = nullptr; cand = nullptr;
-        o_scores = nullptr; o_ids = nullptr; o_counts = nullptr;
-        h_Q = h_scores = nullptr; h_ids = nullptr; h_counts = h_flags = h_stats = h_cnt = nullptr;
-        cap_b = cap_ld = cap_k = 0; cap_sample = 0; cand_cap = 0;
-    }
-    void release() {
-        release_device();
-        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
-        if (st) { cudaStreamDestroy(st); st = nullptr; }
-    }
-};
-
-// Peer exchange of the one-process-per-GPU deployment (kernels.cuh "peer exchange"): this rank's gather window,
-// the peers' windows opened over CUDA IPC (or plain pointers inside one process), and a synchronous query context.
-struct Xchg {
-    int world = 0, rank = 0, cap = 0, slots = 4;
-    int64_t rec_words = 0;
-    unsigned char* block = nullptr;                      // [flags: slots*world u64, padded to 256 B][window]
-    size_t flags_bytes = 0;
-    std::vector<unsigned char*> peer_block;              // per rank (own entry = block)
-    std::vector<void*> ipc_opened;
-    bool connected = false;
-    unsigned long long seq = 0;
-    unsigned long long timeout_ns = 30ull * 1000000000ull;   // merge kernel gives up waiting for a peer (SVSB_XCHG_TIMEOUT_MS)
-    // Pipelined path: the merge of query j is enqueued on the side stream BEHIND the selection of query j+1, so a
-    // peer has a whole query time to deliver its record before this rank's side stream would wait for it.
-    struct DeferredMerge {
-        bool pending = false;
-        int slot = 0, k = 0; unsigned long long seq = 0;
-        u64* sk = nullptr; int64_t* sp = nullptr;
-        float* out_scores = nullptr; int64_t* out_ids = nullptr; int32_t* out_count = nullptr;
-    } deferred;
-    cudaEvent_t ev_join = nullptr;
-    // synchronous path (svsb_query_peer): own stream, device query, pinned staging; results land in pinned
-    // host memory straight from the merge kernel (mapped, no copy back)
-    cudaStream_t st = nullptr;
-    DevWs ws;
-    float* h_q = nullptr; int h_q_cap = 0;
-    float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_count = nullptr; int64_t h_cap = 0;
-    u64* flags_of(unsigned char* b, int slot) const { return reinterpret_cast<u64*>(b) + (size_t)slot * world; }
-    u64* rec_of(unsigned char* b, int slot, int src) const {
-        return reinterpret_cast<u64*>(b + flags_bytes) + ((size_t)slot * world + src) * rec_words;
-    }
-};
-
-struct svsb_engine {
-    std::vector<int> devs;
-    std::mutex mu;                          // guards current, loading, pool bookkeeping
-    std::condition_variable cv;
-    std::shared_ptr<Generation> current;
-    uint64_t next_gen = 1;
-    std::unique_ptr<Loading> loading;
-    std::vector<Slab> slabs; int64_t slab_bytes_rows = 0, slab_ids_cap = 0;
-    std::vector<cudaStream_t> copy_st;      // per device
-    std::vector<std::unique_ptr<QueryCtx>> pool_free;
-    int ctx_total = 0, ctx_max = 4;
-    // batched path (one batch at a time)
-    std::mutex batch_mu;
-    std::unique_ptr<struct BatchWs> batch_ws;
-    // bench state
-    std::vector<float*> bench_q; int bench_nq = 0, bench_d = 0, bench_ld = 0;
-    std::unique_ptr<QueryCtx> bench_ctx;
-    std::vector<cudaEvent_t> bench_kev;                  // similarity-kernel timing events of svsb_bench_run (device 0)
-    // sharded deployment (one process per GPU)
-    int64_t shard_row0 = 0;                              // global row of this engine's first row
-    std::vector<std::unique_ptr<DevWs>> shard_ws;        // workspaces for svsb_enqueue_local_topk (by slot)
-    std::vector<cudaEvent_t> kev; size_t kev_used = 0;   // similarity-kernel timing events
-    cudaStream_t side_st = nullptr;                      // selection kernels of the pipelined sharded path
-    std::vector<char> sel_pending;                       // per slot: a selection is (or was) in flight on side_st
-    std::unique_ptr<Xchg> xchg;
-};
-
-static inline int round_up4(int d) { return (d + 3) & ~3; }
 
 // ------------------------------------------------------------------------------------------------
 // context pool
@@ -322,9 +49,6 @@ static void ctx_destroy(svsb_engine* e, QueryCtx* c) {
     if (c->h_scores) cudaFreeHost(c->h_scores);
     if (c->h_ids) cudaFreeHost(c->h_ids);
     if (c->h_count) cudaFreeHost(c->h_count);
-    void* ptrs[] = {c->g_keys, c->g_ids, c->g_counts, c->m_scores, c->m_ids, c->m_count};
-    for (void* p : ptrs) if (p) cudaFree(p);
-    if (c->ev_merge) cudaEventDestroy(c->ev_merge);
 }
 static int ctx_acquire(svsb_engine* e, std::unique_ptr<QueryCtx>& out) {
     std::unique_lock<std::mutex> lk(e->mu);
@@ -361,30 +85,10 @@ static int ctx_ensure_host(QueryCtx* c, int ld, int64_t k) {
     }
     return SVSB_OK;
 }
-static int ctx_ensure_gather(svsb_engine* e, QueryCtx* c, int64_t k) {
-    CU(cudaSetDevice(e->devs[0]));
-    const int64_t nd = (int64_t)e->devs.size();
-    if (!c->g_counts) {
-        CU(cudaMalloc(&c->g_counts, (size_t)nd * 4)); CU(cudaMalloc(&c->m_count, 64));
-        CU(cudaEventCreateWithFlags(&c->ev_merge, cudaEventDisableTiming));
-    }
-    if (k > c->g_stride) {
-        void* ptrs[] = {c->g_keys, c->g_ids, c->m_scores, c->m_ids};
-        for (void* p : ptrs) if (p) cudaFree(p);
-        c->g_keys = nullptr; c->g_ids = nullptr; c->m_scores = nullptr; c->m_ids = nullptr; c->g_stride = 0;
-        CU(cudaMalloc(&c->g_keys, (size_t)(nd * k) * 8));
-        CU(cudaMalloc(&c->g_ids, (size_t)(nd * k) * 8));
-        CU(cudaMalloc(&c->m_scores, (size_t)k * 4));
-        CU(cudaMalloc(&c->m_ids, (size_t)k * 8));
-        c->g_stride = k; c->m_cap = k;
-    }
-    return SVSB_OK;
-}
-
 // ------------------------------------------------------------------------------------------------
 // lifetime
 // ------------------------------------------------------------------------------------------------
-extern "C" int svsb_create(const int* device_ids, int n_dev, svsb_t** out) {
+int engine_create(const int* device_ids, int n_dev, bool as_kid, svsb_engine** out) {
     if (!out) return fail(SVSB_E_INVALID, "svsb_create: out is NULL");
     *out = nullptr;
     int count = 0;
@@ -420,22 +124,20 @@ extern "C" int svsb_create(const int* device_ids, int n_dev, svsb_t** out) {
         cudaStream_t st;
         CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         e->copy_st.push_back(st);
-        // peer access to device 0 for the candidate gather (ignored if unsupported: copies then stage via host)
-        if (i > 0 && e->devs[i] != e->devs[0]) {
-            int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, e->devs[i], e->devs[0]) == cudaSuccess && can) {
-                cudaError_t pe = cudaDeviceEnablePeerAccess(e->devs[0], 0);
-                if (pe != cudaSuccess) (void)cudaGetLastError();
-            }
-            CU(cudaSetDevice(e->devs[0]));
-            if (cudaDeviceCanAccessPeer(&can, e->devs[0], e->devs[i]) == cudaSuccess && can) {
-                cudaError_t pe = cudaDeviceEnablePeerAccess(e->devs[i], 0);
-                if (pe != cudaSuccess) (void)cudaGetLastError();
-            }
-        }
     }
-    *out = e.release();
+    e->is_kid = as_kid;
+    svsb_engine* raw = e.release();
+    if (raw->devs.size() > 1) {
+        // one shard engine + one worker thread per device, gather windows connected over peer memory (multi.cu)
+        int rc = multi_create(raw);
+        if (rc != SVSB_OK) { const std::string msg = g_err; svsb_destroy(raw); g_err = msg; return rc; }
+    }
+    *out = raw;
     return SVSB_OK;
+}
+
+extern "C" int svsb_create(const int* device_ids, int n_dev, svsb_t** out) {
+    return engine_create(device_ids, n_dev, false, out);
 }
 
 static void free_slabs(svsb_engine* e) {
@@ -461,11 +163,20 @@ static void xchg_release(svsb_engine* e) {
     if (x->h_scores) cudaFreeHost(x->h_scores);
     if (x->h_ids) cudaFreeHost(x->h_ids);
     if (x->h_count) cudaFreeHost(x->h_count);
+    for (auto& t : x->tk) {
+        if (t.h_q) cudaFreeHost(t.h_q);
+        if (t.d_q) cudaFree(t.d_q);
+        if (t.h_scores) cudaFreeHost(t.h_scores);
+        if (t.h_ids) cudaFreeHost(t.h_ids);
+        if (t.h_count) cudaFreeHost(t.h_count);
+        if (t.ev) cudaEventDestroy(t.ev);
+    }
     e->xchg.reset();
 }
 
 extern "C" void svsb_destroy(svsb_t* e) {
     if (!e) return;
+    multi_destroy(e);                       // workers joined, shard engines gone, before anything they use is freed
     for (size_t i = 0; i < e->devs.size(); ++i) { cudaSetDevice(e->devs[i]); cudaDeviceSynchronize(); }
     e->loading.reset();
     e->current.reset();
@@ -501,11 +212,17 @@ static int alloc_generation(svsb_engine* e, int64_t n, int d, std::shared_ptr<Ge
         g->shards.push_back(s);
     }
     if (n + e->shard_row0 > 0xfffffff0ll) return fail(SVSB_E_INVALID, "more than 2^32 rows in total are not supported");
+    g->n_live = n;
     for (auto& s : g->shards) {
+        s.n_live = s.n;
         if (s.n == 0 || g->ld == 0) continue;
         CU(cudaSetDevice(s.dev));
-        CU(cudaMalloc(&s.M, (size_t)s.n * g->ld * 4));
-        CU(cudaMalloc(&s.ids, (size_t)s.n * 8));
+        s.buf.reset(new ShardBuf());
+        s.buf->dev = s.dev;
+        CU(cudaMalloc(&s.buf->M, (size_t)s.n * g->ld * 4));
+        CU(cudaMalloc(&s.buf->ids, (size_t)s.n * 8));
+        s.buf->cap_rows = s.n;
+        s.M = s.buf->M; s.ids = s.buf->ids;
     }
     out = g;
     return SVSB_OK;
@@ -647,7 +364,7 @@ extern "C" int svsb_load_rows(svsb_t* e, const float* rows, const int64_t* emb_i
     return SVSB_OK;
 }
 
-static int finish_generation(svsb_engine* e, Generation* g, int norm_mode) {
+int finish_generation(svsb_engine* e, Generation* g, int norm_mode) {
     // row norms on every shard; stats reduced on the host (two words per shard)
     g->max_dev = 0.f; g->n_out_of_tol = 0;
     std::vector<u64*> stats(g->shards.size(), nullptr);
@@ -688,12 +405,10 @@ extern "C" int svsb_load_end(svsb_t* e, uint64_t* generation) {
     for (auto& s : e->slabs) { int rc = slab_wait(e, s); if (rc != SVSB_OK) { e->loading.reset(); return rc; } }
     int rc = finish_generation(e, L->gen.get(), L->norm_mode);
     if (rc != SVSB_OK) { e->loading.reset(); return rc; }
-    std::lock_guard<std::mutex> lk(e->mu);
-    L->gen->id = e->next_gen++;
-    e->current = L->gen;
-    if (generation) *generation = L->gen->id;
+    L->gen->norm_mode = L->norm_mode;
+    rc = publish_generation(e, L->gen, generation);
     e->loading.reset();
-    return SVSB_OK;
+    return rc;
 }
 
 extern "C" int svsb_load_abort(svsb_t* e) {
@@ -721,11 +436,7 @@ extern "C" int svsb_load_synthetic(svsb_t* e, int64_t n, int32_t d, uint64_t see
     // after normalisation the deviation statistics describe the raw rows; recompute for the stored ones
     rc = finish_generation(e, g.get(), SVSB_NORM_CHECK);
     if (rc != SVSB_OK) return rc;
-    std::lock_guard<std::mutex> lk(e->mu);
-    g->id = e->next_gen++;
-    e->current = g;
-    if (generation) *generation = g->id;
-    return SVSB_OK;
+    return publish_generation(e, g, generation);
 }
 
 extern "C" int svsb_invalidate(svsb_t* e) {
@@ -741,7 +452,16 @@ extern "C" int svsb_is_loaded(svsb_t* e) {
     return e->current ? 1 : 0;
 }
 
-static std::shared_ptr<Generation> pin(svsb_engine* e) {
+int publish_generation(svsb_engine* e, const std::shared_ptr<Generation>& g, uint64_t* generation) {
+    { std::lock_guard<std::mutex> lk(e->mu); g->id = e->next_gen++; }
+    if (e->multi) { int rc = multi_publish(e, g); if (rc != SVSB_OK) return rc; }   // per-device views + workspaces first
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->current = g;
+    if (generation) *generation = g->id;
+    return SVSB_OK;
+}
+
+std::shared_ptr<Generation> pin(svsb_engine* e) {
     std::lock_guard<std::mutex> lk(e->mu);
     return e->current;
 }
@@ -750,7 +470,7 @@ extern "C" int svsb_shape(svsb_t* e, int64_t* n, int32_t* d) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     auto g = pin(e);
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
-    if (n) *n = g->n;
+    if (n) *n = g->n_live;                  // what embeddings_matrix.shape[0] is to the reference: rows a query can return
     if (d) *d = g->d;
     return SVSB_OK;
 }
@@ -764,21 +484,54 @@ extern "C" int svsb_norm_stats(svsb_t* e, float* max_abs_dev, int64_t* n_out_of_
     return SVSB_OK;
 }
 
+// copy physical rows [a, b) of shard s to the host (rows: d floats each; either output may be NULL)
+static int copy_rows_out(const Generation* g, const Shard& s, int64_t a, int64_t b, float* rows, int64_t* emb_ids) {
+    if (a >= b) return SVSB_OK;
+    CU(cudaSetDevice(s.dev));
+    if (rows && g->d > 0)
+        CU(cudaMemcpy2D(rows, (size_t)g->d * 4, s.M + a * g->ld, (size_t)g->ld * 4, (size_t)g->d * 4, (size_t)(b - a), cudaMemcpyDeviceToHost));
+    if (emb_ids) CU(cudaMemcpy(emb_ids, s.ids + a, (size_t)(b - a) * 8, cudaMemcpyDeviceToHost));
+    return SVSB_OK;
+}
+
 extern "C" int svsb_read_rows(svsb_t* e, int64_t row0, int64_t count, float* rows, int64_t* emb_ids) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     auto g = pin(e);
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
-    if (row0 < 0 || count < 0 || row0 + count > g->n) return fail(SVSB_E_INVALID, "svsb_read_rows: range out of bounds");
-    const int64_t base = g->shards.empty() ? 0 : g->shards[0].row0;      // local row 0 in global numbering
-    for (auto& s0 : g->shards) {
-        Shard s = s0; s.row0 -= base;
-        const int64_t a = std::max(row0, s.row0), b = std::min(row0 + count, s.row0 + s.n);
-        if (a >= b) continue;
+    if (row0 < 0 || count < 0 || row0 + count > g->n_live) return fail(SVSB_E_INVALID, "svsb_read_rows: range out of bounds");
+    // rows are addressed as a fresh rebuild would number them: live rows only, in row order
+    int64_t logical = 0;                                         // live rows before the current position
+    std::vector<uint8_t> live;
+    for (auto& s : g->shards) {
+        if (s.n == 0) continue;
+        if (logical >= row0 + count) break;
+        if (!s.live) {                                           // no tombstones in this shard: one contiguous copy
+            const int64_t a = std::max(row0, logical), b = std::min(row0 + count, logical + s.n);
+            if (a < b) {
+                int rc = copy_rows_out(g.get(), s, a - logical, b - logical, rows ? rows + (a - row0) * g->d : nullptr,
+                                       emb_ids ? emb_ids + (a - row0) : nullptr);
+                if (rc != SVSB_OK) return rc;
+            }
+            logical += s.n;
+            continue;
+        }
+        live.resize((size_t)s.n);
         CU(cudaSetDevice(s.dev));
-        if (rows && g->d > 0)
-            CU(cudaMemcpy2D(rows + (a - row0) * g->d, (size_t)g->d * 4, s.M + (a - s.row0) * g->ld, (size_t)g->ld * 4,
-                            (size_t)g->d * 4, (size_t)(b - a), cudaMemcpyDeviceToHost));
-        if (emb_ids) CU(cudaMemcpy(emb_ids + (a - row0), s.ids + (a - s.row0), (size_t)(b - a) * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(live.data(), s.live, (size_t)s.n, cudaMemcpyDeviceToHost));
+        int64_t r = 0;
+        while (r < s.n && logical < row0 + count) {
+            if (!live[r]) { ++r; continue; }
+            int64_t r1 = r;
+            while (r1 < s.n && live[r1]) ++r1;                   // run of live rows [r, r1) = logical [logical, logical + r1 - r)
+            const int64_t a = std::max(row0, logical), b = std::min(row0 + count, logical + (r1 - r));
+            if (a < b) {
+                int rc = copy_rows_out(g.get(), s, r + (a - logical), r + (b - logical), rows ? rows + (a - row0) * g->d : nullptr,
+                                       emb_ids ? emb_ids + (a - row0) : nullptr);
+                if (rc != SVSB_OK) return rc;
+            }
+            logical += r1 - r;
+            r = r1;
+        }
     }
     return SVSB_OK;
 }
@@ -786,22 +539,7 @@ extern "C" int svsb_read_rows(svsb_t* e, int64_t row0, int64_t count, float* row
 // ------------------------------------------------------------------------------------------------
 // the hot path
 // ------------------------------------------------------------------------------------------------
-// Enqueue GEMV + local top-k for one shard on its workspace stream.  d_q: device query (ld floats).
-static int enqueue_local(DevWs& w, const Generation* g, const Shard& s, const float* d_q, int64_t kk) {
-    const int shift = group_shift_for(s.n);
-    w.gmax_dirty = true;
-    CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, d_q, w.scores, w.gmax, shift));
-    if (kk <= K_FAST_MAX)
-        CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
-                         w.out_keys, w.out_scores, w.out_ids, w.out_count));
-    else
-        CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
-                                w.out_keys, w.out_scores, w.out_ids, w.out_count));
-    w.gmax_dirty = false;
-    return SVSB_OK;
-}
-
-static int prepare_ws(DevWs& w, const Generation* g, const Shard& s, int64_t kk) {
+int prepare_ws(DevWs& w, const Generation* g, const Shard& s, int64_t kk) {
     int rc;
     if ((rc = w.ensure_rows(s.n)) != SVSB_OK) return rc;
     if ((rc = w.ensure_q(g->ld)) != SVSB_OK) return rc;
@@ -810,114 +548,68 @@ static int prepare_ws(DevWs& w, const Generation* g, const Shard& s, int64_t kk)
     return SVSB_OK;
 }
 
-// Gather per-device lists on device 0 and merge.  Results land in c->m_scores / m_ids / m_count (device 0).
-static int enqueue_gather_merge(svsb_engine* e, QueryCtx* c, const Generation* g, int64_t kk) {
-    const int nd = (int)e->devs.size();
-    DevWs& w0 = c->ws[0];
-    int live = 0;
-    for (int i = 0; i < nd; ++i) {
-        const Shard& s = g->shards[i];
-        DevWs& w = c->ws[i];
-        CU(cudaSetDevice(w.dev));
-        if (s.n == 0) { CU(cudaSetDevice(w0.dev)); CU(cudaMemsetAsync(c->g_counts + i, 0, 4, w0.st)); continue; }
-        ++live;
-        const int64_t kl = std::min(kk, s.n);
-        if (i == 0) {
-            CU(cudaMemcpyAsync(c->g_keys, w.out_keys, (size_t)kl * 8, cudaMemcpyDeviceToDevice, w.st));
-            CU(cudaMemcpyAsync(c->g_ids, w.out_ids, (size_t)kl * 8, cudaMemcpyDeviceToDevice, w.st));
-            CU(cudaMemcpyAsync(c->g_counts, w.out_count, 4, cudaMemcpyDeviceToDevice, w.st));
-        } else if (w.dev == w0.dev) {                     // virtual shard on the same GPU (tests)
-            if (c->merge_recorded) CU(cudaStreamWaitEvent(w.st, c->ev_merge, 0));
-            CU(cudaMemcpyAsync(c->g_keys + (int64_t)i * c->g_stride, w.out_keys, (size_t)kl * 8, cudaMemcpyDeviceToDevice, w.st));
-            CU(cudaMemcpyAsync(c->g_ids + (int64_t)i * c->g_stride, w.out_ids, (size_t)kl * 8, cudaMemcpyDeviceToDevice, w.st));
-            CU(cudaMemcpyAsync(c->g_counts + i, w.out_count, 4, cudaMemcpyDeviceToDevice, w.st));
-        } else {
-            // the previous merge on device 0 must have finished reading the gather buffers
-            if (c->merge_recorded) CU(cudaStreamWaitEvent(w.st, c->ev_merge, 0));
-            CU(cudaMemcpyPeerAsync(c->g_keys + (int64_t)i * c->g_stride, w0.dev, w.out_keys, w.dev, (size_t)kl * 8, w.st));
-            CU(cudaMemcpyPeerAsync(c->g_ids + (int64_t)i * c->g_stride, w0.dev, w.out_ids, w.dev, (size_t)kl * 8, w.st));
-            CU(cudaMemcpyPeerAsync(c->g_counts + i, w0.dev, w.out_count, w.dev, 4, w.st));
-        }
-        if (i != 0) { CU(cudaEventRecord(w.ev, w.st)); CU(cudaSetDevice(w0.dev)); CU(cudaStreamWaitEvent(w0.st, w.ev, 0)); }
-    }
-    (void)live;
-    CU(cudaSetDevice(w0.dev));
-    CU(launch_merge(w0.st, c->g_keys, c->g_ids, c->g_counts, nd, (int)c->g_stride, (int)kk, w0.mscr_keys, w0.mscr_ids,
-                    c->m_scores, c->m_ids, c->m_count));
-    CU(cudaEventRecord(c->ev_merge, w0.st));
-    c->merge_recorded = true;
-    return SVSB_OK;
-}
-
-static int query_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, const float* q, int32_t d, int32_t k,
-                     float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+// Argument checks shared by the synchronous and the submit / wait forms.  Returns 1 when there is nothing to compute
+// (k <= 0), 0 to go on (kk set), or a negative error code.
+static int query_check(const std::shared_ptr<Generation>& g, const float* q, int32_t d, int32_t k, float* out_scores,
+                       int64_t* out_emb_ids, int32_t* out_count, int64_t& kk) {
     if (!out_count) return fail(SVSB_E_INVALID, "svsb_query: out_count is NULL");
     *out_count = 0;
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident (call svsb_load_* first)");
-    if (g->n == 0 || d != g->d) {
+    if (g->n_live == 0 || d != g->d) {
         char buf[200];
         snprintf(buf, sizeof buf, "shapes (%lld,%d) and (%d,) not aligned: %d (dim 1) != %d (dim 0)",
-                 (long long)g->n, g->n == 0 ? 0 : g->d, d, g->n == 0 ? 0 : g->d, d);
+                 (long long)g->n_live, g->n_live == 0 ? 0 : g->d, d, g->n_live == 0 ? 0 : g->d, d);
         return fail(SVSB_E_SHAPE, buf);
     }
-    if (k <= 0) return SVSB_OK;                                   // util.py:200-201
+    if (k <= 0) return 1;                                         // util.py:200-201
     if (!q || !out_scores || !out_emb_ids) return fail(SVSB_E_INVALID, "svsb_query: NULL buffer");
-    const int64_t kk = std::min<int64_t>(k, g->n);               // util.py:198-199
-    const int nd = (int)e->devs.size();
-    if (nd > 1 && kk > K_FAST_MAX) return fail(SVSB_E_INVALID, "k > 2048 is not supported with more than one device yet");
+    kk = std::min<int64_t>(k, g->n_live);                        // util.py:198-199
+    return 0;
+}
 
-    CtxLease lease(e);
-    int rc = ctx_acquire(e, lease.c);
-    if (rc != SVSB_OK) return rc;
-    QueryCtx* c = lease.c.get();
+// Single device: enqueue one query on context c.  k <= 2048: no copy-engine operation at all -- a small kernel reads
+// the query from the pinned staging buffer and the selection kernel writes (score, id, count) straight into pinned host
+// memory (both are device-accessible under unified addressing), so a call is 3 launches + 1 synchronize.
+// reserve_sm: leave one SM to the selection kernels of OTHER in-flight queries (svsb_query_submit keeps several going).
+static int enqueue_single(QueryCtx* c, const Generation* g, const float* q, int32_t d, int64_t kk, bool reserve_sm) {
+    const Shard& s = g->shards[0];
+    DevWs& w = c->ws[0];
+    int rc;
     if ((rc = ctx_ensure_host(c, g->ld, kk)) != SVSB_OK) return rc;
+    if ((rc = prepare_ws(w, g, s, kk)) != SVSB_OK) return rc;
     memcpy(c->h_q, q, (size_t)d * 4);
     for (int i = d; i < g->ld; ++i) c->h_q[i] = 0.f;
-
-    // Single device, k <= 2048: no copy-engine operation at all -- a small kernel reads the query from the pinned
-    // staging buffer and the selection kernel writes (score, id, count) straight into pinned host memory (both are
-    // device-accessible under unified addressing), so the call is 3 launches + 1 synchronize.
-    const bool zero_copy = nd == 1 && kk <= K_FAST_MAX;
-    for (int i = 0; i < nd; ++i) {
-        const Shard& s = g->shards[i];
-        if (s.n == 0) continue;
-        DevWs& w = c->ws[i];
-        if ((rc = prepare_ws(w, g.get(), s, kk)) != SVSB_OK) return rc;
-        CU(cudaSetDevice(w.dev));
-        if (zero_copy) {
-            const int shift = group_shift_for(s.n);
-            *c->h_count = -1;
-            CU(launch_stage_query(w.st, c->h_q, w.d_q, g->ld));
-            w.gmax_dirty = true;
-            {   // programmatic dependent launch: the similarity kernel streams its first tiles under the staging kernel
-                PdlScope pdl(env_int("SVSB_PDL", 1) != 0);
-                CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift));
-            }
-            CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
-                             w.out_keys, c->h_scores, c->h_ids, c->h_count));
-            w.gmax_dirty = false;
-            continue;
+    CU(cudaSetDevice(w.dev));
+    const int shift = group_shift_for(s.n);
+    *c->h_count = -1;
+    if (kk <= K_FAST_MAX) {
+        CU(launch_stage_query(w.st, c->h_q, w.d_q, g->ld));
+        w.gmax_dirty = true;
+        {   // programmatic dependent launch: the similarity kernel streams its first tiles under the staging kernel
+            PdlScope pdl(env_int("SVSB_PDL", 1) != 0);
+            CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift, 0, 0, 0, reserve_sm ? 1 : 0, s.live));
         }
-        CU(cudaMemcpyAsync(w.d_q, c->h_q, (size_t)g->ld * 4, cudaMemcpyHostToDevice, w.st));
-        if ((rc = enqueue_local(w, g.get(), s, w.d_q, kk)) != SVSB_OK) return rc;
+        CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
+                         w.out_keys, c->h_scores, c->h_ids, c->h_count));
+        w.gmax_dirty = false;
+        return SVSB_OK;
     }
-    DevWs& w0 = c->ws[0];
-    if (zero_copy) {
-        // results are already on their way to host memory
-    } else if (nd == 1) {
-        CU(cudaMemcpyAsync(c->h_scores, w0.out_scores, (size_t)kk * 4, cudaMemcpyDeviceToHost, w0.st));
-        CU(cudaMemcpyAsync(c->h_ids, w0.out_ids, (size_t)kk * 8, cudaMemcpyDeviceToHost, w0.st));
-        CU(cudaMemcpyAsync(c->h_count, w0.out_count, 4, cudaMemcpyDeviceToHost, w0.st));
-    } else {
-        if ((rc = ctx_ensure_gather(e, c, std::max<int64_t>(kk, 128))) != SVSB_OK) return rc;
-        if ((int64_t)nd * c->g_stride > K_FAST_MAX && (rc = w0.ensure_merge_scratch((int64_t)nd * c->g_stride)) != SVSB_OK) return rc;
-        if ((rc = enqueue_gather_merge(e, c, g.get(), kk)) != SVSB_OK) return rc;
-        CU(cudaMemcpyAsync(c->h_scores, c->m_scores, (size_t)kk * 4, cudaMemcpyDeviceToHost, w0.st));
-        CU(cudaMemcpyAsync(c->h_ids, c->m_ids, (size_t)kk * 8, cudaMemcpyDeviceToHost, w0.st));
-        CU(cudaMemcpyAsync(c->h_count, c->m_count, 4, cudaMemcpyDeviceToHost, w0.st));
-    }
-    CU(cudaSetDevice(w0.dev));
-    CU(cudaStreamSynchronize(w0.st));
+    CU(cudaMemcpyAsync(w.d_q, c->h_q, (size_t)g->ld * 4, cudaMemcpyHostToDevice, w.st));
+    w.gmax_dirty = true;
+    CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift, 0, 0, 0, 0, s.live));
+    CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
+                            w.out_keys, w.out_scores, w.out_ids, w.out_count));
+    w.gmax_dirty = false;
+    CU(cudaMemcpyAsync(c->h_scores, w.out_scores, (size_t)kk * 4, cudaMemcpyDeviceToHost, w.st));
+    CU(cudaMemcpyAsync(c->h_ids, w.out_ids, (size_t)kk * 8, cudaMemcpyDeviceToHost, w.st));
+    CU(cudaMemcpyAsync(c->h_count, w.out_count, 4, cudaMemcpyDeviceToHost, w.st));
+    return SVSB_OK;
+}
+
+static int finish_single(QueryCtx* c, int64_t kk, float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    DevWs& w = c->ws[0];
+    CU(cudaSetDevice(w.dev));
+    CU(cudaStreamSynchronize(w.st));
     const int32_t cnt = *c->h_count;
     if (cnt != (int32_t)kk) {
         char buf[120]; snprintf(buf, sizeof buf, "internal: selection returned %d results, expected %lld", cnt, (long long)kk);
@@ -929,14 +621,79 @@ static int query_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, const
     return SVSB_OK;
 }
 
+static int query_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, const float* q, int32_t d, int32_t k,
+                     float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    int64_t kk = 0;
+    int rc = query_check(g, q, d, k, out_scores, out_emb_ids, out_count, kk);
+    if (rc != 0) return rc < 0 ? rc : SVSB_OK;
+    if (e->multi) return multi_query(e, g, q, d, kk, out_scores, out_emb_ids, out_count);
+    CtxLease lease(e);
+    if ((rc = ctx_acquire(e, lease.c)) != SVSB_OK) return rc;
+    if ((rc = enqueue_single(lease.c.get(), g.get(), q, d, kk, false)) != SVSB_OK) return rc;
+    return finish_single(lease.c.get(), kk, out_scores, out_emb_ids, out_count);
+}
+
 extern "C" int svsb_query(svsb_t* e, const float* q, int32_t d, int32_t k,
                           float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     return query_gen(e, pin(e), q, d, k, out_scores, out_emb_ids, out_count);
 }
 
+// ---- submit / wait: the same query with several in flight from one host thread ---------------------------------
+// A pending query owns a context (its stream, workspace and pinned staging) or, on a multi-device engine, a ticket.
+struct svsb_pending {
+    std::unique_ptr<QueryCtx> ctx;
+    svsb_ticket* ticket = nullptr;
+    std::shared_ptr<Generation> gen;
+    int64_t kk = 0;
+};
+
+extern "C" int svsb_query_submit(svsb_t* e, const float* q, int32_t d, int32_t k, svsb_pending_t** out) {
+    if (!e || !out) return fail(SVSB_E_INVALID, "svsb_query_submit: NULL argument");
+    *out = nullptr;
+    auto g = pin(e);
+    int32_t dummy = 0;
+    float fs; int64_t fi;                                        // outputs are checked at wait time; satisfy the NULL test here
+    int64_t kk = 0;
+    int rc = query_check(g, q, d, k, &fs, &fi, &dummy, kk);
+    if (rc < 0) return rc;
+    std::unique_ptr<svsb_pending> p(new svsb_pending());
+    p->gen = g; p->kk = rc == 1 ? 0 : kk;
+    if (rc == 0) {
+        if (e->multi) {
+            if (kk > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_query_submit: k <= 2048 on a multi-device engine (use svsb_query)");
+            if ((rc = multi_submit(e, g, q, d, kk, &p->ticket)) != SVSB_OK) return rc;
+        } else {
+            if ((rc = ctx_acquire(e, p->ctx)) != SVSB_OK) return rc;
+            // several queries in flight: each similarity pass leaves one SM to the (single-CTA) selections of the others
+            if ((rc = enqueue_single(p->ctx.get(), g.get(), q, d, kk, sm_count(e->devs[0]) > 8)) != SVSB_OK) { ctx_release(e, p->ctx); return rc; }
+        }
+    }
+    *out = p.release();
+    return SVSB_OK;
+}
+
+extern "C" int svsb_query_wait(svsb_t* e, svsb_pending_t* p, float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    if (!e || !p) return fail(SVSB_E_INVALID, "svsb_query_wait: NULL argument");
+    std::unique_ptr<svsb_pending> own(p);
+    int rc = SVSB_OK;
+    if (out_count) *out_count = 0;
+    const bool bad_out = !out_count || (p->kk > 0 && (!out_scores || !out_emb_ids));
+    if (p->ticket) {
+        float* s = out_scores; int64_t* i = out_emb_ids; int32_t cnt = 0;
+        std::vector<float> ts; std::vector<int64_t> ti;
+        if (bad_out) { ts.resize((size_t)p->kk); ti.resize((size_t)p->kk); s = ts.data(); i = ti.data(); }
+        rc = multi_wait(e, p->ticket, s, i, bad_out ? &cnt : out_count);      // always releases the ticket
+    } else if (p->ctx) {
+        if (!bad_out) rc = finish_single(p->ctx.get(), p->kk, out_scores, out_emb_ids, out_count);
+        else { cudaSetDevice(p->ctx->ws[0].dev); cudaStreamSynchronize(p->ctx->ws[0].st); }
+        ctx_release(e, p->ctx);
+    }
+    if (rc == SVSB_OK && bad_out) return fail(SVSB_E_INVALID, "svsb_query_wait: NULL buffer");
+    return rc;
+}
+
 // ---- snapshots: a query handle that keeps "the arrays it fetched" alive across an invalidate ----
-struct svsb_snapshot { std::shared_ptr<Generation> gen; };
 
 extern "C" int svsb_snapshot_acquire(svsb_t* e, svsb_snap_t** out) {
     if (!e || !out) return fail(SVSB_E_INVALID, "svsb_snapshot_acquire: NULL argument");
@@ -949,7 +706,7 @@ extern "C" int svsb_snapshot_acquire(svsb_t* e, svsb_snap_t** out) {
 extern "C" void svsb_snapshot_release(svsb_snap_t* s) { delete s; }
 extern "C" int svsb_snapshot_shape(svsb_snap_t* s, int64_t* n, int32_t* d, uint64_t* generation) {
     if (!s || !s->gen) return fail(SVSB_E_INVALID, "snapshot is NULL");
-    if (n) *n = s->gen->n;
+    if (n) *n = s->gen->n_live;
     if (d) *d = s->gen->d;
     if (generation) *generation = s->gen->id;
     return SVSB_OK;
@@ -979,6 +736,7 @@ struct BatchPlan {
 // kernel (flag 16 -> the caller redoes the batch with guaranteed thresholds).
 static bool batch_plan(svsb_engine* e, const Generation* g, int32_t k, BatchPlan& P, bool guaranteed = false) {
     if (e->devs.size() != 1 || g->shards.size() != 1) return false;
+    if (g->has_tombstones()) return false;     // a tombstoned row could stand in for a live one among the coarse candidates
     const Shard& s = g->shards[0];
     if (s.n != g->n || g->n < env_int("SVSB_BATCH_MIN_ROWS", 4096) || g->n > 0x7fffff00ll || g->d < 16) return false;
     const int64_t kk = std::min<int64_t>(k, g->n);
@@ -1157,7 +915,9 @@ static int query_batch_gen(svsb_engine* e, const std::shared_ptr<Generation>& g,
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident (call svsb_load_* first)");
     for (int32_t i = 0; i < b; ++i) out_counts[i] = 0;
     BatchPlan P;
-    const bool coarse = g->n > 0 && d == g->d && k > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
+    if (e->multi && g->n_live > 0 && d == g->d && k > 0 && b >= 2 && out_scores && out_emb_ids)
+        return multi_query_batch(e, g, Q, b, d, k, out_scores, out_emb_ids, out_counts);
+    const bool coarse = g->n_live > 0 && d == g->d && k > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
     if (!coarse)                                      // same results, one similarity pass per query
         return query_batch_loop(e, g, Q, b, d, k, out_scores, out_emb_ids, out_counts);
     if (!out_scores || !out_emb_ids) return fail(SVSB_E_INVALID, "svsb_query_batch: NULL buffer");
@@ -1256,6 +1016,7 @@ static int top_pairs_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, i
     if (n_pairs <= 0 || N < 2 || g->d == 0) return SVSB_OK;       // get_top_k: k <= 0 -> [] (util.py:200-201); no pairs
     if (!out_scores || !out_ids_a || !out_ids_b) return fail(SVSB_E_INVALID, "svsb_top_pairs: NULL buffer");
     if (e->devs.size() != 1 || g->shards.size() != 1) return fail(SVSB_E_INVALID, "svsb_top_pairs: single-device engines only");
+    if (g->has_tombstones()) return fail(SVSB_E_INVALID, "svsb_top_pairs: the resident generation has tombstoned rows (reload to compact it)");
     if (N > 0x7fffff00ll) return fail(SVSB_E_INVALID, "svsb_top_pairs: too many rows");
     const float R = 1.0f + g->max_dev;
     if (!(R <= 8.0f)) return fail(SVSB_E_INVALID, "svsb_top_pairs: rows are too far from unit norm for the fp16 coarse pass");
@@ -1455,59 +1216,60 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
     auto g = pin(e);
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
     if (e->bench_nq == 0 || e->bench_d != g->d) return fail(SVSB_E_SHAPE, "svsb_bench_run: upload queries of the matrix's d first");
-    if (k <= 0 || iters <= 0 || g->n == 0) return fail(SVSB_E_INVALID, "svsb_bench_run: bad arguments");
-    const int64_t kk = std::min<int64_t>(k, g->n);
-    const int nd = (int)e->devs.size();
-    if (nd > 1 && kk > K_FAST_MAX) return fail(SVSB_E_INVALID, "k > 2048 is not supported with more than one device yet");
+    if (k <= 0 || iters <= 0 || g->n_live == 0) return fail(SVSB_E_INVALID, "svsb_bench_run: bad arguments");
+    const int64_t kk = std::min<int64_t>(k, g->n_live);
+    const int64_t l0 = g_launches.load();
     int rc;
+    if (e->multi) {                                     // several devices: the fused path with its tickets in flight (multi.cu)
+        rc = multi_bench_run(e, g, k, iters, total_ms, gemv_ms);
+        if (launches) *launches = g_launches.load() - l0;
+        return rc;
+    }
     if (!e->bench_ctx) { if ((rc = ctx_create(e, e->bench_ctx)) != SVSB_OK) return rc; }
     QueryCtx* c = e->bench_ctx.get();
-    for (int i = 0; i < nd; ++i) if (g->shards[i].n && (rc = prepare_ws(c->ws[i], g.get(), g->shards[i], kk)) != SVSB_OK) return rc;
-    if (nd > 1) {
-        if ((rc = ctx_ensure_gather(e, c, std::max<int64_t>(kk, 128))) != SVSB_OK) return rc;
-        if ((int64_t)nd * c->g_stride > K_FAST_MAX && (rc = c->ws[0].ensure_merge_scratch((int64_t)nd * c->g_stride)) != SVSB_OK) return rc;
-    }
-    // gemv_ms requested: bracket every similarity-kernel launch on device 0 with events INSIDE the timed loop
-    // (one launch in KTIME_EVERY: the two event records cost ~5 us of stream time per bracketed launch, 4 % of a
-    // 125 k-row shard's query -- profiles/r01_shard_probe.txt -- and the loop being timed should be the product's)
-    const bool ktime = gemv_ms != nullptr && g->shards[0].n > 0;
+    DevWs& w0 = c->ws[0];
+    const Shard& s = g->shards[0];
+    if ((rc = prepare_ws(w0, g.get(), s, kk)) != SVSB_OK) return rc;
+    // gemv_ms requested: bracket similarity-kernel launches with events INSIDE the timed loop (one launch in
+    // KTIME_EVERY: the two event records cost ~5 us of stream time per bracketed launch, 4 % of a 125 k-row shard's
+    // query -- profiles/r01_shard_probe.txt -- and the loop being timed should be the product's)
+    const bool ktime = gemv_ms != nullptr;
     constexpr int KTIME_EVERY = 8;
     auto timed_it = [&](int it) { return ktime && it % KTIME_EVERY == 0; };
-    if (ktime && (rc = ensure_kernel_events(e, c->ws[0].dev, (size_t)iters * 2)) != SVSB_OK) return rc;
-    // Single device, k <= 2048: software pipeline.  The similarity kernel of query i+1 (stream A, all SMs but one)
-    // runs while the one-CTA selection kernel of query i (stream B) finishes on the SM left free; two buffer sets.
-    const bool pipelined = nd == 1 && kk <= K_FAST_MAX && env_int("SVSB_PIPELINE", 1) != 0 && sm_count(c->ws[0].dev) > 8;
+    if (ktime && (rc = ensure_kernel_events(e, w0.dev, (size_t)iters * 2)) != SVSB_OK) return rc;
+    // k <= 2048: software pipeline.  The similarity kernel of query i+1 (stream A, all SMs but one) runs while the
+    // one-CTA selection kernel of query i (stream B) finishes on the SM left free; two buffer sets.
+    const bool pipelined = kk <= K_FAST_MAX && env_int("SVSB_PIPELINE", 1) != 0 && sm_count(w0.dev) > 8;
     if (pipelined) {
         if (!c->alt) {
             c->alt.reset(new DevWs());
             DevWs& a = *c->alt;
-            a.dev = c->ws[0].dev;
+            a.dev = w0.dev;
             CU(cudaSetDevice(a.dev));
             CU(cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking));
             a.own_stream = true;
             CU(cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&a.ev_sel, cudaEventDisableTiming));
         }
-        if ((rc = prepare_ws(*c->alt, g.get(), g->shards[0], kk)) != SVSB_OK) return rc;
+        if ((rc = prepare_ws(*c->alt, g.get(), s, kk)) != SVSB_OK) return rc;
     }
-    std::vector<cudaEvent_t>& g_kev = e->bench_kev;
-    const int64_t l0 = g_launches.load();
-    for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaStreamSynchronize(c->ws[i].st)); }
+    std::vector<cudaEvent_t>& kev = e->bench_kev;
+    const int shift = group_shift_for(s.n);
+    CU(cudaSetDevice(w0.dev));
+    CU(cudaStreamSynchronize(w0.st));
     if (pipelined) CU(cudaStreamSynchronize(c->alt->st));
-    for (int i = 0; i < nd; ++i) { CU(cudaSetDevice(c->ws[i].dev)); CU(cudaEventRecord(c->ws[i].ev0, c->ws[i].st)); }
+    CU(cudaEventRecord(w0.ev0, w0.st));
     if (pipelined) {
-        DevWs& w0 = c->ws[0]; DevWs& w1 = *c->alt;
-        const Shard& s = g->shards[0];
-        const int shift = group_shift_for(s.n);
+        DevWs& w1 = *c->alt;
         cudaStream_t sa = w0.st, sb = w1.st;
         for (int it = 0; it < iters; ++it) {
             DevWs& W = (it & 1) ? w1 : w0;
             const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
             if (it >= 2) CU(cudaStreamWaitEvent(sa, W.ev_sel, 0));           // selection of query it-2 is done with W
-            if (timed_it(it)) CU(cudaEventRecord(g_kev[2 * it], sa));
+            if (timed_it(it)) CU(cudaEventRecord(kev[2 * it], sa));
             W.gmax_dirty = true;
-            CU(launch_gemv(sa, W.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, W.scores, W.gmax, shift, 0, 0, 0, /*reserve_sms=*/1));
-            if (timed_it(it)) CU(cudaEventRecord(g_kev[2 * it + 1], sa));
+            CU(launch_gemv(sa, W.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, W.scores, W.gmax, shift, 0, 0, 0, /*reserve_sms=*/1, s.live));
+            if (timed_it(it)) CU(cudaEventRecord(kev[2 * it + 1], sa));
             CU(cudaEventRecord(W.ev, sa));
             CU(cudaStreamWaitEvent(sb, W.ev, 0));
             CU(launch_select(sb, W.scores, s.n, W.gmax, shift, (int)kk, s.ids, s.row0, W.cand, W.cand_cap,
@@ -1521,47 +1283,29 @@ extern "C" int svsb_bench_run(svsb_t* e, int32_t k, int32_t iters, float* total_
     } else {
         for (int it = 0; it < iters; ++it) {
             const int64_t qoff = (int64_t)(it % e->bench_nq) * e->bench_ld;
-            for (int i = 0; i < nd; ++i) {
-                if (!g->shards[i].n) continue;
-                CU(cudaSetDevice(c->ws[i].dev));
-                if (timed_it(it) && i == 0) {
-                    DevWs& w = c->ws[0]; const Shard& s = g->shards[0];
-                    const int shift = group_shift_for(s.n);
-                    CU(cudaEventRecord(g_kev[2 * it], w.st));
-                    w.gmax_dirty = true;
-                    CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, w.scores, w.gmax, shift));
-                    CU(cudaEventRecord(g_kev[2 * it + 1], w.st));
-                    if (kk <= K_FAST_MAX)
-                        CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
-                                         w.out_keys, w.out_scores, w.out_ids, w.out_count));
-                    else
-                        CU(launch_fullsort_topk(w.st, w.scores, s.n, w.gmax, shift, kk, s.ids, s.row0, w.sortbuf,
-                                                w.out_keys, w.out_scores, w.out_ids, w.out_count));
-                    w.gmax_dirty = false;
-                } else if ((rc = enqueue_local(c->ws[i], g.get(), g->shards[i], e->bench_q[i] + qoff, kk)) != SVSB_OK) return rc;
-            }
-            if (nd > 1 && (rc = enqueue_gather_merge(e, c, g.get(), kk)) != SVSB_OK) return rc;
+            if (timed_it(it)) CU(cudaEventRecord(kev[2 * it], w0.st));
+            w0.gmax_dirty = true;
+            CU(launch_gemv(w0.st, w0.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + qoff, w0.scores, w0.gmax, shift, 0, 0, 0, 0, s.live));
+            if (timed_it(it)) CU(cudaEventRecord(kev[2 * it + 1], w0.st));
+            if (kk <= K_FAST_MAX)
+                CU(launch_select(w0.st, w0.scores, s.n, w0.gmax, shift, (int)kk, s.ids, s.row0, w0.cand, w0.cand_cap,
+                                 w0.out_keys, w0.out_scores, w0.out_ids, w0.out_count));
+            else
+                CU(launch_fullsort_topk(w0.st, w0.scores, s.n, w0.gmax, shift, kk, s.ids, s.row0, w0.sortbuf,
+                                        w0.out_keys, w0.out_scores, w0.out_ids, w0.out_count));
+            w0.gmax_dirty = false;
         }
-        c->last = &c->ws[0];
+        c->last = &w0;
     }
-    float best = 0.f;
-    for (int i = 0; i < nd; ++i) {
-        CU(cudaSetDevice(c->ws[i].dev));
-        CU(cudaEventRecord(c->ws[i].ev1, c->ws[i].st));
-    }
-    for (int i = 0; i < nd; ++i) {
-        CU(cudaSetDevice(c->ws[i].dev));
-        CU(cudaEventSynchronize(c->ws[i].ev1));
-        float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ws[i].ev0, c->ws[i].ev1));
-        if (ms > best) best = ms;
-    }
-    if (total_ms) *total_ms = best;
+    CU(cudaEventRecord(w0.ev1, w0.st));
+    CU(cudaEventSynchronize(w0.ev1));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, w0.ev0, w0.ev1));
+    if (total_ms) *total_ms = ms;
     if (launches) *launches = g_launches.load() - l0;
     if (ktime) {
-        CU(cudaSetDevice(c->ws[0].dev));
         float sum = 0.f; int cnt = 0;
         for (int it = 0; it < iters; ++it)
-            if (timed_it(it)) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, g_kev[2 * it], g_kev[2 * it + 1])); sum += ms; ++cnt; }
+            if (timed_it(it)) { float t = 0.f; CU(cudaEventElapsedTime(&t, kev[2 * it], kev[2 * it + 1])); sum += t; ++cnt; }
         *gemv_ms = sum * (float)iters / (float)cnt;            // mean bracketed launch x launches
     } else if (gemv_ms) *gemv_ms = 0.f;
     return SVSB_OK;
@@ -1579,14 +1323,15 @@ extern "C" int svsb_debug_select_phases(svsb_t* e, int32_t qi, int32_t k, uint64
     if (!e->bench_ctx) { if ((rc = ctx_create(e, e->bench_ctx)) != SVSB_OK) return rc; }
     DevWs& w = e->bench_ctx->ws[0];
     const Shard& s = g->shards[0];
-    const int64_t kk = std::min<int64_t>(k, s.n);
+    const int64_t kk = std::min<int64_t>(k, s.n_live);
+    if (kk < 1) return fail(SVSB_E_INVALID, "svsb_debug_select_phases: no live rows");
     if ((rc = prepare_ws(w, g.get(), s, kk)) != SVSB_OK) return rc;
     CU(cudaSetDevice(w.dev));
     u64* dbg = nullptr;
     CU(cudaMalloc(&dbg, 16 * 8));
     CU(cudaMemsetAsync(dbg, 0, 16 * 8, w.st));
     const int shift = group_shift_for(s.n);
-    CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + (int64_t)qi * e->bench_ld, w.scores, w.gmax, shift));
+    CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, e->bench_q[0] + (int64_t)qi * e->bench_ld, w.scores, w.gmax, shift, 0, 0, 0, 0, s.live));
     CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
                      w.out_keys, w.out_scores, w.out_ids, w.out_count, dbg));
     CU(cudaMemcpyAsync(stamps16, dbg, 16 * 8, cudaMemcpyDeviceToHost, w.st));
@@ -1600,7 +1345,7 @@ extern "C" int svsb_bench_run_batch(svsb_t* e, int32_t k, int32_t iters, float* 
     auto g = pin(e);
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
     if (e->bench_nq == 0 || e->bench_d != g->d) return fail(SVSB_E_SHAPE, "svsb_bench_run_batch: upload queries of the matrix's d first");
-    if (k <= 0 || iters <= 0 || g->n == 0) return fail(SVSB_E_INVALID, "svsb_bench_run_batch: bad arguments");
+    if (k <= 0 || iters <= 0 || g->n_live == 0) return fail(SVSB_E_INVALID, "svsb_bench_run_batch: bad arguments");
     if (e->bench_nq > COARSE_MAX_BATCH) return fail(SVSB_E_INVALID, "svsb_bench_run_batch: at most 2048 uploaded queries");
     BatchPlan P;
     if (!batch_plan(e, g.get(), k, P)) return fail(SVSB_E_INVALID, "svsb_bench_run_batch: this matrix / k does not take the coarse path");
@@ -1654,19 +1399,20 @@ extern "C" int svsb_bench_batch_result(svsb_t* e, int32_t qi, int32_t k, float* 
 }
 
 extern "C" int svsb_bench_last_result(svsb_t* e, int32_t k, float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
-    if (!e || !e->bench_ctx) return fail(SVSB_E_STATE, "svsb_bench_last_result: no bench run yet");
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     if (!out_scores || !out_emb_ids || !out_count) return fail(SVSB_E_INVALID, "svsb_bench_last_result: NULL buffer");
+    if (e->multi) return multi_bench_last_result(e, k, out_scores, out_emb_ids, out_count);
+    if (!e->bench_ctx || !e->bench_ctx->last) return fail(SVSB_E_STATE, "svsb_bench_last_result: no bench run yet");
     QueryCtx* c = e->bench_ctx.get();
-    const bool multi = e->devs.size() > 1;
-    DevWs& w0 = (!multi && c->last) ? *c->last : c->ws[0];
+    DevWs& w0 = *c->last;
     CU(cudaSetDevice(w0.dev));
     CU(cudaStreamSynchronize(c->ws[0].st));
     if (c->alt) CU(cudaStreamSynchronize(c->alt->st));
     int32_t cnt = 0;
-    CU(cudaMemcpy(&cnt, multi ? c->m_count : w0.out_count, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&cnt, w0.out_count, 4, cudaMemcpyDeviceToHost));
     if (cnt < 0 || cnt > k) return fail(SVSB_E_INVALID, "svsb_bench_last_result: k smaller than the result");
-    CU(cudaMemcpy(out_scores, multi ? c->m_scores : w0.out_scores, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(out_emb_ids, multi ? c->m_ids : w0.out_ids, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_scores, w0.out_scores, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_emb_ids, w0.out_ids, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
     *out_count = cnt;
     return SVSB_OK;
 }
@@ -1682,10 +1428,16 @@ extern "C" int svsb_set_shard(svsb_t* e, int64_t global_row0) {
     return SVSB_OK;
 }
 
+static int enqueue_local_topk_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, void* stream, int32_t slot, const float* d_query,
+                                  int32_t k, int64_t* d_record, int32_t flags);
 extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, const float* d_query, int32_t k,
                                        int64_t* d_record, int32_t flags) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
-    auto g = pin(e);
+    return enqueue_local_topk_gen(e, pin(e), stream, slot, d_query, k, d_record, flags);
+}
+
+static int enqueue_local_topk_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, void* stream, int32_t slot, const float* d_query,
+                                  int32_t k, int64_t* d_record, int32_t flags) {
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
     if (e->devs.size() != 1) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: single-device engines only");
     if (slot < 0 || slot >= 8) return fail(SVSB_E_INVALID, "svsb_enqueue_local_topk: slot out of range (0..7)");
@@ -1696,7 +1448,7 @@ extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, co
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s.dev));
     int32_t* d_count = reinterpret_cast<int32_t*>(d_record + 2 * (int64_t)k);
-    if (s.n == 0) { CU(cudaMemsetAsync(d_count, 0, 8, st)); return SVSB_OK; }
+    if (s.n_live == 0) { CU(cudaMemsetAsync(d_count, 0, 8, st)); return SVSB_OK; }
     if ((size_t)slot >= e->shard_ws.size()) e->shard_ws.resize(slot + 1);
     if (e->sel_pending.size() < e->shard_ws.size()) e->sel_pending.resize(e->shard_ws.size(), 0);
     if (!e->shard_ws[slot]) { e->shard_ws[slot].reset(new DevWs()); e->shard_ws[slot]->dev = s.dev; }
@@ -1720,7 +1472,7 @@ extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, co
         CU(cudaEventRecord(e->kev[e->kev_used], st));
     }
     w.gmax_dirty = true;
-    CU(launch_gemv(st, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, pipelined ? 1 : 0));
+    CU(launch_gemv(st, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, pipelined ? 1 : 0, s.live));
     if (time_kernel) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st)); e->kev_used += 2; }
     cudaStream_t sel_st = st;
     if (pipelined) {
@@ -1728,7 +1480,7 @@ extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, co
         CU(cudaStreamWaitEvent(e->side_st, w.ev, 0));
         sel_st = e->side_st;
     }
-    CU(launch_select(sel_st, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
+    CU(launch_select(sel_st, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n_live), s.ids, s.row0, w.cand, w.cand_cap,
                      reinterpret_cast<u64*>(d_record), w.out_scores, d_record + k, d_count));
     w.gmax_dirty = false;
     if (pipelined) { CU(cudaEventRecord(w.ev_sel, e->side_st)); e->sel_pending[slot] = 1; }
@@ -1742,17 +1494,21 @@ extern "C" int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, co
 extern "C" int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, int64_t* d_records,
                                         int32_t* n_fallback) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
-    auto g = pin(e);
+    return batch_local_records_gen(e, pin(e), (cudaStream_t)stream, d_Q, b, k, d_records, n_fallback);
+}
+
+int batch_local_records_gen(svsb_engine* e, const std::shared_ptr<Generation>& g, cudaStream_t stream, const float* d_Q, int32_t b,
+                            int32_t k, int64_t* d_records, int32_t* n_fallback) {
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
     if (e->devs.size() != 1) return fail(SVSB_E_INVALID, "svsb_batch_local_records: single-device engines only");
     if (b < 0 || k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_batch_local_records: bad arguments (1 <= k <= 2048)");
     if (b == 0) return SVSB_OK;
     if (!d_Q || !d_records) return fail(SVSB_E_INVALID, "svsb_batch_local_records: NULL pointer");
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = stream;
     const int64_t rec = 2 * (int64_t)k + 1;
     int fallbacks = 0;
     BatchPlan P;
-    const bool coarse = g->n > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
+    const bool coarse = g->n_live > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
     std::vector<char> todo((size_t)b, coarse ? 0 : 1);
     if (coarse) {
         std::lock_guard<std::mutex> lk(e->batch_mu);
@@ -1781,7 +1537,7 @@ extern "C" int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_
     for (int32_t i = 0; i < b; ++i) {
         if (!todo[i]) continue;
         ++fallbacks;
-        int rc = svsb_enqueue_local_topk(e, stream, 0, d_Q + (int64_t)i * g->ld, k, d_records + (int64_t)i * rec, 0);
+        int rc = enqueue_local_topk_gen(e, g, stream, 0, d_Q + (int64_t)i * g->ld, k, d_records + (int64_t)i * rec, 0);
         if (rc != SVSB_OK) return rc;
     }
     if (n_fallback) *n_fallback = fallbacks;
@@ -1944,6 +1700,7 @@ static int xchg_flush_merge(svsb_engine* e, cudaStream_t st_sel) {
     m.pending = false;
     CU(launch_merge_window(st_sel, x->rec_of(x->block, m.slot, 0), x->flags_of(x->block, m.slot), m.seq, x->world, x->cap, m.k,
                            x->timeout_ns, m.sk, m.sp, m.out_scores, m.out_ids, m.out_count));
+    if (m.ev_done) { CU(cudaEventRecord(m.ev_done, st_sel)); m.ev_done = nullptr; }
     return SVSB_OK;
 }
 
@@ -1959,7 +1716,7 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
     const Shard& s = g->shards[0];
     PeerPush push{};
     const int slot = xchg_next(x, push);
-    if (s.n == 0) {
+    if (s.n_live == 0) {
         CU(launch_push_empty(st_sel, push));
     } else {
         const int shift = group_shift_for(s.n);
@@ -1967,11 +1724,11 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
         w.gmax_dirty = true;
         {
             PdlScope pdl(pdl_gemv);                               // only after the staging kernel of the synchronous path
-            CU(launch_gemv(st_main, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, reserve_sms));
+            CU(launch_gemv(st_main, s.dev, s.M, s.n, g->d, g->ld, d_query, w.scores, w.gmax, shift, 0, 0, 0, reserve_sms, s.live));
         }
         if (time_kernel) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st_main)); e->kev_used += 2; }
         if (st_sel != st_main) { CU(cudaEventRecord(ev_main_done, st_main)); CU(cudaStreamWaitEvent(st_sel, ev_main_done, 0)); }
-        CU(launch_select(st_sel, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n), s.ids, s.row0, w.cand, w.cand_cap,
+        CU(launch_select(st_sel, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n_live), s.ids, s.row0, w.cand, w.cand_cap,
                          w.out_keys, w.out_scores, w.out_ids, w.out_count, nullptr, &push));
         w.gmax_dirty = false;
     }
@@ -1983,7 +1740,7 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
         if (rc != SVSB_OK) return rc;
         Xchg::DeferredMerge& m = x->deferred;
         m.pending = true; m.slot = slot; m.k = k; m.seq = push.seq; m.sk = sk; m.sp = sp;
-        m.out_scores = out_scores; m.out_ids = out_ids; m.out_count = out_count;
+        m.out_scores = out_scores; m.out_ids = out_ids; m.out_count = out_count; m.ev_done = nullptr;
         return SVSB_OK;
     }
     CU(launch_merge_window(st_sel, x->rec_of(x->block, slot, 0), x->flags_of(x->block, slot), push.seq, x->world, x->cap, k,
@@ -2055,6 +1812,94 @@ extern "C" int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
     if (cnt < 0 || cnt > k) return fail(SVSB_E_CUDA, "svsb_query_peer: internal: merge returned a bad count");
     memcpy(out_scores, x->h_scores, (size_t)cnt * 4);
     memcpy(out_emb_ids, x->h_ids, (size_t)cnt * 8);
+    *out_count = cnt;
+    return SVSB_OK;
+}
+
+// ---- the synchronous peer query with several in flight: submit / wait ---------------------------------------------
+// Same kernels as svsb_query_peer, arranged like the device-resident pipelined loop: the similarity pass runs on the
+// exchange's stream leaving one SM free, selection + push and the (deferred) waiting merge run on the side stream, so
+// query j+1's matrix pass overlaps query j's selection, exchange, merge and host round trip.
+static int xchg_ensure_tickets(svsb_engine* e, const Generation* g) {
+    Xchg* x = e->xchg.get();
+    CU(cudaSetDevice(e->devs[0]));
+    const bool grow = g->ld > x->tk_ld;
+    for (auto& t : x->tk) {
+        if (t.busy && grow) return fail(SVSB_E_STATE, "svsb_query_peer_submit: the matrix changed shape with queries pending");
+        if (grow) {
+            if (t.h_q) cudaFreeHost(t.h_q);
+            if (t.d_q) cudaFree(t.d_q);
+            t.h_q = nullptr; t.d_q = nullptr;
+            CU(cudaMallocHost(&t.h_q, (size_t)g->ld * 4));
+            CU(cudaMalloc(&t.d_q, (size_t)g->ld * 4));
+        }
+        if (!t.h_scores) {
+            CU(cudaMallocHost(&t.h_scores, (size_t)x->cap * 4));
+            CU(cudaMallocHost(&t.h_ids, (size_t)x->cap * 8));
+            CU(cudaMallocHost(&t.h_count, 64));
+            CU(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+        }
+    }
+    if (grow) x->tk_ld = g->ld;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_query_peer_submit(svsb_t* e, const float* q, int32_t d, int32_t k, int32_t* ticket) {
+    if (!e || !ticket) return fail(SVSB_E_INVALID, "svsb_query_peer_submit: NULL argument");
+    *ticket = -1;
+    if (!e->xchg || !e->xchg->connected) return fail(SVSB_E_STATE, "svsb_query_peer_submit: exchange not connected");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (d != g->d) return fail(SVSB_E_SHAPE, "svsb_query_peer_submit: query dimension does not match the matrix");
+    Xchg* x = e->xchg.get();
+    if (k < 1 || k > x->cap) return fail(SVSB_E_INVALID, "svsb_query_peer_submit: 1 <= k <= k_max of the exchange");
+    if (!q) return fail(SVSB_E_INVALID, "svsb_query_peer_submit: NULL buffer");
+    int rc = xchg_prepare(e, g.get());
+    if (rc != SVSB_OK) return rc;
+    if ((rc = xchg_ensure_tickets(e, g.get())) != SVSB_OK) return rc;
+    const int ti = x->tk_next;
+    Xchg::Ticket& t = x->tk[ti];
+    if (t.busy) return fail(SVSB_E_STATE, "svsb_query_peer_submit: 3 queries are pending already (wait for the oldest first)");
+    memcpy(t.h_q, q, (size_t)d * 4);
+    for (int i = d; i < g->ld; ++i) t.h_q[i] = 0.f;
+    *t.h_count = -1;
+    const int slot = (int)(x->seq & 1);                        // workspace set (xchg_enqueue takes sequence number seq + 1)
+    DevWs& w = *e->shard_ws[slot];
+    CU(cudaSetDevice(e->devs[0]));
+    if (e->sel_pending[slot]) CU(cudaStreamWaitEvent(x->st, w.ev_sel, 0));      // the set's previous selection is done with it
+    CU(launch_stage_query(x->st, t.h_q, t.d_q, g->ld));
+    rc = xchg_enqueue(e, g.get(), w, x->st, e->side_st, w.ev, t.d_q, k, t.h_scores, t.h_ids, t.h_count, false, /*reserve_sms=*/1,
+                      /*defer_merge=*/true, w.ev_sel, /*pdl_gemv=*/env_int("SVSB_PDL", 1) != 0);
+    if (rc != SVSB_OK) return rc;
+    e->sel_pending[slot] = 1;
+    x->deferred.ev_done = t.ev;                                // recorded when this query's merge is enqueued
+    t.busy = true; t.k = k; t.seq = x->seq;
+    x->tk_next = (ti + 1) % Xchg::N_TICKETS;
+    *ticket = ti;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_query_peer_wait(svsb_t* e, int32_t ticket, float* out_scores, int64_t* out_emb_ids, int32_t* out_count) {
+    if (!e || !out_count) return fail(SVSB_E_INVALID, "svsb_query_peer_wait: NULL argument");
+    *out_count = 0;
+    if (!e->xchg) return fail(SVSB_E_STATE, "svsb_query_peer_wait: no exchange");
+    Xchg* x = e->xchg.get();
+    if (ticket < 0 || ticket >= Xchg::N_TICKETS || !x->tk[ticket].busy) return fail(SVSB_E_INVALID, "svsb_query_peer_wait: no such pending query");
+    Xchg::Ticket& t = x->tk[ticket];
+    CU(cudaSetDevice(e->devs[0]));
+    if (x->deferred.pending && x->deferred.seq == t.seq) {      // nobody submitted behind it: enqueue its merge now
+        int rc = xchg_flush_merge(e, e->side_st);
+        if (rc != SVSB_OK) { t.busy = false; return rc; }
+    }
+    t.busy = false;
+    CU(cudaEventSynchronize(t.ev));
+    const int32_t cnt = *t.h_count;
+    if (cnt == MERGE_WINDOW_TIMED_OUT)
+        return fail(SVSB_E_STATE, "svsb_query_peer_wait: a peer's record did not arrive in time (a rank died or left the call sequence)");
+    if (cnt < 0 || cnt > t.k) return fail(SVSB_E_CUDA, "svsb_query_peer_wait: internal: merge returned a bad count");
+    if (cnt > 0 && (!out_scores || !out_emb_ids)) return fail(SVSB_E_INVALID, "svsb_query_peer_wait: NULL buffer");
+    memcpy(out_scores, t.h_scores, (size_t)cnt * 4);
+    memcpy(out_emb_ids, t.h_ids, (size_t)cnt * 8);
     *out_count = cnt;
     return SVSB_OK;
 }

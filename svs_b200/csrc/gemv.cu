@@ -24,7 +24,7 @@ namespace svsb {
 template <int R, int U, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 gemv_ldg_kernel(const float4* __restrict__ M, int64_t n, int d4, const float4* __restrict__ q,
-                float* __restrict__ scores, u64* __restrict__ gmax, int group_shift)
+                float* __restrict__ scores, u64* __restrict__ gmax, int group_shift, const uint8_t* __restrict__ live)
 {
     extern __shared__ float4 sq[];
     pdl_wait();                                   // the query (and the scores buffer) belong to the previous kernels
@@ -78,6 +78,7 @@ gemv_ldg_kernel(const float4* __restrict__ M, int64_t n, int d4, const float4* _
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float s = warp_sum((acc[r].x + acc[r].y) + (acc[r].z + acc[r].w));
+            if (live && r0 + r < n && !live[r0 + r]) s = dead_score();      // tombstoned row: sorts below every real score
             if (r0 + r < n) {
                 u64 key = make_key(s, (uint32_t)(r0 + r));
                 kmax = key > kmax ? key : kmax;
@@ -123,7 +124,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 template <int CW, int NQ>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, int stages,
-                const float* __restrict__ q, float* __restrict__ scores, u64* __restrict__ gmax, int group_shift)
+                const float* __restrict__ q, float* __restrict__ scores, u64* __restrict__ gmax, int group_shift,
+                const uint8_t* __restrict__ live)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t row_bytes = (uint32_t)d4 * 16u;
@@ -188,6 +190,8 @@ gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, i
             u64 kmax = 0;
             for (int r = warp; r < rows; r += CW) {
                 const float4* p = tile + (size_t)r * d4;
+                // tombstone byte of this row (svsb_apply_mutations); issued ahead of the row's arithmetic
+                const uint8_t alive = live ? __ldg(live + r0 + r) : (uint8_t)1;
                 float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
                 if (NQ > 0) {
                     float4 m[NQ > 0 ? NQ : 1];
@@ -203,7 +207,8 @@ gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, i
                     for (; c + 32 < d4; c += 64) { fma4(a0, p[c], sq[c]); fma4(a1, p[c + 32], sq[c + 32]); }
                     if (c < d4) fma4(a0, p[c], sq[c]);
                 }
-                const float sc = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
+                float sc = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
+                if (!alive) sc = dead_score();
                 if (lane == 0) {
                     scores[r0 + r] = sc;
                     const u64 k0 = make_key(sc, (uint32_t)(r0 + r));
@@ -236,7 +241,7 @@ int sm_count(int device) {
 
 template <int R, int U, int THREADS>
 static cudaError_t run_ldg(cudaStream_t st, int device, const float* M, int64_t n, int d4, const float* q,
-                           float* scores, u64* gmax, int group_shift, int blocks_per_sm)
+                           float* scores, u64* gmax, int group_shift, const uint8_t* live, int blocks_per_sm)
 {
     auto kern = gemv_ldg_kernel<R, U, THREADS>;
     const size_t smem = (size_t)d4 * 16;
@@ -258,26 +263,28 @@ static cudaError_t run_ldg(cudaStream_t st, int device, const float* M, int64_t 
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     e = launch_kernel(kern, dim3((unsigned)grid), dim3(THREADS), smem, st, reinterpret_cast<const float4*>(M), n, d4,
-                      reinterpret_cast<const float4*>(q), scores, gmax, group_shift);
+                      reinterpret_cast<const float4*>(q), scores, gmax, group_shift, live);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <int CW, int NQ>
 static cudaError_t run_tma_inst(cudaStream_t st, int64_t grid, size_t smem, const float* M, int64_t n, int d4,
-                                int tile_rows, int stages, const float* q, float* scores, u64* gmax, int group_shift)
+                                int tile_rows, int stages, const float* q, float* scores, u64* gmax, int group_shift,
+                                const uint8_t* live)
 {
     auto kern = gemv_tma_kernel<CW, NQ>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = launch_kernel(kern, dim3((unsigned)grid), dim3((CW + 1) * 32), smem, st, M, n, d4, tile_rows, stages, q, scores, gmax, group_shift);
+    e = launch_kernel(kern, dim3((unsigned)grid), dim3((CW + 1) * 32), smem, st, M, n, d4, tile_rows, stages, q, scores, gmax, group_shift, live);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // tile_rows / stages: 0 = default.  cw: consumer warps (8 or 16; 0 = default).
 static cudaError_t run_tma(cudaStream_t st, int device, const float* M, int64_t n, int d4, const float* q,
-                           float* scores, u64* gmax, int group_shift, int tile_rows, int stages, int cw, int reserve_sms)
+                           float* scores, u64* gmax, int group_shift, const uint8_t* live, int tile_rows, int stages, int cw,
+                           int reserve_sms)
 {
     const size_t row_bytes = (size_t)d4 * 16;
     const int nq = d4 <= 64 ? 2 : d4 <= 192 ? 6 : d4 <= 384 ? 12 : d4 <= 768 ? 24 : 0;
@@ -301,7 +308,7 @@ static cudaError_t run_tma(cudaStream_t st, int device, const float* M, int64_t 
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
 #define SVSB_TMA_CASE(CWV, NQV) \
-    return run_tma_inst<CWV, NQV>(st, grid, smem, M, n, d4, tile_rows, stages, q, scores, gmax, group_shift)
+    return run_tma_inst<CWV, NQV>(st, grid, smem, M, n, d4, tile_rows, stages, q, scores, gmax, group_shift, live)
     if (cw == 16) {
         switch (nq) { case 2: SVSB_TMA_CASE(16, 2); case 6: SVSB_TMA_CASE(16, 6); case 12: SVSB_TMA_CASE(16, 12);
                       case 24: SVSB_TMA_CASE(16, 24); default: SVSB_TMA_CASE(16, 0); }
@@ -330,7 +337,7 @@ cudaError_t preload_gemv_kernels()
 
 cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld,
                         const float* q, float* scores, u64* gmax, int group_shift,
-                        int variant, int tune_a, int tune_b, int reserve_sms)
+                        int variant, int tune_a, int tune_b, int reserve_sms, const uint8_t* live)
 {
     (void)d;
     if (n <= 0) return cudaSuccess;
@@ -345,23 +352,23 @@ cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, 
     }
     if (variant == 2) {
         // tune_a = tile rows, tune_b = stages + 100 * consumer warps (e.g. 1604 = 16 warps, 4 stages)
-        cudaError_t e = run_tma(st, device, M, n, d4, q, scores, gmax, group_shift, tune_a, tune_b % 100, tune_b / 100, reserve_sms);
+        cudaError_t e = run_tma(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_a, tune_b % 100, tune_b / 100, reserve_sms);
         if (e != cudaErrorInvalidConfiguration) return e;
         (void)cudaGetLastError();
         tune_a = 0; tune_b = 0;                               // TMA knobs mean nothing to the LDG kernel
     }
     // LDG variant; tune_a selects the (R, U, THREADS) instantiation, tune_b caps blocks per SM
     switch (tune_a) {
-        case 1:  return run_ldg<4, 2, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        case 2:  return run_ldg<4, 3, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        case 3:  return run_ldg<8, 1, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        case 4:  return run_ldg<8, 2, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        case 5:  return run_ldg<2, 4, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        case 6:  return run_ldg<2, 6, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        case 7:  return run_ldg<4, 3, 512>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        case 8:  return run_ldg<4, 4, 128>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        case 9:  return run_ldg<8, 3, 128>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
-        default: return run_ldg<4, 3, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, tune_b);
+        case 1:  return run_ldg<4, 2, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        case 2:  return run_ldg<4, 3, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        case 3:  return run_ldg<8, 1, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        case 4:  return run_ldg<8, 2, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        case 5:  return run_ldg<2, 4, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        case 6:  return run_ldg<2, 6, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        case 7:  return run_ldg<4, 3, 512>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        case 8:  return run_ldg<4, 4, 128>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        case 9:  return run_ldg<8, 3, 128>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
+        default: return run_ldg<4, 3, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
     }
 }
 

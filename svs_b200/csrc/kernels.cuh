@@ -41,9 +41,12 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
 // variant: 0 = auto, 1 = LDG.128 streaming kernel, 2 = TMA-bulk (cp.async.bulk + mbarrier ring) kernel.
 // tune_a/tune_b: variant-specific knobs (0 = default), see gemv.cu.  reserve_sms: SMs the persistent grid leaves
 // free (the pipelined paths run the previous query's selection kernel there, concurrently).
+// live (optional): one byte per row, 0 = tombstoned (svsb_apply_mutations): such a row's score is written as
+// dead_score(), whose key sorts below every real score's, so it is selected only after all live rows.
 cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld,
                         const float* q, float* scores, u64* gmax, int group_shift,
-                        int variant = 0, int tune_a = 0, int tune_b = 0, int reserve_sms = 0);
+                        int variant = 0, int tune_a = 0, int tune_b = 0, int reserve_sms = 0,
+                        const uint8_t* live = nullptr);
 
 // ---- K3/K4: exact top-k ---------------------------------------------------------------------
 // Inputs: scores[n], gmax[ceil(n >> shift)] (consumed and reset to zero), ids[n] (may be null: ids = rows).
@@ -81,6 +84,10 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
                             int64_t count_list_stride, int64_t count_batch_stride,
                             u64* scratch_keys, int64_t* scratch_ids,
                             float* out_scores, int64_t* out_ids, int32_t* out_count);
+
+// Any k: merge n_lists lists, each SORTED descending with unique keys (list l at keys / ids [l * stride ..), counts[l] valid).
+cudaError_t launch_merge_sorted_big(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts, int n_lists,
+                                    int64_t stride, int64_t k, float* out_scores, int64_t* out_ids, int32_t* out_count);
 
 // ---- peer exchange (select.cu): candidate records pushed into every rank's window, merged after a flag wait ----
 // A window holds `slots` x `world` records of rec_words = 2*cap + 2 u64 words: [keys(cap) | ids(cap) | count | pad],

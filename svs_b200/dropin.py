@@ -30,6 +30,7 @@ import numpy as np
 
 from . import _lib
 from .matrix import DeviceEmbeddingsMatrix
+from .mutations import LoggingConnection, MutationLog
 
 _ORIGINALS: dict = {}
 # svsb_top_pairs refusals that the reference's np.dot(M, M.T) + get_top_pairs still answers (include/svsb200.h)
@@ -95,14 +96,17 @@ class _Coalescer:
 
 
 def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, normalize: bool = False,
-            pairwise: Optional[bool] = None, coalesce: bool = True, prewarm: bool = False) -> None:
+            pairwise: Optional[bool] = None, coalesce: bool = True, prewarm: bool = True, incremental: bool = True) -> None:
     """Patch `svs` in place.  Idempotent.  `devices`: CUDA devices to row-shard the matrix over.
     `pairwise`: also route document_top_pairwise_scores to the engine (default: yes on a single device; the
     multi-device engine keeps the reference's host NumPy path for it).
     `coalesce`: batch concurrent AsyncKB.retrieve calls into one engine call (see _Coalescer).
-    `prewarm`: create the engine (= the CUDA context, ~2 s once per process on a B200 box,
+    `prewarm` (default on): create the engine (= the CUDA context, ~2 s once per process on a B200 box,
     profiles/r01_first_query_probe.txt) on a background thread as soon as a KB object exists, instead of inside the
-    first retrieve."""
+    first retrieve.
+    `incremental` (default on): bulk adds / deletes UPDATE the device matrix (append + tombstone) instead of forcing the
+    full rebuild the reference does (kb.py:1062, 1086, 1523, 1541): the querier's connection is wrapped so that every
+    `INSERT INTO embeddings` / `DELETE FROM embeddings` of a committed transaction is logged (svs_b200.mutations)."""
     if pairwise is None:
         pairwise = devices is None or len(devices) <= 1
     if svs_module is None:
@@ -118,7 +122,7 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
 
         def __init__(self) -> None:
             super().__init__()
-            self.device = DeviceEmbeddingsMatrix(devices, normalize)
+            self.device = DeviceEmbeddingsMatrix(devices, normalize, incremental)
             self.coalescer = _Coalescer() if coalesce else None
             if prewarm:
                 self.device.prewarm()
@@ -224,7 +228,7 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
         """document_top_pairwise_scores (kb.py:1642-1671) with `superheavy()` = np.dot(M, M.T) + get_top_pairs replaced by
         one engine call that never materialises the N x N scores."""
         assert self.db is not None
-        matrix = self.embeddings_matrix.device.get_sync(self.db)
+        matrix = self.embeddings_matrix.device.get_sync(self.db, compact=True)   # the pair kernels want no tombstones
         n_docs = matrix.shape[0]
         log.info(f"computing pairwise similarity over {n_docs} documents")
         try:
@@ -245,7 +249,7 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
         loop = asyncio.get_running_loop()
         async with self._get_lock():
             db = await self._ensure_db()
-            matrix = await self.embeddings_matrix.device.get(db)
+            matrix = await self.embeddings_matrix.device.get(db, compact=True)
         n_docs = matrix.shape[0]
         log.info(f"computing pairwise similarity over {n_docs} documents")
         try:
@@ -266,7 +270,51 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
             db = await self._ensure_db()
             await self.embeddings_matrix.device.get(db)
 
+    # ---- mutation log: the querier's connection tells the log about embeddings inserts / deletes; _DB.__exit__ commits
+    #      or drops the transaction's records (kb.py:793-821).  __aenter__ / __aexit__ call these through `self`.
+    db_cls = getattr(kb, "_DB", None)
+    orig_enter = db_cls.__enter__ if db_cls is not None else None
+    orig_exit = db_cls.__exit__ if db_cls is not None else None
+
+    def db_enter(self: Any) -> Any:
+        q = orig_enter(self)
+        mlog = self.__dict__.get("_svsb_log")
+        if mlog is None:
+            mlog = self.__dict__["_svsb_log"] = MutationLog()
+        mlog.begin()
+        q.conn = LoggingConnection(q.conn, mlog)
+        return q
+
+    def db_exit(self: Any, exc_type: Any, exc_val: Any, exc_tb: Any) -> Any:
+        mlog = self.__dict__.get("_svsb_log")
+        try:
+            ret = orig_exit(self, exc_type, exc_val, exc_tb)
+        except BaseException:
+            if mlog is not None:
+                mlog.rollback()                          # the commit itself failed
+            raise
+        if mlog is not None:
+            if exc_type is None:
+                mlog.commit()
+            else:
+                mlog.rollback()
+        return ret
+
+    def kb_close(self: Any, *a: Any, **kw: Any) -> Any:
+        try:
+            return _ORIGINALS["KB.close"](self, *a, **kw)
+        finally:
+            self.embeddings_matrix.device.close()        # invalidate() keeps the (stale) matrix resident; close frees it
+
+    async def akb_close(self: Any, *a: Any, **kw: Any) -> Any:
+        try:
+            return await _ORIGINALS["AsyncKB.close"](self, *a, **kw)
+        finally:
+            self.embeddings_matrix.device.close()
+
     _ORIGINALS.update({
+        "_DB": db_cls, "_DB.__enter__": orig_enter, "_DB.__exit__": orig_exit,
+        "KB.close": getattr(kb.KB, "close", None), "AsyncKB.close": getattr(kb.AsyncKB, "close", None),
         "module": kb, "_EmbeddingsMatrix": host_cls, "KB.retrieve": kb.KB.retrieve,
         "AsyncKB.retrieve": kb.AsyncKB.retrieve, "AsyncKB.load": kb.AsyncKB.load,
         "KB.pairs": kb.KB.document_top_pairwise_scores, "AsyncKB.pairs": kb.AsyncKB.document_top_pairwise_scores,
@@ -280,6 +328,13 @@ def install(svs_module: Any = None, devices: Optional[Sequence[int]] = None, nor
         kb.AsyncKB.document_top_pairwise_scores = atop_pairwise
     kb.KB.retrieve_many = retrieve_many                  # additive: batched retrieve
     kb.AsyncKB.retrieve_many = aretrieve_many
+    if incremental and db_cls is not None:
+        db_cls.__enter__ = db_enter
+        db_cls.__exit__ = db_exit
+    if _ORIGINALS["KB.close"] is not None:
+        kb.KB.close = kb_close
+    if _ORIGINALS["AsyncKB.close"] is not None:
+        kb.AsyncKB.close = akb_close
 
 
 def uninstall() -> None:
@@ -296,4 +351,11 @@ def uninstall() -> None:
     for cls in (kb.KB, kb.AsyncKB):
         if "retrieve_many" in cls.__dict__:
             delattr(cls, "retrieve_many")
+    if _ORIGINALS.get("_DB") is not None:
+        _ORIGINALS["_DB"].__enter__ = _ORIGINALS["_DB.__enter__"]
+        _ORIGINALS["_DB"].__exit__ = _ORIGINALS["_DB.__exit__"]
+    if _ORIGINALS.get("KB.close") is not None:
+        kb.KB.close = _ORIGINALS["KB.close"]
+    if _ORIGINALS.get("AsyncKB.close") is not None:
+        kb.AsyncKB.close = _ORIGINALS["AsyncKB.close"]
     _ORIGINALS.clear()

@@ -161,6 +161,46 @@ class Engine:
         n = C.c_int64()
         return n.value if self._lib.svsb_shape(self._h, C.byref(n), None) == _lib.SVSB_OK else 0
 
+    def submit(self, q: np.ndarray, k: int) -> "Pending":
+        """Start a query and return at once; `.result()` of the returned handle blocks for its (scores, ids).  Keeping
+        two or three in flight hides the per-call launch / selection / host round-trip latency behind the next query's
+        similarity pass (include/svsb200.h: svsb_query_submit)."""
+        q = _f32c(q)
+        if q.ndim != 1:
+            raise ValueError("query vector must be 1-D")
+        cap = clamp_k(k, self._rows_or_zero())
+        k = cap if int(k) > 0 else int(max(k, -1))
+        h = C.c_void_p()
+        check(self._lib.svsb_query_submit(self._h, q.ctypes.data, q.shape[0], k, C.byref(h)))
+        return Pending(self, h, cap)
+
+    def apply_mutations(self, del_ids, add_ids, add_rows: Optional[np.ndarray]) -> int:
+        """Incremental update (include/svsb200.h: svsb_apply_mutations): tombstone the rows with embeddings.id in
+        `del_ids`, append `add_rows` (n_add, d) with ids `add_ids` (ascending, above every live id).  Publishes a new
+        generation that shares the matrix buffers with the old one; raises EngineError (SVSB_E_STATE) when the batch
+        cannot be applied incrementally -- the caller then rebuilds."""
+        dels = np.ascontiguousarray(np.asarray(del_ids, dtype=np.int64).reshape(-1))
+        aids = np.ascontiguousarray(np.asarray(add_ids, dtype=np.int64).reshape(-1))
+        n_add = int(aids.shape[0])
+        if n_add:
+            rows = _f32c(add_rows)
+            if rows.ndim != 2 or rows.shape[0] != n_add:
+                raise ValueError("add_rows must be (len(add_ids), d)")
+            d = int(rows.shape[1])
+        else:
+            rows, d = np.zeros((0, 0), np.float32), 0
+        gen = C.c_uint64()
+        check(self._lib.svsb_apply_mutations(self._h, dels.ctypes.data if len(dels) else None, len(dels),
+                                             rows.ctypes.data if n_add else None, aids.ctypes.data if n_add else None, n_add, d,
+                                             C.byref(gen)))
+        return gen.value
+
+    def generation_rows(self) -> Tuple[int, int]:
+        """(physical rows incl. tombstoned ones, live rows) of the resident generation."""
+        p, l = C.c_int64(), C.c_int64()
+        check(self._lib.svsb_generation_rows(self._h, C.byref(p), C.byref(l)))
+        return p.value, l.value
+
     def snapshot(self) -> "Snapshot":
         """Pin the resident generation (the reference's `embeddings_matrix, emb_id_lookup` references)."""
         return Snapshot(self)
@@ -270,6 +310,30 @@ class Engine:
         return [(float(a), int(b)) for a, b in zip(s[:cnt.value], i[:cnt.value])]
 
 
+class Pending:
+    """A query in flight (Engine.submit).  `.result()` must be called exactly once."""
+
+    def __init__(self, engine: Engine, handle: C.c_void_p, cap: int):
+        self._engine, self._h, self._cap = engine, handle, cap
+
+    def result(self) -> Tuple[np.ndarray, np.ndarray]:
+        if self._h is None:
+            raise RuntimeError("result() was already taken")
+        scores = np.empty(self._cap, dtype=np.float32)
+        ids = np.empty(self._cap, dtype=np.int64)
+        cnt = C.c_int32()
+        h, self._h = self._h, None
+        check(self._engine._lib.svsb_query_wait(self._engine._h, h, scores.ctypes.data, ids.ctypes.data, C.byref(cnt)))
+        return scores[:cnt.value], ids[:cnt.value]
+
+    def __del__(self):  # pragma: no cover - a handle nobody waited for still has to be released
+        try:
+            if self._h is not None and self._engine._h.value:
+                self.result()
+        except Exception:
+            pass
+
+
 class _PinnedBlock:
     """Owner of one svsb_host_alloc allocation; arrays made over it keep it alive through their .base chain."""
 
@@ -311,6 +375,9 @@ class Snapshot:
         check(self._lib.svsb_snapshot_shape(self._s, C.byref(n), C.byref(d), C.byref(gen)))
         self.shape = (n.value, d.value if n.value else 0)
         self.generation = gen.value
+        p, l = C.c_int64(), C.c_int64()
+        check(self._lib.svsb_snapshot_rows(self._s, C.byref(p), C.byref(l)))
+        self.physical_rows, self.live_rows = p.value, l.value      # differ once rows were tombstoned (apply_mutations)
 
     def query(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
         q = _f32c(q)

@@ -20,6 +20,7 @@ from typing import Any, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from . import _lib
 from .engine import Engine, Snapshot
 
 _LOG = logging.getLogger(__name__)
@@ -33,6 +34,8 @@ class DeviceMatrix:
         self._snap: Snapshot = engine.snapshot()    # pins this generation until the handle dies
         self.shape = self._snap.shape               # (N, D); (0, 0) for an empty table, like the reference
         self.generation = self._snap.generation
+        # rows deleted since the last full build stay in the buffer as tombstones (incremental updates)
+        self.has_tombstones = self._snap.physical_rows != self._snap.live_rows
 
     def __len__(self) -> int:
         return self.shape[0]
@@ -112,14 +115,22 @@ def load_from_connection(engine: Engine, conn: sqlite3.Connection, normalize: bo
 
 
 class DeviceEmbeddingsMatrix:
-    """Drop-in for `_EmbeddingsMatrix` (src/svs/kb.py:856-893)."""
+    """Drop-in for `_EmbeddingsMatrix` (src/svs/kb.py:856-893).
 
-    def __init__(self, devices: Optional[Sequence[int]] = None, normalize: bool = False) -> None:
+    `invalidate()` marks the device matrix stale instead of dropping it.  The next `get_sync` / `get` brings it up to
+    date: incrementally (append + tombstone, `Engine.apply_mutations`) when the database object carries a mutation log
+    that vouches for everything that happened since (`svs_b200.mutations`, attached by `install()`), else by the full
+    rebuild inside a DB transaction exactly as the reference does (kb.py:870-877)."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, normalize: bool = False, incremental: bool = True) -> None:
         self._devices = list(devices) if devices is not None else None
         self._normalize = normalize
+        self._incremental = incremental
         self._engine: Optional[Engine] = None        # created lazily on first load (SURVEY 3.5)
         self._matrix: Optional[DeviceMatrix] = None
+        self._stale = False
         self._mu = threading.Lock()
+        self.stats = {"full_builds": 0, "incremental_updates": 0, "incremental_fallbacks": 0}
 
     def _get_engine(self) -> Engine:
         if self._engine is None:
@@ -139,52 +150,120 @@ class DeviceEmbeddingsMatrix:
         return t
 
     def invalidate(self) -> None:
-        """kb.py:861-864.  In-flight queries keep the generation they started on."""
-        _LOG.info("invalidating cached device vectors; they'll be re-built next time you `retrieve()`")
+        """kb.py:861-864.  In-flight queries keep the generation they started on.  The resident matrix is kept (stale)
+        so that the next retrieve can update it in place of a rebuild; `drop()` frees it."""
+        _LOG.info("invalidating cached device vectors; they'll be brought up to date next time you `retrieve()`")
         with self._mu:
-            self._matrix = None
-            if self._engine is not None:
-                self._engine.invalidate()
+            if self._matrix is not None:
+                self._stale = True
+            if not self._incremental:
+                self._drop_locked()
 
-    def _build(self, q: Any) -> DeviceMatrix:
-        conn = q.conn if hasattr(q, "conn") else q
+    def _drop_locked(self) -> None:
+        had = self._matrix is not None
+        self._matrix = None
+        self._stale = False
+        if had and self._engine is not None:
+            self._engine.invalidate()
+
+    def drop(self) -> None:
+        """Free the device matrix now (the pre-incremental behaviour of invalidate)."""
         with self._mu:
+            self._drop_locked()
+
+    def _try_incremental(self, db: Any) -> Optional[DeviceMatrix]:
+        """Apply the committed mutations to the stale matrix.  None = not possible, do the full rebuild."""
+        log = getattr(db, "_svsb_log", None)
+        m = self._matrix
+        if log is None or m is None or self._engine is None or not self._incremental:
+            return None
+        batch = log.take()
+        if batch is None:
+            return None
+        dels, add_ids, blobs = batch
+        if not dels and not add_ids:
+            return m                                     # e.g. documents without embeddings were added / deleted
+        d = m.shape[1]
+        if m.shape[0] == 0 or any(len(b) != d * 4 for b in blobs):
+            return None
+        # past this fraction of dead rows a rebuild (which also compacts) is the better deal
+        physical, live = self._engine.generation_rows()
+        dead_after = physical - live + len(dels)
+        if dead_after > 64 and dead_after * 4 > physical + len(add_ids):
+            return None
+        rows = np.frombuffer(b"".join(blobs), dtype="<f4").reshape(len(blobs), d) if blobs else None
+        try:
+            self._engine.apply_mutations(dels, add_ids, rows)
+        except _lib.EngineError as ex:
+            if ex.code != _lib.SVSB_E_STATE:
+                raise
+            _LOG.info("incremental update not applicable (%s); rebuilding", ex)
+            self.stats["incremental_fallbacks"] += 1
+            return None
+        self.stats["incremental_updates"] += 1
+        return DeviceMatrix(self._engine)
+
+    def _build(self, q: Any, db: Any = None) -> DeviceMatrix:
+        conn = q.conn if hasattr(q, "conn") else q
+        log = getattr(db, "_svsb_log", None)
+        if log is not None:
+            log.take()                                   # the scan below sees everything committed so far
+        with self._mu:
+            self._drop_locked()                          # never two full generations resident at once
             engine = self._get_engine()
+        self.stats["full_builds"] += 1
         return load_from_connection(engine, conn, self._normalize)
 
-    def get_sync(self, db: Any) -> DeviceMatrix:
-        """kb.py:866-877: cached handle, or rebuild inside a DB transaction."""
+    def _current(self, db: Any) -> Optional[DeviceMatrix]:
         m = self._matrix
-        if m is not None:
+        if m is not None and not self._stale:
             _LOG.info("using cached device vectors")
+            return m
+        if m is not None:
+            m2 = self._try_incremental(db)
+            if m2 is not None:
+                _LOG.info("updated cached device vectors incrementally")
+                self._matrix, self._stale = m2, False
+                return m2
+        return None
+
+    def get_sync(self, db: Any, compact: bool = False) -> DeviceMatrix:
+        """kb.py:866-877: cached handle, or bring it up to date (incrementally, else rebuild inside a DB transaction).
+        compact: the caller needs a matrix without tombstones (the pairwise path)."""
+        m = self._current(db)
+        if m is not None and not (compact and m.has_tombstones):
             return m
         _LOG.info("re-building cached device vectors...")
         with db as q:
-            m = self._build(q)
+            m = self._build(q, db)
         _LOG.info("re-building cached device vectors... DONE!")
-        self._matrix = m
+        self._matrix, self._stale = m, False
         return m
 
-    async def get(self, db: Any) -> DeviceMatrix:
-        """kb.py:879-893: same, with the build in the default executor."""
+    async def get(self, db: Any, compact: bool = False) -> DeviceMatrix:
+        """kb.py:879-893: same, with the heavy part in the default executor."""
+        loop = asyncio.get_running_loop()
         m = self._matrix
-        if m is not None:
-            _LOG.info("using cached device vectors")
+        if m is not None and self._stale:
+            m = await loop.run_in_executor(None, self._current, db)
+        else:
+            m = self._current(db)
+        if m is not None and not (compact and m.has_tombstones):
             return m
         _LOG.info("re-building cached device vectors...")
 
         def heavy() -> DeviceMatrix:
             with db as q:
-                return self._build(q)
-        loop = asyncio.get_running_loop()
+                return self._build(q, db)
         m = await loop.run_in_executor(None, heavy)
         _LOG.info("re-building cached device vectors... DONE!")
-        self._matrix = m
+        self._matrix, self._stale = m, False
         return m
 
     def close(self) -> None:
         with self._mu:
             self._matrix = None
+            self._stale = False
             if self._engine is not None:
                 self._engine.close()
                 self._engine = None

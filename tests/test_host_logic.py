@@ -20,10 +20,12 @@ class FakeSnapshot:
     batches = []                                   # sizes of the retrieve_many calls seen (coalescer test)
 
     def __init__(self, eng):
-        self.shape = (eng.n, eng.d if eng.n else 0)
+        live = eng.live if eng.live is not None else np.ones(eng.n, bool)
+        self.shape = (int(live.sum()), eng.d if eng.n else 0)
         self.generation = eng.gen
-        self._rows = eng.rows.copy()
-        self._ids = eng.ids.copy()
+        self.physical_rows, self.live_rows = eng.n, int(live.sum())
+        self._rows = eng.rows[live].copy()
+        self._ids = eng.ids[live].copy()
 
     def retrieve(self, q, n):
         return [(0.0, int(i)) for i in self._ids[:max(0, n)]]
@@ -47,6 +49,7 @@ class FakeEngine:
         self.n = self.d = 0
         self.rows = np.zeros((0, 0), np.float32)
         self.ids = np.zeros(0, np.int64)
+        self.live = None
 
     def load_begin(self, n, d, normalize=False):
         self.calls.append(("begin", n, d, normalize))
@@ -74,7 +77,7 @@ class FakeEngine:
 
     def load_end(self):
         assert self._filled == self._n
-        self.n, self.d, self.rows, self.ids = self._n, self._d, self._rows, self._ids
+        self.n, self.d, self.rows, self.ids, self.live = self._n, self._d, self._rows, self._ids, None
         self.gen += 1
         self.loaded = True
         self.calls.append(("end",))
@@ -86,6 +89,40 @@ class FakeEngine:
     def invalidate(self):
         self.calls.append(("invalidate",))
         self.loaded = False
+
+    def generation_rows(self):
+        live = self.live if self.live is not None else np.ones(self.n, bool)
+        return self.n, int(live.sum())
+
+    def apply_mutations(self, del_ids, add_ids, add_rows):
+        """The contract of svsb_apply_mutations (include/svsb200.h) restated in NumPy."""
+        import svs_b200
+        from svs_b200 import _lib
+        self.calls.append(("apply", list(del_ids), list(add_ids)))
+        def refuse(why):
+            raise svs_b200.EngineError(_lib.SVSB_E_STATE, why)
+        if not self.loaded or self.n == 0:
+            refuse("nothing resident")
+        live = self.live.copy() if self.live is not None else np.ones(self.n, bool)
+        if len(set(del_ids)) != len(del_ids):
+            refuse("duplicate delete")
+        for e in del_ids:
+            hit = np.nonzero((self.ids == e) & live)[0]
+            if len(hit) != 1:
+                refuse(f"id {e} is not live")
+            live[hit[0]] = False
+        add_ids = list(add_ids)
+        if add_ids:
+            if add_rows.shape != (len(add_ids), self.d) or any(b <= a for a, b in zip(add_ids, add_ids[1:])):
+                refuse("bad rows")
+            if live.any() and add_ids[0] <= self.ids[live].max():
+                refuse("id not above every live id")
+            self.rows = np.concatenate([self.rows, np.asarray(add_rows, np.float32)])
+            self.ids = np.concatenate([self.ids, np.asarray(add_ids, np.int64)])
+            live = np.concatenate([live, np.ones(len(add_ids), bool)])
+        self.n, self.live = len(self.ids), live
+        self.gen += 1
+        return self.gen
 
     def snapshot(self):
         return FakeSnapshot(self)
@@ -166,9 +203,10 @@ def test_device_embeddings_matrix_cache_protocol(tmp_path, fake_engine):
     m1 = cache.get_sync(db)
     assert db.entered == 1 and len(fake_engine) == 1
     assert cache.get_sync(db) is m1 and db.entered == 1           # hit: no rebuild (kb.py:867-869)
-    cache.invalidate()
+    cache.invalidate()                                            # marks the device matrix stale, keeps it resident ...
+    assert ("invalidate",) not in fake_engine[0].calls
+    m2 = cache.get_sync(db)                                       # ... no mutation log on this db: the full rebuild, old one dropped first
     assert ("invalidate",) in fake_engine[0].calls
-    m2 = cache.get_sync(db)
     assert m2 is not m1 and db.entered == 2 and m2.generation == m1.generation + 1
     # the old handle still answers from the generation it pinned
     assert m1.retrieve(np.zeros(64, np.float32), 3) == m2.retrieve(np.zeros(64, np.float32), 3)
@@ -245,7 +283,7 @@ def test_install_and_uninstall_patch_only_the_seam(fake_engine):
         assert mod.kb.KB.retrieve is not orig_retrieve
         kb = mod.kb.KB()
         assert isinstance(kb.embeddings_matrix.device, svs_b200.DeviceEmbeddingsMatrix)
-        kb.embeddings_matrix.invalidate()                          # drops host AND device caches
+        kb.embeddings_matrix.invalidate()                          # drops the host cache, marks the device cache stale
         assert kb.embeddings_matrix.invalidations == 1
         svs_b200.install(mod)                                      # idempotent
     finally:
@@ -277,8 +315,9 @@ def test_install_on_the_real_reference_package(fake_engine, tmp_path, monkeypatc
         assert fake_engine[0].calls[0] == ("begin", 3, 3, False)
         with kb.bulk_del_docs() as del_doc:
             del_doc(1)
-        assert ("invalidate",) in fake_engine[0].calls            # kb.py:1541 reached the device cache
-        assert [r["doc"]["text"] for r in kb.retrieve("q", 5)] == ["b", "c"]
+        assert [r["doc"]["text"] for r in kb.retrieve("q", 5)] == ["b", "c"]      # kb.py:1541 reached the device cache ...
+        assert ("apply", [1], []) in fake_engine[0].calls         # ... as an incremental update: one tombstone, no rebuild
+        assert [c[0] for c in fake_engine[0].calls].count("begin") == 1
         pair = kb.document_top_pairwise_scores(1)[0]               # pairwise now asks the (fake) engine for the pair
         assert (pair[0], pair[1]["text"], pair[2]["text"]) == (0.5, "b", "c")
         many = kb.retrieve_many(["q1", "q2", "q3"], 1)             # additive batched API: one embed call, one engine call
