@@ -363,6 +363,56 @@ def parity_sharded(dist, rank, world, sr, k: int, queries: np.ndarray, got_lists
 # ---------------------------------------------------------------------------------------------------
 # our arm, one GPU
 # ---------------------------------------------------------------------------------------------------
+def e2e_pipelined(eng, queries: np.ndarray, k: int, steps: int, in_flight: int = 3):
+    """The e2e metric with `in_flight` queries pending (Engine.submit / Pending.result): host query in, host result out for
+    every query.  Returns (queries/s, the first len(queries) results)."""
+    first = []
+    for i in range(8):
+        eng.submit(queries[i], k).result()
+    nq = steps * QUERIES_PER_STEP
+    pend = []
+    t0 = time.perf_counter()
+    for j in range(nq):
+        pend.append(eng.submit(queries[j % len(queries)], k))
+        if len(pend) == in_flight:
+            r = pend.pop(0).result()
+            if len(first) < len(queries):
+                first.append(r)
+    for p in pend:
+        r = p.result()
+        if len(first) < len(queries):
+            first.append(r)
+    return nq / (time.perf_counter() - t0), first
+
+
+def incremental_probe(eng, n: int, d: int, k: int) -> dict:
+    """a one-document add (and a delete) on the resident matrix, then the next retrieve --
+    what the reference answers with a full rebuild (src/svs/kb.py:1523, 573-618).  The new row must come back first."""
+    rng = np.random.default_rng(99)
+    out = {}
+    next_id = n + 1                                               # synthetic ids are 1..n
+    for tag in ("first_add_then_retrieve_ms", "next_add_then_retrieve_ms"):
+        row = rng.random((1, d), dtype=np.float32)
+        row /= np.sqrt((row * row).sum())
+        t0 = time.perf_counter()
+        eng.apply_mutations([], [next_id], row)
+        s, i = eng.query(row[0], k)
+        out[tag] = (time.perf_counter() - t0) * 1e3
+        if int(i[0]) != next_id or abs(float(s[0]) - 1.0) > 1e-5:
+            raise AssertionError("incremental add: the new row is not the best match of itself")
+        next_id += 1
+    t0 = time.perf_counter()
+    eng.apply_mutations([next_id - 1, 17], [], None)
+    s, i = eng.query(row[0], k)
+    out["delete_then_retrieve_ms"] = (time.perf_counter() - t0) * 1e3
+    if next_id - 1 in i.tolist() or 17 in i.tolist():
+        raise AssertionError("incremental delete: a tombstoned row was returned")
+    phys, live = eng.generation_rows()
+    out.update({"rows_physical": phys, "rows_live": live,
+                "note": "first add re-allocates the matrix with head-room (one device-to-device copy); later adds append in place"})
+    return out
+
+
 def leg_single(name: str, steps: int, warmup: int, headline: bool, cpu: bool) -> dict:
     """Single-query workloads (c1, c2, c4, c5) on one GPU."""
     import svs_b200
@@ -399,11 +449,16 @@ def leg_single(name: str, steps: int, warmup: int, headline: bool, cpu: bool) ->
     for s in range(steps):
         for j in range(QUERIES_PER_STEP):
             eng.query(queries[(s * QUERIES_PER_STEP + j) % len(queries)], k)
-    e2e_qps = nq / (time.perf_counter() - t0)
+    e2e_sync_qps = nq / (time.perf_counter() - t0)
+    e2e_qps, piped = e2e_pipelined(eng, queries, k, steps)
     # parity of the timed paths: PARITY_QUERIES of the e2e calls' answers judged by the oracle over all rows, and the
     # device-resident loop's last answer must equal the e2e call's for the same query, bit for bit
     pq = [0, 1, QUERIES_PER_STEP // 2, (QUERIES_PER_STEP - 1) % len(queries)][:PARITY_QUERIES]
     got = [eng.retrieve(queries[j], k) for j in pq]
+    for j in pq:                                                 # the pipelined e2e loop returned the same bits
+        s_, i_ = piped[j]
+        if [(float(a), int(b)) for a, b in zip(s_, i_)] != got[pq.index(j)]:
+            raise AssertionError(f"{name}: svsb_query_submit/wait and svsb_query disagree")
     parity = parity_single(eng, n, k, queries[pq], got)
     parity["device_resident_loop_bits_equal_e2e"] = bool(last_timed == eng.retrieve(queries[(QUERIES_PER_STEP - 1) % len(queries)], k))
     if not parity["device_resident_loop_bits_equal_e2e"]:
@@ -424,10 +479,15 @@ def leg_single(name: str, steps: int, warmup: int, headline: bool, cpu: bool) ->
                      "algorithmic_bytes_per_launch": algo_bytes, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "whole_query_frac": (algo_bytes * nq / (total_ms / 1e3) / 1e9) / peak},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": QUERIES_PER_STEP * d * 4,
-                "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 12 + 4)},
+                "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 12 + 4),
+                "how": "svsb_query_submit / svsb_query_wait from one host thread, 3 queries in flight; every query goes in from host "
+                       "memory and its k results come back to host memory inside the timed region",
+                "one_query_in_flight": e2e_sync_qps},
         "parity": parity,
         "gpu_launches": int(launches), "clocks": clocks, "load_synthetic_s": load_s,
     }
+    if headline:
+        line["incremental_update"] = incremental_probe(eng, n, d, k)
     if cpu:
         line["cpu_baseline"] = cpu_baseline_of(name, queries)
     eng.close()
@@ -525,6 +585,10 @@ class Spmd:
         self.exchange = args.exchange
         torch.cuda.set_device(self.local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.cpu_group = dist.new_group(backend="gloo")          # host-side barriers that put no kernel on any GPU
+
+    def cpu_barrier(self):
+        self.dist.barrier(group=self.cpu_group)
 
     def max_over_ranks(self, *vals):
         t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
@@ -574,11 +638,34 @@ def leg_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
         for j in range(QUERIES_PER_STEP):                       # host query in, host (scores, ids) arrays out, as Engine.query at N=1
             sr.retrieve_arrays(queries[(s * QUERIES_PER_STEP + j) % len(queries)], k)
     torch.cuda.synchronize(); dist.barrier()
+    (e2e_sync_s,) = sp.max_over_ranks(time.perf_counter() - t0)
+    # the same with 3 queries in flight (svsb_query_peer_submit / _wait): every query still goes in from host memory and
+    # comes back to host memory inside the timed region
+    piped = []
+    for i in range(4):
+        sr.wait(sr.submit(queries[i], k))
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pend = []
+    for j in range(nq):
+        pend.append(sr.submit(queries[j % len(queries)], k))
+        if len(pend) == 3:
+            r = sr.wait(pend.pop(0))
+            if len(piped) < QUERIES_PER_STEP:
+                piped.append(r)
+    for p in pend:
+        r = sr.wait(p)
+        if len(piped) < QUERIES_PER_STEP:
+            piped.append(r)
+    torch.cuda.synchronize(); dist.barrier()
     (e2e_s,) = sp.max_over_ranks(time.perf_counter() - t0)
     # parity: the e2e path's answers for PARITY_QUERIES of the timed queries, judged by the oracle on every shard
     pq = [0, 1, QUERIES_PER_STEP // 2, (QUERIES_PER_STEP - 1) % len(queries)][:PARITY_QUERIES]
     got = [sr.retrieve(queries[j], k) for j in pq]
     same = bool(last_timed == got[-1])
+    for j in pq:
+        s_, i_ = piped[j]
+        same = same and [(float(a), int(b)) for a, b in zip(s_, i_)] == got[pq.index(j)]
     parity = parity_sharded(dist, rank, world, sr, k, queries[pq], got)
     launches = torch.tensor([svs_b200.launch_count() - l0], device="cuda", dtype=torch.int64)
     shard_bytes = sr.local_rows * d * 4
@@ -587,7 +674,7 @@ def leg_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
     if rank != 0:
         return {}
     if not same:
-        raise AssertionError(f"{name}: the device-resident loop and the synchronous peer query disagree")
+        raise AssertionError(f"{name}: the device-resident loop, svsb_query_peer and svsb_query_peer_submit/wait disagree")
     parity["device_resident_loop_bits_equal_e2e"] = same
     achieved = shard_bytes * nq / (gemv_ms / 1e3) / 1e9
     return {
@@ -608,7 +695,9 @@ def leg_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
                      "algorithmic_bytes_per_launch": shard_bytes,
                      "whole_query_frac": (shard_bytes * nq / (total_ms / 1e3) / 1e9) / peak},
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": QUERIES_PER_STEP * d * 4,
-                "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 12 + 4)},
+                "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 12 + 4),
+                "how": "svsb_query_peer_submit / _wait on every rank, 3 queries in flight; host query in, host result out",
+                "one_query_in_flight": nq / e2e_sync_s},
         "parity": parity,
         "gpu_launches": int(launches[0]), "clocks": clocks,
     }
@@ -680,6 +769,73 @@ def leg_batch_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
     }
 
 
+def leg_inprocess(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
+    """The SAME workload on the SAME GPUs through ONE process: `svs_b200.Engine(devices=[0..N-1])`, the engine that
+    `svs_b200.install(svs, devices=[...])` puts behind KB.retrieve (src/svs/kb.py:1608-1640).  Rank 0 drives all N GPUs
+    (one worker thread per device, records pushed into device 0's window over NVLink); the other ranks have freed
+    their shards and wait on a host-side barrier."""
+    import svs_b200
+    from svs_b200.engine import Engine
+    sp.torch.cuda.empty_cache()
+    sp.cpu_barrier()
+    out = {}
+    if sp.rank == 0:
+        n, d, k, _ = WORKLOADS[name]
+        world = sp.world
+        queries = unit_queries(128, d, 1)
+        peak, peak_src = measured_peak_gbs()
+        eng = Engine(list(range(world)))
+        eng.load_synthetic(n, d, seed=0, id0=1, id_step=1)
+        eng.bench_set_queries(queries)
+        for _ in range(warmup):
+            eng.bench_run(k, QUERIES_PER_STEP)
+        total_ms = gemv_ms = 0.0
+        launches = 0
+        for _ in range(steps):
+            r = eng.bench_run(k, QUERIES_PER_STEP, with_gemv=True)
+            total_ms += r["total_ms"]; gemv_ms += r["gemv_ms"]; launches += r["launches"]
+        last_timed = eng.bench_last_result(k)
+        nq = steps * QUERIES_PER_STEP
+        for i in range(8):
+            eng.query(queries[i], k)
+        t0 = time.perf_counter()
+        for j in range(nq):
+            eng.query(queries[j % len(queries)], k)
+        e2e_sync_qps = nq / (time.perf_counter() - t0)
+        e2e_qps, piped = e2e_pipelined(eng, queries, k, steps)
+        pq = [0, 1, QUERIES_PER_STEP // 2, (QUERIES_PER_STEP - 1) % len(queries)][:PARITY_QUERIES]
+        got = [eng.retrieve(queries[j], k) for j in pq]
+        same = last_timed == got[-1]
+        for j in pq:
+            s_, i_ = piped[j]
+            same = same and [(float(a), int(b)) for a, b in zip(s_, i_)] == got[pq.index(j)]
+        if not same:
+            raise AssertionError(f"{name} in-process: device-resident loop, svsb_query and svsb_query_submit/wait disagree")
+        parity = parity_single(eng, n, k, queries[pq], got)
+        parity["device_resident_loop_bits_equal_e2e"] = True
+        shard_bytes = -(-n // world) * d * 4
+        achieved = shard_bytes * nq / (gemv_ms / 1e3) / 1e9
+        out = {
+            "value": nq / (total_ms / 1e3), "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "ms_per_query": total_ms / nq, "dtype": "f32", "config": config_of(name), "scaling": "strong",
+            "run": {"queries_per_step": QUERIES_PER_STEP,
+                    "parallelism": f"ONE process, {world} GPUs: a shard engine + a host worker thread per device, k-candidate records pushed "
+                                   "into device 0's window over NVLink peer memory by the selection kernels, one waiting merge kernel; "
+                                   "3 queries in flight"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "gemv_tma_kernel (device 0's shard, sampled launches)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": shard_bytes,
+                         "whole_query_frac": (shard_bytes * nq / (total_ms / 1e3) / 1e9) / peak},
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": QUERIES_PER_STEP * d * 4,
+                    "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 12 + 4),
+                    "how": "svsb_query_submit / svsb_query_wait from one host thread, 3 queries in flight", "one_query_in_flight": e2e_sync_qps},
+            "parity": parity, "gpu_launches": int(launches),
+        }
+        eng.close()
+    sp.cpu_barrier()
+    return out
+
+
 def summary_of(leg: dict) -> dict:
     """What a sub-config contributes to the headline line."""
     keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "ms_per_query", "latency_ms", "dtype", "config", "run",
@@ -699,6 +855,7 @@ def main():
     ap.add_argument("--only", action="store_true", help="headline workload only")
     ap.add_argument("--config-steps", type=int, default=5, help="timed steps of each attached config leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inprocess", action="store_true", help="N>1: skip the one-process-all-GPUs leg of the headline workload")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
                     help="N>1, single queries: fused push over NVLink peer memory (default) or NCCL all-gather + merge")
     args = ap.parse_args()
@@ -746,6 +903,10 @@ def main():
         fn = leg_batch_sharded if name == "c3" else leg_sharded
         return fn(sp, name, steps, args.warmup)
     line = run_n(args.workload, args.steps)
+    if not args.no_inprocess and args.workload != "c3":
+        inproc = leg_inprocess(sp, args.workload, args.steps, args.warmup)
+        if sp.rank == 0:
+            line["inprocess"] = inproc
     if extra:
         cfgs = {}
         for c in extra:

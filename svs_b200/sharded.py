@@ -151,6 +151,20 @@ class CudaShardBackend:
                                               C.byref(cnt)))
         return s[:cnt.value], i[:cnt.value]
 
+    def query_peer_submit(self, q: np.ndarray, k: int) -> int:
+        """Start a host-buffer query (svsb_query_peer_submit); up to 3 may be pending.  Returns the ticket."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        t = C.c_int32()
+        self._check(self._lib.svsb_query_peer_submit(self.engine._h, q.ctypes.data, q.shape[0], k, C.byref(t)))
+        return t.value
+
+    def query_peer_wait(self, ticket: int, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        s = np.empty(k, dtype=np.float32)
+        i = np.empty(k, dtype=np.int64)
+        cnt = C.c_int32()
+        self._check(self._lib.svsb_query_peer_wait(self.engine._h, ticket, s.ctypes.data, i.ctypes.data, C.byref(cnt)))
+        return s[:cnt.value], i[:cnt.value]
+
     def join(self) -> None:
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.svsb_enqueue_join(self.engine._h, C.c_void_p(st)))
@@ -338,6 +352,26 @@ class ShardedRetriever:
         o_s, o_i, o_c = self._micro_batch([dq[0]], k, False)
         cnt = int(o_c[0].item())                                   # synchronises the stream
         return o_s[0, :cnt].cpu().numpy(), o_i[0, :cnt].cpu().numpy()
+
+    def submit(self, query_vec: np.ndarray, n: int):
+        """Start a retrieve (host query in) and return a handle for `wait`; up to 3 may be pending, every rank submits the
+        same sequence.  The next query's matrix pass overlaps this one's selection, exchange, merge and host round trip."""
+        q = np.ascontiguousarray(query_vec, dtype=np.float32)
+        if q.ndim != 1 or q.shape[0] != self.d or self.n == 0:
+            raise ValueError(f"shapes ({self.n},{self.d if self.n else 0}) and ({q.shape[0]},) not aligned")
+        if n > 2048 and self.n > 2048:
+            raise NotImplementedError("n > 2048 is not supported by the sharded path")
+        k = min(int(n), 2048, self.n)
+        if k <= 0 or self.exchange != "peer":
+            return ("done", self.retrieve_arrays(q, n))           # nothing to overlap: answered synchronously
+        self._ensure_peer()
+        return ("ticket", self.backend.query_peer_submit(q, k), k)
+
+    def wait(self, handle) -> Tuple[np.ndarray, np.ndarray]:
+        """(scores, embeddings.id) of a submitted retrieve; oldest first."""
+        if handle[0] == "done":
+            return handle[1]
+        return self.backend.query_peer_wait(handle[1], handle[2])
 
     def retrieve(self, query_vec: np.ndarray, n: int) -> List[Tuple[float, int]]:
         """The reference's superheavy() result, on every rank: host query in, host list out."""

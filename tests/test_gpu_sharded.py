@@ -240,6 +240,46 @@ def test_peer_exchange_synchronous_query_from_two_threads_and_an_empty_shard():
                 b.close()
 
 
+def test_peer_exchange_submit_wait_keeps_three_queries_in_flight():
+    """svsb_query_peer_submit / _wait: host buffers in and out with up to 3 queries pending per rank.  Submits are
+    non-blocking, so one host thread drives all virtual ranks SPMD; every rank must get the bits the single-device
+    engine computes for the whole matrix."""
+    pytest.importorskip("torch")
+    import svs_b200
+    n, d = 25_000, 192
+    m = oracle.synth_matrix_uniform(n, d, 45)
+    ids = np.arange(7, 7 + n, dtype=np.int64)
+    qs = oracle.synth_queries(30, d, 46)
+    with svs_b200.Engine([0]) as one:
+        one.load(m, ids)
+        want = {k: [one.query(q, k) for q in qs] for k in (10, 100, 1200)}
+    oracle.compare_retrieval(list(zip(*[x.tolist() for x in want[100][0]])), oracle.superheavy(m, ids, qs[0], 100),
+                             oracle.scores_of(m, qs[0]), ids)
+    for world in (2, 3):
+        backs = _two_backends(m, ids, world)
+        try:
+            for k in (10, 100, 1200):
+                pend, got = [], [[] for _ in backs]
+                for q in qs:
+                    pend.append([b.query_peer_submit(q, k) for b in backs])
+                    if len(pend) == 3:
+                        with pytest.raises(svs_b200.EngineError, match="pending already"):
+                            backs[0].query_peer_submit(q, k)                 # a 4th is refused (nothing enqueued), not queued
+                        for r, b in enumerate(backs):
+                            got[r].append(b.query_peer_wait(pend[0][r], k))
+                        pend.pop(0)
+                for p in pend:
+                    for r, b in enumerate(backs):
+                        got[r].append(b.query_peer_wait(p[r], k))
+                for r in range(world):
+                    assert len(got[r]) == len(qs)
+                    for a, w in zip(got[r], want[k]):
+                        assert np.array_equal(a[0].view(np.uint32), w[0].view(np.uint32)) and np.array_equal(a[1], w[1])
+        finally:
+            for b in backs:
+                b.close()
+
+
 def test_peer_exchange_missing_peer_times_out_instead_of_hanging():
     """A rank whose peer never issues the query must get an error after SVSB_XCHG_TIMEOUT_MS, not a hung GPU."""
     pytest.importorskip("torch")
