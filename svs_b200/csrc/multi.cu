@@ -260,6 +260,19 @@ int multi_publish(svsb_engine* e, const std::shared_ptr<Generation>& g) {
         if (g->ld > 0 && (rc = x->ws.ensure_q(g->ld)) != SVSB_OK) return rc;
         if ((rc = x->ws.ensure_out(K_FAST_MAX)) != SVSB_OK) return rc;
         if (i == 0 && (rc = x->ws.ensure_merge_scratch((int64_t)nd * K_FAST_MAX)) != SVSB_OK) return rc;
+        // the fused path is software-pipelined per device: two workspace sets alternate, selection + push run on a side stream
+        if (!kid->side_st) CU(cudaStreamCreateWithFlags(&kid->side_st, cudaStreamNonBlocking));
+        if (kid->shard_ws.size() < 2) kid->shard_ws.resize(2);
+        if (kid->sel_pending.size() < 2) kid->sel_pending.resize(2, 0);
+        for (int t = 0; t < 2; ++t) {
+            if (!kid->shard_ws[t]) { kid->shard_ws[t].reset(new DevWs()); kid->shard_ws[t]->dev = s.dev; }
+            DevWs& w = *kid->shard_ws[t];
+            if (s.n > 0 && (rc = w.ensure_rows(s.n)) != SVSB_OK) return rc;
+            if (g->ld > 0 && (rc = w.ensure_q(g->ld)) != SVSB_OK) return rc;
+            if ((rc = w.ensure_out(K_FAST_MAX)) != SVSB_OK) return rc;
+            if (!w.ev) CU(cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming));
+            if (!w.ev_sel) CU(cudaEventCreateWithFlags(&w.ev_sel, cudaEventDisableTiming));
+        }
         return SVSB_OK;
     });
 }
@@ -278,14 +291,19 @@ struct FastJob {
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;    // optional bracket of device 0's similarity kernel
 };
 
+// Per device, software-pipelined like the one-process-per-GPU loop (engine.cu: svsb_enqueue_query_peer): the similarity
+// pass of query j runs on the device's main stream with one SM left free, its selection + push on the side stream on
+// that SM, so query j+1's matrix pass overlaps query j's selection, push and (device 0) merge.  Two workspace sets
+// alternate; ev_sel of a set gates the similarity pass two queries on.
 static int kid_fast(Multi* m, int i, const FastJob& j) {
     svsb_engine* kid = m->kids[i];
     Xchg* x = kid->xchg.get();
     Xchg* xr = m->kids[0]->xchg.get();
     const Generation* cg = j.g->child_gen[i].get();
     const Shard& s = cg->shards[0];
-    DevWs& w = x->ws;
-    cudaStream_t st = x->st;
+    const int set = (int)(j.seq & 1);
+    DevWs& w = *kid->shard_ws[set];
+    cudaStream_t st = x->st, side = kid->side_st;
     CU(cudaSetDevice(s.dev));
     const int slot = (int)(j.seq % (unsigned long long)xr->slots);
     PeerPush push{};
@@ -293,34 +311,41 @@ static int kid_fast(Multi* m, int i, const FastJob& j) {
     push.rec[0] = xr->rec_of(xr->block, slot, i);
     push.flag[0] = xr->flags_of(xr->block, slot) + i;
     if (s.n_live == 0) {
-        CU(launch_push_empty(st, push));
-    } else {
-        const int shift = group_shift_for(s.n);
-        const float* dq = j.d_q ? j.d_q[i] + j.q_off : w.d_q;
-        if (!j.d_q) CU(launch_stage_query(st, j.h_q, w.d_q, cg->ld));
-        if (i == 0 && j.kev0) CU(cudaEventRecord(j.kev0, st));
-        w.gmax_dirty = true;
-        {   // the similarity kernel streams its first tiles under the staging kernel (programmatic dependent launch)
-            PdlScope pdl(!j.d_q && env_int("SVSB_PDL", 1) != 0);
-            CU(launch_gemv(st, s.dev, s.M, s.n, cg->d, cg->ld, dq, w.scores, w.gmax, shift, 0, 0, 0, 0, s.live));
-        }
-        if (i == 0 && j.kev1) CU(cudaEventRecord(j.kev1, st));
-        CU(launch_select(st, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(j.kk, s.n_live), s.ids, s.row0, w.cand, w.cand_cap,
-                         w.out_keys, w.out_scores, w.out_ids, w.out_count, nullptr, &push));
-        w.gmax_dirty = false;
+        CU(launch_push_empty(side, push));
+        return SVSB_OK;
     }
+    const int shift = group_shift_for(s.n);
+    const bool pipelined = sm_count(s.dev) > 8;
+    if (kid->sel_pending[set]) CU(cudaStreamWaitEvent(st, w.ev_sel, 0));   // the set's previous selection is done with it
+    const float* dq = j.d_q ? j.d_q[i] + j.q_off : w.d_q;
+    if (!j.d_q) CU(launch_stage_query(st, j.h_q, w.d_q, cg->ld));
+    if (i == 0 && j.kev0) CU(cudaEventRecord(j.kev0, st));
+    w.gmax_dirty = true;
+    {   // the similarity kernel streams its first tiles under the staging kernel (programmatic dependent launch)
+        PdlScope pdl(!j.d_q && env_int("SVSB_PDL", 1) != 0);
+        CU(launch_gemv(st, s.dev, s.M, s.n, cg->d, cg->ld, dq, w.scores, w.gmax, shift, 0, 0, 0, pipelined ? 1 : 0, s.live));
+    }
+    if (i == 0 && j.kev1) CU(cudaEventRecord(j.kev1, st));
+    CU(cudaEventRecord(w.ev, st));
+    CU(cudaStreamWaitEvent(side, w.ev, 0));
+    CU(launch_select(side, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(j.kk, s.n_live), s.ids, s.row0, w.cand, w.cand_cap,
+                     w.out_keys, w.out_scores, w.out_ids, w.out_count, nullptr, &push));
+    w.gmax_dirty = false;
+    CU(cudaEventRecord(w.ev_sel, side));
+    kid->sel_pending[set] = 1;
     return SVSB_OK;
 }
 
-// Device 0's waiting merge, enqueued by the submitting thread AFTER every device's selection (with its push) has been
-// enqueued: a kernel that waits is only ever launched behind everything it waits for, so no host-side operation with an
-// implicit device synchronisation (cudaMalloc / cudaFree of a concurrent load, ...) can come between a spinning merge
-// and the launch of a push it needs -- with several virtual shards on ONE device that would otherwise deadlock until the
-// merge's timeout.
+// Device 0's waiting merge, enqueued (on device 0's side stream) by the submitting thread AFTER every device's
+// selection with its push has been enqueued: a kernel that waits is only ever launched behind everything it waits for,
+// so no host-side operation with an implicit device synchronisation (cudaMalloc / cudaFree of a concurrent load, ...)
+// can come between a spinning merge and the launch of a push it needs -- with several virtual shards on ONE device that
+// would otherwise deadlock until the merge's timeout.
 static int root_merge(Multi* m, const FastJob& j) {
-    Xchg* xr = m->kids[0]->xchg.get();
+    svsb_engine* root = m->kids[0];
+    Xchg* xr = root->xchg.get();
     DevWs& w = xr->ws;
-    cudaStream_t st = xr->st;
+    cudaStream_t st = root->side_st;
     const int nd = (int)m->kids.size();
     const int slot = (int)(j.seq % (unsigned long long)xr->slots);
     CU(cudaSetDevice(root_dev(m)));
