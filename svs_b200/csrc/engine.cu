@@ -184,6 +184,7 @@ extern "C" void svsb_destroy(svsb_t* e) {
     e->pool_free.clear();
     if (e->bench_ctx) ctx_destroy(e, e->bench_ctx.get());
     if (e->batch_ws) e->batch_ws->release();
+    if (e->mq_ws) e->mq_ws->release();
     for (auto& w : e->shard_ws) if (w) w->release();
     xchg_release(e);
     if (e->side_st) { cudaSetDevice(e->devs[0]); cudaStreamDestroy(e->side_st); }
@@ -896,6 +897,78 @@ extern "C" int svsb_host_free(void* p) {
     return SVSB_OK;
 }
 
+// ---- small exact batches: ONE pass over the matrix for up to 8 warps' worth of queries (gemv.cu: gemv_tma_mq_kernel),
+//      then one selection CTA per query.  Same bits as the single-query kernels; no fp16 shadow, any k <= 2048, tombstones ok.
+struct MqPlan { int bq = 0, chunk = 0, max_b = 0; };
+static bool mq_plan(const Generation* g, int64_t kk, MqPlan& P) {
+    if (env_int("SVSB_MQ", 1) == 0 || g->shards.size() != 1 || g->n_live == 0) return false;
+    P.bq = gemv_mq_queries_per_warp(g->ld);
+    if (P.bq == 0 || kk < 1 || kk > K_FAST_MAX) return false;
+    // per launch: `groups` x bq queries, each streamed byte read `groups` times from shared memory.  4 groups is the
+    // measured sweet spot (profiles/r02_mq_sweep.txt); bounded by 2 GB of score vectors.
+    P.chunk = std::min(8, std::max(1, env_int("SVSB_MQ_GROUPS", 4))) * P.bq;
+    const int64_t by_mem = std::max<int64_t>(1, (2ll << 30) / std::max<int64_t>(g->shards[0].n * 4, 1));
+    if (P.chunk > by_mem) P.chunk = (int)by_mem;
+    // Which path answers a batch when the tensor-core coarse pass is ALSO available (profiles/r02_mq_sweep.txt, 1M rows):
+    // the coarse pass reads the fp16 shadow (half the bytes) and costs ~0.72 ms at d = 1536 / 0.40 ms at d = 768 for any
+    // b <= 256 while k is small, so it wins from 4 queries on (multi-query: 0.96 ms for 4, 1.2 ms for 8); its exact refine
+    // grows with k, and at k = 1000 (d = 3072) it needs 8.3 ms for 4 queries against 1.8 ms here -- large k stays exact
+    // multi-query at every batch size.  Batches the coarse pass cannot take (tombstones, k > 1024, no room for the
+    // shadow matrix) run as multi-query passes regardless.
+    P.max_b = env_int("SVSB_MQ_MAX", kk > 256 ? 0x7fffffff : 3);
+    return P.chunk >= 2;
+}
+
+static int mq_ws_get(svsb_engine* e, MqWs*& out) {
+    if (!e->mq_ws) { e->mq_ws.reset(new MqWs()); e->mq_ws->dev = e->devs[0]; }
+    out = e->mq_ws.get();
+    return SVSB_OK;
+}
+
+// enqueue gemv + selection for b (<= chunk) device-resident queries dQ[b][ld] on st; outputs through `os` strides
+static int mq_enqueue(MqWs* w, const Generation* g, cudaStream_t st, const float* dQ, int b, int64_t kk, const SelectStrides& os,
+                      u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count) {
+    const Shard& s = g->shards[0];
+    const int shift = group_shift_for(w->cap_n);                 // group layout of the workspace (>= this shard's rows)
+    CU(cudaSetDevice(w->dev));
+    w->gmax_dirty = true;
+    CU(launch_gemv_mq(st, w->dev, s.M, s.n, g->d, g->ld, dQ, b, w->scores, w->cap_n, w->gmax, w->G, shift, s.live, 0));
+    SelectStrides ss = os;
+    ss.scores = w->cap_n; ss.gmax = w->G; ss.cand = w->cand_cap;
+    CU(launch_select_batch(st, b, ss, w->scores, s.n, w->gmax, shift, (int)std::min<int64_t>(kk, s.n_live), s.ids, s.row0, w->cand, w->cand_cap,
+                           out_keys, out_scores, out_ids, out_count));
+    w->gmax_dirty = false;
+    return SVSB_OK;
+}
+
+static int query_batch_mq(svsb_engine* e, const std::shared_ptr<Generation>& g, const MqPlan& P, const float* Q, int32_t b, int32_t d,
+                          int32_t k, int64_t kk, float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    MqWs* w = nullptr;
+    int rc = mq_ws_get(e, w);
+    if (rc != SVSB_OK) return rc;
+    const Shard& s = g->shards[0];
+    const int ld = g->ld;
+    for (int32_t c0 = 0; c0 < b; c0 += P.chunk) {
+        const int bc = std::min<int32_t>(P.chunk, b - c0);
+        if ((rc = w->ensure(std::min<int32_t>(P.chunk, b), s.n, ld, kk)) != SVSB_OK) return rc;
+        CU(cudaStreamSynchronize(w->st));                        // h_Q is free again
+        for (int i = 0; i < bc; ++i) {
+            float* dst = w->h_Q + (size_t)i * ld;
+            memcpy(dst, Q + (size_t)(c0 + i) * d, (size_t)d * 4);
+            for (int c = d; c < ld; ++c) dst[c] = 0.f;
+        }
+        CU(cudaMemcpyAsync(w->dQ, w->h_Q, (size_t)bc * ld * 4, cudaMemcpyHostToDevice, w->st));
+        SelectStrides os; os.keys = kk; os.oscores = kk; os.ids = kk; os.count = 1;
+        if ((rc = mq_enqueue(w, g.get(), w->st, w->dQ, bc, kk, os, w->o_keys, w->o_scores, w->o_ids, w->o_counts)) != SVSB_OK) return rc;
+        CU(cudaMemcpy2DAsync(out_scores + (int64_t)c0 * k, (size_t)k * 4, w->o_scores, (size_t)kk * 4, (size_t)kk * 4, (size_t)bc, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaMemcpy2DAsync(out_emb_ids + (int64_t)c0 * k, (size_t)k * 8, w->o_ids, (size_t)kk * 8, (size_t)kk * 8, (size_t)bc, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaMemcpyAsync(out_counts + c0, w->o_counts, (size_t)bc * 4, cudaMemcpyDeviceToHost, w->st));
+        CU(cudaStreamSynchronize(w->st));
+    }
+    return SVSB_OK;
+}
+
 static int query_batch_loop(svsb_engine* e, const std::shared_ptr<Generation>& g, const float* Q, int32_t b, int32_t d, int32_t k,
                             float* out_scores, int64_t* out_emb_ids, int32_t* out_counts) {
     const int64_t kstride = k > 0 ? k : 0;
@@ -917,7 +990,11 @@ static int query_batch_gen(svsb_engine* e, const std::shared_ptr<Generation>& g,
     BatchPlan P;
     if (e->multi && g->n_live > 0 && d == g->d && k > 0 && b >= 2 && out_scores && out_emb_ids)
         return multi_query_batch(e, g, Q, b, d, k, out_scores, out_emb_ids, out_counts);
-    const bool coarse = g->n_live > 0 && d == g->d && k > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
+    bool coarse = g->n_live > 0 && d == g->d && k > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
+    MqPlan MP;
+    if (g->n_live > 0 && d == g->d && k > 0 && b >= 2 && out_scores && out_emb_ids && !e->multi &&
+        mq_plan(g.get(), std::min<int64_t>(k, g->n_live), MP) && (b <= MP.max_b || !coarse))
+        return query_batch_mq(e, g, MP, Q, b, d, k, std::min<int64_t>(k, g->n_live), out_scores, out_emb_ids, out_counts);
     if (!coarse)                                      // same results, one similarity pass per query
         return query_batch_loop(e, g, Q, b, d, k, out_scores, out_emb_ids, out_counts);
     if (!out_scores || !out_emb_ids) return fail(SVSB_E_INVALID, "svsb_query_batch: NULL buffer");
@@ -1508,7 +1585,28 @@ int batch_local_records_gen(svsb_engine* e, const std::shared_ptr<Generation>& g
     const int64_t rec = 2 * (int64_t)k + 1;
     int fallbacks = 0;
     BatchPlan P;
-    const bool coarse = g->n_live > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
+    bool coarse = g->n_live > 0 && b >= env_int("SVSB_BATCH_MIN", 4) && batch_plan(e, g.get(), k, P);
+    MqPlan MP;
+    if (b >= 2 && mq_plan(g.get(), std::min<int64_t>(k, g->n_live), MP) && (b <= MP.max_b || !coarse)) {
+        // small batch (or no tensor-core path for this shard): multi-query passes straight into the records
+        std::lock_guard<std::mutex> lk(e->batch_mu);
+        MqWs* w = nullptr;
+        int rc = mq_ws_get(e, w);
+        if (rc != SVSB_OK) return rc;
+        const Shard& s = g->shards[0];
+        for (int32_t c0 = 0; c0 < b; c0 += MP.chunk) {
+            const int bc = std::min<int32_t>(MP.chunk, b - c0);
+            if ((rc = w->ensure(std::min<int32_t>(MP.chunk, b), s.n, g->ld, k)) != SVSB_OK) return rc;
+            CU(cudaStreamSynchronize(w->st));                    // the workspace's own (zeroing) work is done before `st` uses it
+            int64_t* r0 = d_records + (int64_t)c0 * rec;
+            SelectStrides os; os.keys = rec; os.oscores = k; os.ids = rec; os.count = 2 * rec;
+            if ((rc = mq_enqueue(w, g.get(), st, d_Q + (int64_t)c0 * g->ld, bc, k, os, reinterpret_cast<u64*>(r0), w->o_scores, r0 + k,
+                                 reinterpret_cast<int32_t*>(r0 + 2 * (int64_t)k))) != SVSB_OK) return rc;
+            if (c0 + MP.chunk < b) CU(cudaStreamSynchronize(st));   // the next chunk reuses the score vectors
+        }
+        if (n_fallback) *n_fallback = 0;
+        return SVSB_OK;
+    }
     std::vector<char> todo((size_t)b, coarse ? 0 : 1);
     if (coarse) {
         std::lock_guard<std::mutex> lk(e->batch_mu);

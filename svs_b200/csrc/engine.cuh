@@ -242,6 +242,69 @@ struct BatchWs {
     }
 };
 
+// workspace of the small-batch exact path (gemv_tma_mq_kernel + one selection CTA per query)
+struct MqWs {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    int cap_b = 0, cap_ld = 0; int64_t cap_n = 0, G = 0, cand_cap = 0, cap_out = 0;
+    float* dQ = nullptr; float* scores = nullptr; u64* gmax = nullptr; u64* cand = nullptr;
+    u64* o_keys = nullptr; float* o_scores = nullptr; int64_t* o_ids = nullptr; int32_t* o_counts = nullptr;
+    float* h_Q = nullptr;
+    bool gmax_dirty = false;
+
+    int ensure(int b, int64_t n, int ld, int64_t k) {
+        cudaSetDevice(dev);
+        if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (b > cap_b || n > cap_n) {
+            CU(cudaStreamSynchronize(st));
+            const int nb = std::max(b, cap_b); const int64_t nn = std::max(n, cap_n);
+            void* ptrs[] = {scores, gmax, cand, o_counts};
+            for (void* p : ptrs) if (p) cudaFree(p);
+            scores = nullptr; gmax = nullptr; cand = nullptr; o_counts = nullptr; cap_b = 0; cap_n = 0;
+            const int shift = group_shift_for(nn);
+            G = (nn + ((int64_t)1 << shift) - 1) >> shift;
+            cand_cap = std::min<int64_t>((int64_t)K_FAST_MAX << shift, nn) + K_FAST_MAX;
+            CU(cudaMalloc(&scores, (size_t)nb * nn * 4));
+            CU(cudaMalloc(&gmax, (size_t)nb * G * 8));
+            CU(cudaMalloc(&cand, (size_t)nb * cand_cap * 8));
+            CU(cudaMalloc(&o_counts, (size_t)nb * 4));
+            cap_b = nb; cap_n = nn; gmax_dirty = true; cap_out = 0; cap_ld = 0;
+        }
+        if (gmax_dirty) {
+            CU(cudaMemsetAsync(gmax, 0, (size_t)cap_b * G * 8, st));
+            gmax_dirty = false;
+        }
+        if (ld > cap_ld) {
+            CU(cudaStreamSynchronize(st));
+            if (dQ) cudaFree(dQ);
+            if (h_Q) cudaFreeHost(h_Q);
+            dQ = nullptr; h_Q = nullptr; cap_ld = 0;
+            CU(cudaMalloc(&dQ, (size_t)cap_b * ld * 4));
+            CU(cudaMallocHost(&h_Q, (size_t)cap_b * ld * 4));
+            cap_ld = ld;
+        }
+        if ((int64_t)cap_b * k > cap_out) {
+            CU(cudaStreamSynchronize(st));
+            void* ptrs[] = {o_keys, o_scores, o_ids};
+            for (void* p : ptrs) if (p) cudaFree(p);
+            o_keys = nullptr; o_scores = nullptr; o_ids = nullptr; cap_out = 0;
+            const int64_t e = (int64_t)cap_b * k;
+            CU(cudaMalloc(&o_keys, (size_t)e * 8));
+            CU(cudaMalloc(&o_scores, (size_t)e * 4));
+            CU(cudaMalloc(&o_ids, (size_t)e * 8));
+            cap_out = e;
+        }
+        return SVSB_OK;
+    }
+    void release() {
+        cudaSetDevice(dev);
+        void* ptrs[] = {dQ, scores, gmax, cand, o_keys, o_scores, o_ids, o_counts};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        if (h_Q) cudaFreeHost(h_Q);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
 // Peer exchange of the one-process-per-GPU deployment (kernels.cuh "peer exchange"): this rank's gather window,
 // the peers' windows opened over CUDA IPC (or plain pointers inside one process), and a synchronous query context.
 struct Xchg {
@@ -301,6 +364,7 @@ struct svsb_engine {
     // batched path (one batch at a time)
     std::mutex batch_mu;
     std::unique_ptr<struct BatchWs> batch_ws;
+    std::unique_ptr<MqWs> mq_ws;            // small exact batches (guarded by batch_mu as well)
     // bench state
     std::vector<float*> bench_q; int bench_nq = 0, bench_d = 0, bench_ld = 0;
     std::unique_ptr<QueryCtx> bench_ctx;

@@ -226,6 +226,158 @@ gemv_tma_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, i
 }
 
 // =============================================================================================
+// variant 2b: the same ring, several queries per pass (small exact batches)
+// =============================================================================================
+// b queries against the matrix in ONE pass over HBM, bit-identical to b single-query passes: every (row, query) dot
+// product is computed by one warp with exactly gemv_tma_kernel's arithmetic (lane l owns the float4 chunks l, l+32, ...;
+// even chunks accumulate into a0, odd ones into a1; same combine, same xor tree).  The consumer warps are split into
+// `groups` groups; a warp keeps BQ queries (its slice of each) in registers -- 4 * NQ * BQ of them, which is why the
+// consumers run at 240 registers (setmaxnreg: the producer warpgroup gives its registers up) -- and the warps of a group
+// share the rows of a tile.  Shared-memory traffic per streamed byte: 1 write (TMA) + `groups` reads, against ~5x
+// headroom of shared-memory over HBM bandwidth per SM; the FMA pipe sees b FMAs per streamed float (b = 8: 40 %).
+// Warps 0-3: producer warpgroup (one lane issues the bulk copies); warps 4-11: consumers.
+// Two fp32 FMAs per instruction (Blackwell FFMA2, PTX fma.rn.f32x2): each half is an ordinary IEEE round-to-nearest FMA,
+// so the bits equal two fmaf calls; what halves is the number of issue slots the b-fold arithmetic of a row needs.
+struct f4x2 { u64 xy, zw; };                                    // a float4 held as two packed pairs
+__device__ __forceinline__ void fma4_x2(f4x2& acc, const f4x2& a, const f4x2& b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.xy) : "l"(a.xy), "l"(b.xy));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.zw) : "l"(a.zw), "l"(b.zw));
+}
+__device__ __forceinline__ f4x2 as_f4x2(const ulonglong2& v) { f4x2 r; r.xy = v.x; r.zw = v.y; return r; }
+__device__ __forceinline__ float4 as_float4(const f4x2& v) {
+    float4 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v.xy));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(v.zw));
+    return r;
+}
+
+// FULL: d4 == 32 * NQ exactly (d = 1536, 3072, 768, 256 ...): no per-chunk bounds predicate / zero select.
+template <int NQ, int BQ, bool FULL>
+__global__ void __launch_bounds__(384, 1)
+gemv_tma_mq_kernel(const float* __restrict__ M, int64_t n, int d4, int tile_rows, int stages,
+                   const float* __restrict__ Q, int b, int groups, float* __restrict__ scores, int64_t n_stride,
+                   u64* __restrict__ gmax, int64_t g_stride, int group_shift, const uint8_t* __restrict__ live)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t row_bytes = (uint32_t)d4 * 16u;
+    const uint32_t stage_bytes = (uint32_t)tile_rows * row_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_bytes);
+    uint64_t* empty = full + stages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int CW = 8;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == 0 && lane == 0) {
+            u64 policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            int s = 0; uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                mbar_wait(&empty[s], phase ^ 1u);
+                const int64_t r0 = t * tile_rows;
+                const int64_t left = n - r0;
+                const uint32_t rows = left < tile_rows ? (uint32_t)left : (uint32_t)tile_rows;
+                const uint32_t bytes = rows * row_bytes;
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(smem_raw + (size_t)s * stage_bytes, M + r0 * (int64_t)d4 * 4, bytes, &full[s], policy);
+                if (++s == stages) { s = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+        const int cw = warp - 4, grp = cw % groups, sub = cw / groups, nsub = CW / groups;
+        f4x2 qr[BQ][NQ];
+#pragma unroll
+        for (int u = 0; u < BQ; ++u) {
+            int qi = grp * BQ + u;
+            if (qi > b - 1) qi = b - 1;                          // padding slots recompute the last query; never stored
+            const ulonglong2* qp = reinterpret_cast<const ulonglong2*>(Q) + (int64_t)qi * d4;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                const int c = lane + 32 * j;
+                qr[u][j] = as_f4x2((FULL || c < d4) ? __ldcg(qp + c) : make_ulonglong2(0ull, 0ull));
+            }
+        }
+        int s = 0; uint32_t phase = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int64_t r0 = t * tile_rows;
+            const int64_t left = n - r0;
+            const int rows = left < tile_rows ? (int)left : tile_rows;
+            mbar_wait(&full[s], phase);
+            const ulonglong2* tile = reinterpret_cast<const ulonglong2*>(smem_raw + (size_t)s * stage_bytes);
+            for (int r = sub; r < rows; r += nsub) {
+                const ulonglong2* p = tile + (size_t)r * d4;
+                const uint8_t alive = live ? __ldg(live + r0 + r) : (uint8_t)1;
+                f4x2 a0[BQ], a1[BQ];
+#pragma unroll
+                for (int u = 0; u < BQ; ++u) { a0[u].xy = 0ull; a0[u].zw = 0ull; a1[u] = a0[u]; }
+                // With 192 registers of queries there is no room to load the whole row slice ahead of the arithmetic (as
+                // the single-query kernel does): keep PF loads in flight instead, issued a chunk ahead of their FMAs --
+                // without it every chunk pays a shared-memory round trip with only two warps per scheduler to hide it
+                // (measured: 2.1 ms instead of 1.0 ms for 8 queries at 1M x 1536).
+                constexpr int PF = (4 * NQ * BQ >= 192) ? 2 : NQ;
+                ulonglong2 mb[PF];
+#pragma unroll
+                for (int j = 0; j < PF && j < NQ; ++j) { const int c = lane + 32 * j; mb[j] = (FULL || c < d4) ? p[c] : make_ulonglong2(0ull, 0ull); }
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    const f4x2 m = as_f4x2(mb[j % PF]);
+                    if (j + PF < NQ) { const int c = lane + 32 * (j + PF); mb[j % PF] = (FULL || c < d4) ? p[c] : make_ulonglong2(0ull, 0ull); }
+#pragma unroll
+                    for (int u = 0; u < BQ; ++u) { if (j & 1) fma4_x2(a1[u], m, qr[u][j]); else fma4_x2(a0[u], m, qr[u][j]); }
+                }
+                // the BQ xor trees advance in lockstep (BQ independent shuffles per round instead of BQ serial trees), then
+                // lane u publishes query u: one predicated block of stores for the whole row
+                float v[BQ];
+#pragma unroll
+                for (int u = 0; u < BQ; ++u) {
+                    const float4 x0 = as_float4(a0[u]), x1 = as_float4(a1[u]);
+                    v[u] = ((x0.x + x1.x) + (x0.y + x1.y)) + ((x0.z + x1.z) + (x0.w + x1.w));
+                }
+                // BQ xor trees in one: at distance 16 a lane keeps the upper or the lower half of the queries and trades the
+                // other half with its partner, at distance 8 a quarter, ... -- every addition is still x[l] + x[l ^ o] of ONE
+                // query at the distances 16, 8, 4, 2, 1 in that order, i.e. exactly warp_sum's tree (fp32 addition is
+                // commutative bit for bit), with 2*BQ - 2 + log2(32 / BQ) shuffles instead of 5 * BQ.
+                int o = 16;
+#pragma unroll
+                for (int cnt = BQ; cnt > 1; cnt >>= 1, o >>= 1) {
+                    const int half = cnt >> 1;
+                    const bool up = (lane & o) != 0;
+#pragma unroll
+                    for (int i = 0; i < half; ++i) {
+                        const float send = up ? v[i] : v[i + half];
+                        const float keep = up ? v[i + half] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                }
+#pragma unroll
+                for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+                float sc = v[0];                                 // the sum of query u_of(lane), complete in every lane
+                if (!alive) sc = dead_score();
+                // which query this lane holds: bit 4 picked a half, bit 3 a quarter, ...; lanes with the low bits clear publish
+                constexpr int LANES_PER_Q = 32 / BQ;
+                int u_mine = 0;
+#pragma unroll
+                for (int step = 0, bit = 16, w = BQ >> 1; w >= 1; ++step, bit >>= 1, w >>= 1) u_mine += (lane & bit) ? w : 0;
+                const int qi = grp * BQ + u_mine;
+                if ((lane & (LANES_PER_Q - 1)) == 0 && qi < b) {
+                    scores[(int64_t)qi * n_stride + r0 + r] = sc;
+                    atomicMax(&gmax[(int64_t)qi * g_stride + ((r0 + r) >> group_shift)], make_key(sc, (uint32_t)(r0 + r)));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == stages) { s = 0; phase ^= 1u; }
+        }
+    }
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
 int sm_count(int device) {
@@ -370,6 +522,75 @@ cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, 
         case 9:  return run_ldg<8, 3, 128>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
         default: return run_ldg<4, 3, 256>(st, device, M, n, d4, q, scores, gmax, group_shift, live, tune_b);
     }
+}
+
+// ---- multi-query launcher ---------------------------------------------------------------------
+template <int NQ, int BQ, bool FULL>
+static cudaError_t run_mq_inst2(cudaStream_t st, int64_t grid, size_t smem, const float* M, int64_t n, int d4, int tile_rows, int stages,
+                               const float* Q, int b, int groups, float* scores, int64_t n_stride, u64* gmax, int64_t g_stride,
+                               int group_shift, const uint8_t* live)
+{
+    auto kern = gemv_tma_mq_kernel<NQ, BQ, FULL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)grid, 384, smem, st>>>(M, n, d4, tile_rows, stages, Q, b, groups, scores, n_stride, gmax, g_stride, group_shift, live);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int NQ, int BQ>
+static cudaError_t run_mq_inst(cudaStream_t st, int64_t grid, size_t smem, const float* M, int64_t n, int d4, int tile_rows, int stages,
+                               const float* Q, int b, int groups, float* scores, int64_t n_stride, u64* gmax, int64_t g_stride,
+                               int group_shift, const uint8_t* live)
+{
+    if (d4 == 32 * NQ)
+        return run_mq_inst2<NQ, BQ, true>(st, grid, smem, M, n, d4, tile_rows, stages, Q, b, groups, scores, n_stride, gmax, g_stride, group_shift, live);
+    return run_mq_inst2<NQ, BQ, false>(st, grid, smem, M, n, d4, tile_rows, stages, Q, b, groups, scores, n_stride, gmax, g_stride, group_shift, live);
+}
+
+int gemv_mq_queries_per_warp(int ld) {
+    const int d4 = ld / 4;
+    return d4 <= 64 ? 8 : d4 <= 192 ? 4 : d4 <= 384 ? 4 : d4 <= 768 ? 2 : 0;   // 16 * NQ * BQ query + 8 * BQ accumulator registers <= ~224
+}
+
+cudaError_t launch_gemv_mq(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld, const float* Q, int b,
+                           float* scores, int64_t n_stride, u64* gmax, int64_t g_stride, int group_shift, const uint8_t* live,
+                           int reserve_sms)
+{
+    (void)d;
+    if (n <= 0 || b <= 0) return cudaSuccess;
+    const int d4 = ld / 4;
+    const int bq_hi = gemv_mq_queries_per_warp(ld);
+    if (bq_hi == 0) return cudaErrorInvalidConfiguration;       // rows too long for register-resident queries
+    int bq = bq_hi;
+    if (bq_hi > 2 && b <= bq_hi / 2) bq = bq_hi / 2;             // fewer wasted FMAs for a small batch
+    int groups = 1;
+    while (groups * bq < b) groups <<= 1;
+    if (groups > 8) return cudaErrorInvalidConfiguration;       // the caller chunks larger batches
+    const size_t row_bytes = (size_t)d4 * 16;
+    int tile_rows = 64;
+    while (tile_rows > 1 && (size_t)tile_rows * row_bytes > 48 * 1024) tile_rows >>= 1;
+    if (tile_rows < 8 / groups) { /* every warp of a group still gets whole rows: fine, some idle */ }
+    const int stages = 3;
+    const size_t smem = (size_t)stages * tile_rows * row_bytes + (size_t)stages * 16 + 64;
+    const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+    int64_t grid = sm_count(device) - reserve_sms;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    const int nq = d4 <= 64 ? 2 : d4 <= 192 ? 6 : d4 <= 384 ? 12 : 24;
+#define SVSB_MQ_CASE(NQV, BQV) \
+    return run_mq_inst<NQV, BQV>(st, grid, smem, M, n, d4, tile_rows, stages, Q, b, groups, scores, n_stride, gmax, g_stride, group_shift, live)
+    switch (nq * 100 + bq) {
+        case 204: SVSB_MQ_CASE(2, 4);
+        case 208: SVSB_MQ_CASE(2, 8);
+        case 602: SVSB_MQ_CASE(6, 2);
+        case 604: SVSB_MQ_CASE(6, 4);
+        case 1202: SVSB_MQ_CASE(12, 2);
+        case 1204: SVSB_MQ_CASE(12, 4);
+        case 2402: SVSB_MQ_CASE(24, 2);
+        default: return cudaErrorInvalidConfiguration;
+    }
+#undef SVSB_MQ_CASE
 }
 
 }  // namespace svsb

@@ -48,6 +48,14 @@ cudaError_t launch_gemv(cudaStream_t st, int device, const float* M, int64_t n, 
                         int variant = 0, int tune_a = 0, int tune_b = 0, int reserve_sms = 0,
                         const uint8_t* live = nullptr);
 
+// b queries Q[b][ld] in ONE pass over the matrix: scores[q * n_stride + r], gmax[q * g_stride + (r >> shift)] (zero on
+// entry), bit-identical to b launch_gemv calls.  cudaErrorInvalidConfiguration: rows too long (ld > 3072) or b larger
+// than 8 warps' worth of queries (8 * gemv_mq_queries_per_warp(ld)); the caller chunks / falls back.
+int gemv_mq_queries_per_warp(int ld);
+cudaError_t launch_gemv_mq(cudaStream_t st, int device, const float* M, int64_t n, int d, int ld, const float* Q, int b,
+                           float* scores, int64_t n_stride, u64* gmax, int64_t g_stride, int group_shift,
+                           const uint8_t* live = nullptr, int reserve_sms = 0);
+
 // ---- K3/K4: exact top-k ---------------------------------------------------------------------
 // Inputs: scores[n], gmax[ceil(n >> shift)] (consumed and reset to zero), ids[n] (may be null: ids = rows).
 // Outputs (device): out_keys[k] (key with GLOBAL row = row0 + local row), out_scores[k], out_ids[k],
@@ -62,6 +70,13 @@ cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* 
                           u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count,
                           u64* dbg = nullptr,    // dbg: optional 16 x u64 of %globaltimer phase stamps
                           const PeerPush* push = nullptr);
+// The same for b queries in one launch (one CTA per query, on b different SMs): query q reads scores + q * s.scores,
+// gmax + q * s.gmax, uses cand + q * s.cand and writes out_keys + q * s.keys, out_scores + q * s.oscores,
+// out_ids + q * s.ids, out_count + q * s.count (strides in elements of the respective array).
+struct SelectStrides { int64_t scores = 0, gmax = 0, cand = 0, keys = 0, oscores = 0, ids = 0, count = 0; };
+cudaError_t launch_select_batch(cudaStream_t st, int b, const SelectStrides& s, const float* scores, int64_t n, u64* gmax, int group_shift,
+                                int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
+                                u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count);
 
 // Large-k path (k > K_FAST_MAX): sort all n keys.  sortbuf has next_pow2(n) entries.  Also zeroes gmax.
 cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n, u64* gmax, int group_shift,

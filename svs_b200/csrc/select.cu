@@ -197,10 +197,16 @@ __global__ void __launch_bounds__(SEL_THREADS, 1)
 select_topk_kernel(const float* __restrict__ scores, int64_t n, u64* gmax, int group_shift,
                    int k, const int64_t* __restrict__ ids, int64_t row0, u64* cand, int64_t cand_cap,
                    u64* __restrict__ out_keys, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                   int32_t* __restrict__ out_count, u64* __restrict__ dbg, const __grid_constant__ PeerPush push)
+                   int32_t* __restrict__ out_count, u64* __restrict__ dbg, const __grid_constant__ PeerPush push,
+                   const SelectStrides bs)
 {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelectKeysSmem& big = *reinterpret_cast<SelectKeysSmem*>(sel_smem_raw);
+    {   // one CTA per query of a batch (grid 1, all strides 0: the single query)
+        const int64_t qi = blockIdx.x;
+        scores += qi * bs.scores; gmax += qi * bs.gmax; cand += qi * bs.cand;
+        out_keys += qi * bs.keys; out_scores += qi * bs.oscores; out_ids += qi * bs.ids; out_count += qi * bs.count;
+    }
 #define SEL_STAMP(i) do { if (dbg && threadIdx.x == 0) { u64 t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[i] = t_; } } while (0)
     pdl_wait();                                    // scores and group maxima come from the similarity kernel
     pdl_trigger();
@@ -354,9 +360,29 @@ cudaError_t launch_select(cudaStream_t st, const float* scores, int64_t n, u64* 
     }
     if (((n + ((int64_t)1 << group_shift) - 1) >> group_shift) > SEL_KEYS_CAP) return cudaErrorInvalidValue;
     cudaError_t le = launch_kernel(select_topk_kernel, dim3(1), dim3(SEL_THREADS), sizeof(SelectKeysSmem), st, scores, n, gmax, group_shift, k,
-                                   ids, row0, cand, cand_cap, out_keys, out_scores, out_ids, out_count, dbg, pp);
+                                   ids, row0, cand, cand_cap, out_keys, out_scores, out_ids, out_count, dbg, pp, SelectStrides{});
     count_launch();
     return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+cudaError_t launch_select_batch(cudaStream_t st, int b, const SelectStrides& bs, const float* scores, int64_t n, u64* gmax, int group_shift,
+                                int k, const int64_t* ids, int64_t row0, u64* cand, int64_t cand_cap,
+                                u64* out_keys, float* out_scores, int64_t* out_ids, int32_t* out_count)
+{
+    if (b < 1 || k < 1 || k > K_FAST_MAX || n < 1) return cudaErrorInvalidValue;
+    static bool attr_set[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectKeysSmem));
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    if (((n + ((int64_t)1 << group_shift) - 1) >> group_shift) > SEL_KEYS_CAP) return cudaErrorInvalidValue;
+    PeerPush none{};
+    select_topk_kernel<<<b, SEL_THREADS, sizeof(SelectKeysSmem), st>>>(scores, n, gmax, group_shift, k, ids, row0, cand, cand_cap,
+                                                                       out_keys, out_scores, out_ids, out_count, nullptr, none, bs);
+    count_launch();
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,6 +18,13 @@ def engine():
     e.close()
 
 
+@pytest.fixture(autouse=True)
+def _coarse_path_for_every_batch_size(monkeypatch):
+    """This file tests the tensor-core path; small batches would otherwise take the exact multi-query passes
+    (tests/test_gpu_mq.py), which answer up to SVSB_MQ_MAX queries when both paths are available."""
+    monkeypatch.setenv("SVSB_MQ_MAX", "1")
+
+
 def _unit(rng, shape, dist):
     m = rng.random(shape, dtype=np.float32) if dist == "uniform" else rng.standard_normal(shape).astype(np.float32)
     m /= np.maximum(np.sqrt((m * m).sum(axis=1)), 1e-12)[:, None]
