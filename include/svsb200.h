@@ -74,6 +74,22 @@ int svsb_load_commit_slab(svsb_t* e, int64_t count);
 /* Finish: wait for the copies, run the row-norm kernel, publish atomically.  Fails with
  * SVSB_E_STATE if fewer/more than n rows were supplied (the reference asserts, kb.py:616). */
 int svsb_load_end(svsb_t* e, uint64_t* generation);
+/* The whole of build_embeddings_matrix (src/svs/kb.py:573-618) natively: scan the `embeddings` table (kb.py:80-83) of the
+ * SQLite file at `path` in rowid order -- the reference's scan order, kb.py:603-609 -- on private READ-ONLY connections
+ * (libsqlite3.so.0 bound at run time; `threads` connections scan contiguous rowid ranges in parallel, 0 = default),
+ * blobs copied verbatim (float32 little-endian, src/svs/embeddings/util.py:15-23) through pinned slabs to their final
+ * rows on the device(s), then the row-norm kernel, then atomic publication.  The reference's checks are kept: every blob
+ * has the first row's length (kb.py:613), the row count matches COUNT(*) (kb.py:616).  Call it where the reference
+ * rebuilds -- inside the KB's transaction, when its connection has nothing uncommitted.  SVSB_E_STATE: no libsqlite3,
+ * cannot open the file (":memory:"), ragged rows ...: the caller falls back to svsb_load_begin / _rows / _end. */
+int svsb_load_sqlite(svsb_t* e, const char* path, int32_t norm_mode, int32_t threads, uint64_t* generation, int64_t* n_out,
+                     int32_t* d_out);
+/* 1 if libsqlite3 could be bound. */
+int svsb_sqlite_available(void);
+/* The same scan into host arrays (no device involved): rows[capacity_rows][d] and/or emb_ids[capacity_rows] (either may
+ * be NULL; both NULL just reports the shape).  d_expected >= 0 must match the table's row length. */
+int svsb_sqlite_read(const char* path, int32_t threads, float* rows, int64_t* emb_ids, int64_t capacity_rows, int32_t d_expected,
+                     int64_t* n_out, int32_t* d_out);
 /* Abandon a load in progress (the resident generation, if any, is untouched). */
 int svsb_load_abort(svsb_t* e);
 /* Bench/test support: fill n x d on the device(s) from the counter-based generator

@@ -29,6 +29,9 @@ tmp = tempfile.mkdtemp(prefix="svsb_load_")
 path = os.path.join(tmp, "kb.sqlite")
 conn = sqlite3.connect(path, isolation_level=None, check_same_thread=False)
 conn.execute("CREATE TABLE embeddings (id INTEGER PRIMARY KEY, embedding BLOB NOT NULL) STRICT;")
+# the part of the reference's docs table the loader's count uses (kb.py:85-96)
+conn.execute("CREATE TABLE docs (id INTEGER PRIMARY KEY, embedding INTEGER REFERENCES embeddings(id));")
+conn.execute("CREATE INDEX idx_docs_embedding ON docs(embedding);")
 rng = np.random.default_rng(0)
 t0 = time.perf_counter()
 conn.execute("BEGIN;")
@@ -37,6 +40,7 @@ for a in range(0, n, step):
     m = rng.random((min(step, n - a), d), dtype=np.float32)
     m /= np.sqrt((m * m).sum(axis=1))[:, None]
     conn.executemany("INSERT INTO embeddings (id, embedding) VALUES (?, ?);", ((a + i + 1, m[i].tobytes()) for i in range(len(m))))
+    conn.executemany("INSERT INTO docs (embedding) VALUES (?);", ((a + i + 1,) for i in range(len(m))))
 conn.execute("COMMIT;")
 print(f"built {n} x {d} ({n * d * 4 / 1e9:.2f} GB of blobs, file {os.path.getsize(path) / 1e9:.2f} GB) in {time.perf_counter() - t0:.1f}s")
 
@@ -72,8 +76,21 @@ for rep in range(2):
     t0 = time.perf_counter()
     dm = matrix_mod.load_from_connection(eng, conn)
     dt = time.perf_counter() - t0
-    print(f"svs_b200 load_from_connection: {n} rows in {dt:.2f}s = {n / dt:.0f} rows/s = {n * d * 4 / dt / 1e9:.3f} GB/s"
-          f"  ({(sample / ref_s) and (n / dt) / (sample / ref_s):.1f}x the reference decode)")
+    print(f"svs_b200 load_from_connection (scan through the Python connection): {n} rows in {dt:.2f}s = {n / dt:.0f} rows/s = "
+          f"{n * d * 4 / dt / 1e9:.3f} GB/s  ({(sample / ref_s) and (n / dt) / (sample / ref_s):.1f}x the reference decode)")
+if not fake:
+    # the native scan (svsb_load_sqlite: libsqlite3 bound at run time, T read-only connections over rowid ranges)
+    for threads in (1, 2, 4, 8, 16, 0):
+        t0 = time.perf_counter()
+        eng.load_sqlite(path, threads=threads)
+        dt = time.perf_counter() - t0
+        print(f"svs_b200 svsb_load_sqlite threads={threads or 'default'}: {n} rows in {dt:.2f}s = {n / dt:.0f} rows/s = "
+              f"{n * d * 4 / dt / 1e9:.3f} GB/s", flush=True)
+    from svs_b200.engine import sqlite_read
+    t0 = time.perf_counter()
+    hm, hid = sqlite_read(path, 0)
+    dt = time.perf_counter() - t0
+    print(f"svsb_sqlite_read (host arrays only, default threads): {n * d * 4 / dt / 1e9:.3f} GB/s")
 if not fake:
     rows, ids = eng.read_rows(0, min(n, 5000))
     assert rows.tobytes() == mat[:len(rows)].tobytes() and (ids == np.arange(1, len(ids) + 1)).all(), "device matrix != blobs"

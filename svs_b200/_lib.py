@@ -36,6 +36,9 @@ SIGNATURES = {
     "svsb_load_acquire_slab": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_i64_p]),
     "svsb_load_commit_slab": (C.c_int, [C.c_void_p, C.c_int64]),
     "svsb_load_end": (C.c_int, [C.c_void_p, c_u64_p]),
+    "svsb_load_sqlite": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, c_u64_p, c_i64_p, c_i32_p]),
+    "svsb_sqlite_available": (C.c_int, []),
+    "svsb_sqlite_read": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, c_i64_p, c_i32_p]),
     "svsb_load_abort": (C.c_int, [C.c_void_p]),
     "svsb_load_synthetic": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, c_u64_p]),
     "svsb_invalidate": (C.c_int, [C.c_void_p]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsvsb200.so")
-SOURCES = ["gemv.cu", "select.cu", "rows.cu", "coarse.cu", "batch.cu", "pairs.cu", "engine.cu", "multi.cu", "mutate.cu"]
+SOURCES = ["gemv.cu", "select.cu", "rows.cu", "coarse.cu", "batch.cu", "pairs.cu", "engine.cu", "multi.cu", "mutate.cu", "loader.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-cudart", "static"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -199,7 +199,7 @@ extern "C" void svsb_destroy(svsb_t* e) {
 // ------------------------------------------------------------------------------------------------
 // load path
 // ------------------------------------------------------------------------------------------------
-static int alloc_generation(svsb_engine* e, int64_t n, int d, std::shared_ptr<Generation>& out) {
+int alloc_generation(svsb_engine* e, int64_t n, int d, std::shared_ptr<Generation>& out) {
     std::shared_ptr<Generation> g(new Generation());
     g->n = n; g->d = d; g->ld = round_up4(d);
     const int64_t nd = (int64_t)e->devs.size();

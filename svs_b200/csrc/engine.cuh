@@ -394,6 +394,7 @@ struct svsb_snapshot { std::shared_ptr<Generation> gen; };
 std::shared_ptr<Generation> pin(svsb_engine* e);
 int prepare_ws(DevWs& w, const Generation* g, const Shard& s, int64_t kk);
 int engine_create(const int* device_ids, int n_dev, bool as_kid, svsb_engine** out);
+int alloc_generation(svsb_engine* e, int64_t n, int d, std::shared_ptr<Generation>& out);
 int finish_generation(svsb_engine* e, Generation* g, int norm_mode);
 // publish `g` as the engine's resident generation (assigns the id; builds the per-device views of a multi-device engine)
 int publish_generation(svsb_engine* e, const std::shared_ptr<Generation>& g, uint64_t* generation);

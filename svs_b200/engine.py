@@ -5,6 +5,7 @@ Everything numeric happens in libsvsb200.so on the GPU; this module only marshal
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -111,6 +112,15 @@ class Engine:
         for rows, ids in chunks:
             self.load_rows(rows, ids)
         return self.load_end()
+
+    def load_sqlite(self, path: str, normalize: bool = False, threads: int = 0) -> Tuple[int, int]:
+        """build_embeddings_matrix (src/svs/kb.py:573-618) natively: scan the `embeddings` table of the SQLite file at
+        `path` on private read-only connections (include/svsb200.h: svsb_load_sqlite).  Returns (n, d).  Raises
+        EngineError(SVSB_E_STATE) when the native scan does not apply; the caller then uses the generic load path."""
+        gen, n, d = C.c_uint64(), C.c_int64(), C.c_int32()
+        check(self._lib.svsb_load_sqlite(self._h, os.fsencode(str(path)), _lib.NORM_NORMALIZE if normalize else _lib.NORM_CHECK,
+                                         int(threads), C.byref(gen), C.byref(n), C.byref(d)))
+        return n.value, d.value
 
     def load_synthetic(self, n: int, d: int, seed: int = 0, id0: int = 0, id_step: int = 1) -> int:
         gen = C.c_uint64()
@@ -445,6 +455,20 @@ class Snapshot:
             self.release()
         except Exception:
             pass
+
+
+def sqlite_read(path: str, threads: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """The native table scan into host arrays (svsb_sqlite_read): (matrix float32 (n, d), embeddings.id int64 (n,)) in
+    rowid order -- no device involved; what svsb_load_sqlite feeds the device with."""
+    lib = _lib.load()
+    n, d = C.c_int64(), C.c_int32()
+    check(lib.svsb_sqlite_read(os.fsencode(str(path)), int(threads), None, None, 0, -1, C.byref(n), C.byref(d)))
+    rows = np.empty((n.value, d.value), dtype=np.float32)
+    ids = np.empty(n.value, dtype=np.int64)
+    if n.value:
+        check(lib.svsb_sqlite_read(os.fsencode(str(path)), int(threads), rows.ctypes.data, ids.ctypes.data, n.value, d.value,
+                                   C.byref(n), C.byref(d)))
+    return rows, ids
 
 
 def launch_count() -> int:

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import asyncio
 import logging
+import os
 import sqlite3
 import threading
 from typing import Any, List, Optional, Sequence, Tuple
@@ -56,8 +57,27 @@ class DeviceMatrix:
         return self._snap.retrieve_many(query_vecs, n)
 
 
-def load_from_connection(engine: Engine, conn: sqlite3.Connection, normalize: bool = False) -> DeviceMatrix:
-    """build_embeddings_matrix (src/svs/kb.py:573-618) into the device cache."""
+def _native_scan_applies(path: Any) -> bool:
+    if path is None or os.environ.get("SVSB_NATIVE_LOAD", "1") == "0":
+        return False
+    p = str(path)
+    return p != ":memory:" and not p.startswith("file:") and os.path.isfile(p)
+
+
+def load_from_connection(engine: Engine, conn: sqlite3.Connection, normalize: bool = False, path: Any = None) -> DeviceMatrix:
+    """build_embeddings_matrix (src/svs/kb.py:573-618) into the device cache.
+
+    path: the database file behind `conn`, if known.  The scan then runs natively (svsb_load_sqlite: parallel read-only
+    connections of libsqlite3 feeding pinned slabs, no per-row Python) -- same rows, same order; when that does not
+    apply (in-memory database, no libsqlite3, anything it refuses) the generic scan through `conn` below does it."""
+    if _native_scan_applies(path) and hasattr(engine, "load_sqlite"):
+        try:
+            engine.load_sqlite(path, normalize)
+            return DeviceMatrix(engine)
+        except _lib.EngineError as ex:
+            if ex.code != _lib.SVSB_E_STATE:
+                raise
+            _LOG.info("native SQLite scan not applicable (%s); scanning through the connection", ex)
     n = conn.execute("SELECT COUNT(*) FROM embeddings;").fetchone()[0]
     assert isinstance(n, int)
     first = conn.execute("SELECT embedding FROM embeddings LIMIT 1;").fetchone()
@@ -212,7 +232,7 @@ class DeviceEmbeddingsMatrix:
             self._drop_locked()                          # never two full generations resident at once
             engine = self._get_engine()
         self.stats["full_builds"] += 1
-        return load_from_connection(engine, conn, self._normalize)
+        return load_from_connection(engine, conn, self._normalize, path=getattr(db, "path", None))
 
     def _current(self, db: Any) -> Optional[DeviceMatrix]:
         m = self._matrix

@@ -72,3 +72,49 @@ def test_synthetic_generator_matches_the_oracle_bit_for_bit():
         assert (ids == 100 + 3 * np.arange(1000, 1064)).all()
         dev, bad = e.norm_stats()
         assert bad == 0 and dev < 1e-6
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0]])
+def test_native_sqlite_scan_loads_the_same_device_matrix(tmp_path, devices, monkeypatch):
+    """svsb_load_sqlite (parallel read-only libsqlite3 connections -> pinned slabs -> device rows) against the generic
+    scan through a Python connection and against the oracle's build_embeddings_matrix (src/svs/kb.py:573-618)."""
+    import svs_b200
+    monkeypatch.setenv("SVSB_ALLOW_DUP_DEVICES", "1")
+    g = golden_npz("kb_small_matrix.npz")
+    with svs_b200.Engine(devices) as e:
+        n, d = e.load_sqlite(os.path.join(GOLDEN, "kb_small.sqlite"))
+        assert (n, d) == g["matrix"].shape == e.shape
+        rows, ids = e.read_rows(0, n)
+        assert rows.tobytes() == g["matrix"].tobytes() and (ids == g["emb_ids"]).all()
+    # a larger table with holes in the rowids, d not a multiple of 4 (padded leading dimension), several threads
+    path = str(tmp_path / "big.sqlite")
+    conn = sqlite3.connect(path)
+    conn.execute("CREATE TABLE embeddings (id INTEGER PRIMARY KEY, embedding BLOB NOT NULL);")
+    rng = np.random.default_rng(5)
+    src = rng.standard_normal((60_000, 130)).astype("<f4")
+    src /= np.sqrt((src * src).sum(axis=1))[:, None]
+    conn.executemany("INSERT INTO embeddings (embedding) VALUES (?);", ((r.tobytes(),) for r in src))
+    conn.execute("DELETE FROM embeddings WHERE id % 11 = 3;")
+    conn.commit()
+    want_m, want_ids = oracle.build_embeddings_matrix(conn)
+    q = oracle.synth_queries(2, 130, 6, dist="normal")
+    with svs_b200.Engine(devices) as e, svs_b200.Engine([0]) as ref:
+        for threads in (1, 3, 8):
+            assert e.load_sqlite(path, threads=threads) == want_m.shape
+            rows, ids = e.read_rows(0, len(want_ids))
+            assert rows.tobytes() == want_m.tobytes() and (ids == want_ids).all()
+        dev, bad = e.norm_stats()
+        assert bad == 0 and dev < 1e-6
+        m1 = svs_b200.load_from_connection(ref, conn)              # the generic path
+        m2 = svs_b200.load_from_connection(e, conn, path=path)     # the native path through the same entry point
+        for x in q:
+            assert m1.retrieve(x, 50) == m2.retrieve(x, 50)
+        oracle.compare_retrieval(m2.retrieve(q[0], 50), oracle.superheavy(want_m, want_ids, q[0], 50), oracle.scores_of(want_m, q[0]), want_ids)
+        # what the native scan refuses is a refusal (SVSB_E_STATE), and load_from_connection falls back from it
+        conn.execute("INSERT INTO embeddings (embedding) VALUES (?);", (b"\x00" * 12,))
+        conn.commit()
+        with pytest.raises(svs_b200.EngineError):
+            e.load_sqlite(path)
+        assert e.shape == want_m.shape                             # the resident matrix was left alone
+        with pytest.raises(AssertionError):                        # the generic scan asserts like the reference (kb.py:613)
+            svs_b200.load_from_connection(e, conn, path=path)
