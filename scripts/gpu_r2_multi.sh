@@ -11,6 +11,9 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
   timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu_n$N.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2_pytest_gpu_n$N.log
 fi
 timeout 600 $TR --master-port 29611 scripts/sharded_check.py > gpurun_out/r2_sharded_check_n$N.log 2>&1; echo "sharded_check rc=$?"; tail -3 gpurun_out/r2_sharded_check_n$N.log
+if [ "${SOAK:-0}" != "0" ]; then
+  timeout 900 $TR --master-port 29621 scripts/peer_soak.py $SOAK > gpurun_out/r2_peer_soak_n$N.log 2>&1; echo "soak rc=$?"; tail -2 gpurun_out/r2_peer_soak_n$N.log
+fi
 timeout 1200 $TR --master-port 29612 bench.py --gpus $N --steps ${STEPS:-20} --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench n$N rc=$?"; tail -c 1500 gpurun_out/r2_bench_n$N.err
 python - $N <<'PY'
 import json, sys
