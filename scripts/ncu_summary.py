@@ -99,6 +99,8 @@ if __name__ == "__main__":
             ("prof_coarse.ncu-rep", "batched coarse contraction (coarse_gemm_kernel<1> sample pass, <0> filter pass), workload c3",
              "c3", "coarse_gemm_kernel<0"),
             ("prof_refine.ncu-rep", "batched path: sample_threshold_kernel and refine_kernel, workload c3", None, None),
+            ("prof_mq.ncu-rep", "small exact batches (scripts/mq_profile.py): gemv_tma_mq_kernel (4 and 8 queries per pass) and the batched "
+             "selection (one CTA per query), 1M x 1536, k = 100", "c2_mq", "gemv_tma_mq"),
             ("prof_peer.ncu-rep", "peer exchange at world size 1 (scripts/peer_profile.py): select_topk_kernel with the fused push, "
              "merge_window_kernel; 1M x 1536 shard, k = 100", None, None)):
         p = os.path.join(OUT, rep)

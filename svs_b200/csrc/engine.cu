@@ -49,6 +49,7 @@ static void ctx_destroy(svsb_engine* e, QueryCtx* c) {
     if (c->h_scores) cudaFreeHost(c->h_scores);
     if (c->h_ids) cudaFreeHost(c->h_ids);
     if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->ev_gemv) cudaEventDestroy(c->ev_gemv);
 }
 static int ctx_acquire(svsb_engine* e, std::unique_ptr<QueryCtx>& out) {
     std::unique_lock<std::mutex> lk(e->mu);
@@ -188,6 +189,7 @@ extern "C" void svsb_destroy(svsb_t* e) {
     for (auto& w : e->shard_ws) if (w) w->release();
     xchg_release(e);
     if (e->side_st) { cudaSetDevice(e->devs[0]); cudaStreamDestroy(e->side_st); }
+    if (e->submit_st) { cudaSetDevice(e->devs[0]); cudaStreamDestroy(e->submit_st); }
     for (auto ev : e->kev) cudaEventDestroy(ev);
     if (!e->bench_kev.empty()) { cudaSetDevice(e->devs[0]); for (auto ev : e->bench_kev) cudaEventDestroy(ev); }
     for (size_t i = 0; i < e->bench_q.size(); ++i) if (e->bench_q[i]) { cudaSetDevice(e->devs[i]); cudaFree(e->bench_q[i]); }
@@ -572,7 +574,8 @@ static int query_check(const std::shared_ptr<Generation>& g, const float* q, int
 // the query from the pinned staging buffer and the selection kernel writes (score, id, count) straight into pinned host
 // memory (both are device-accessible under unified addressing), so a call is 3 launches + 1 synchronize.
 // reserve_sm: leave one SM to the selection kernels of OTHER in-flight queries (svsb_query_submit keeps several going).
-static int enqueue_single(QueryCtx* c, const Generation* g, const float* q, int32_t d, int64_t kk, bool reserve_sm) {
+static int enqueue_single(QueryCtx* c, const Generation* g, const float* q, int32_t d, int64_t kk, bool reserve_sm,
+                          svsb_engine* chain = nullptr) {
     const Shard& s = g->shards[0];
     DevWs& w = c->ws[0];
     int rc;
@@ -584,11 +587,24 @@ static int enqueue_single(QueryCtx* c, const Generation* g, const float* q, int3
     const int shift = group_shift_for(s.n);
     *c->h_count = -1;
     if (kk <= K_FAST_MAX) {
-        CU(launch_stage_query(w.st, c->h_q, w.d_q, g->ld));
+        cudaStream_t gst = w.st;                                 // stream of the staging + similarity kernels
+        std::unique_lock<std::mutex> chain_lk;
+        if (chain) {
+            chain_lk = std::unique_lock<std::mutex>(chain->chain_mu);
+            if (!chain->submit_st) CU(cudaStreamCreateWithFlags(&chain->submit_st, cudaStreamNonBlocking));
+            if (!c->ev_gemv) CU(cudaEventCreateWithFlags(&c->ev_gemv, cudaEventDisableTiming));
+            gst = chain->submit_st;
+        }
+        CU(launch_stage_query(gst, c->h_q, w.d_q, g->ld));
         w.gmax_dirty = true;
         {   // programmatic dependent launch: the similarity kernel streams its first tiles under the staging kernel
             PdlScope pdl(env_int("SVSB_PDL", 1) != 0);
-            CU(launch_gemv(w.st, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift, 0, 0, 0, reserve_sm ? 1 : 0, s.live));
+            CU(launch_gemv(gst, w.dev, s.M, s.n, g->d, g->ld, w.d_q, w.scores, w.gmax, shift, 0, 0, 0, reserve_sm ? 1 : 0, s.live));
+        }
+        if (chain) {
+            CU(cudaEventRecord(c->ev_gemv, gst));
+            chain_lk.unlock();
+            CU(cudaStreamWaitEvent(w.st, c->ev_gemv, 0));
         }
         CU(launch_select(w.st, w.scores, s.n, w.gmax, shift, (int)kk, s.ids, s.row0, w.cand, w.cand_cap,
                          w.out_keys, c->h_scores, c->h_ids, c->h_count));
@@ -667,7 +683,7 @@ extern "C" int svsb_query_submit(svsb_t* e, const float* q, int32_t d, int32_t k
         } else {
             if ((rc = ctx_acquire(e, p->ctx)) != SVSB_OK) return rc;
             // several queries in flight: each similarity pass leaves one SM to the (single-CTA) selections of the others
-            if ((rc = enqueue_single(p->ctx.get(), g.get(), q, d, kk, sm_count(e->devs[0]) > 8)) != SVSB_OK) { ctx_release(e, p->ctx); return rc; }
+            if ((rc = enqueue_single(p->ctx.get(), g.get(), q, d, kk, sm_count(e->devs[0]) > 8, e)) != SVSB_OK) { ctx_release(e, p->ctx); return rc; }
         }
     }
     *out = p.release();

@@ -193,6 +193,7 @@ struct QueryCtx {
     u64* g_keys = nullptr; int64_t* g_ids = nullptr; int32_t* g_counts = nullptr; int64_t g_stride = 0;
     float* m_scores = nullptr; int64_t* m_ids = nullptr; int32_t* m_count = nullptr; int64_t m_cap = 0;
     cudaEvent_t ev_merge = nullptr; bool merge_recorded = false;   // last merge that read g_keys / g_ids
+    cudaEvent_t ev_gemv = nullptr;         // svsb_query_submit: this context's similarity pass has finished
 };
 
 struct Slab {
@@ -361,6 +362,11 @@ struct svsb_engine {
     std::vector<cudaStream_t> copy_st;      // per device
     std::vector<std::unique_ptr<QueryCtx>> pool_free;
     int ctx_total = 0, ctx_max = 4;
+    // svsb_query_submit keeps several contexts in flight.  Their similarity passes all go down ONE stream, back to back
+    // (pass j+1 starts when pass j ends, so the one SM each pass leaves free really is free for the single-CTA
+    // selections, which run on the contexts' own streams) -- the structure of the device-resident pipelined loop.
+    std::mutex chain_mu;
+    cudaStream_t submit_st = nullptr;
     // batched path (one batch at a time)
     std::mutex batch_mu;
     std::unique_ptr<struct BatchWs> batch_ws;
