@@ -13,6 +13,8 @@
 //     peer-to-peer to device 0 and merged there by one kernel.
 #include "engine.cuh"
 
+#include <chrono>
+
 thread_local std::string g_err;
 static thread_local bool g_pdl = false;
 namespace svsb { void set_pdl(bool on) { g_pdl = on; } bool pdl_enabled() { return g_pdl; } }
@@ -51,12 +53,17 @@ static void ctx_destroy(svsb_engine* e, QueryCtx* c) {
     if (c->h_count) cudaFreeHost(c->h_count);
     if (c->ev_gemv) cudaEventDestroy(c->ev_gemv);
 }
-static int ctx_acquire(svsb_engine* e, std::unique_ptr<QueryCtx>& out) {
+// timeout_ms > 0: give up (SVSB_E_STATE) when no context frees up in time -- svsb_query_submit from a caller that already
+// holds every context as a pending handle would otherwise wait for itself
+static int ctx_acquire(svsb_engine* e, std::unique_ptr<QueryCtx>& out, int timeout_ms = 0) {
     std::unique_lock<std::mutex> lk(e->mu);
     while (true) {
         if (!e->pool_free.empty()) { out = std::move(e->pool_free.back()); e->pool_free.pop_back(); return SVSB_OK; }
         if (e->ctx_total < e->ctx_max) { ++e->ctx_total; break; }
-        e->cv.wait(lk);
+        if (timeout_ms > 0) {
+            if (e->cv.wait_for(lk, std::chrono::milliseconds(timeout_ms)) == std::cv_status::timeout && e->pool_free.empty())
+                return fail(SVSB_E_STATE, "svsb_query_submit: every query context is pending already (wait for the oldest first)");
+        } else e->cv.wait(lk);
     }
     lk.unlock();
     int rc = ctx_create(e, out);
@@ -681,7 +688,7 @@ extern "C" int svsb_query_submit(svsb_t* e, const float* q, int32_t d, int32_t k
             if (kk > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_query_submit: k <= 2048 on a multi-device engine (use svsb_query)");
             if ((rc = multi_submit(e, g, q, d, kk, &p->ticket)) != SVSB_OK) return rc;
         } else {
-            if ((rc = ctx_acquire(e, p->ctx)) != SVSB_OK) return rc;
+            if ((rc = ctx_acquire(e, p->ctx, env_int("SVSB_SUBMIT_TIMEOUT_MS", 5000))) != SVSB_OK) return rc;
             // several queries in flight: each similarity pass leaves one SM to the (single-CTA) selections of the others
             if ((rc = enqueue_single(p->ctx.get(), g.get(), q, d, kk, sm_count(e->devs[0]) > 8, e)) != SVSB_OK) { ctx_release(e, p->ctx); return rc; }
         }

@@ -100,7 +100,7 @@ constexpr int TICKETS = 3;
 }  // namespace
 
 struct svsb_ticket {
-    float* h_q = nullptr;                          // pinned + portable: every device's staging kernel reads it over PCIe
+    float* h_q = nullptr; int q_cap = 0;           // pinned + portable: every device's staging kernel reads it over PCIe
     float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_count = nullptr;    // pinned: device 0's merge writes them
     float* d_scores = nullptr; int64_t* d_ids = nullptr; int32_t* d_count = nullptr;    // device 0: bench (device-resident) outputs
     cudaEvent_t ev = nullptr;                      // device 0's stream: this ticket's merge is done
@@ -123,7 +123,6 @@ struct Multi {
     std::condition_variable cv;
     unsigned long long seq = 0;
     svsb_ticket tk[TICKETS];
-    int q_cap = 0;
     // device 0: gathered lists + outputs of the large-k / batched paths, pinned staging for their results
     u64* g_keys = nullptr; int64_t* g_ids = nullptr; int64_t g_cap = 0; int32_t* g_counts = nullptr;
     float* m_scores = nullptr; int64_t* m_ids = nullptr; int32_t* m_count = nullptr; int64_t m_cap = 0;
@@ -131,6 +130,7 @@ struct Multi {
     float* b_scores = nullptr; int64_t* b_ids = nullptr; int32_t* b_counts = nullptr; int64_t b_cap = 0, b_cnt_cap = 0;
     float* h_big_scores = nullptr; int64_t* h_big_ids = nullptr; int64_t h_big_cap = 0; int32_t* h_big_count = nullptr;
     float* h_Q = nullptr; int64_t h_Q_cap = 0;     // pinned staging of a batch's queries (read by every device)
+    u64* b_sk = nullptr; int64_t* b_sp = nullptr; int64_t b_scr_cap = 0;   // the batch merge's own scratch (fused merges in flight use device 0's)
     std::vector<cudaEvent_t> kev;                  // bench: similarity-kernel brackets on device 0
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     svsb_ticket* last = nullptr;                   // bench: ticket holding the last result
@@ -203,7 +203,8 @@ void multi_destroy(svsb_engine* e) {
             if (t.d_count) cudaFree(t.d_count);
             if (t.ev) cudaEventDestroy(t.ev);
         }
-        void* dp[] = {m->g_keys, m->g_ids, m->g_counts, m->m_scores, m->m_ids, m->m_count, m->g_rec, m->b_scores, m->b_ids, m->b_counts};
+        void* dp[] = {m->g_keys, m->g_ids, m->g_counts, m->m_scores, m->m_ids, m->m_count, m->g_rec, m->b_scores, m->b_ids, m->b_counts,
+                      m->b_sk, m->b_sp};
         for (void* p : dp) if (p) cudaFree(p);
         void* hp[] = {m->h_big_scores, m->h_big_ids, m->h_big_count, m->h_Q};
         for (void* p : hp) if (p) cudaFreeHost(p);
@@ -218,19 +219,16 @@ void multi_destroy(svsb_engine* e) {
     e->multi = nullptr;
 }
 
-// Wait until no query is in flight (caller holds m->mu): allocations and the gather-by-copy paths run on a quiet queue.
-static void drain_locked(Multi* m, std::unique_lock<std::mutex>& lk) {
-    m->cv.wait(lk, [m] { for (auto& t : m->tk) if (t.busy) return false; return true; });
-}
-
 // Per-device views of generation g + every buffer the fused path uses, sized NOW: allocations are implicit
 // synchronisation points and must not land between the enqueueing of one query on two devices (a merge kernel
 // spinning for a peer whose kernels wait behind a cudaMalloc never ends -- DESIGN.md section 4, K6).
 int multi_publish(svsb_engine* e, const std::shared_ptr<Generation>& g) {
     Multi* m = e->multi;
     const int nd = (int)m->kids.size();
+    // m->mu: no query is half-enqueued while the buffers below are (re)allocated.  Queries already in flight are fully
+    // enqueued and keep running; a cudaFree of a buffer they use waits for them.  (Not a wait for the tickets themselves:
+    // a caller may hold a pending svsb_query_submit handle while it loads.)
     std::unique_lock<std::mutex> lk(m->mu);
-    drain_locked(m, lk);
     g->child_gen.clear();
     for (int i = 0; i < nd; ++i) {
         std::shared_ptr<Generation> cg(new Generation());
@@ -240,15 +238,6 @@ int multi_publish(svsb_engine* e, const std::shared_ptr<Generation>& g) {
         cg->max_dev = g->max_dev; cg->n_out_of_tol = g->n_out_of_tol;
         cg->shards.push_back(s);
         g->child_gen.push_back(cg);
-    }
-    if (g->ld > m->q_cap) {
-        CU(cudaSetDevice(root_dev(m)));
-        for (auto& t : m->tk) {
-            if (t.h_q) cudaFreeHost(t.h_q);
-            t.h_q = nullptr;
-            CU(cudaHostAlloc(&t.h_q, (size_t)g->ld * 4, cudaHostAllocPortable));
-        }
-        m->q_cap = g->ld;
     }
     return m->pool->run_all([&](int i) -> int {
         svsb_engine* kid = m->kids[i];
@@ -360,8 +349,11 @@ static int root_merge(Multi* m, const FastJob& j) {
 // caller holds m->mu: a ticket nobody uses (blocks until one is released)
 static svsb_ticket* free_ticket_locked(Multi* m, std::unique_lock<std::mutex>& lk) {
     svsb_ticket* t = nullptr;
-    m->cv.wait(lk, [&] { for (auto& c : m->tk) if (!c.busy) { t = &c; return true; } return false; });
-    return t;
+    // other threads release tickets within a query time; a caller that already holds every ticket as a pending handle
+    // would wait for itself -- give up with an error instead
+    const bool ok = m->cv.wait_for(lk, std::chrono::milliseconds(env_int("SVSB_SUBMIT_TIMEOUT_MS", 5000)),
+                                   [&] { for (auto& c : m->tk) if (!c.busy) { t = &c; return true; } return false; });
+    return ok ? t : nullptr;
 }
 
 // caller holds m->mu and got `t` from free_ticket_locked without releasing the lock since
@@ -394,6 +386,14 @@ int multi_submit(svsb_engine* e, const std::shared_ptr<Generation>& g, const flo
     Multi* m = e->multi;
     std::unique_lock<std::mutex> lk(m->mu);
     svsb_ticket* t = free_ticket_locked(m, lk);
+    if (!t) return fail(SVSB_E_STATE, "svsb_query_submit: 3 queries are pending already (wait for the oldest first)");
+    if (g->ld > t->q_cap) {                        // this ticket is free and nothing is half-enqueued (we hold m->mu)
+        CU(cudaSetDevice(root_dev(m)));
+        if (t->h_q) cudaFreeHost(t->h_q);
+        t->h_q = nullptr; t->q_cap = 0;
+        CU(cudaHostAlloc(&t->h_q, (size_t)g->ld * 4, cudaHostAllocPortable));
+        t->q_cap = g->ld;
+    }
     memcpy(t->h_q, q, (size_t)d * 4);
     for (int i = d; i < g->ld; ++i) t->h_q[i] = 0.f;
     t->gen = g;
@@ -444,12 +444,17 @@ static int multi_query_big(svsb_engine* e, const std::shared_ptr<Generation>& g,
                            float* out_scores, int64_t* out_ids, int32_t* out_count) {
     Multi* m = e->multi;
     const int nd = (int)m->kids.size();
-    std::unique_lock<std::mutex> lk(m->mu);
-    drain_locked(m, lk);
-    svsb_ticket& t = m->tk[0];
-    memcpy(t.h_q, q, (size_t)d * 4);
-    for (int i = d; i < g->ld; ++i) t.h_q[i] = 0.f;
+    std::unique_lock<std::mutex> lk(m->mu);        // exclusive use of the gather scratch; fused queries in flight keep running
     CU(cudaSetDevice(root_dev(m)));
+    if (g->ld > m->h_Q_cap) {
+        if (m->h_Q) cudaFreeHost(m->h_Q);
+        m->h_Q = nullptr; m->h_Q_cap = 0;
+        CU(cudaHostAlloc(&m->h_Q, (size_t)g->ld * 4, cudaHostAllocPortable));
+        m->h_Q_cap = g->ld;
+    }
+    float* hq = m->h_Q;
+    memcpy(hq, q, (size_t)d * 4);
+    for (int i = d; i < g->ld; ++i) hq[i] = 0.f;
     if (kk > m->g_cap) {
         void* ptrs[] = {m->g_keys, m->g_ids, m->m_scores, m->m_ids};
         for (void* p : ptrs) if (p) cudaFree(p);
@@ -480,7 +485,7 @@ static int multi_query_big(svsb_engine* e, const std::shared_ptr<Generation>& g,
             int rc2 = prepare_ws(w, cg, s, kl);
             if (rc2 != SVSB_OK) return rc2;
             const int shift = group_shift_for(s.n);
-            CU(cudaMemcpyAsync(w.d_q, t.h_q, (size_t)cg->ld * 4, cudaMemcpyHostToDevice, x->st));
+            CU(cudaMemcpyAsync(w.d_q, hq, (size_t)cg->ld * 4, cudaMemcpyHostToDevice, x->st));
             w.gmax_dirty = true;
             CU(launch_gemv(x->st, s.dev, s.M, s.n, cg->d, cg->ld, w.d_q, w.scores, w.gmax, shift, 0, 0, 0, 0, s.live));
             if (kl <= K_FAST_MAX)
@@ -538,8 +543,7 @@ int multi_query_batch(svsb_engine* e, const std::shared_ptr<Generation>& g, cons
         }
         return SVSB_OK;
     }
-    std::unique_lock<std::mutex> lk(m->mu);
-    drain_locked(m, lk);
+    std::unique_lock<std::mutex> lk(m->mu);        // exclusive use of the gather scratch; fused queries in flight keep running
     const int kr = (int)kk;                         // entries per record
     const int64_t rec = 2 * (int64_t)kr + 1;
     const int ld = g->ld;
@@ -570,9 +574,15 @@ int multi_query_batch(svsb_engine* e, const std::shared_ptr<Generation>& g, cons
         CU(cudaMalloc(&m->b_counts, (size_t)b * 4));
         m->b_cap = (int64_t)b * kr; m->b_cnt_cap = b;
     }
-    DevWs& w0 = m->kids[0]->xchg->ws;
     int rc;
-    if ((int64_t)nd * kr > K_FAST_MAX && (rc = w0.ensure_merge_scratch((int64_t)b * nd * kr)) != SVSB_OK) return rc;
+    if ((int64_t)nd * kr > K_FAST_MAX && (int64_t)b * nd * kr > m->b_scr_cap) {
+        if (m->b_sk) cudaFree(m->b_sk);
+        if (m->b_sp) cudaFree(m->b_sp);
+        m->b_sk = nullptr; m->b_sp = nullptr; m->b_scr_cap = 0;
+        CU(cudaMalloc(&m->b_sk, (size_t)b * nd * kr * 8));
+        CU(cudaMalloc(&m->b_sp, (size_t)b * nd * kr * 8));
+        m->b_scr_cap = (int64_t)b * nd * kr;
+    }
     rc = m->pool->run_all([&](int i) -> int {
         svsb_engine* kid = m->kids[i];
         KidScratch& ks = m->scratch[i];
@@ -605,7 +615,7 @@ int multi_query_batch(svsb_engine* e, const std::shared_ptr<Generation>& g, cons
         if ((rc = copy_to_root(m, i, m->g_rec + (int64_t)i * b * rec, m->scratch[i].rec, (size_t)b * rec * 8, rst)) != SVSB_OK) return rc;
     }
     u64* sk = nullptr; int64_t* sp = nullptr;
-    if ((int64_t)nd * kr > K_FAST_MAX) { sk = w0.mscr_keys; sp = w0.mscr_ids; }
+    if ((int64_t)nd * kr > K_FAST_MAX) { sk = m->b_sk; sp = m->b_sp; }
     CU(launch_merge_ex(rst, reinterpret_cast<const u64*>(m->g_rec), m->g_rec + kr, reinterpret_cast<const int32_t*>(m->g_rec + 2 * (int64_t)kr),
                        nd, kr, kr, b, (int64_t)b * rec, rec, (int64_t)b * rec * 2, rec * 2, sk, sp, m->b_scores, m->b_ids, m->b_counts));
     // results: (b, kr) on the device, (b, k) at the caller
@@ -629,10 +639,6 @@ int multi_bench_run(svsb_engine* e, const std::shared_ptr<Generation>& g, int32_
     while (ktime && m->kev.size() < (size_t)iters * 2) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); m->kev.push_back(ev); }
     cudaStream_t rst = m->kids[0]->xchg->st;
     std::vector<svsb_ticket*> ring;
-    {
-        std::unique_lock<std::mutex> lk(m->mu);
-        drain_locked(m, lk);
-    }
     for (auto* kid : m->kids) { CU(cudaSetDevice(kid->devs[0])); CU(cudaStreamSynchronize(kid->xchg->st)); }
     CU(cudaSetDevice(root_dev(m)));
     CU(cudaEventRecord(m->ev0, rst));
@@ -647,6 +653,7 @@ int multi_bench_run(svsb_engine* e, const std::shared_ptr<Generation>& g, int32_
         if (ktime && it % KTIME_EVERY == 0) { j.kev0 = m->kev[2 * it]; j.kev1 = m->kev[2 * it + 1]; }
         std::unique_lock<std::mutex> lk(m->mu);
         svsb_ticket* t = free_ticket_locked(m, lk);
+        if (!t) return fail(SVSB_E_STATE, "svsb_bench_run: no free ticket (pending svsb_query_submit handles?)");
         int rc = submit_locked(m, t, j, /*host_out=*/false);
         if (rc != SVSB_OK) return rc;
         ring.push_back(t);

@@ -111,6 +111,38 @@ def test_submit_wait_keeps_several_queries_in_flight(engines):
         assert len(e.submit(qs[0], 0).result()[0]) == 0            # k <= 0: nothing to compute, still a handle
         with pytest.raises(ValueError):
             e.submit(np.zeros(d + 3, np.float32), k)
+        # a caller that holds every slot as a pending handle gets an error, not a wait for itself
+        import svs_b200
+        os.environ["SVSB_SUBMIT_TIMEOUT_MS"] = "200"
+        held = []
+        with pytest.raises(svs_b200.EngineError, match="pending already"):
+            for _ in range(8):
+                held.append(e.submit(qs[1], k))
+        assert len(held) in (3, 4) and all(_same(p.result(), want[1]) for p in held)
+        del os.environ["SVSB_SUBMIT_TIMEOUT_MS"]
+
+
+def test_a_pending_query_does_not_block_loads_or_other_query_forms_on_its_thread(engines):
+    """One thread: submit, then -- with the handle still pending -- a full ranking, a batch and a reload.  None of them may
+    wait for the handle to be waited for (they would wait for ever)."""
+    one, multi = engines
+    n, d = 12_000, 64
+    m = oracle.synth_matrix_normal(n, d, 61)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qs = oracle.synth_queries(4, d, 62, dist="normal")
+    one.load(m, ids)
+    want = one.query(qs[0], 30)
+    for e in multi.values():
+        e.load(m, ids)
+        pend = [e.submit(qs[0], 30), e.submit(qs[0], 30)]
+        assert _same(e.query(qs[1], n), one.query(qs[1], n))              # k > 2048: the gather path
+        s, i, c = e.query_batch(qs, 9)
+        assert _same((s[2], i[2]), one.query(qs[2], 9))
+        e.load(m[:6000], ids[:6000])                                       # a new generation of a different size
+        assert all(_same(p.result(), want) for p in pend)                  # the pending queries answer from THEIR generation
+        one.load(m[:6000], ids[:6000])
+        assert _same(e.query(qs[0], 30), one.query(qs[0], 30))
+        one.load(m, ids)
 
 
 def test_caller_threads_share_a_multi_device_engine(engines):
