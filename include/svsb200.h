@@ -278,6 +278,10 @@ int svsb_query_peer(svsb_t* e, const float* q, int32_t d, int32_t k,
  * SM reserved for them.  Do not interleave with svsb_enqueue_query_peer while tickets are pending. */
 int svsb_query_peer_submit(svsb_t* e, const float* q, int32_t d, int32_t k, int32_t* ticket);
 int svsb_query_peer_wait(svsb_t* e, int32_t ticket, float* out_scores, int64_t* out_emb_ids, int32_t* out_count);
+/* Development aid: with SVSB_XCHG_STAMPS=1 in the environment at svsb_xchg_create, the selection and merge kernels of
+ * the synchronous svsb_query_peer stamp %globaltimer (ns) into a ring of 1024 queries x 40 words: per query
+ * [16 selection stamps as svsb_debug_select_phases | seq, merge start, merge done, -, time rank r's flag was seen x world]. */
+int svsb_xchg_read_stamps(svsb_t* e, uint64_t* out, int64_t capacity_words);
 /* Make `stream` wait for everything the pipelined svsb_enqueue_local_topk / svsb_enqueue_query_peer calls have issued
  * on the side stream (it also enqueues the last peer query's deferred merge). */
 int svsb_enqueue_join(svsb_t* e, void* stream);

@@ -81,6 +81,7 @@ SIGNATURES = {
     "svsb_query_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
     "svsb_query_peer_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_i32_p]),
     "svsb_query_peer_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, c_i32_p]),
+    "svsb_xchg_read_stamps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "svsb_enqueue_local_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "svsb_batch_local_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, c_i32_p]),
     "svsb_enqueue_join": (C.c_int, [C.c_void_p, C.c_void_p]),

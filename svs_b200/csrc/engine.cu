@@ -164,6 +164,7 @@ static void xchg_release(svsb_engine* e) {
     if (x->st) cudaStreamSynchronize(x->st);
     for (void* p : x->ipc_opened) cudaIpcCloseMemHandle(p);
     if (x->block) cudaFree(x->block);
+    if (x->stamps) cudaFree(x->stamps);
     x->ws.release();
     if (x->st) cudaStreamDestroy(x->st);
     if (x->ev_join) cudaEventDestroy(x->ev_join);
@@ -1692,6 +1693,11 @@ extern "C" int svsb_xchg_create(svsb_t* e, int32_t world, int32_t rank, int32_t 
     CU(cudaMallocHost(&x->h_ids, (size_t)k_max * 8));
     CU(cudaMallocHost(&x->h_count, 64));
     x->h_cap = k_max;
+    if (env_int("SVSB_XCHG_STAMPS", 0)) {
+        CU(cudaMalloc(&x->stamps, (size_t)Xchg::STAMP_RING * Xchg::STAMP_WORDS * 8));
+        CU(cudaMemset(x->stamps, 0, (size_t)Xchg::STAMP_RING * Xchg::STAMP_WORDS * 8));
+        CU(cudaDeviceSynchronize());
+    }
     x->peer_block.assign(world, nullptr);
     x->peer_block[rank] = x->block;
     if (handle_out) {
@@ -1849,8 +1855,9 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
         }
         if (time_kernel) { CU(cudaEventRecord(e->kev[e->kev_used + 1], st_main)); e->kev_used += 2; }
         if (st_sel != st_main) { CU(cudaEventRecord(ev_main_done, st_main)); CU(cudaStreamWaitEvent(st_sel, ev_main_done, 0)); }
+        u64* sel_stamps = (x->stamps && !defer_merge) ? x->stamps + (push.seq % Xchg::STAMP_RING) * Xchg::STAMP_WORDS : nullptr;
         CU(launch_select(st_sel, w.scores, s.n, w.gmax, shift, (int)std::min<int64_t>(k, s.n_live), s.ids, s.row0, w.cand, w.cand_cap,
-                         w.out_keys, w.out_scores, w.out_ids, w.out_count, nullptr, &push));
+                         w.out_keys, w.out_scores, w.out_ids, w.out_count, sel_stamps, &push));
         w.gmax_dirty = false;
     }
     if (ev_sel_done) CU(cudaEventRecord(ev_sel_done, st_sel));   // the workspace's scores are free from here on
@@ -1865,7 +1872,8 @@ static int xchg_enqueue(svsb_engine* e, const Generation* g, DevWs& w, cudaStrea
         return SVSB_OK;
     }
     CU(launch_merge_window(st_sel, x->rec_of(x->block, slot, 0), x->flags_of(x->block, slot), push.seq, x->world, x->cap, k,
-                           x->timeout_ns, sk, sp, out_scores, out_ids, out_count));
+                           x->timeout_ns, sk, sp, out_scores, out_ids, out_count,
+                           x->stamps ? x->stamps + (push.seq % Xchg::STAMP_RING) * Xchg::STAMP_WORDS + 16 : nullptr));
     return SVSB_OK;
 }
 
@@ -2022,6 +2030,19 @@ extern "C" int svsb_query_peer_wait(svsb_t* e, int32_t ticket, float* out_scores
     memcpy(out_scores, t.h_scores, (size_t)cnt * 4);
     memcpy(out_emb_ids, t.h_ids, (size_t)cnt * 8);
     *out_count = cnt;
+    return SVSB_OK;
+}
+
+// Measurement aid: copy the stamp ring (SVSB_XCHG_STAMPS=1 at svsb_xchg_create) to the host: STAMP_RING x 40 u64, entry
+// seq % 1024 = [16 selection-kernel stamps (svsb_debug_select_phases layout) | seq, merge start, merge done, -, flag seen x world].
+extern "C" int svsb_xchg_read_stamps(svsb_t* e, uint64_t* out, int64_t capacity_words) {
+    if (!e || !out) return fail(SVSB_E_INVALID, "svsb_xchg_read_stamps: NULL argument");
+    if (!e->xchg || !e->xchg->stamps) return fail(SVSB_E_STATE, "svsb_xchg_read_stamps: create the exchange with SVSB_XCHG_STAMPS=1");
+    const int64_t words = (int64_t)Xchg::STAMP_RING * Xchg::STAMP_WORDS;
+    if (capacity_words < words) return fail(SVSB_E_INVALID, "svsb_xchg_read_stamps: buffer too small (1024 x 40 words)");
+    CU(cudaSetDevice(e->devs[0]));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, e->xchg->stamps, (size_t)words * 8, cudaMemcpyDeviceToHost));
     return SVSB_OK;
 }
 

@@ -338,6 +338,10 @@ struct Xchg {
     static constexpr int N_TICKETS = 3;
     Ticket tk[N_TICKETS];
     int tk_ld = 0, tk_next = 0;
+    // measurement aid (SVSB_XCHG_STAMPS=1): %globaltimer stamps of the last STAMP_RING synchronous peer queries --
+    // selection kernel phases (16 words) + merge kernel (24 words) per query
+    static constexpr int STAMP_RING = 1024, STAMP_WORDS = 40;
+    u64* stamps = nullptr;
     cudaEvent_t ev_join = nullptr;
     // synchronous path (svsb_query_peer): own stream, device query, pinned staging; results land in pinned
     // host memory straight from the merge kernel (mapped, no copy back)

@@ -130,7 +130,8 @@ cudaError_t launch_push_empty(cudaStream_t st, const PeerPush& push);
 constexpr int MERGE_WINDOW_TIMED_OUT = -2;
 cudaError_t launch_merge_window(cudaStream_t st, const u64* slot_base, const u64* flags, unsigned long long seq,
                                 int world, int cap, int k, unsigned long long timeout_ns, u64* scratch_keys, int64_t* scratch_ids,
-                                float* out_scores, int64_t* out_ids, int32_t* out_count);
+                                float* out_scores, int64_t* out_ids, int32_t* out_count,
+                                u64* stamps = nullptr);   // optional 24 x u64: [seq, t_start, t_done, -, t_flag_seen[world]] (%globaltimer ns)
 
 // ---- K0: load path ---------------------------------------------------------------------------
 // Row L2 norms; optionally divide rows by their norm.  stats[0] = float bits of max | ||row|| - 1 |

@@ -707,7 +707,7 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 merge_window_kernel(const u64* slot_base, const u64* flags, u64 seq, int world, int cap, int k, u64 timeout_ns,
                     u64* sk, int64_t* sp, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                    int32_t* __restrict__ out_count)
+                    int32_t* __restrict__ out_count, u64* __restrict__ stamps)
 {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelectSmem& sm = *reinterpret_cast<SelectSmem*>(sel_smem_raw);
@@ -715,6 +715,8 @@ merge_window_kernel(const u64* slot_base, const u64* flags, u64 seq, int world, 
     const int64_t rec_words = 2 * (int64_t)cap + 2;
     pdl_wait();                                    // scratch / outputs may still be in use by the previous kernel
     if (tid == 0) sm.counter = 0;
+    // measurement aid (SVSB_XCHG_STAMPS=1): when did this merge start, when had rank r's record arrived (%globaltimer, ns)
+    if (stamps && tid == 0) { u64 t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[0] = seq; stamps[1] = t_; }
     __syncthreads();
     if (tid < world) {
         // A peer that died or left the SPMD sequence must not hang this GPU: give up after timeout_ns and report it.
@@ -729,6 +731,7 @@ merge_window_kernel(const u64* slot_base, const u64* flags, u64 seq, int world, 
                 else if (now - t0 > timeout_ns) { atomicAdd(&sm.counter, 1u); break; }
             }
         }
+        if (stamps) { u64 t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[4 + tid] = t_; }
     }
     __syncthreads();
     if (sm.counter != 0) { if (tid == 0) *out_count = MERGE_WINDOW_TIMED_OUT; return; }
@@ -756,6 +759,7 @@ merge_window_kernel(const u64* slot_base, const u64* flags, u64 seq, int world, 
         const int kk_s = min(k, total_s);
         if (rank_merge_emit(sm, world, cnt, off, total_s, kk_s, out_scores, out_ids)) {
             if (tid == 0) *out_count = kk_s;
+            if (stamps && tid == 0) { u64 t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[2] = t_; }
             return;
         }
         if (tid == 0) sm.counter = (uint32_t)total_s;         // unsorted input: fall through to the bitonic sort
@@ -842,7 +846,7 @@ cudaError_t launch_merge_sorted_big(cudaStream_t st, const u64* keys, const int6
 
 cudaError_t launch_merge_window(cudaStream_t st, const u64* slot_base, const u64* flags, unsigned long long seq,
                                 int world, int cap, int k, unsigned long long timeout_ns, u64* scratch_keys, int64_t* scratch_ids,
-                                float* out_scores, int64_t* out_ids, int32_t* out_count)
+                                float* out_scores, int64_t* out_ids, int32_t* out_count, u64* stamps)
 {
     if (world < 1 || world > XCHG_MAX_RANKS || k < 1 || k > K_FAST_MAX || cap < k) return cudaErrorInvalidValue;
     static bool attr_set[64] = {false};
@@ -856,7 +860,7 @@ cudaError_t launch_merge_window(cudaStream_t st, const u64* slot_base, const u64
     if (big && (!scratch_keys || !scratch_ids)) return cudaErrorInvalidValue;
     cudaError_t le = launch_kernel(merge_window_kernel, dim3(1), dim3(SEL_THREADS), sizeof(SelectSmem), st, slot_base, flags, (u64)seq, world, cap, k,
                                    (u64)timeout_ns, big ? scratch_keys : (u64*)nullptr, big ? scratch_ids : (int64_t*)nullptr,
-                                   out_scores, out_ids, out_count);
+                                   out_scores, out_ids, out_count, stamps);
     count_launch();
     return le != cudaSuccess ? le : cudaGetLastError();
 }
