@@ -111,8 +111,9 @@ int svsb_load_synthetic(svsb_t* e, int64_t n, int32_t d, uint64_t seed, int64_t 
  *                             Rows are appended behind the last row (the last shard of a multi-device engine); the
  *                             buffer grows geometrically (one device-to-device copy) when it is full.
  * Deletes are applied first (an id deleted and re-inserted in one transaction is a tombstone plus an append).
- * SVSB_E_STATE: no generation resident, a del id that is not live, ids not ascending, or d mismatch -- nothing is
- * published and the caller falls back to the full rebuild.  The result equals a fresh rebuild bit for bit: same ids,
+ * SVSB_E_STATE: no generation resident, a del id that is not live, ids not ascending, d mismatch, or the resident
+ * generation was replaced while the update was being built -- nothing is published and the caller falls back to the full
+ * rebuild.  One update at a time (serialised inside); do not run it concurrently with svsb_load_begin .. svsb_load_end.  The result equals a fresh rebuild bit for bit: same ids,
  * same scores (tests/test_gpu_mutate.py).  Generations with tombstones answer batches and large k through the exact
  * kernels; svsb_top_pairs asks for a reload (SVSB_E_INVALID). */
 int svsb_apply_mutations(svsb_t* e, const int64_t* del_ids, int64_t n_del, const float* add_rows, const int64_t* add_ids,

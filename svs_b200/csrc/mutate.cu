@@ -198,5 +198,8 @@ extern "C" int svsb_apply_mutations(svsb_t* e, const int64_t* del_ids, int64_t n
     }
     ng->n = 0; ng->n_live = 0;
     for (auto& s : ng->shards) { ng->n += s.n; ng->n_live += s.n_live; }
+    // the update is relative to generation g: if a load (or an invalidate) replaced it meanwhile, publishing this view would
+    // resurrect the old table -- refuse, the caller rebuilds
+    if (pin(e) != g) return fail(SVSB_E_STATE, "svsb_apply_mutations: the resident generation changed during the update (rebuild)");
     return publish_generation(e, ng, generation);
 }
