@@ -729,7 +729,8 @@ def leg_batch_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
     torch.cuda.synchronize(); dist.barrier()
     (total_ms,) = sp.max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if rank == 0 else None
-    fallbacks = sr.last_fallbacks
+    fallbacks = sr.last_fallbacks + sr.last_batch_unanswered()    # queries of the last timed batch the coarse pass did not answer
+    global_plan = sr._global_plan(k)
     for _ in range(2):
         sr.retrieve_many_arrays(queries, k)
     dist.barrier(); torch.cuda.synchronize()
@@ -757,7 +758,10 @@ def leg_batch_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
         "dtype": "f32 results (f16 tensor-core coarse pass + exact f32 re-score)", "data": "synthetic",
         "config": config_of(name),
         "run": {"queries_per_step": BATCH, "per_gpu_f16_shadow_gb": local_rows * d * 2 / 1e9,
-                "parallelism": f"row-sharded over {world} GPUs, one NCCL all-gather of {BATCH} k-candidate records per rank per batch + merge kernel"},
+                "parallelism": (f"row-sharded over {world} GPUs; per batch: one all-gather of {BATCH} x 32 sample maxima (ONE filter threshold per "
+                                f"query for all ranks, order statistic {global_plan[0]} of the union sample), one all-gather of {BATCH} k-candidate "
+                                "records per rank, one verifying merge launch; no host synchronisation in between" if global_plan else
+                                f"row-sharded over {world} GPUs, per-rank thresholds, one NCCL all-gather of {BATCH} k-candidate records per rank per batch + merge kernel")},
         "ms_per_query": total_ms / nq,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
                      "traffic": None, "kernel": "whole batch step per GPU (coarse passes + refine + exchange + merge), rank-max time",

@@ -242,6 +242,27 @@ int svsb_enqueue_local_topk(svsb_t* e, void* stream, int32_t slot, const float* 
  * Synchronises `stream` once per 2048 queries. */
 int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, int64_t* d_records,
                              int32_t* n_fallback);
+/* Batches with ONE filter threshold per query for all ranks (the sharded form of retrieve_many; reference: a loop of
+ * superheavy(), src/svs/kb.py:1622-1627, over a matrix that no longer lives in one place).  With svsb_batch_local_records
+ * every rank finds its OWN top k, so the per-batch costs do not shrink with the shard; here each rank only keeps and
+ * re-scores what can reach the GLOBAL top k.  Per batch of b <= 2048 queries, on every rank, nothing synchronises:
+ *   1. svsb_batch_sample_tops      -> d_tops[b][32]: the 32 largest coarse scores of this rank's sample, descending
+ *   2. the caller all-gathers them -> d_tops_all[world][b][32]
+ *   3. svsb_batch_global_records   -> threshold = (sample_rank-th largest of the union) - 2 eps, filter pass, exact
+ *      re-score of every candidate, records [keys | ids | count, ver] (count may be < k; count -1 = this rank could not
+ *      answer the query; ver = candidates provably above the threshold's margin)
+ *   4. the caller all-gathers the records; svsb_enqueue_merge_batch_records(verify_k = min(k, global rows)) merges
+ *      and VERIFIES: out_count -1 (on every rank alike) = redo this query with the exact path (svsb_query_peer /
+ *      svsb_enqueue_local_topk); otherwise the result equals the single-query kernels' bit for bit.
+ * svsb_batch_global_probe tells whether this rank can take part (eligible) and what the caller needs to choose ONE
+ * sample_rank and ONE max_row_norm for all ranks: with f = max over ranks of sample_rows / local_rows and
+ * lambda = min(k, global rows) * f, sample_rank = ceil(lambda + 6 sqrt(lambda) + 4) must be <= 32 (else use
+ * svsb_batch_local_records); max_row_norm = the largest over the ranks.  Steps 1 and 3 of one batch must not be
+ * interleaved with another batch on the same engine. */
+int svsb_batch_global_probe(svsb_t* e, int32_t k, int32_t* eligible, int64_t* sample_rows, int64_t* local_rows, float* max_row_norm);
+int svsb_batch_sample_tops(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, float max_row_norm, float* d_tops);
+int svsb_batch_global_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, const float* d_tops_all,
+                              int32_t world, int32_t sample_rank, int64_t* d_records);
 /* ---- peer exchange: the exchange step fused into the kernels, over NVLink / NVSwitch peer memory ----------
  * Replaces "all-gather the records over NCCL, then merge" for single queries: every rank owns a GATHER WINDOW in its
  * HBM (slots x world records + one flag word per record); the selection kernel's epilogue stores its record into the
@@ -289,6 +310,10 @@ int svsb_enqueue_join(svsb_t* e, void* stream);
 /* d_records: all-gathered records, [n_lists][batch][2k+1].  Outputs [batch][k], [batch][k], [batch]. */
 int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
                                int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts);
+/* The same for the records of svsb_batch_global_records: a query comes out with count -1 when any rank's record says
+ * -1 or the ranks' verification counts add up to less than verify_k. */
+int svsb_enqueue_merge_batch_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
+                                     int32_t k, int32_t verify_k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts);
 /* Sum (ms) of the similarity-kernel durations bracketed by svsb_enqueue_local_topk(time_kernel=1) since the
  * last collect; waits for them to finish. */
 int svsb_kernel_time_collect(svsb_t* e, float* ms);

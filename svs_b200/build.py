@@ -40,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-O3,-Wall",
-           "-cudart", "static"]
+           "-cudart", "static", "--threads", "8"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]

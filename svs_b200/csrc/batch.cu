@@ -44,12 +44,148 @@ sample_threshold_kernel(const __half* __restrict__ sample, int64_t sample_rows, 
     if (threadIdx.x == 0) thr[q] = ordered_to_f32(o) - 2.0f * eps[q];
 }
 
+// The same order statistic, the fast way (rank <= 256 and a sample of >= 2048 rows: every configuration the engine
+// plans).  "Thread maxima + exact refilter" -- the trick of the selection kernel (select.cu) in miniature: with tau0 =
+// the rank-th largest of the 256 per-thread maxima, at least `rank` sample values are >= tau0, so the rank-th largest
+// overall is among the values >= tau0 -- typically rank plus a handful, because the top of a sample is spread over
+// the threads.  Those are collected into shared memory and rank-counted (duplicates counted, as np.partition would).
+// Two passes over the sample (the second one out of L1/L2), four barriers, no histogram.  Threads without sample values
+// (fewer than 256 vectors) rank last with key 0; the launcher requires rank <= number of vectors.  Works on the raw fp16 bits
+// (order-preserving 16-bit keys); the result converts to the very float the generic kernel returns.
+constexpr int ST_THREADS = 256;
+constexpr int ST_LIST = 1024;
+
+__device__ __forceinline__ uint32_t h16_ordered(uint32_t h) { return (h & 0x8000u) ? (~h & 0xffffu) : (h | 0x8000u); }
+__device__ __forceinline__ float ordered16_to_f32(uint32_t o) {
+    const uint32_t h = (o & 0x8000u) ? (o & 0x7fffu) : (~o & 0xffffu);
+    return __half2float(__ushort_as_half((unsigned short)h));
+}
+
+// TOP == false: thr[q] = (rank-th largest of the sample) - 2 eps[q].
+// TOP == true : top[q][0..SAMPLE_TOPX) = the SAMPLE_TOPX largest sample values, descending (the sharded path exchanges
+//               them and takes the order statistic of the UNION of all ranks' samples, union_threshold_kernel).
+template <bool TOP>
+__global__ void __launch_bounds__(ST_THREADS)
+sample_order_kernel(const __half* __restrict__ sample, int64_t sample_rows, int rank, const float* __restrict__ eps,
+                    float* __restrict__ thr, float* __restrict__ top)
+{
+    __shared__ uint32_t mx[ST_THREADS];
+    __shared__ uint32_t list[ST_LIST];
+    __shared__ uint32_t hist[RF_BINS];
+    __shared__ uint32_t scratch[72];
+    __shared__ uint32_t small[RF_SMALL];
+    __shared__ uint32_t s_tau0, s_count, s_ans;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const __half* s = sample + (size_t)q * sample_rows;
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);          // sample_rows is a multiple of 128: rows are 256-byte aligned
+    const int nvec = (int)(sample_rows >> 3);
+    const int want = TOP ? SAMPLE_TOPX : rank;
+    uint32_t m = 0;
+    for (int v = tid; v < nvec; v += ST_THREADS) {
+        const uint4 x = s4[v];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { m = max(m, h16_ordered(w[u] & 0xffffu)); m = max(m, h16_ordered(w[u] >> 16)); }
+    }
+    if (tid == 0) s_count = 0;
+    // keys made distinct by the thread number: the want-th largest of the thread maxima under (value desc, thread asc)
+    const uint32_t tau0 = block_select_unique<uint32_t>((m << 8) | (uint32_t)(ST_THREADS - 1 - tid), want, mx, &s_tau0) >> 8;
+    for (int v = tid; v < nvec; v += ST_THREADS) {
+        const uint4 x = s4[v];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t o = h16_ordered((u & 1) ? (w[u >> 1] >> 16) : (w[u >> 1] & 0xffffu));
+            if (o >= tau0) { const uint32_t p = atomicAdd(&s_count, 1u); if (p < (uint32_t)ST_LIST) list[p] = o; }
+        }
+    }
+    __syncthreads();
+    const int c = (int)s_count;
+    if (c > ST_LIST) {                                            // a thousand ties at the top of the sample: generic select
+        if (TOP) {                                                // +inf thresholds keep nothing: the query goes to the exact path
+            if (tid < SAMPLE_TOPX) top[(size_t)q * SAMPLE_TOPX + tid] = __int_as_float(0x7f800000);
+            return;
+        }
+        const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(__half2float(s[i])); }, sample_rows, rank,
+                                                 hist, scratch, small);
+        if (tid == 0) thr[q] = ordered_to_f32(o) - 2.0f * eps[q];
+        return;
+    }
+    for (int i = tid; i < c; i += ST_THREADS) {
+        const uint32_t mine = list[i];
+        if (TOP) {
+            int rk = 0;
+            for (int j = 0; j < c; ++j) { const uint32_t o = list[j]; rk += (o > mine || (o == mine && j < i)) ? 1 : 0; }
+            if (rk < SAMPLE_TOPX) top[(size_t)q * SAMPLE_TOPX + rk] = ordered16_to_f32(mine);
+        } else {
+            uint32_t gt = 0, ge = 0;
+            for (int j = 0; j < c; ++j) { const uint32_t o = list[j]; gt += o > mine ? 1u : 0u; ge += o >= mine ? 1u : 0u; }
+            if (gt < (uint32_t)rank && ge >= (uint32_t)rank) s_ans = mine;     // equal values write the same word
+        }
+    }
+    if (TOP) return;
+    __syncthreads();
+    if (tid == 0) thr[q] = ordered16_to_f32(s_ans) - 2.0f * eps[q];
+}
+
+static bool sample_fast_ok(int64_t sample_rows, int rank) {
+    static const bool off = [] { const char* v = getenv("SVSB_SAMPLE_GENERIC"); return v && atoi(v) != 0; }();
+    // every thread whose maximum takes part in the ranking must own at least one vector of 8 sample values
+    return !off && rank >= 1 && rank <= ST_THREADS && (sample_rows & 127) == 0 && rank <= (sample_rows >> 3);
+}
+
 cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t sample_rows, int b, int rank, const float* eps,
                                     float* thr)
 {
     if (b <= 0) return cudaSuccess;
     if (rank < 1 || rank > sample_rows) return cudaErrorInvalidValue;
-    sample_threshold_kernel<<<b, RF_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, rank, eps, thr);
+    if (sample_fast_ok(sample_rows, rank))
+        sample_order_kernel<false><<<b, ST_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, rank, eps, thr, nullptr);
+    else
+        sample_threshold_kernel<<<b, RF_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, rank, eps, thr);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample_top(cudaStream_t st, const void* sample, int64_t sample_rows, int b, float* top)
+{
+    if (b <= 0) return cudaSuccess;
+    if (!sample_fast_ok(sample_rows, SAMPLE_TOPX)) return cudaErrorInvalidValue;
+    sample_order_kernel<true><<<b, ST_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, SAMPLE_TOPX, nullptr, nullptr, top);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// thr[q] = (rank-th largest of the union of the ranks' top lists tops[r][q][0..SAMPLE_TOPX)) - 2 eps[q]; rank <=
+// SAMPLE_TOPX, so the union's rank-th largest is the rank-th largest of ALL ranks' sample values.  One warp per query.
+__global__ void __launch_bounds__(256)
+union_threshold_kernel(const float* __restrict__ tops, int world, int b, int rank, const float* __restrict__ eps, float* __restrict__ thr)
+{
+    __shared__ uint32_t vals[8][XCHG_MAX_RANKS * SAMPLE_TOPX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + warp;
+    if (q >= b) return;
+    const int n = world * SAMPLE_TOPX;
+    for (int i = lane; i < n; i += 32)
+        vals[warp][i] = f32_to_ordered(tops[((size_t)(i / SAMPLE_TOPX) * b + q) * SAMPLE_TOPX + (i % SAMPLE_TOPX)]);
+    __syncwarp();
+    uint32_t ans = 0; bool have = false;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t mine = vals[warp][i];
+        uint32_t gt = 0, ge = 0;
+        for (int j = 0; j < n; ++j) { const uint32_t o = vals[warp][j]; gt += o > mine ? 1u : 0u; ge += o >= mine ? 1u : 0u; }
+        if (gt < (uint32_t)rank && ge >= (uint32_t)rank) { ans = mine; have = true; }
+    }
+    const uint32_t who = __ballot_sync(0xffffffffu, have);
+    ans = __shfl_sync(0xffffffffu, ans, who ? __ffs(who) - 1 : 0);
+    if (lane == 0) thr[q] = ordered_to_f32(ans) - 2.0f * eps[q];
+}
+
+cudaError_t launch_union_threshold(cudaStream_t st, const float* tops, int world, int b, int rank, const float* eps, float* thr)
+{
+    if (b <= 0) return cudaSuccess;
+    if (world < 1 || world > XCHG_MAX_RANKS || rank < 1 || rank > SAMPLE_TOPX) return cudaErrorInvalidValue;
+    union_threshold_kernel<<<(b + 7) / 8, 256, 0, st>>>(tops, world, b, rank, eps, thr);
     count_launch();
     return cudaGetLastError();
 }
@@ -177,26 +313,241 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
     if (tid == 0) *out_count = kk;
 }
 
+// ---------------------------------------------------------------------------------------------
+// refine, split by what bounds each phase (the default; the one-CTA-per-query kernel above is kept for A/B measurement,
+// SVSB_REFINE_FUSED=1).  The fused kernel holds 94 KB of shared memory and 512 threads through its select, filter and
+// sort phases, during which its SM's share of the HBM idles (ncu: 43 % DRAM throughput).  Split:
+//   refine_select_kernel   one small CTA per query: tau~, cutoff, verification, survivors' rows -> global list
+//   rescore_kernel         grid-wide, nothing but the exact fp32 dot products: (query, slice of its survivors) per CTA,
+//                          3-12 KB of shared memory (the query), four CTAs per SM, two rows in flight per warp
+//   refine_sort_kernel     one small CTA per query: sort the survivors' exact keys, emit the top kk
+// mode bit 0 (REFINE_PARTIAL, sharded path with a GLOBAL threshold): fewer than kk local candidates is the normal case
+//   (the shard holds only its part of the global top kk): every candidate is re-scored, the record's count is what
+//   there is, and the count word's high half carries ver = #{candidates with coarse >= thr + 2 eps}; the merge adds
+//   ver over the ranks: sum >= kk proves thr <= (global kk-th largest coarse score) - 2 eps, i.e. no shard's list
+//   misses a row of the global top kk.
+// mode bit 1 (REFINE_DEFER): a query the coarse path cannot answer (flags[q] != 0) gets count -1 in its record
+//   instead of waiting for the host to read the flags; the merge propagates it and the caller redoes such queries.
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_LIST = 1024;                   // candidates at or above tau0 the fast select ranks in shared memory (<= RF_BINS)
+
+__global__ void __launch_bounds__(RS_THREADS)
+refine_select_kernel(int64_t n, int k, const u64* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int cand_cap,
+                     const float* __restrict__ eps, const float* __restrict__ thr, int32_t* __restrict__ flags, int mode,
+                     RefineScratch sc, int32_t* __restrict__ stats)
+{
+    __shared__ uint32_t cached[RF_CACHE];
+    __shared__ uint32_t hist[RF_BINS];
+    __shared__ uint32_t scratch[72];
+    __shared__ uint32_t small[RF_SMALL];
+    __shared__ u64 sel_sorted[RS_THREADS];
+    __shared__ u64 sel_bcast;
+    __shared__ uint32_t counter, vcount, lcount;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int kk = (int)min((int64_t)k, n);
+    const bool partial = (mode & REFINE_PARTIAL) != 0;
+    if (tid == 0) { sc.cnt[q] = 0; sc.ver[q] = 0; if (stats) stats[q] = 0; counter = 0; vcount = 0; }
+    if (flags[q] != 0) return;                                       // already routed to the exact path
+    const int total = cand_cnt[q];
+    if (total > cand_cap || (!partial && total < kk)) {
+        if (tid == 0) flags[q] = total > cand_cap ? 2 : 4;
+        return;
+    }
+    const u64* cq = cand + (size_t)q * cand_cap;
+    {
+        const int lim = min(total, RF_CACHE);
+        for (int i0 = tid; i0 < lim; i0 += RS_THREADS * 4) {
+            u64 kv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * RS_THREADS; kv[u] = i < lim ? cq[i] : 0ull; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * RS_THREADS; if (i < lim) cached[i] = (uint32_t)(kv[u] >> 32); }
+        }
+    }
+    __syncthreads();
+    auto score_o = [&](int64_t i) { return i < RF_CACHE ? cached[i] : (uint32_t)(cq[i] >> 32); };
+    float cutoff = __int_as_float(0xff800000);                       // -inf: keep every candidate (partial, total < kk)
+    if (total >= kk) {
+        uint32_t tau_o = 0;
+        bool have = false;
+        if (kk <= RS_THREADS / 2) {
+            // "thread maxima + exact refilter" (see sample_order_kernel): tau0 = the kk-th largest of the per-thread maxima is a
+            // lower bound of tau~ with about kk .. 1.3 kk candidates at or above it; those are rank-counted in shared memory
+            uint32_t m = 0;
+            for (int i = tid; i < total; i += RS_THREADS) m = max(m, score_o(i));
+            if (tid == 0) lcount = 0;
+            const uint32_t tau0 = (uint32_t)(block_select_unique<u64>(((u64)m << 32) | (u64)(RS_THREADS - 1 - tid), kk, sel_sorted, &sel_bcast) >> 32);
+            for (int i = tid; i < total; i += RS_THREADS) {
+                const uint32_t o = score_o(i);
+                if (o >= tau0) { const uint32_t p = atomicAdd(&lcount, 1u); if (p < (uint32_t)RS_LIST) hist[p] = o; }
+            }
+            __syncthreads();
+            const int c = (int)lcount;
+            if (c <= RS_LIST) {
+                for (int i = tid; i < c; i += RS_THREADS) {
+                    const uint32_t mine = hist[i];
+                    uint32_t gt = 0, ge = 0;
+                    for (int j = 0; j < c; ++j) { const uint32_t o = hist[j]; gt += o > mine ? 1u : 0u; ge += o >= mine ? 1u : 0u; }
+                    if (gt < (uint32_t)kk && ge >= (uint32_t)kk) scratch[7] = mine;   // equal values write the same word
+                }
+                __syncthreads();
+                tau_o = scratch[7];
+                have = true;
+            }
+            __syncthreads();
+        }
+        if (!have) tau_o = block_kth_largest_o32(score_o, total, kk, hist, scratch, small);
+        cutoff = ordered_to_f32(tau_o) - 2.0f * eps[q];
+        // The list holds exactly the rows with coarse >= thr[q] and at least kk of them, so tau_o IS the kk-th largest
+        // coarse score of all (local) rows; rows with coarse in [cutoff, thr[q]) would be missing from the list.
+        if (!partial && thr && !(cutoff >= thr[q])) { if (tid == 0) flags[q] = REFINE_FLAG_THRESHOLD_HIGH; return; }
+    }
+    const float vthr = partial ? __fadd_ru(thr[q], __fmul_ru(2.0f, eps[q])) : 0.f;
+    uint32_t* rows = sc.rows + (size_t)q * REFINE_SURVIVOR_CAP;
+    for (int i0 = 0; i0 < total; i0 += RS_THREADS) {
+        const int i = i0 + tid;
+        const float s = i < total ? ordered_to_f32(score_o(i)) : 0.f;
+        if (i < total && s >= cutoff) {
+            const uint32_t p = atomicAdd(&counter, 1u);
+            if (p < (uint32_t)REFINE_SURVIVOR_CAP) rows[p] = key_row(cq[i]);
+        }
+        if (partial) {
+            const uint32_t v = __ballot_sync(0xffffffffu, i < total && s >= vthr);
+            if (lane == 0 && v) atomicAdd(&vcount, (uint32_t)__popc(v));
+        }
+    }
+    __syncthreads();
+    const int C = (int)counter;
+    if (C > REFINE_SURVIVOR_CAP) { if (tid == 0) flags[q] = 8; return; }
+    if (tid == 0) { sc.cnt[q] = C; sc.ver[q] = (int32_t)vcount; if (stats) stats[q] = C; }
+}
+
+// Exact fp32 re-score, one warp per survivor.  Summation order == gemv_tma_kernel (gemv.cu): lane l takes the float4
+// chunks l, l+32, ...; even chunks accumulate into a0, odd ones into a1; then the same combine + xor tree.  Two
+// survivors per warp iteration: twice the loads in flight, each row's own summation order untouched.
+__global__ void __launch_bounds__(RS_THREADS)
+rescore_kernel(const float* __restrict__ M, int d4, const float* __restrict__ Q, int ldq, RefineScratch sc)
+{
+    extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+    float4* sq = reinterpret_cast<float4*>(rs_smem_raw);
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RS_THREADS / 32;
+    const int C = sc.cnt[q];                                          // 0 for flagged queries
+    const int first = blockIdx.y * nwarps, stride = gridDim.y * nwarps;
+    if (first >= C) return;
+    for (int c = tid; c < d4; c += RS_THREADS) sq[c] = reinterpret_cast<const float4*>(Q + (size_t)q * ldq)[c];
+    __syncthreads();
+    const uint32_t* rows = sc.rows + (size_t)q * REFINE_SURVIVOR_CAP;
+    u64* keys = sc.keys + (size_t)q * REFINE_SURVIVOR_CAP;
+    const float4* M4 = reinterpret_cast<const float4*>(M);
+    for (int i = first + warp; i < C; i += 2 * stride) {
+        const int i2 = i + stride;
+        const bool two = i2 < C;
+        const uint32_t rowa = rows[i], rowb = rows[two ? i2 : i];
+        const float4* pa = M4 + (int64_t)rowa * d4;                  // candidate keys carry LOCAL rows
+        const float4* pb = M4 + (int64_t)rowb * d4;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        int c = lane;
+        for (; c + 96 < d4; c += 128) {
+            const float4 m0 = ldg_stream(pa + c), m1 = ldg_stream(pa + c + 32), m2 = ldg_stream(pa + c + 64), m3 = ldg_stream(pa + c + 96);
+            const float4 n0 = ldg_stream(pb + c), n1 = ldg_stream(pb + c + 32), n2 = ldg_stream(pb + c + 64), n3 = ldg_stream(pb + c + 96);
+            const float4 q0 = sq[c], q1 = sq[c + 32], q2 = sq[c + 64], q3 = sq[c + 96];
+            fma4(a0, m0, q0); fma4(a1, m1, q1); fma4(a0, m2, q2); fma4(a1, m3, q3);
+            fma4(b0, n0, q0); fma4(b1, n1, q1); fma4(b0, n2, q2); fma4(b1, n3, q3);
+        }
+        for (; c + 32 < d4; c += 64) {
+            const float4 m0 = ldg_stream(pa + c), m1 = ldg_stream(pa + c + 32);
+            const float4 n0 = ldg_stream(pb + c), n1 = ldg_stream(pb + c + 32);
+            const float4 q0 = sq[c], q1 = sq[c + 32];
+            fma4(a0, m0, q0); fma4(a1, m1, q1);
+            fma4(b0, n0, q0); fma4(b1, n1, q1);
+        }
+        if (c < d4) {
+            const float4 m0 = ldg_stream(pa + c), n0 = ldg_stream(pb + c);
+            const float4 q0 = sq[c];
+            fma4(a0, m0, q0); fma4(b0, n0, q0);
+        }
+        const float sa = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
+        const float sb = warp_sum(((b0.x + b1.x) + (b0.y + b1.y)) + ((b0.z + b1.z) + (b0.w + b1.w)));
+        if (lane == 0) { keys[i] = make_key(sa, rowa); if (two) keys[i2] = make_key(sb, rowb); }
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t row0, const int32_t* __restrict__ flags, int mode,
+                   RefineScratch sc, RefineOut out)
+{
+    extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+    u64* sk = reinterpret_cast<u64*>(rs_smem_raw);                   // np2 (<= REFINE_SURVIVOR_CAP) keys, or 2 x 256 for the rank sort
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int kk = (int)min((int64_t)k, n);
+    int32_t* out_count = out.counts + (int64_t)q * out.count_stride;
+    if (flags[q] != 0) {
+        if (tid == 0) { out_count[0] = (mode & REFINE_DEFER) ? -1 : 0; if (mode & REFINE_PARTIAL) out_count[1] = 0; }
+        return;
+    }
+    const int C = sc.cnt[q];
+    const u64* keys = sc.keys + (size_t)q * REFINE_SURVIVOR_CAP;
+    const u64* sorted;
+    if (C <= RANK_SORT_MAX) {
+        if (tid < C) sk[tid] = keys[tid];
+        __syncthreads();
+        block_rank_sort_desc(sk, sk + RANK_SORT_MAX, C);
+        sorted = sk + RANK_SORT_MAX;
+    } else {
+        int np2 = 1; while (np2 < C) np2 <<= 1;
+        for (int i = tid; i < np2; i += RS_THREADS) sk[i] = i < C ? keys[i] : 0ull;
+        __syncthreads();
+        block_bitonic_desc<false>(sk, nullptr, np2);
+        sorted = sk;
+    }
+    const int cnt = min(kk, C);
+    for (int i = tid; i < cnt; i += RS_THREADS) {
+        const u64 key = sorted[i];
+        const uint32_t row = key_row(key);
+        const int64_t grow = row0 + (int64_t)row;                    // global row (row0 = first row of this shard)
+        if (out.scores) out.scores[(int64_t)q * out.stride + i] = key_score(key);
+        if (out.keys) out.keys[(int64_t)q * out.stride + i] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
+        out.ids[(int64_t)q * out.stride + i] = ids ? ids[row] : grow;
+    }
+    if (tid == 0) { out_count[0] = cnt; if (mode & REFINE_PARTIAL) out_count[1] = sc.ver[q]; }
+}
+
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
-                          const float* eps, const float* thr, int32_t* flags, RefineOut out, int32_t* stats)
+                          const float* eps, const float* thr, int32_t* flags, RefineOut out, int32_t* stats,
+                          const RefineScratch* scratch, int mode)
 {
     if (b <= 0) return cudaSuccess;
     if (!out.ids || !out.counts) return cudaErrorInvalidValue;
     if (k < 1 || (ld & 3) || ldq < ld) return cudaErrorInvalidValue;
     const int64_t kk = k < n ? k : n;
     if (kk > REFINE_SURVIVOR_CAP) return cudaErrorInvalidValue;
-    const size_t smem = ((sizeof(RefineSmem) + 15) & ~(size_t)15) + (size_t)ld * 4;
+    static const bool fused_env = [] { const char* v = getenv("SVSB_REFINE_FUSED"); return v && atoi(v) != 0; }();
+    const bool fused = (fused_env || !scratch || !scratch->rows) && mode == 0;
+    if (!fused && (!scratch || !scratch->rows || !scratch->keys || !scratch->cnt || !scratch->ver)) return cudaErrorInvalidValue;
+    if ((mode & REFINE_PARTIAL) && !thr) return cudaErrorInvalidValue;
     static bool attr_set[64] = {false};
     int dev = 0; cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    refine_kernel<<<b, RF_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, thr, flags, out, stats);
-    count_launch();
+    if (fused) {
+        const size_t smem = ((sizeof(RefineSmem) + 15) & ~(size_t)15) + (size_t)ld * 4;
+        if (smem > 200 * 1024) return cudaErrorInvalidValue;
+        refine_kernel<<<b, RF_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, thr, flags, out, stats);
+        count_launch();
+        return cudaGetLastError();
+    }
+    if ((size_t)ld * 4 > 200 * 1024) return cudaErrorInvalidValue;
+    refine_select_kernel<<<b, RS_THREADS, 0, st>>>(n, k, cand, cand_cnt, cand_cap, eps, thr, flags, mode, *scratch, stats);
+    static const int split = [] { const char* v = getenv("SVSB_RESCORE_SPLIT"); const int x = v ? atoi(v) : 0; return x >= 1 && x <= 64 ? x : 4; }();
+    rescore_kernel<<<dim3(b, split), RS_THREADS, (size_t)ld * 4, st>>>(M, ld / 4, Q, ldq, *scratch);
+    refine_sort_kernel<<<b, RS_THREADS, (size_t)REFINE_SURVIVOR_CAP * 8, st>>>(n, k, ids, row0, flags, mode, *scratch, out);
+    count_launch(3);
     return cudaGetLastError();
 }
 

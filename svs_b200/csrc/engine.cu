@@ -833,6 +833,9 @@ static int batch_ws_ensure(BatchWs* w, const BatchPlan& P, int b_pad) {
         CU(cudaMalloc(&w->flags, (size_t)nb * 4)); CU(cudaMalloc(&w->cand_cnt, (size_t)nb * 4)); CU(cudaMalloc(&w->stats, (size_t)nb * 4));
         CU(cudaMalloc(&w->sample, (size_t)nb * ns * 4));
         CU(cudaMalloc(&w->cand, (size_t)nb * P.cand_cap * 8));
+        CU(cudaMalloc(&w->rs.rows, (size_t)nb * REFINE_SURVIVOR_CAP * 4)); CU(cudaMalloc(&w->rs.keys, (size_t)nb * REFINE_SURVIVOR_CAP * 8));
+        CU(cudaMalloc(&w->rs.cnt, (size_t)nb * 4)); CU(cudaMalloc(&w->rs.ver, (size_t)nb * 4));
+        CU(cudaMalloc(&w->tops, (size_t)nb * SAMPLE_TOPX * 4));
         CU(cudaMalloc(&w->o_scores, (size_t)nb * nk * 4)); CU(cudaMalloc(&w->o_ids, (size_t)nb * nk * 8)); CU(cudaMalloc(&w->o_counts, (size_t)nb * 4));
         CU(cudaMallocHost(&w->h_Q, (size_t)nb * nld * 4));
         CU(cudaMallocHost(&w->h_scores, (size_t)nb * nk * 4)); CU(cudaMallocHost(&w->h_ids, (size_t)nb * nk * 8));
@@ -885,7 +888,7 @@ static int batch_enqueue(BatchWs* w, const Generation* g, const BatchPlan& P, co
     RefineOut o{w->o_scores, nullptr, w->o_ids, (int64_t)P.k, w->o_counts, 1};
     if (out) o = *out;
     CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, dQ, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->thr, w->flags,
-                     o, w->stats));
+                     o, w->stats, &w->rs, 0));
     return SVSB_OK;
 }
 
@@ -1666,6 +1669,105 @@ int batch_local_records_gen(svsb_engine* e, const std::shared_ptr<Generation>& g
     return SVSB_OK;
 }
 
+// ---- sharded batches with a GLOBAL filter threshold --------------------------------------------
+// With local thresholds every rank finds ITS OWN top kk: it samples, filters and re-scores for a cut at local rank kk,
+// although the shard holds only ~kk / world of the global top kk -- the fixed per-batch costs do not shrink with the
+// shard (round 1: 31 % scaling efficiency at 8 GPUs).  Here the ranks agree on ONE threshold per query: each extracts the
+// SAMPLE_TOPX largest coarse scores of its own sample (svsb_batch_sample_tops), the caller all-gathers those b x 32
+// floats, and every rank takes the sample_rank-th largest of the UNION (svsb_batch_global_records) -- an order
+// statistic of a sample of ALL rows, so the filter keeps ~(global rank sample_rank / f) / world rows per rank.  Every
+// candidate is re-scored exactly; the record carries ver = #{coarse >= thr + 2 eps}; the merge adds ver over the ranks
+// and accepts the query only if the sum reaches kk (then thr <= tau~_global - 2 eps: no rank's list misses a row of
+// the global top kk).  Nothing in between reads a flag on the host: a query the coarse path cannot vouch for comes
+// out of the merge with count -1 on EVERY rank and the caller redoes it with the exact kernels.
+static bool batch_plan_global(svsb_engine* e, const Generation* g, int32_t k, BatchPlan& P) {
+    if (!batch_plan(e, g, k, P)) return false;
+    // sample fraction f with kk * f ~ 3: the union's order statistic of rank ~ 3 + 6 sqrt(3) + 4 < SAMPLE_TOPX
+    int64_t want = (int64_t)std::ceil(3.0 * (double)g->n / (double)std::max(1, k));
+    if (const char* v = getenv("SVSB_BATCH_GLOBAL_SAMPLE_ROWS")) want = atoll(v);
+    int64_t st = std::min<int64_t>(std::max<int64_t>((want + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS, 2), P.n_tiles);
+    P.s_tiles = (int)st;
+    P.tile_stride = std::max(1, P.n_tiles / P.s_tiles);
+    P.sample_rows = (int64_t)P.s_tiles * COARSE_TILE_ROWS;
+    P.sample_alloc_rows = std::max(P.sample_alloc_rows, P.sample_rows);
+    P.sample_rank = 0;                                   // the caller's: it depends on every rank's sample fraction
+    return P.sample_rows >= 8 * SAMPLE_TOPX;             // launch_sample_top: SAMPLE_TOPX threads with at least one vector each
+}
+
+extern "C" int svsb_batch_global_probe(svsb_t* e, int32_t k, int32_t* eligible, int64_t* sample_rows, int64_t* local_rows,
+                                       float* max_row_norm) {
+    if (!e || !eligible || !sample_rows || !local_rows || !max_row_norm) return fail(SVSB_E_INVALID, "svsb_batch_global_probe: NULL argument");
+    *eligible = 0; *sample_rows = 0; *local_rows = 0; *max_row_norm = 1.f;
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    *local_rows = g->n_live;
+    BatchPlan P;
+    if (k < 1 || k > K_FAST_MAX || env_int("SVSB_BATCH_GLOBAL", 1) == 0 || g->n_live == 0 || !batch_plan_global(e, g.get(), k, P)) return SVSB_OK;
+    *eligible = 1; *sample_rows = P.sample_rows; *max_row_norm = P.max_row_norm;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_batch_sample_tops(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, float max_row_norm, float* d_tops) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (b < 1 || b > COARSE_MAX_BATCH || !d_Q || !d_tops) return fail(SVSB_E_INVALID, "svsb_batch_sample_tops: 1 <= b <= 2048, non-NULL buffers");
+    BatchPlan P;
+    if (!batch_plan_global(e, g.get(), k, P)) return fail(SVSB_E_STATE, "svsb_batch_sample_tops: this shard / k is not eligible (svsb_batch_global_probe)");
+    if (!(max_row_norm >= P.max_row_norm) || !(max_row_norm <= 8.1f)) return fail(SVSB_E_INVALID, "svsb_batch_sample_tops: max_row_norm below this shard's own, or unsafe for fp16 operands");
+    P.max_row_norm = max_row_norm;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = nullptr;
+    int rc = batch_ws_get(e, w);
+    if (rc != SVSB_OK) return rc;
+    if ((rc = ensure_m16(g.get(), P, st)) != SVSB_OK) return rc;
+    const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+    if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
+    CU(cudaSetDevice(w->dev));
+    CU(launch_queries_to_f16(st, d_Q, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags));
+    CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, st));
+    CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
+                          nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
+    CU(launch_sample_top(st, w->sample, P.sample_rows, b, d_tops));
+    w->global_gen = g->id; w->global_b = b; w->global_k = k;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_batch_global_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, const float* d_tops_all,
+                                         int32_t world, int32_t sample_rank, int64_t* d_records) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (b < 1 || b > COARSE_MAX_BATCH || !d_Q || !d_tops_all || !d_records) return fail(SVSB_E_INVALID, "svsb_batch_global_records: 1 <= b <= 2048, non-NULL buffers");
+    if (world < 1 || world > XCHG_MAX_RANKS || sample_rank < 1 || sample_rank > SAMPLE_TOPX)
+        return fail(SVSB_E_INVALID, "svsb_batch_global_records: 1 <= world <= 16, 1 <= sample_rank <= 32");
+    BatchPlan P;
+    if (!batch_plan_global(e, g.get(), k, P)) return fail(SVSB_E_STATE, "svsb_batch_global_records: this shard / k is not eligible");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = e->batch_ws.get();
+    if (!w || w->global_gen != g->id || w->global_b != b || w->global_k != k)
+        return fail(SVSB_E_STATE, "svsb_batch_global_records: no matching svsb_batch_sample_tops call precedes it");
+    w->global_gen = 0;
+    {   // this rank's own statistical requirement must be covered by the caller's rank (it maximises over the ranks)
+        const double lam = (double)P.kk * std::min(1.0, (double)P.sample_rows / (double)P.n);
+        if ((double)sample_rank < std::ceil(lam + 6.0 * std::sqrt(lam) + 4.0) && sample_rank < SAMPLE_TOPX && env_int("SVSB_BATCH_GLOBAL_ANY_RANK", 0) == 0)
+            return fail(SVSB_E_INVALID, "svsb_batch_global_records: sample_rank below this shard's own bound");
+    }
+    const Shard& s = g->shards[0];
+    CU(cudaSetDevice(w->dev));
+    const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+    CU(launch_union_threshold(st, d_tops_all, world, b, sample_rank, w->eps, w->thr));
+    CU(launch_coarse_gemm(st, w->dev, 0, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.n_tiles, 1,
+                          w->thr, w->cand, w->cand_cnt, P.cand_cap, nullptr, 0));
+    const int64_t rec = 2 * (int64_t)k + 1;
+    RefineOut o{nullptr, reinterpret_cast<u64*>(d_records), d_records + k, rec, reinterpret_cast<int32_t*>(d_records + 2 * (int64_t)k), 2 * rec};
+    CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, d_Q, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->thr, w->flags,
+                     o, w->stats, &w->rs, REFINE_PARTIAL | REFINE_DEFER));
+    return SVSB_OK;
+}
+
 // ---- peer exchange: the fused selection + exchange step and the waiting merge (kernels.cuh, select.cu) -------------
 static int xchg_prepare(svsb_engine* e, const Generation* g);
 static int xchg_flush_merge(svsb_engine* e, cudaStream_t st_sel);
@@ -2076,11 +2178,11 @@ extern "C" int svsb_kernel_time_collect(svsb_t* e, float* ms) {
     return SVSB_OK;
 }
 
-extern "C" int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
-                                          int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts) {
+static int enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
+                                 int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts, int verify_k, const char* who) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
-    if (n_lists < 1 || batch < 1 || k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_enqueue_merge_records: bad arguments");
-    if (!d_records || !d_out_scores || !d_out_ids || !d_out_counts) return fail(SVSB_E_INVALID, "svsb_enqueue_merge_records: NULL pointer");
+    if (n_lists < 1 || batch < 1 || k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, std::string(who) + ": bad arguments");
+    if (!d_records || !d_out_scores || !d_out_ids || !d_out_counts) return fail(SVSB_E_INVALID, std::string(who) + ": NULL pointer");
     CU(cudaSetDevice(e->devs[0]));
     const int64_t rec = 2 * (int64_t)k + 1;
     u64* sk = nullptr; int64_t* sp = nullptr;
@@ -2093,8 +2195,17 @@ extern "C" int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t
     CU(launch_merge_ex((cudaStream_t)stream, reinterpret_cast<const u64*>(d_records), d_records + k,
                        reinterpret_cast<const int32_t*>(d_records + 2 * (int64_t)k), n_lists, k, k, batch,
                        (int64_t)batch * rec, rec, (int64_t)batch * rec * 2, rec * 2, sk, sp,
-                       d_out_scores, d_out_ids, d_out_counts));
+                       d_out_scores, d_out_ids, d_out_counts, verify_k));
     return SVSB_OK;
+}
+extern "C" int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
+                                          int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts) {
+    return enqueue_merge_records(e, stream, d_records, n_lists, batch, k, d_out_scores, d_out_ids, d_out_counts, -1, "svsb_enqueue_merge_records");
+}
+extern "C" int svsb_enqueue_merge_batch_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
+                                                int32_t k, int32_t verify_k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts) {
+    if (verify_k < 0 || verify_k > k) return fail(SVSB_E_INVALID, "svsb_enqueue_merge_batch_records: 0 <= verify_k <= k");
+    return enqueue_merge_records(e, stream, d_records, n_lists, batch, k, d_out_scores, d_out_ids, d_out_counts, verify_k, "svsb_enqueue_merge_batch_records");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -221,18 +221,23 @@ struct BatchWs {
     float* dQ = nullptr; void* dQ16 = nullptr;
     float* eps = nullptr; float* thr = nullptr; int32_t* flags = nullptr; int32_t* cand_cnt = nullptr; int32_t* stats = nullptr;
     float* sample = nullptr; u64* cand = nullptr;
+    RefineScratch rs = {nullptr, nullptr, nullptr, nullptr};     // split refine: survivors' rows / exact keys / counts
+    float* tops = nullptr;                                        // [cap_b][SAMPLE_TOPX]: this rank's largest sample values (sharded path)
+    uint64_t global_gen = 0; int global_b = 0, global_k = 0;      // svsb_batch_sample_tops -> svsb_batch_global_records hand-over
     float* o_scores = nullptr; int64_t* o_ids = nullptr; int32_t* o_counts = nullptr;
     float* h_Q = nullptr; float* h_scores = nullptr; int64_t* h_ids = nullptr; int32_t* h_counts = nullptr;
     int32_t* h_flags = nullptr; int32_t* h_stats = nullptr; int32_t* h_cnt = nullptr;
 
     void release_device() {
         cudaSetDevice(dev);
-        void* ptrs[] = {dQ, dQ16, eps, thr, flags, cand_cnt, stats, sample, cand, o_scores, o_ids, o_counts};
+        void* ptrs[] = {dQ, dQ16, eps, thr, flags, cand_cnt, stats, sample, cand, o_scores, o_ids, o_counts,
+                        rs.rows, rs.keys, rs.cnt, rs.ver, tops};
         for (void* p : ptrs) if (p) cudaFree(p);
         void* hp[] = {h_Q, h_scores, h_ids, h_counts, h_flags, h_stats, h_cnt};
         for (void* p : hp) if (p) cudaFreeHost(p);
         dQ = nullptr; dQ16 = nullptr; eps = thr = nullptr; flags = cand_cnt = stats = nullptr; sample = nullptr; cand = nullptr;
         o_scores = nullptr; o_ids = nullptr; o_counts = nullptr;
+        rs = {nullptr, nullptr, nullptr, nullptr}; tops = nullptr;
         h_Q = h_scores = nullptr; h_ids = nullptr; h_counts = h_flags = h_stats = h_cnt = nullptr;
         cap_b = cap_ld = cap_k = 0; cap_sample = 0; cand_cap = 0;
     }

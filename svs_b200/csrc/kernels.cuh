@@ -98,7 +98,8 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
                             int n_lists, int cap, int k, int batch, int64_t list_stride, int64_t batch_stride,
                             int64_t count_list_stride, int64_t count_batch_stride,
                             u64* scratch_keys, int64_t* scratch_ids,
-                            float* out_scores, int64_t* out_ids, int32_t* out_count);
+                            float* out_scores, int64_t* out_ids, int32_t* out_count,
+                            int verify_k = -1);   // >= 0: count words are [count, ver] pairs, see MergeLayout (select.cu)
 
 // Any k: merge n_lists lists, each SORTED descending with unique keys (list l at keys / ids [l * stride ..), counts[l] valid).
 cudaError_t launch_merge_sorted_big(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts, int n_lists,
@@ -184,9 +185,22 @@ struct RefineOut {
     float* scores; u64* keys; int64_t* ids; int64_t stride;
     int32_t* counts; int64_t count_stride;
 };
+// Global scratch of the split refine (batch.cu): survivors' rows and exact keys, [b][REFINE_SURVIVOR_CAP] each, and per
+// query the survivor count and the verification count (REFINE_PARTIAL).
+struct RefineScratch { uint32_t* rows; u64* keys; int32_t* cnt; int32_t* ver; };
+constexpr int REFINE_PARTIAL = 1;     // sharded path, global threshold: < kk local candidates is normal; count word = [count, ver]
+constexpr int REFINE_DEFER = 2;       // a flagged query gets count -1 in its record (no host read of the flags in between)
+// scratch == nullptr (and mode == 0): the one-kernel variant (also SVSB_REFINE_FUSED=1).
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
-                          const float* eps, const float* thr, int32_t* flags, RefineOut out, int32_t* stats);
+                          const float* eps, const float* thr, int32_t* flags, RefineOut out, int32_t* stats,
+                          const RefineScratch* scratch = nullptr, int mode = 0);
+// Sharded path with a GLOBAL filter threshold: every rank extracts the SAMPLE_TOPX largest values of its own sample
+// (top[q][0..SAMPLE_TOPX), descending), the lists are exchanged, and thr[q] = (rank-th largest of the union) - 2 eps[q]
+// on every rank (rank <= SAMPLE_TOPX; tops = [world][b][SAMPLE_TOPX]).
+constexpr int SAMPLE_TOPX = 32;
+cudaError_t launch_sample_top(cudaStream_t st, const void* sample, int64_t sample_rows, int b, float* top);
+cudaError_t launch_union_threshold(cudaStream_t st, const float* tops, int world, int b, int rank, const float* eps, float* thr);
 constexpr int REFINE_FLAG_THRESHOLD_HIGH = 16;
 
 // ---- pairwise top pairs (pairs.cu): global candidate list on top of the coarse pass's pairwise mode --------

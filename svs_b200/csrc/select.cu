@@ -545,7 +545,27 @@ cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n
 struct MergeLayout {
     int n_lists, cap, k;
     int64_t list_stride, batch_stride, count_list_stride, count_batch_stride;
+    // verify_k >= 0 (batched records of the global-threshold path, batch.cu REFINE_PARTIAL | REFINE_DEFER): a list's count
+    // word is the pair [count, ver]; count < 0 on any list, or sum(ver) < verify_k, means the coarse pass could not vouch
+    // for this query: out_count = -1 and the caller redoes it with the exact kernels.
+    int verify_k;
 };
+
+// true: the query's records are good.  All threads call it; uses sm.bcast32[0..1].
+__device__ inline bool merge_records_verified(SelectSmem& sm, const int32_t* counts, const MergeLayout& L) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { sm.bcast32[0] = 0; sm.bcast32[1] = 0; }
+    __syncthreads();
+    if (tid < L.n_lists) {
+        const int32_t* c = counts + (int64_t)tid * L.count_list_stride;
+        if (c[0] < 0) atomicOr(&sm.bcast32[0], 1);
+        else atomicAdd(&sm.bcast32[1], max(0, c[1]));
+    }
+    __syncthreads();
+    const bool ok = sm.bcast32[0] == 0 && sm.bcast32[1] >= L.verify_k;
+    __syncthreads();
+    return ok;
+}
 
 // Rank merge of n_lists lists that are each sorted descending (what the selection / refine kernels emit): list l sits at
 // sm.sortbuf[off[l] .. off[l] + cnt[l]) with its payload beside it; keys are unique (the row is in the low word), so the
@@ -595,6 +615,7 @@ merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids
     out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
     uint32_t* cnt = sm.hist;                                  // per-list counts and offsets (list order is kept);
     uint32_t* off = sm.hist + 1024;                           // n_lists <= 1023 (launcher)
+    if (L.verify_k >= 0 && !merge_records_verified(sm, counts, L)) { if (tid == 0) out_count[b] = -1; return; }
     if (tid < L.n_lists) cnt[tid] = (uint32_t)max(0, min(counts[(int64_t)tid * L.count_list_stride], L.cap));
     __syncthreads();
     if (tid == 0) { uint32_t o = 0; for (int l = 0; l < L.n_lists; ++l) { off[l] = o; o += cnt[l]; } off[L.n_lists] = o; }
@@ -636,6 +657,7 @@ merge_lists_big_kernel(const u64* __restrict__ keys, const int64_t* __restrict__
     counts += (int64_t)b * L.count_batch_stride;
     out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
     sk += (int64_t)b * span; sp += (int64_t)b * span;
+    if (L.verify_k >= 0 && !merge_records_verified(sm, counts, L)) { if (tid == 0) out_count[b] = -1; return; }
     if (tid == 0) sm.counter = 0;
     __syncthreads();
     for (int64_t i = tid; i < span; i += blockDim.x) {
@@ -673,7 +695,7 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
                             int n_lists, int cap, int k, int batch, int64_t list_stride, int64_t batch_stride,
                             int64_t count_list_stride, int64_t count_batch_stride,
                             u64* scratch_keys, int64_t* scratch_ids,
-                            float* out_scores, int64_t* out_ids, int32_t* out_count)
+                            float* out_scores, int64_t* out_ids, int32_t* out_count, int verify_k)
 {
     if (n_lists < 1 || n_lists > 1023 || cap < 1 || k < 1 || k > K_FAST_MAX || batch < 1) return cudaErrorInvalidValue;
     static bool attr_set[64][2] = {{false}};
@@ -686,7 +708,7 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
         if (e != cudaSuccess) return e;
         attr_set[dev][big] = true;
     }
-    MergeLayout L{n_lists, cap, k, list_stride, batch_stride, count_list_stride, count_batch_stride};
+    MergeLayout L{n_lists, cap, k, list_stride, batch_stride, count_list_stride, count_batch_stride, verify_k};
     if (big) {
         if (!scratch_keys || !scratch_ids) return cudaErrorInvalidValue;
         merge_lists_big_kernel<<<batch, SEL_THREADS, sizeof(SelectSmem), st>>>(keys, ids, counts, L, scratch_keys, scratch_ids,

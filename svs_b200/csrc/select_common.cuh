@@ -61,6 +61,37 @@ __device__ inline void block_rank_sort_desc(const u64* src, u64* dst, int c) {
     __syncthreads();
 }
 
+// The rank-th largest (1-based) of ONE key per thread, keys pairwise distinct; blockDim.x a multiple of 32, <= 1024.
+// Every warp sorts its 32 keys with a shuffle bitonic network; a key's global rank is its position in its own warp's
+// list plus, per other warp, the number of greater keys there (binary search in shared memory) -- ~35 shared-memory
+// reads per thread instead of blockDim.x.  sorted: blockDim.x keys, bcast: one key (shared).  All threads get the result.
+template <class K>
+__device__ inline K block_select_unique(K key, int rank, K* sorted, K* bcast) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const K o = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+            key = keep_max ? (key > o ? key : o) : (key < o ? key : o);
+        }
+    }
+    sorted[tid] = key;                                         // warp w's list, descending: sorted[32 w .. 32 w + 32)
+    __syncthreads();
+    int r = lane;
+    for (int w = 0; w < nw; ++w) {
+        if (w == warp) continue;
+        const K* L = sorted + 32 * w;
+        int lo = 0, hi = 32;                                   // entries of L greater than key
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (L[mid] > key) lo = mid + 1; else hi = mid; }
+        r += lo;
+    }
+    if (r == rank - 1) *bcast = key;
+    __syncthreads();
+    return *bcast;
+}
+
 constexpr int KTH_BINS = 2048;
 constexpr int KTH_SMALL = 256;
 constexpr int KTH_UNROLL = 1;

@@ -112,6 +112,32 @@ class CudaShardBackend:
                                                        queries.shape[0], k, C.c_void_p(records.data_ptr()), C.byref(nfb)))
         return nfb.value
 
+    # -- batches with one GLOBAL filter threshold per query (include/svsb200.h svsb_batch_global_*) --------
+    def batch_global_probe(self, k: int) -> Tuple[bool, int, int, float]:
+        """(eligible, sample rows, local rows, max row norm) of this shard for the global-threshold batch path."""
+        el, sr, lr, nr = C.c_int32(), C.c_int64(), C.c_int64(), C.c_float()
+        self._check(self._lib.svsb_batch_global_probe(self.engine._h, k, C.byref(el), C.byref(sr), C.byref(lr), C.byref(nr)))
+        return bool(el.value), sr.value, lr.value, float(nr.value)
+
+    def new_tops(self, count: int):
+        return self.torch.zeros((count, 32), dtype=self.torch.float32, device=self.device)
+
+    def batch_sample_tops(self, queries, k: int, max_row_norm: float, tops) -> None:
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_batch_sample_tops(self.engine._h, C.c_void_p(st), C.c_void_p(queries.data_ptr()), queries.shape[0], k,
+                                                     C.c_float(max_row_norm), C.c_void_p(tops.data_ptr())))
+
+    def batch_global_records(self, queries, k: int, tops_all, world: int, sample_rank: int, records) -> None:
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_batch_global_records(self.engine._h, C.c_void_p(st), C.c_void_p(queries.data_ptr()), queries.shape[0], k,
+                                                        C.c_void_p(tops_all.data_ptr()), world, sample_rank, C.c_void_p(records.data_ptr())))
+
+    def enqueue_merge_verified(self, gathered, n_lists: int, batch: int, k: int, verify_k: int, out_scores, out_ids, out_counts) -> None:
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_enqueue_merge_batch_records(self.engine._h, C.c_void_p(st), C.c_void_p(gathered.data_ptr()),
+                                                               n_lists, batch, k, verify_k, C.c_void_p(out_scores.data_ptr()),
+                                                               C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_counts.data_ptr())))
+
     # -- peer exchange (fused selection + exchange over NVLink peer memory) -------------------------
     def exchange_handle(self, world: int, rank: int, k_max: int = 2048) -> bytes:
         """Allocate this rank's gather window; returns its CUDA IPC handle (64 bytes) for the other ranks."""
@@ -206,11 +232,15 @@ class ShardedRetriever:
         self.local_rows = 0
         self._queries = None
         self._bufs = {}
+        self._plans = {}
+        self._epoch = 0
         self.last_fallbacks = 0
+        self._last_counts = None
 
     # -- load ------------------------------------------------------------------------------------
     def load_synthetic(self, n: int, d: int, seed: int = 0, id0: int = 0, id_step: int = 1) -> None:
         self.n, self.d = n, d
+        self._epoch += 1
         self.row0, self.local_rows = partition(n, self.world, self.rank)
         self.backend.set_shard(self.row0)
         self.backend.load_synthetic(self.local_rows, d, seed, id0, id_step)
@@ -218,6 +248,7 @@ class ShardedRetriever:
     def load_global(self, rows: np.ndarray, emb_ids: np.ndarray) -> None:
         """Every rank passes the same global (n, d) matrix / ids and keeps only its slice (tests, small KBs)."""
         self.n, self.d = rows.shape
+        self._epoch += 1
         self.row0, self.local_rows = partition(self.n, self.world, self.rank)
         self.backend.set_shard(self.row0)
         sl = slice(self.row0, self.row0 + self.local_rows)
@@ -295,19 +326,63 @@ class ShardedRetriever:
         return self.backend.collect_kernel_ms() * count / timed if time_gemv else 0.0
 
     # -- batches ---------------------------------------------------------------------------------
+    def _global_plan(self, k: int):
+        """(sample_rank, max_row_norm) if EVERY rank can run the batched pipeline with one global filter threshold per
+        query (include/svsb200.h svsb_batch_global_*), else None.  Agreed once per (k, load) through one object
+        all-gather of the ranks' probes, so that all ranks take the same branch."""
+        key = (k, self._epoch)
+        if key not in self._plans:
+            plan = None
+            if self.world > 1 and hasattr(self.backend, "batch_global_probe"):
+                probes: List[Optional[tuple]] = [None] * self.world
+                self.dist.all_gather_object(probes, self.backend.batch_global_probe(k), group=self.group)
+                if all(p[0] for p in probes):
+                    f = max(min(1.0, p[1] / max(1, p[2])) for p in probes)      # largest sample fraction of any rank
+                    lam = min(k, self.n) * f
+                    rank = int(np.ceil(lam + 6.0 * np.sqrt(lam) + 4.0))         # P(the sample holds `rank` of the top k) ~ 1e-9
+                    if rank <= 32:
+                        plan = (rank, max(p[3] for p in probes))
+            self._plans[key] = plan
+        return self._plans[key]
+
     def _batch(self, dq, k: int):
         """b device queries -> (scores (b, k), ids (b, k), counts (b,)) device tensors, identical on every rank:
-        per-rank batched local top-k, ONE all-gather of b records per rank, ONE merge launch (a CTA per query)."""
+        per-rank batched candidate records, ONE all-gather of b records per rank, ONE merge launch (a CTA per query).
+        With a global plan the ranks first agree on one filter threshold per query (a b x 32-float all-gather), each
+        keeps and re-scores only what can reach the GLOBAL top k, and a query the coarse pass could not vouch for has
+        count -1 on every rank (the caller redoes it with the exact path); nothing synchronises with the host."""
         b = dq.shape[0]
         key = ("batch", k, b)
         if key not in self._bufs:
             self._bufs[key] = (self.backend.new_records(b, k), self.backend.new_records(self.world * b, k),
                                self.backend.new_outputs(b, k))
         rec, gath, (o_s, o_i, o_c) = self._bufs[key]
-        self.last_fallbacks = self.backend.batch_local(dq, k, rec)
+        plan = self._global_plan(k)
+        if plan is None:
+            self.last_fallbacks = self.backend.batch_local(dq, k, rec)
+            self.dist.all_gather_into_tensor(gath.view(-1), rec.view(-1), group=self.group)
+            self.backend.enqueue_merge(gath, self.world, b, k, o_s, o_i, o_c)
+            self._last_counts = None
+            return o_s, o_i, o_c
+        sample_rank, max_row_norm = plan
+        self.last_fallbacks = 0
+        tkey = ("tops", b)
+        if tkey not in self._bufs:
+            self._bufs[tkey] = (self.backend.new_tops(min(b, 2048)), self.backend.new_tops(self.world * min(b, 2048)))
+        tops, tops_all = self._bufs[tkey]
+        for c0 in range(0, b, 2048):
+            bc = min(2048, b - c0)
+            self.backend.batch_sample_tops(dq[c0:c0 + bc], k, max_row_norm, tops)
+            self.dist.all_gather_into_tensor(tops_all[:self.world * bc].view(-1), tops[:bc].view(-1), group=self.group)
+            self.backend.batch_global_records(dq[c0:c0 + bc], k, tops_all, self.world, sample_rank, rec[c0:c0 + bc])
         self.dist.all_gather_into_tensor(gath.view(-1), rec.view(-1), group=self.group)
-        self.backend.enqueue_merge(gath, self.world, b, k, o_s, o_i, o_c)
+        self.backend.enqueue_merge_verified(gath, self.world, b, k, min(k, self.n), o_s, o_i, o_c)
+        self._last_counts = o_c
         return o_s, o_i, o_c
+
+    def last_batch_unanswered(self) -> int:
+        """Queries of the last global-threshold batch that came out with count -1 (synchronises); 0 otherwise."""
+        return 0 if self._last_counts is None else int((self._last_counts < 0).sum().item())
 
     def run_batch(self, k: int) -> None:
         """One batch of ALL uploaded queries, device-resident end to end (bench path)."""
@@ -327,7 +402,13 @@ class ShardedRetriever:
         k = min(int(n), 2048, self.n)                               # get_top_k clips n to the row count (util.py:198-199)
         o_s, o_i, o_c = self._batch(self.backend.device_queries(Q), k)
         cnt = o_c.cpu().numpy()                                     # synchronises the stream
-        return o_s.cpu().numpy(), o_i.cpu().numpy(), cnt
+        s, i = o_s.cpu().numpy(), o_i.cpu().numpy()
+        redo = np.nonzero(cnt < 0)[0]                               # the coarse pass could not vouch for these (same on every rank)
+        self.last_fallbacks += len(redo)
+        for j in redo:
+            sj, ij = self.retrieve_arrays(Q[j], k)
+            cnt[j] = len(sj); s[j, :len(sj)] = sj; i[j, :len(ij)] = ij
+        return s, i, cnt
 
     def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
         """superheavy() for every row of query_vecs on every rank: host queries in, host lists out."""

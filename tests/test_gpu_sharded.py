@@ -102,6 +102,113 @@ def test_two_shard_engines_batched_records_equal_the_single_query_records():
             b.close()
 
 
+def _global_batch(backs, world, n, qs, k, sample_rank=None):
+    """The global-threshold batch protocol of ShardedRetriever._batch with the all-gathers done by torch.stack."""
+    import torch
+    batch = len(qs)
+    probes = [b.batch_global_probe(k) for b in backs]
+    assert all(p[0] for p in probes), probes
+    f = max(min(1.0, p[1] / p[2]) for p in probes)
+    lam = min(k, n) * f
+    rank = int(np.ceil(lam + 6.0 * np.sqrt(lam) + 4.0)) if sample_rank is None else sample_rank
+    assert rank <= 32
+    norm = max(p[3] for p in probes)
+    dq = backs[0].device_queries(qs)
+    tops = [b.new_tops(batch) for b in backs]
+    for r, b in enumerate(backs):
+        b.batch_sample_tops(dq, k, norm, tops[r])
+    tops_all = torch.stack(tops, dim=0).contiguous()
+    recs = [b.new_records(batch, k) for b in backs]
+    for r, b in enumerate(backs):
+        b.batch_global_records(dq, k, tops_all, world, rank, recs[r])
+    gathered = torch.stack(recs, dim=0).contiguous()
+    o_s, o_i, o_c = backs[0].new_outputs(batch, k)
+    backs[0].enqueue_merge_verified(gathered, world, batch, k, min(k, n), o_s, o_i, o_c)
+    torch.cuda.synchronize()
+    per_rank_counts = [rec[:, 2 * k].cpu().numpy().view(np.int32).reshape(batch, 2) for rec in recs]
+    return o_s.cpu().numpy(), o_i.cpu().numpy(), o_c.cpu().numpy(), dq, per_rank_counts
+
+
+@pytest.mark.parametrize("world,n,d,k", [(2, 24_001, 256, 50), (3, 40_000, 128, 100), (3, 30_000, 64, 7)])
+def test_global_threshold_batch_records_equal_the_single_query_records(world, n, d, k):
+    """svsb_batch_sample_tops -> (all-gather) -> svsb_batch_global_records -> (all-gather) ->
+    svsb_enqueue_merge_batch_records: ONE filter threshold per query for all ranks, every rank re-scores only what can
+    reach the global top k.  Verified answers must equal the per-query records' merge bit for bit and match the oracle."""
+    torch = pytest.importorskip("torch")
+    from svs_b200.sharded import CudaShardBackend, partition
+    batch = 300
+    m = oracle.synth_matrix_uniform(n, d, 8)
+    m[11] = m[n - 5]                                           # exact tie across shards
+    ids = np.cumsum(np.random.default_rng(3).integers(1, 4, size=n)).astype(np.int64)
+    backs = []
+    for r in range(world):
+        b = CudaShardBackend(0)
+        row0, cnt = partition(n, world, r)
+        b.set_shard(row0)
+        b.load_rows(np.ascontiguousarray(m[row0:row0 + cnt]), np.ascontiguousarray(ids[row0:row0 + cnt]))
+        backs.append(b)
+    qs = oracle.synth_queries(batch, d, 9)
+    qs[2] = m[11]
+    try:
+        s, i, c, dq, prc = _global_batch(backs, world, n, qs, k)
+        assert (c == k).all(), np.nonzero(c != k)[0][:10]       # random rows, random queries: every query verified
+        recs = [b.new_records(batch, k) for b in backs]
+        for r, b in enumerate(backs):
+            for j in range(batch):
+                b.enqueue_local(dq[j], k, recs[r][j])
+            b.join()
+        torch.cuda.synchronize()
+        o_s, o_i, o_c = backs[0].new_outputs(batch, k)
+        backs[0].enqueue_merge(torch.stack(recs, dim=0).contiguous(), world, batch, k, o_s, o_i, o_c)
+        torch.cuda.synchronize()
+        assert np.array_equal(s.view(np.uint32), o_s.cpu().numpy().view(np.uint32))
+        assert np.array_equal(i, o_i.cpu().numpy()) and np.array_equal(c, o_c.cpu().numpy())
+        for j in range(0, batch, 37):
+            got = list(zip(s[j, :c[j]].tolist(), i[j, :c[j]].tolist()))
+            oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+        assert i[2, :2].tolist() == [int(ids[11]), int(ids[n - 5])]     # tie: ascending id, across shards
+        assert (sum(p[:, 1].astype(np.int64) for p in prc) >= k).all()     # the ranks' verification counts add up to >= k
+        assert all((p[:, 0] >= 0).all() and (p[:, 0] <= k).all() for p in prc)
+    finally:
+        for b in backs:
+            b.close()
+
+
+def test_global_threshold_batch_refuses_what_it_cannot_verify():
+    """Rows stored in an order correlated with the queries (every shard's strided sample then over-represents the top) and
+    a sample_rank far too small: the thresholds come out too high, the ranks' verification counts do not add up to k,
+    and the merge reports count -1 for such queries -- on the verified ones the answer is still exact."""
+    torch = pytest.importorskip("torch")
+    from svs_b200.sharded import CudaShardBackend, partition
+    world, n, d, k, batch = 2, 20_000, 64, 100, 32
+    m = oracle.synth_matrix_uniform(n, d, 21)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    qs = oracle.synth_queries(batch, d, 22)
+    backs = []
+    for r in range(world):
+        b = CudaShardBackend(0)
+        row0, cnt = partition(n, world, r)
+        b.set_shard(row0)
+        b.load_rows(np.ascontiguousarray(m[row0:row0 + cnt]), np.ascontiguousarray(ids[row0:row0 + cnt]))
+        backs.append(b)
+    try:
+        import os
+        os.environ["SVSB_BATCH_GLOBAL_ANY_RANK"] = "1"         # let the test pass a rank below the statistical bound
+        try:
+            s, i, c, dq, prc = _global_batch(backs, world, n, qs, k, sample_rank=1)
+        finally:
+            del os.environ["SVSB_BATCH_GLOBAL_ANY_RANK"]
+        # threshold = (largest sample value of all) - 2 eps: almost never k rows above it
+        assert (c < 0).sum() >= batch // 2
+        assert set(np.unique(c)) <= {-1, k}
+        for j in np.nonzero(c == k)[0]:
+            got = list(zip(s[j, :k].tolist(), i[j, :k].tolist()))
+            oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+    finally:
+        for b in backs:
+            b.close()
+
+
 def test_merge_records_rank_merge_and_unsorted_fallback():
     """svsb_enqueue_merge_records on crafted records: lists sorted descending take the rank merge (one binary search per
     other list, no sort); a list that is NOT sorted makes the kernel fall back to the bitonic sort.  Both must return
