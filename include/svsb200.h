@@ -249,8 +249,11 @@ int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_Q, int32_t 
  *   1. svsb_batch_sample_tops      -> d_tops[b][32]: the 32 largest coarse scores of this rank's sample, descending
  *   2. the caller all-gathers them -> d_tops_all[world][b][32]
  *   3. svsb_batch_global_records   -> threshold = (sample_rank-th largest of the union) - 2 eps, filter pass, exact
- *      re-score of every candidate, records [keys | ids | count, ver] (count may be < k; count -1 = this rank could not
- *      answer the query; ver = candidates provably above the threshold's margin)
+ *      re-score of every candidate, records [keys(rec_cap) | ids(rec_cap) | count, ver], 2*rec_cap+1 words (count may be
+ *      < k; count -1 = this rank could not answer the query; ver = candidates provably above the threshold's margin).
+ *      rec_cap <= k entries are shipped per rank -- a shard holds ~k/world of the global top k, so records an eighth
+ *      the size do on 8 GPUs; a rank with more sets bit 30 of count and the merge accepts the query only if that
+ *      list's last shipped entry does not make the global top k (then nothing behind it can).
  *   4. the caller all-gathers the records; svsb_enqueue_merge_batch_records(verify_k = min(k, global rows)) merges
  *      and VERIFIES: out_count -1 (on every rank alike) = redo this query with the exact path (svsb_query_peer /
  *      svsb_enqueue_local_topk); otherwise the result equals the single-query kernels' bit for bit.
@@ -262,7 +265,7 @@ int svsb_batch_local_records(svsb_t* e, void* stream, const float* d_Q, int32_t 
 int svsb_batch_global_probe(svsb_t* e, int32_t k, int32_t* eligible, int64_t* sample_rows, int64_t* local_rows, float* max_row_norm);
 int svsb_batch_sample_tops(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, float max_row_norm, float* d_tops);
 int svsb_batch_global_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, const float* d_tops_all,
-                              int32_t world, int32_t sample_rank, int64_t* d_records);
+                              int32_t world, int32_t sample_rank, int32_t rec_cap, int64_t* d_records);
 /* ---- peer exchange: the exchange step fused into the kernels, over NVLink / NVSwitch peer memory ----------
  * Replaces "all-gather the records over NCCL, then merge" for single queries: every rank owns a GATHER WINDOW in its
  * HBM (slots x world records + one flag word per record); the selection kernel's epilogue stores its record into the
@@ -313,7 +316,8 @@ int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records
 /* The same for the records of svsb_batch_global_records: a query comes out with count -1 when any rank's record says
  * -1 or the ranks' verification counts add up to less than verify_k. */
 int svsb_enqueue_merge_batch_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
-                                     int32_t k, int32_t verify_k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts);
+                                     int32_t rec_cap, int32_t k, int32_t verify_k, float* d_out_scores, int64_t* d_out_ids,
+                                     int32_t* d_out_counts);
 /* Sum (ms) of the similarity-kernel durations bracketed by svsb_enqueue_local_topk(time_kernel=1) since the
  * last collect; waits for them to finish. */
 int svsb_kernel_time_collect(svsb_t* e, float* ms);

@@ -87,8 +87,8 @@ SIGNATURES = {
     "svsb_batch_global_probe": (C.c_int, [C.c_void_p, C.c_int32, c_i32_p, c_i64_p, c_i64_p, c_float_p]),
     "svsb_batch_sample_tops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "svsb_batch_global_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
-                                            C.c_void_p]),
-    "svsb_enqueue_merge_batch_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_void_p]),
+    "svsb_enqueue_merge_batch_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "svsb_enqueue_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "svsb_enqueue_merge_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

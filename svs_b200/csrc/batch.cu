@@ -501,7 +501,8 @@ refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t ro
         block_bitonic_desc<false>(sk, nullptr, np2);
         sorted = sk;
     }
-    const int cnt = min(kk, C);
+    const int full = min(kk, C);
+    const int cnt = (out.cap > 0 && (mode & REFINE_PARTIAL)) ? min(full, out.cap) : full;
     for (int i = tid; i < cnt; i += RS_THREADS) {
         const u64 key = sorted[i];
         const uint32_t row = key_row(key);
@@ -510,7 +511,7 @@ refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t ro
         if (out.keys) out.keys[(int64_t)q * out.stride + i] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
         out.ids[(int64_t)q * out.stride + i] = ids ? ids[row] : grow;
     }
-    if (tid == 0) { out_count[0] = cnt; if (mode & REFINE_PARTIAL) out_count[1] = sc.ver[q]; }
+    if (tid == 0) { out_count[0] = cnt | (cnt < full ? REFINE_COUNT_TRUNCATED : 0); if (mode & REFINE_PARTIAL) out_count[1] = sc.ver[q]; }
 }
 
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,

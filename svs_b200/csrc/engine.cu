@@ -1683,7 +1683,9 @@ int batch_local_records_gen(svsb_engine* e, const std::shared_ptr<Generation>& g
 static bool batch_plan_global(svsb_engine* e, const Generation* g, int32_t k, BatchPlan& P) {
     if (!batch_plan(e, g, k, P)) return false;
     // sample fraction f with kk * f ~ 3: the union's order statistic of rank ~ 3 + 6 sqrt(3) + 4 < SAMPLE_TOPX
-    int64_t want = (int64_t)std::ceil(3.0 * (double)g->n / (double)std::max(1, k));
+    // ... but no more than ONE wave of the sample pass (40 tiles x 4 query blocks of a 1024-query batch): a bigger sample
+    // costs more than the tighter threshold saves in re-scored rows (profiles/r02_c3_phases_n2.txt: 118 tiles = 73 us)
+    int64_t want = std::min<int64_t>((int64_t)std::ceil(3.0 * (double)g->n / (double)std::max(1, k)), 40 * COARSE_TILE_ROWS);
     if (const char* v = getenv("SVSB_BATCH_GLOBAL_SAMPLE_ROWS")) want = atoll(v);
     int64_t st = std::min<int64_t>(std::max<int64_t>((want + COARSE_TILE_ROWS - 1) / COARSE_TILE_ROWS, 2), P.n_tiles);
     P.s_tiles = (int)st;
@@ -1735,13 +1737,14 @@ extern "C" int svsb_batch_sample_tops(svsb_t* e, void* stream, const float* d_Q,
 }
 
 extern "C" int svsb_batch_global_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, const float* d_tops_all,
-                                         int32_t world, int32_t sample_rank, int64_t* d_records) {
+                                         int32_t world, int32_t sample_rank, int32_t rec_cap, int64_t* d_records) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     auto g = pin(e);
     if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
     if (b < 1 || b > COARSE_MAX_BATCH || !d_Q || !d_tops_all || !d_records) return fail(SVSB_E_INVALID, "svsb_batch_global_records: 1 <= b <= 2048, non-NULL buffers");
     if (world < 1 || world > XCHG_MAX_RANKS || sample_rank < 1 || sample_rank > SAMPLE_TOPX)
         return fail(SVSB_E_INVALID, "svsb_batch_global_records: 1 <= world <= 16, 1 <= sample_rank <= 32");
+    if (rec_cap < 1 || rec_cap > k) return fail(SVSB_E_INVALID, "svsb_batch_global_records: 1 <= rec_cap <= k");
     BatchPlan P;
     if (!batch_plan_global(e, g.get(), k, P)) return fail(SVSB_E_STATE, "svsb_batch_global_records: this shard / k is not eligible");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1761,8 +1764,8 @@ extern "C" int svsb_batch_global_records(svsb_t* e, void* stream, const float* d
     CU(launch_union_threshold(st, d_tops_all, world, b, sample_rank, w->eps, w->thr));
     CU(launch_coarse_gemm(st, w->dev, 0, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.n_tiles, 1,
                           w->thr, w->cand, w->cand_cnt, P.cand_cap, nullptr, 0));
-    const int64_t rec = 2 * (int64_t)k + 1;
-    RefineOut o{nullptr, reinterpret_cast<u64*>(d_records), d_records + k, rec, reinterpret_cast<int32_t*>(d_records + 2 * (int64_t)k), 2 * rec};
+    const int64_t rec = 2 * (int64_t)rec_cap + 1;
+    RefineOut o{nullptr, reinterpret_cast<u64*>(d_records), d_records + rec_cap, rec, reinterpret_cast<int32_t*>(d_records + 2 * (int64_t)rec_cap), 2 * rec, rec_cap};
     CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, d_Q, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->thr, w->flags,
                      o, w->stats, &w->rs, REFINE_PARTIAL | REFINE_DEFER));
     return SVSB_OK;
@@ -2178,34 +2181,36 @@ extern "C" int svsb_kernel_time_collect(svsb_t* e, float* ms) {
     return SVSB_OK;
 }
 
-static int enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
+static int enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch, int32_t cap,
                                  int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts, int verify_k, const char* who) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
-    if (n_lists < 1 || batch < 1 || k < 1 || k > K_FAST_MAX) return fail(SVSB_E_INVALID, std::string(who) + ": bad arguments");
+    if (n_lists < 1 || batch < 1 || k < 1 || k > K_FAST_MAX || cap < 1 || cap > k) return fail(SVSB_E_INVALID, std::string(who) + ": bad arguments");
+    if (cap < k && ((int64_t)n_lists * cap > K_FAST_MAX || n_lists > 16)) return fail(SVSB_E_INVALID, std::string(who) + ": truncated records need n_lists <= 16 and n_lists * rec_cap <= 2048");
     if (!d_records || !d_out_scores || !d_out_ids || !d_out_counts) return fail(SVSB_E_INVALID, std::string(who) + ": NULL pointer");
     CU(cudaSetDevice(e->devs[0]));
-    const int64_t rec = 2 * (int64_t)k + 1;
+    const int64_t rec = 2 * (int64_t)cap + 1;
     u64* sk = nullptr; int64_t* sp = nullptr;
-    if ((int64_t)n_lists * k > K_FAST_MAX) {
+    if ((int64_t)n_lists * cap > K_FAST_MAX) {
         if (e->shard_ws.empty() || !e->shard_ws[0]) { e->shard_ws.resize(std::max<size_t>(1, e->shard_ws.size())); e->shard_ws[0].reset(new DevWs()); e->shard_ws[0]->dev = e->devs[0]; }
         int rc = e->shard_ws[0]->ensure_merge_scratch((int64_t)batch * n_lists * k);
         if (rc != SVSB_OK) return rc;
         sk = e->shard_ws[0]->mscr_keys; sp = e->shard_ws[0]->mscr_ids;
     }
-    CU(launch_merge_ex((cudaStream_t)stream, reinterpret_cast<const u64*>(d_records), d_records + k,
-                       reinterpret_cast<const int32_t*>(d_records + 2 * (int64_t)k), n_lists, k, k, batch,
+    CU(launch_merge_ex((cudaStream_t)stream, reinterpret_cast<const u64*>(d_records), d_records + cap,
+                       reinterpret_cast<const int32_t*>(d_records + 2 * (int64_t)cap), n_lists, cap, k, batch,
                        (int64_t)batch * rec, rec, (int64_t)batch * rec * 2, rec * 2, sk, sp,
                        d_out_scores, d_out_ids, d_out_counts, verify_k));
     return SVSB_OK;
 }
 extern "C" int svsb_enqueue_merge_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
                                           int32_t k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts) {
-    return enqueue_merge_records(e, stream, d_records, n_lists, batch, k, d_out_scores, d_out_ids, d_out_counts, -1, "svsb_enqueue_merge_records");
+    return enqueue_merge_records(e, stream, d_records, n_lists, batch, k, k, d_out_scores, d_out_ids, d_out_counts, -1, "svsb_enqueue_merge_records");
 }
 extern "C" int svsb_enqueue_merge_batch_records(svsb_t* e, void* stream, const int64_t* d_records, int32_t n_lists, int32_t batch,
-                                                int32_t k, int32_t verify_k, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts) {
+                                                int32_t rec_cap, int32_t k, int32_t verify_k, float* d_out_scores, int64_t* d_out_ids,
+                                                int32_t* d_out_counts) {
     if (verify_k < 0 || verify_k > k) return fail(SVSB_E_INVALID, "svsb_enqueue_merge_batch_records: 0 <= verify_k <= k");
-    return enqueue_merge_records(e, stream, d_records, n_lists, batch, k, d_out_scores, d_out_ids, d_out_counts, verify_k, "svsb_enqueue_merge_batch_records");
+    return enqueue_merge_records(e, stream, d_records, n_lists, batch, rec_cap, k, d_out_scores, d_out_ids, d_out_counts, verify_k, "svsb_enqueue_merge_batch_records");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -184,7 +184,9 @@ cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t
 struct RefineOut {
     float* scores; u64* keys; int64_t* ids; int64_t stride;
     int32_t* counts; int64_t count_stride;
+    int cap = 0;     // > 0 (REFINE_PARTIAL records only): ship at most cap entries; bit 30 of count = there were more
 };
+constexpr int32_t REFINE_COUNT_TRUNCATED = 1 << 30;
 // Global scratch of the split refine (batch.cu): survivors' rows and exact keys, [b][REFINE_SURVIVOR_CAP] each, and per
 // query the survivor count and the verification count (REFINE_PARTIAL).
 struct RefineScratch { uint32_t* rows; u64* keys; int32_t* cnt; int32_t* ver; };

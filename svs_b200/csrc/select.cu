@@ -547,19 +547,24 @@ struct MergeLayout {
     int64_t list_stride, batch_stride, count_list_stride, count_batch_stride;
     // verify_k >= 0 (batched records of the global-threshold path, batch.cu REFINE_PARTIAL | REFINE_DEFER): a list's count
     // word is the pair [count, ver]; count < 0 on any list, or sum(ver) < verify_k, means the coarse pass could not vouch
-    // for this query: out_count = -1 and the caller redoes it with the exact kernels.
+    // for this query: out_count = -1 and the caller redoes it with the exact kernels.  Lists may be TRUNCATED (bit 30 of
+    // count: the rank had more entries than the record holds, cap < k): fine as long as the list's last shipped entry
+    // does not make the global top k -- then nothing behind it can; otherwise -1 as well.
     int verify_k;
 };
+constexpr int32_t RECORD_TRUNCATED = 1 << 30;
 
-// true: the query's records are good.  All threads call it; uses sm.bcast32[0..1].
+// true: the query's records are good.  All threads call it; uses sm.bcast32[0..2] ([2] = bit l set: list l is truncated,
+// l < 31 -- the launcher keeps n_lists <= 16 when records may be truncated).
 __device__ inline bool merge_records_verified(SelectSmem& sm, const int32_t* counts, const MergeLayout& L) {
     const int tid = threadIdx.x;
-    if (tid == 0) { sm.bcast32[0] = 0; sm.bcast32[1] = 0; }
+    if (tid == 0) { sm.bcast32[0] = 0; sm.bcast32[1] = 0; sm.bcast32[2] = 0; }
     __syncthreads();
     if (tid < L.n_lists) {
         const int32_t* c = counts + (int64_t)tid * L.count_list_stride;
         if (c[0] < 0) atomicOr(&sm.bcast32[0], 1);
         else atomicAdd(&sm.bcast32[1], max(0, c[1]));
+        if (c[0] >= 0 && (c[0] & RECORD_TRUNCATED)) atomicOr(&sm.bcast32[2], 1 << min(tid, 30));
     }
     __syncthreads();
     const bool ok = sm.bcast32[0] == 0 && sm.bcast32[1] >= L.verify_k;
@@ -572,8 +577,11 @@ __device__ inline bool merge_records_verified(SelectSmem& sm, const int32_t* cou
 // global rank of an element is its index in its own list plus, for every other list, the number of keys greater than
 // it (one binary search each).  Elements of rank < kk go straight to the output: no sort, no second buffer.
 // Returns false (nothing written) if some list is not sorted; the caller then takes the bitonic path.
+// trunc_mask / k_full / trunc_bad (optional): bit l of trunc_mask = list l was truncated by its sender; *trunc_bad is set
+// when such a list's last entry has rank < k_full, i.e. entries the sender did not ship could belong to the top k_full.
 __device__ bool rank_merge_emit(SelectSmem& sm, int n_lists, const uint32_t* cnt, const uint32_t* off, int total, int kk,
-                                float* __restrict__ out_scores, int64_t* __restrict__ out_ids)
+                                float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                                uint32_t trunc_mask = 0, int k_full = 0, int* trunc_bad = nullptr)
 {
     const int tid = threadIdx.x;
     __shared__ int unsorted;
@@ -598,6 +606,7 @@ __device__ bool rank_merge_emit(SelectSmem& sm, int n_lists, const uint32_t* cnt
             rank += lo - (int)off[m];
         }
         if (rank < kk) { out_scores[rank] = key_score(key); out_ids[rank] = sm.payload[i]; }
+        if (trunc_mask && ((trunc_mask >> l) & 1u) && i == (int)(off[l] + cnt[l]) - 1 && rank < k_full) *trunc_bad = 1;
     }
     return true;
 }
@@ -616,7 +625,14 @@ merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids
     uint32_t* cnt = sm.hist;                                  // per-list counts and offsets (list order is kept);
     uint32_t* off = sm.hist + 1024;                           // n_lists <= 1023 (launcher)
     if (L.verify_k >= 0 && !merge_records_verified(sm, counts, L)) { if (tid == 0) out_count[b] = -1; return; }
-    if (tid < L.n_lists) cnt[tid] = (uint32_t)max(0, min(counts[(int64_t)tid * L.count_list_stride], L.cap));
+    const uint32_t trunc_mask = L.verify_k >= 0 ? (uint32_t)sm.bcast32[2] : 0u;
+    __shared__ int trunc_bad;
+    if (tid == 0) trunc_bad = 0;
+    if (tid < L.n_lists) {
+        int32_t c = counts[(int64_t)tid * L.count_list_stride];
+        if (L.verify_k >= 0) c &= ~RECORD_TRUNCATED;
+        cnt[tid] = (uint32_t)max(0, min(c, L.cap));
+    }
     __syncthreads();
     if (tid == 0) { uint32_t o = 0; for (int l = 0; l < L.n_lists; ++l) { off[l] = o; o += cnt[l]; } off[L.n_lists] = o; }
     __syncthreads();
@@ -631,10 +647,12 @@ merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids
     __syncthreads();
     const int total = (int)off[L.n_lists];
     const int kk = min(L.k, total);
-    if (rank_merge_emit(sm, L.n_lists, cnt, off, total, kk, out_scores, out_ids)) {
-        if (tid == 0) out_count[b] = kk;
+    if (rank_merge_emit(sm, L.n_lists, cnt, off, total, kk, out_scores, out_ids, trunc_mask, L.k, &trunc_bad)) {
+        __syncthreads();
+        if (tid == 0) out_count[b] = trunc_bad ? -1 : kk;
         return;
     }
+    if (L.verify_k >= 0) { if (tid == 0) out_count[b] = -1; return; }     // verified records are always sorted
     int np2 = 1; while (np2 < total) np2 <<= 1;
     for (int i = total + tid; i < np2; i += blockDim.x) { sm.sortbuf[i] = 0ull; sm.payload[i] = -1; }
     __syncthreads();
@@ -657,12 +675,12 @@ merge_lists_big_kernel(const u64* __restrict__ keys, const int64_t* __restrict__
     counts += (int64_t)b * L.count_batch_stride;
     out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
     sk += (int64_t)b * span; sp += (int64_t)b * span;
-    if (L.verify_k >= 0 && !merge_records_verified(sm, counts, L)) { if (tid == 0) out_count[b] = -1; return; }
+    if (L.verify_k >= 0 && (!merge_records_verified(sm, counts, L) || sm.bcast32[2] != 0)) { if (tid == 0) out_count[b] = -1; return; }
     if (tid == 0) sm.counter = 0;
     __syncthreads();
     for (int64_t i = tid; i < span; i += blockDim.x) {
         const int l = (int)(i / L.cap), p = (int)(i - (int64_t)l * L.cap);
-        if (p < min(counts[(int64_t)l * L.count_list_stride], L.cap)) {
+        if (p < min(counts[(int64_t)l * L.count_list_stride] & (L.verify_k >= 0 ? ~RECORD_TRUNCATED : -1), L.cap)) {
             const uint32_t slot = atomicAdd(&sm.counter, 1u);
             sk[slot] = keys[(int64_t)l * L.list_stride + p];
             sp[slot] = ids[(int64_t)l * L.list_stride + p];

@@ -127,15 +127,18 @@ class CudaShardBackend:
         self._check(self._lib.svsb_batch_sample_tops(self.engine._h, C.c_void_p(st), C.c_void_p(queries.data_ptr()), queries.shape[0], k,
                                                      C.c_float(max_row_norm), C.c_void_p(tops.data_ptr())))
 
-    def batch_global_records(self, queries, k: int, tops_all, world: int, sample_rank: int, records) -> None:
+    def batch_global_records(self, queries, k: int, tops_all, world: int, sample_rank: int, rec_cap: int, records) -> None:
+        """records: (b, 2 * rec_cap + 1) int64 -- at most rec_cap entries per query are shipped."""
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.svsb_batch_global_records(self.engine._h, C.c_void_p(st), C.c_void_p(queries.data_ptr()), queries.shape[0], k,
-                                                        C.c_void_p(tops_all.data_ptr()), world, sample_rank, C.c_void_p(records.data_ptr())))
+                                                        C.c_void_p(tops_all.data_ptr()), world, sample_rank, rec_cap,
+                                                        C.c_void_p(records.data_ptr())))
 
-    def enqueue_merge_verified(self, gathered, n_lists: int, batch: int, k: int, verify_k: int, out_scores, out_ids, out_counts) -> None:
+    def enqueue_merge_verified(self, gathered, n_lists: int, batch: int, rec_cap: int, k: int, verify_k: int, out_scores, out_ids,
+                               out_counts) -> None:
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.svsb_enqueue_merge_batch_records(self.engine._h, C.c_void_p(st), C.c_void_p(gathered.data_ptr()),
-                                                               n_lists, batch, k, verify_k, C.c_void_p(out_scores.data_ptr()),
+                                                               n_lists, batch, rec_cap, k, verify_k, C.c_void_p(out_scores.data_ptr()),
                                                                C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_counts.data_ptr())))
 
     # -- peer exchange (fused selection + exchange over NVLink peer memory) -------------------------
@@ -327,7 +330,7 @@ class ShardedRetriever:
 
     # -- batches ---------------------------------------------------------------------------------
     def _global_plan(self, k: int):
-        """(sample_rank, max_row_norm) if EVERY rank can run the batched pipeline with one global filter threshold per
+        """(sample_rank, max_row_norm, entries shipped per rank) if EVERY rank can run the batched pipeline with one global filter threshold per
         query (include/svsb200.h svsb_batch_global_*), else None.  Agreed once per (k, load) through one object
         all-gather of the ranks' probes, so that all ranks take the same branch."""
         key = (k, self._epoch)
@@ -341,7 +344,13 @@ class ShardedRetriever:
                     lam = min(k, self.n) * f
                     rank = int(np.ceil(lam + 6.0 * np.sqrt(lam) + 4.0))         # P(the sample holds `rank` of the top k) ~ 1e-9
                     if rank <= 32:
-                        plan = (rank, max(p[3] for p in probes))
+                        # entries shipped per rank and query: a shard holds Binomial(k, 1/world) of the global top k; a
+                        # rank with more says so and the merge checks whether that mattered (-1 -> exact path)
+                        share = min(k, self.n) / self.world
+                        cap = min(k, int(np.ceil(share + 6.0 * np.sqrt(share) + 4.0)))
+                        if self.world * cap > 2048 or self.world > 16:
+                            cap = k
+                        plan = (rank, max(p[3] for p in probes), cap)
             self._plans[key] = plan
         return self._plans[key]
 
@@ -352,19 +361,20 @@ class ShardedRetriever:
         keeps and re-scores only what can reach the GLOBAL top k, and a query the coarse pass could not vouch for has
         count -1 on every rank (the caller redoes it with the exact path); nothing synchronises with the host."""
         b = dq.shape[0]
+        plan = self._global_plan(k)
+        cap = k if plan is None else plan[2]
         key = ("batch", k, b)
         if key not in self._bufs:
-            self._bufs[key] = (self.backend.new_records(b, k), self.backend.new_records(self.world * b, k),
+            self._bufs[key] = (self.backend.new_records(b, cap), self.backend.new_records(self.world * b, cap),
                                self.backend.new_outputs(b, k))
         rec, gath, (o_s, o_i, o_c) = self._bufs[key]
-        plan = self._global_plan(k)
         if plan is None:
             self.last_fallbacks = self.backend.batch_local(dq, k, rec)
             self.dist.all_gather_into_tensor(gath.view(-1), rec.view(-1), group=self.group)
             self.backend.enqueue_merge(gath, self.world, b, k, o_s, o_i, o_c)
             self._last_counts = None
             return o_s, o_i, o_c
-        sample_rank, max_row_norm = plan
+        sample_rank, max_row_norm, cap = plan
         self.last_fallbacks = 0
         tkey = ("tops", b)
         if tkey not in self._bufs:
@@ -374,9 +384,9 @@ class ShardedRetriever:
             bc = min(2048, b - c0)
             self.backend.batch_sample_tops(dq[c0:c0 + bc], k, max_row_norm, tops)
             self.dist.all_gather_into_tensor(tops_all[:self.world * bc].view(-1), tops[:bc].view(-1), group=self.group)
-            self.backend.batch_global_records(dq[c0:c0 + bc], k, tops_all, self.world, sample_rank, rec[c0:c0 + bc])
+            self.backend.batch_global_records(dq[c0:c0 + bc], k, tops_all, self.world, sample_rank, cap, rec[c0:c0 + bc])
         self.dist.all_gather_into_tensor(gath.view(-1), rec.view(-1), group=self.group)
-        self.backend.enqueue_merge_verified(gath, self.world, b, k, min(k, self.n), o_s, o_i, o_c)
+        self.backend.enqueue_merge_verified(gath, self.world, b, cap, k, min(k, self.n), o_s, o_i, o_c)
         self._last_counts = o_c
         return o_s, o_i, o_c
 

@@ -102,7 +102,7 @@ def test_two_shard_engines_batched_records_equal_the_single_query_records():
             b.close()
 
 
-def _global_batch(backs, world, n, qs, k, sample_rank=None):
+def _global_batch(backs, world, n, qs, k, sample_rank=None, cap=None):
     """The global-threshold batch protocol of ShardedRetriever._batch with the all-gathers done by torch.stack."""
     import torch
     batch = len(qs)
@@ -118,14 +118,15 @@ def _global_batch(backs, world, n, qs, k, sample_rank=None):
     for r, b in enumerate(backs):
         b.batch_sample_tops(dq, k, norm, tops[r])
     tops_all = torch.stack(tops, dim=0).contiguous()
-    recs = [b.new_records(batch, k) for b in backs]
+    cap = k if cap is None else cap
+    recs = [b.new_records(batch, cap) for b in backs]
     for r, b in enumerate(backs):
-        b.batch_global_records(dq, k, tops_all, world, rank, recs[r])
+        b.batch_global_records(dq, k, tops_all, world, rank, cap, recs[r])
     gathered = torch.stack(recs, dim=0).contiguous()
     o_s, o_i, o_c = backs[0].new_outputs(batch, k)
-    backs[0].enqueue_merge_verified(gathered, world, batch, k, min(k, n), o_s, o_i, o_c)
+    backs[0].enqueue_merge_verified(gathered, world, batch, cap, k, min(k, n), o_s, o_i, o_c)
     torch.cuda.synchronize()
-    per_rank_counts = [rec[:, 2 * k].cpu().numpy().view(np.int32).reshape(batch, 2) for rec in recs]
+    per_rank_counts = [rec[:, 2 * cap].cpu().numpy().view(np.int32).reshape(batch, 2) for rec in recs]
     return o_s.cpu().numpy(), o_i.cpu().numpy(), o_c.cpu().numpy(), dq, per_rank_counts
 
 
@@ -169,6 +170,28 @@ def test_global_threshold_batch_records_equal_the_single_query_records(world, n,
         assert i[2, :2].tolist() == [int(ids[11]), int(ids[n - 5])]     # tie: ascending id, across shards
         assert (sum(p[:, 1].astype(np.int64) for p in prc) >= k).all()     # the ranks' verification counts add up to >= k
         assert all((p[:, 0] >= 0).all() and (p[:, 0] <= k).all() for p in prc)
+        # truncated records: each rank ships at most `cap` entries.  A generous cap changes nothing; a cap below a
+        # shard's share of the top k must be refused (-1) for exactly the queries where it mattered, never answered wrong.
+        share = k / world
+        for cap in (min(k, int(np.ceil(share + 6.0 * np.sqrt(share) + 4.0))), max(1, int(share))):
+            if world * cap > 2048:
+                continue
+            s2, i2, c2, _, prc2 = _global_batch(backs, world, n, qs, k, cap=cap)
+            ok = c2 == k
+            assert set(np.unique(c2)) <= {-1, k}
+            assert np.array_equal(s2[ok].view(np.uint32), s[ok].view(np.uint32)) and np.array_equal(i2[ok], i[ok])
+            if cap > share + 1:
+                assert ok.mean() > 0.95, (cap, ok.mean())
+            else:
+                assert (~ok).any()                          # some shard held more than k / world of some query's top k
+            need = np.zeros(batch, dtype=bool)              # would the full answer have needed an entry a rank did not ship?
+            top_rows = [set(i[j, :k].tolist()) for j in range(batch)]
+            for r in range(world):
+                row0, cnt = partition(n, world, r)
+                mine = set(ids[row0:row0 + cnt].tolist())
+                for j in range(batch):
+                    need[j] |= len(top_rows[j] & mine) > cap
+            assert not (ok & need).any()
     finally:
         for b in backs:
             b.close()

@@ -215,6 +215,133 @@ def test_peer_exchange_protocol_on_cpu_matches_the_oracle_on_every_rank(world, n
         assert ret[r] == ret[0]
 
 
+class NumpyGlobalBatchBackend(NumpyShardBackend):
+    """CPU restatement of the global-threshold batch protocol (include/svsb200.h svsb_batch_global_*; csrc/batch.cu
+    sample_order_kernel / union_threshold_kernel / refine_* with REFINE_PARTIAL | REFINE_DEFER; csrc/select.cu
+    merge_records_verified): coarse scores = fp16 operands (scaled by 2^12) with an fp32 sum, eps as the engine bounds it,
+    a strided sample, the 32 largest sample values per query exchanged, T = order statistic of the union - 2 eps,
+    candidates = coarse >= T, all re-scored exactly, records [keys(cap) | ids(cap) | count (bit 30: truncated), ver],
+    merge: any count < 0 or sum(ver) < verify_k or a truncated list whose last entry makes the top k -> count -1.
+    Test infrastructure for ShardedRetriever._batch / _global_plan / the redo of unanswered queries."""
+    TOPX = 32
+    SAMPLE_STRIDE = 16
+    spoil_odd_queries = False                                   # push T above everything for odd queries -> count -1
+
+    def batch_global_probe(self, k):
+        n = len(self.m)
+        sample = len(range(0, n, self.SAMPLE_STRIDE))
+        norm = float(np.sqrt((self.m.astype(np.float64) ** 2).sum(axis=1)).max()) * 1.000001 if n else 1.0
+        return (n >= 64 and sample >= self.TOPX, sample, n, norm)
+
+    def new_tops(self, count):
+        return torch.zeros((count, self.TOPX), dtype=torch.float32)
+
+    def _coarse(self, Q):
+        m16 = (self.m * np.float32(4096.0)).astype(np.float16).astype(np.float32)
+        q16 = (Q * np.float32(4096.0)).astype(np.float16).astype(np.float32)
+        return (m16 @ q16.T).T * np.float32(2.0 ** -24)            # (b, n_local)
+
+    def batch_sample_tops(self, queries, k, max_row_norm, tops):
+        Q = queries.numpy()
+        d = Q.shape[1]
+        coef = 2.0 ** -10 + 2.0 ** -22 + d * (2.0 ** -22 + 2.0 ** -23)
+        self._eps = (coef * np.sqrt((Q.astype(np.float64) ** 2).sum(axis=1)) * 1.000001 * max_row_norm + 1e-8).astype(np.float32)
+        self._co = self._coarse(Q)
+        samp = self._co[:, ::self.SAMPLE_STRIDE].astype(np.float16).astype(np.float32)
+        tops.numpy()[:] = -np.sort(-samp, axis=1)[:, :self.TOPX]
+
+    def batch_global_records(self, queries, k, tops_all, world, sample_rank, rec_cap, records):
+        Q = queries.numpy()
+        b = Q.shape[0]
+        union = tops_all.numpy().reshape(world, -1, self.TOPX)[:, :b].transpose(1, 0, 2).reshape(b, -1)
+        T = -np.sort(-union, axis=1)[:, sample_rank - 1] - 2 * self._eps
+        rec = records.numpy()
+        rec[:] = 0
+        for j in range(b):
+            t = T[j] + (1e3 if (self.spoil_odd_queries and j % 2) else 0.0)
+            cand = np.nonzero(self._co[j] >= t)[0]
+            ver = int((self._co[j][cand] >= np.float32(t) + 2 * self._eps[j]).sum())
+            exact = oracle.scores_of(self.m, Q[j])[cand]         # the per-query stand-in's bits (same BLAS call)
+            keys = np_keys(exact, cand + self.row0)
+            order = np.argsort(keys)[::-1][:k]
+            ship = order[:rec_cap]
+            rec[j, :len(ship)] = keys[ship].view(np.int64)
+            rec[j, rec_cap:rec_cap + len(ship)] = self.ids[cand[ship]]
+            cnt = len(ship) | ((1 << 30) if len(order) > len(ship) else 0)
+            rec[j, 2 * rec_cap] = np.int64(cnt) | (np.int64(ver) << 32)
+
+    def enqueue_merge_verified(self, gathered, n_lists, batch, rec_cap, k, verify_k, out_scores, out_ids, out_counts):
+        g = gathered.numpy().reshape(n_lists, batch, 2 * rec_cap + 1)
+        for b in range(batch):
+            keys, ids, last_of_truncated, ver, bad = [], [], [], 0, False
+            for l in range(n_lists):
+                word = int(g[l, b, 2 * rec_cap])
+                c32 = np.int32(np.uint32(word & 0xFFFFFFFF))
+                if c32 < 0:
+                    bad = True
+                    continue
+                c = int(c32) & ~(1 << 30)
+                ver += word >> 32
+                kl = g[l, b, :c].view(np.uint64)
+                keys.append(kl); ids.append(g[l, b, rec_cap:rec_cap + c])
+                if int(c32) & (1 << 30):
+                    last_of_truncated.append(kl[c - 1])
+            keys = np.concatenate(keys) if keys else np.zeros(0, np.uint64)
+            ids = np.concatenate(ids) if ids else np.zeros(0, np.int64)
+            order = np.argsort(keys)[::-1]
+            for last in last_of_truncated:                         # rank of a truncated list's last entry must be >= k
+                bad = bad or int((keys > last).sum()) < k
+            if bad or ver < verify_k:
+                out_counts.numpy()[b] = -1
+                continue
+            order = order[:k]
+            out_scores.numpy()[b, :len(order)] = key_score(keys[order])
+            out_ids.numpy()[b, :len(order)] = ids[order]
+            out_counts.numpy()[b] = len(order)
+
+
+def _global_batch_worker(rank, world, port, n, d, k, spoil, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = oracle.synth_matrix_normal(n, d, 31)
+        m[9] = m[n - 4]                                           # an exact tie across shards
+        ids = np.cumsum(np.random.default_rng(5).integers(1, 4, size=n)).astype(np.int64)
+        be = NumpyGlobalBatchBackend()
+        be.spoil_odd_queries = spoil
+        sr = ShardedRetriever(rank, world, backend=be)
+        sr.load_global(m, ids)
+        plan = sr._global_plan(k)
+        assert plan is not None and 1 <= plan[0] <= 32 and 1 <= plan[2] <= k, plan
+        qs = oracle.synth_queries(21, d, 32, "normal")
+        qs[3] = m[9]
+        many = sr.retrieve_many(qs, k)
+        for j in range(len(qs)):
+            oracle.compare_retrieval(many[j], oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+            assert many[j] == sr.retrieve(qs[j], k)               # the per-query path: same bits
+        assert [i for _, i in many[3][:2]] == [int(ids[9]), int(ids[n - 4])]
+        # odd queries were refused by the merge (count -1 on every rank) and redone by the exact path
+        assert sr.last_fallbacks == (len(qs) // 2 if spoil else 0), sr.last_fallbacks
+        ret[rank] = (plan, many)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,k,spoil", [(2, 3001, 10, False), (3, 4000, 25, False), (2, 2500, 10, True)])
+def test_global_threshold_batches_on_cpu_match_the_oracle_on_every_rank(world, n, k, spoil):
+    """retrieve_many through the global-threshold protocol across PROCESSES: the probes' object all-gather picks one
+    order statistic and one record capacity for all ranks, two tensor all-gathers per batch (sample maxima, records),
+    the verifying merge, and the redo of refused queries through the per-query path."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_global_batch_worker, args=(world, _free_port(), n, 24, k, spoil, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(1, world):
+        assert ret[r] == ret[0]
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
