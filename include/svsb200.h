@@ -266,6 +266,24 @@ int svsb_batch_global_probe(svsb_t* e, int32_t k, int32_t* eligible, int64_t* sa
 int svsb_batch_sample_tops(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, float max_row_norm, float* d_tops);
 int svsb_batch_global_records(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, const float* d_tops_all,
                               int32_t world, int32_t sample_rank, int32_t rec_cap, int64_t* d_records);
+/* The same batch protocol with BOTH exchanges fused into the kernels over NVLink / NVSwitch peer memory: no collective
+ * call.  Every rank owns a BATCH WINDOW (svsb_bxchg_create; 64-byte CUDA IPC handle, exchanged once and opened with
+ * svsb_bxchg_connect; svsb_bxchg_connect_local for several shard engines inside one process); the kernel that extracts a
+ * rank's sample maxima stores them into every rank's window, the kernel that sorts a rank's exact candidates does the
+ * same with its records; each ends with a system-scope release of the batch's sequence number, and the consumers (union
+ * threshold, verifying merge) run behind a one-CTA kernel that acquires the flags of its own window.
+ * svsb_batch_peer enqueues one whole batch (b <= 2048) on `stream`: device queries in, device (b, k) results out,
+ * out_counts[q] = k', -1 (redo this query with the exact path, as svsb_enqueue_merge_batch_records) or -2 (a peer's part
+ * did not arrive within SVSB_XCHG_TIMEOUT_MS).  Every rank calls it with the same arguments in the same order.
+ * rec_cap (<= the window's) / sample_rank / max_row_norm as in svsb_batch_global_records.  svsb_batch_peer_prepare sizes
+ * the workspace up front (needed only when several shard engines share one process). */
+int svsb_bxchg_create(svsb_t* e, int32_t world, int32_t rank, int32_t rec_cap, void* handle_out);
+int svsb_bxchg_connect(svsb_t* e, const void* handles);
+int svsb_bxchg_connect_local(svsb_t* e, svsb_t* const* engines);
+int svsb_bxchg_disconnect(svsb_t* e);
+int svsb_batch_peer_prepare(svsb_t* e, int32_t b, int32_t k);
+int svsb_batch_peer(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, float max_row_norm, int32_t sample_rank,
+                    int32_t rec_cap, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts);
 /* ---- peer exchange: the exchange step fused into the kernels, over NVLink / NVSwitch peer memory ----------
  * Replaces "all-gather the records over NCCL, then merge" for single queries: every rank owns a GATHER WINDOW in its
  * HBM (slots x world records + one flag word per record); the selection kernel's epilogue stores its record into the

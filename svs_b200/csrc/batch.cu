@@ -61,13 +61,30 @@ __device__ __forceinline__ float ordered16_to_f32(uint32_t o) {
     return __half2float(__ushort_as_half((unsigned short)h));
 }
 
+// Publication of a multi-CTA kernel's peer stores (BatchPush): every CTA, after its own stores: barrier, system-scope
+// fence (cumulative over the barrier), device-scope ticket; the CTA that draws the last ticket resets the counter, fences
+// again and release-stores the sequence number into every rank's flag.  All threads of the CTA call it.
+__device__ __forceinline__ void batch_publish(const BatchPush& push) {
+    if (push.world == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int total = gridDim.x * gridDim.y;
+        if (atomicAdd(push.done, 1u) == total - 1u) {
+            *push.done = 0u;
+            __threadfence_system();
+            for (int p = 0; p < push.world; ++p) st_release_sys(push.flag[p], push.seq);
+        }
+    }
+}
+
 // TOP == false: thr[q] = (rank-th largest of the sample) - 2 eps[q].
 // TOP == true : top[q][0..SAMPLE_TOPX) = the SAMPLE_TOPX largest sample values, descending (the sharded path exchanges
 //               them and takes the order statistic of the UNION of all ranks' samples, union_threshold_kernel).
 template <bool TOP>
 __global__ void __launch_bounds__(ST_THREADS)
 sample_order_kernel(const __half* __restrict__ sample, int64_t sample_rows, int rank, const float* __restrict__ eps,
-                    float* __restrict__ thr, float* __restrict__ top)
+                    float* __restrict__ thr, float* __restrict__ top, const __grid_constant__ BatchPush push)
 {
     __shared__ uint32_t mx[ST_THREADS];
     __shared__ uint32_t list[ST_LIST];
@@ -103,7 +120,11 @@ sample_order_kernel(const __half* __restrict__ sample, int64_t sample_rows, int 
     const int c = (int)s_count;
     if (c > ST_LIST) {                                            // a thousand ties at the top of the sample: generic select
         if (TOP) {                                                // +inf thresholds keep nothing: the query goes to the exact path
-            if (tid < SAMPLE_TOPX) top[(size_t)q * SAMPLE_TOPX + tid] = __int_as_float(0x7f800000);
+            if (tid < SAMPLE_TOPX) {
+                if (push.world == 0) top[(size_t)q * SAMPLE_TOPX + tid] = __int_as_float(0x7f800000);
+                for (int p = 0; p < push.world; ++p) static_cast<float*>(push.dst[p])[(size_t)q * SAMPLE_TOPX + tid] = __int_as_float(0x7f800000);
+            }
+            batch_publish(push);
             return;
         }
         const uint32_t o = block_kth_largest_o32([&](int64_t i) { return f32_to_ordered(__half2float(s[i])); }, sample_rows, rank,
@@ -116,14 +137,18 @@ sample_order_kernel(const __half* __restrict__ sample, int64_t sample_rows, int 
         if (TOP) {
             int rk = 0;
             for (int j = 0; j < c; ++j) { const uint32_t o = list[j]; rk += (o > mine || (o == mine && j < i)) ? 1 : 0; }
-            if (rk < SAMPLE_TOPX) top[(size_t)q * SAMPLE_TOPX + rk] = ordered16_to_f32(mine);
+            if (rk < SAMPLE_TOPX) {
+                const float v = ordered16_to_f32(mine);
+                if (push.world == 0) top[(size_t)q * SAMPLE_TOPX + rk] = v;
+                for (int p = 0; p < push.world; ++p) static_cast<float*>(push.dst[p])[(size_t)q * SAMPLE_TOPX + rk] = v;
+            }
         } else {
             uint32_t gt = 0, ge = 0;
             for (int j = 0; j < c; ++j) { const uint32_t o = list[j]; gt += o > mine ? 1u : 0u; ge += o >= mine ? 1u : 0u; }
             if (gt < (uint32_t)rank && ge >= (uint32_t)rank) s_ans = mine;     // equal values write the same word
         }
     }
-    if (TOP) return;
+    if (TOP) { batch_publish(push); return; }
     __syncthreads();
     if (tid == 0) thr[q] = ordered16_to_f32(s_ans) - 2.0f * eps[q];
 }
@@ -140,18 +165,20 @@ cudaError_t launch_sample_threshold(cudaStream_t st, const void* sample, int64_t
     if (b <= 0) return cudaSuccess;
     if (rank < 1 || rank > sample_rows) return cudaErrorInvalidValue;
     if (sample_fast_ok(sample_rows, rank))
-        sample_order_kernel<false><<<b, ST_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, rank, eps, thr, nullptr);
+        sample_order_kernel<false><<<b, ST_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, rank, eps, thr, nullptr, BatchPush());
     else
         sample_threshold_kernel<<<b, RF_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, rank, eps, thr);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_sample_top(cudaStream_t st, const void* sample, int64_t sample_rows, int b, float* top)
+cudaError_t launch_sample_top(cudaStream_t st, const void* sample, int64_t sample_rows, int b, float* top, const BatchPush* push)
 {
     if (b <= 0) return cudaSuccess;
     if (!sample_fast_ok(sample_rows, SAMPLE_TOPX)) return cudaErrorInvalidValue;
-    sample_order_kernel<true><<<b, ST_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, SAMPLE_TOPX, nullptr, nullptr, top);
+    if (push ? (push->world < 1 || push->world > XCHG_MAX_RANKS || !push->done) : !top) return cudaErrorInvalidValue;
+    sample_order_kernel<true><<<b, ST_THREADS, 0, st>>>(reinterpret_cast<const __half*>(sample), sample_rows, SAMPLE_TOPX, nullptr, nullptr, top,
+                                                        push ? *push : BatchPush());
     count_launch();
     return cudaGetLastError();
 }
@@ -159,33 +186,50 @@ cudaError_t launch_sample_top(cudaStream_t st, const void* sample, int64_t sampl
 // thr[q] = (rank-th largest of the union of the ranks' top lists tops[r][q][0..SAMPLE_TOPX)) - 2 eps[q]; rank <=
 // SAMPLE_TOPX, so the union's rank-th largest is the rank-th largest of ALL ranks' sample values.  One warp per query.
 __global__ void __launch_bounds__(256)
-union_threshold_kernel(const float* __restrict__ tops, int world, int b, int rank, const float* __restrict__ eps, float* __restrict__ thr)
+union_threshold_kernel(const float* __restrict__ tops, int64_t list_stride, int world, int b, int rank, const float* __restrict__ eps,
+                       float* __restrict__ thr)
 {
+    // Every rank's list arrives sorted descending, so an entry's rank in the union is its position in its own list plus,
+    // per other list, the number of entries ahead of it (binary search) -- ties broken by (list, position), which makes
+    // the ranks a permutation of 0 .. n-1; the entry of rank `rank - 1` carries the rank-th largest value.
     __shared__ uint32_t vals[8][XCHG_MAX_RANKS * SAMPLE_TOPX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * 8 + warp;
     if (q >= b) return;
     const int n = world * SAMPLE_TOPX;
-    for (int i = lane; i < n; i += 32)
-        vals[warp][i] = f32_to_ordered(tops[((size_t)(i / SAMPLE_TOPX) * b + q) * SAMPLE_TOPX + (i % SAMPLE_TOPX)]);
+    uint32_t* v = vals[warp];
+    for (int l = 0; l < world; ++l)                              // lane = position in list l (SAMPLE_TOPX == 32)
+        v[l * SAMPLE_TOPX + lane] = f32_to_ordered(tops[(size_t)l * list_stride + (size_t)q * SAMPLE_TOPX + lane]);
     __syncwarp();
     uint32_t ans = 0; bool have = false;
-    for (int i = lane; i < n; i += 32) {
-        const uint32_t mine = vals[warp][i];
-        uint32_t gt = 0, ge = 0;
-        for (int j = 0; j < n; ++j) { const uint32_t o = vals[warp][j]; gt += o > mine ? 1u : 0u; ge += o >= mine ? 1u : 0u; }
-        if (gt < (uint32_t)rank && ge >= (uint32_t)rank) { ans = mine; have = true; }
+    for (int l = 0; l < world; ++l) {
+        const uint32_t mine = v[l * SAMPLE_TOPX + lane];
+        int r = lane;
+        for (int m = 0; m < world; ++m) {
+            if (m == l) continue;
+            const uint32_t* L = v + m * SAMPLE_TOPX;
+            int lo = 0, hi = SAMPLE_TOPX;                        // entries of list m ahead of mine: greater, or equal and m < l
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t o = L[mid];
+                if (o > mine || (o == mine && m < l)) lo = mid + 1; else hi = mid;
+            }
+            r += lo;
+        }
+        if (r == rank - 1) { ans = mine; have = true; }
     }
     const uint32_t who = __ballot_sync(0xffffffffu, have);
     ans = __shfl_sync(0xffffffffu, ans, who ? __ffs(who) - 1 : 0);
     if (lane == 0) thr[q] = ordered_to_f32(ans) - 2.0f * eps[q];
+    (void)n;
 }
 
-cudaError_t launch_union_threshold(cudaStream_t st, const float* tops, int world, int b, int rank, const float* eps, float* thr)
+cudaError_t launch_union_threshold(cudaStream_t st, const float* tops, int64_t list_stride, int world, int b, int rank, const float* eps,
+                                   float* thr)
 {
     if (b <= 0) return cudaSuccess;
-    if (world < 1 || world > XCHG_MAX_RANKS || rank < 1 || rank > SAMPLE_TOPX) return cudaErrorInvalidValue;
-    union_threshold_kernel<<<(b + 7) / 8, 256, 0, st>>>(tops, world, b, rank, eps, thr);
+    if (world < 1 || world > XCHG_MAX_RANKS || rank < 1 || rank > SAMPLE_TOPX || list_stride < (int64_t)b * SAMPLE_TOPX) return cudaErrorInvalidValue;
+    union_threshold_kernel<<<(b + 7) / 8, 256, 0, st>>>(tops, list_stride, world, b, rank, eps, thr);
     count_launch();
     return cudaGetLastError();
 }
@@ -330,6 +374,7 @@ refine_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __r
 //   instead of waiting for the host to read the flags; the merge propagates it and the caller redoes such queries.
 // ---------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
+constexpr int RS_CACHE = 2560;                  // candidates whose coarse scores stay in shared memory (more: re-read through L2)
 constexpr int RS_LIST = 1024;                   // candidates at or above tau0 the fast select ranks in shared memory (<= RF_BINS)
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -337,7 +382,7 @@ refine_select_kernel(int64_t n, int k, const u64* __restrict__ cand, const int32
                      const float* __restrict__ eps, const float* __restrict__ thr, int32_t* __restrict__ flags, int mode,
                      RefineScratch sc, int32_t* __restrict__ stats)
 {
-    __shared__ uint32_t cached[RF_CACHE];
+    __shared__ uint32_t cached[RS_CACHE];
     __shared__ uint32_t hist[RF_BINS];
     __shared__ uint32_t scratch[72];
     __shared__ uint32_t small[RF_SMALL];
@@ -347,16 +392,20 @@ refine_select_kernel(int64_t n, int k, const u64* __restrict__ cand, const int32
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int kk = (int)min((int64_t)k, n);
     const bool partial = (mode & REFINE_PARTIAL) != 0;
-    if (tid == 0) { sc.cnt[q] = 0; sc.ver[q] = 0; if (stats) stats[q] = 0; counter = 0; vcount = 0; }
-    if (flags[q] != 0) return;                                       // already routed to the exact path
+    // independent loads first: one round trip instead of a chain of them
+    const int flag_in = flags[q];
     const int total = cand_cnt[q];
+    const float eps_q = eps[q];
+    const float thr_q = thr ? thr[q] : 0.f;
+    if (tid == 0) { sc.cnt[q] = 0; sc.ver[q] = 0; if (stats) stats[q] = 0; counter = 0; vcount = 0; }
+    if (flag_in != 0) return;                                        // already routed to the exact path
     if (total > cand_cap || (!partial && total < kk)) {
         if (tid == 0) flags[q] = total > cand_cap ? 2 : 4;
         return;
     }
     const u64* cq = cand + (size_t)q * cand_cap;
     {
-        const int lim = min(total, RF_CACHE);
+        const int lim = min(total, RS_CACHE);
         for (int i0 = tid; i0 < lim; i0 += RS_THREADS * 4) {
             u64 kv[4];
 #pragma unroll
@@ -366,7 +415,7 @@ refine_select_kernel(int64_t n, int k, const u64* __restrict__ cand, const int32
         }
     }
     __syncthreads();
-    auto score_o = [&](int64_t i) { return i < RF_CACHE ? cached[i] : (uint32_t)(cq[i] >> 32); };
+    auto score_o = [&](int64_t i) { return i < RS_CACHE ? cached[i] : (uint32_t)(cq[i] >> 32); };
     float cutoff = __int_as_float(0xff800000);                       // -inf: keep every candidate (partial, total < kk)
     if (total >= kk) {
         uint32_t tau_o = 0;
@@ -398,12 +447,12 @@ refine_select_kernel(int64_t n, int k, const u64* __restrict__ cand, const int32
             __syncthreads();
         }
         if (!have) tau_o = block_kth_largest_o32(score_o, total, kk, hist, scratch, small);
-        cutoff = ordered_to_f32(tau_o) - 2.0f * eps[q];
+        cutoff = ordered_to_f32(tau_o) - 2.0f * eps_q;
         // The list holds exactly the rows with coarse >= thr[q] and at least kk of them, so tau_o IS the kk-th largest
         // coarse score of all (local) rows; rows with coarse in [cutoff, thr[q]) would be missing from the list.
-        if (!partial && thr && !(cutoff >= thr[q])) { if (tid == 0) flags[q] = REFINE_FLAG_THRESHOLD_HIGH; return; }
+        if (!partial && thr && !(cutoff >= thr_q)) { if (tid == 0) flags[q] = REFINE_FLAG_THRESHOLD_HIGH; return; }
     }
-    const float vthr = partial ? __fadd_ru(thr[q], __fmul_ru(2.0f, eps[q])) : 0.f;
+    const float vthr = partial ? __fadd_ru(thr_q, __fmul_ru(2.0f, eps_q)) : 0.f;
     uint32_t* rows = sc.rows + (size_t)q * REFINE_SURVIVOR_CAP;
     for (int i0 = 0; i0 < total; i0 += RS_THREADS) {
         const int i = i0 + tid;
@@ -475,15 +524,23 @@ rescore_kernel(const float* __restrict__ M, int d4, const float* __restrict__ Q,
 
 __global__ void __launch_bounds__(RS_THREADS)
 refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t row0, const int32_t* __restrict__ flags, int mode,
-                   RefineScratch sc, RefineOut out)
+                   RefineScratch sc, RefineOut out, const __grid_constant__ BatchPush push)
 {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
     u64* sk = reinterpret_cast<u64*>(rs_smem_raw);                   // np2 (<= REFINE_SURVIVOR_CAP) keys, or 2 x 256 for the rank sort
     const int q = blockIdx.x, tid = threadIdx.x;
     const int kk = (int)min((int64_t)k, n);
-    int32_t* out_count = out.counts + (int64_t)q * out.count_stride;
+    int32_t* out_count = push.world ? nullptr : out.counts + (int64_t)q * out.count_stride;
     if (flags[q] != 0) {
-        if (tid == 0) { out_count[0] = (mode & REFINE_DEFER) ? -1 : 0; if (mode & REFINE_PARTIAL) out_count[1] = 0; }
+        if (tid == 0) {
+            const int32_t c0 = (mode & REFINE_DEFER) ? -1 : 0;
+            if (out_count) { out_count[0] = c0; if (mode & REFINE_PARTIAL) out_count[1] = 0; }
+            for (int p = 0; p < push.world; ++p) {
+                int32_t* cw = reinterpret_cast<int32_t*>(static_cast<u64*>(push.dst[p]) + (int64_t)q * out.stride + 2 * out.cap);
+                cw[0] = c0; cw[1] = 0;
+            }
+        }
+        batch_publish(push);
         return;
     }
     const int C = sc.cnt[q];
@@ -507,25 +564,71 @@ refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t ro
         const u64 key = sorted[i];
         const uint32_t row = key_row(key);
         const int64_t grow = row0 + (int64_t)row;                    // global row (row0 = first row of this shard)
-        if (out.scores) out.scores[(int64_t)q * out.stride + i] = key_score(key);
-        if (out.keys) out.keys[(int64_t)q * out.stride + i] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
-        out.ids[(int64_t)q * out.stride + i] = ids ? ids[row] : grow;
+        const u64 gkey = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
+        const int64_t id = ids ? ids[row] : grow;
+        if (push.world == 0) {
+            if (out.scores) out.scores[(int64_t)q * out.stride + i] = key_score(key);
+            if (out.keys) out.keys[(int64_t)q * out.stride + i] = gkey;
+            out.ids[(int64_t)q * out.stride + i] = id;
+        }
+        for (int p = 0; p < push.world; ++p) {                       // the record, straight into every rank's window
+            u64* r = static_cast<u64*>(push.dst[p]) + (int64_t)q * out.stride;
+            r[i] = gkey; r[out.cap + i] = (u64)id;
+        }
     }
-    if (tid == 0) { out_count[0] = cnt | (cnt < full ? REFINE_COUNT_TRUNCATED : 0); if (mode & REFINE_PARTIAL) out_count[1] = sc.ver[q]; }
+    if (tid == 0) {
+        const int32_t c0 = cnt | (cnt < full ? REFINE_COUNT_TRUNCATED : 0), c1 = sc.ver[q];
+        if (out_count) { out_count[0] = c0; if (mode & REFINE_PARTIAL) out_count[1] = c1; }
+        for (int p = 0; p < push.world; ++p) {
+            int32_t* cw = reinterpret_cast<int32_t*>(static_cast<u64*>(push.dst[p]) + (int64_t)q * out.stride + 2 * out.cap);
+            cw[0] = c0; cw[1] = c1;
+        }
+    }
+    batch_publish(push);
+}
+
+__global__ void __launch_bounds__(32)
+wait_flags_kernel(const u64* flags, int world, u64 seq, u64 timeout_ns, int* status)
+{
+    const int tid = threadIdx.x;
+    if (tid < world) {
+        unsigned ns = 32;
+        u64 t0 = 0;
+        while (ld_acquire_sys(flags + tid) < seq) {
+            __nanosleep(ns);
+            if (ns < 1024) ns <<= 1;
+            else {
+                u64 now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > timeout_ns) { atomicOr(status, 1); break; }
+            }
+        }
+    }
+}
+
+cudaError_t launch_wait_flags(cudaStream_t st, const u64* flags, int world, unsigned long long seq, unsigned long long timeout_ns, int* status)
+{
+    if (!flags || !status || world < 1 || world > 32) return cudaErrorInvalidValue;
+    wait_flags_kernel<<<1, 32, 0, st>>>(flags, world, seq, timeout_ns, status);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
                           const float* eps, const float* thr, int32_t* flags, RefineOut out, int32_t* stats,
-                          const RefineScratch* scratch, int mode)
+                          const RefineScratch* scratch, int mode, const BatchPush* push)
 {
     if (b <= 0) return cudaSuccess;
-    if (!out.ids || !out.counts) return cudaErrorInvalidValue;
+    if (push) {
+        if (push->world < 1 || push->world > XCHG_MAX_RANKS || !push->done || out.cap < 1 || out.stride < 2 * (int64_t)out.cap + 1 ||
+            !(mode & REFINE_PARTIAL)) return cudaErrorInvalidValue;
+    } else if (!out.ids || !out.counts) return cudaErrorInvalidValue;
     if (k < 1 || (ld & 3) || ldq < ld) return cudaErrorInvalidValue;
     const int64_t kk = k < n ? k : n;
     if (kk > REFINE_SURVIVOR_CAP) return cudaErrorInvalidValue;
     static const bool fused_env = [] { const char* v = getenv("SVSB_REFINE_FUSED"); return v && atoi(v) != 0; }();
-    const bool fused = (fused_env || !scratch || !scratch->rows) && mode == 0;
+    const bool fused = (fused_env || !scratch || !scratch->rows) && mode == 0 && !push;
     if (!fused && (!scratch || !scratch->rows || !scratch->keys || !scratch->cnt || !scratch->ver)) return cudaErrorInvalidValue;
     if ((mode & REFINE_PARTIAL) && !thr) return cudaErrorInvalidValue;
     static bool attr_set[64] = {false};
@@ -547,9 +650,23 @@ cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, co
     refine_select_kernel<<<b, RS_THREADS, 0, st>>>(n, k, cand, cand_cnt, cand_cap, eps, thr, flags, mode, *scratch, stats);
     static const int split = [] { const char* v = getenv("SVSB_RESCORE_SPLIT"); const int x = v ? atoi(v) : 0; return x >= 1 && x <= 64 ? x : 4; }();
     rescore_kernel<<<dim3(b, split), RS_THREADS, (size_t)ld * 4, st>>>(M, ld / 4, Q, ldq, *scratch);
-    refine_sort_kernel<<<b, RS_THREADS, (size_t)REFINE_SURVIVOR_CAP * 8, st>>>(n, k, ids, row0, flags, mode, *scratch, out);
+    refine_sort_kernel<<<b, RS_THREADS, (size_t)REFINE_SURVIVOR_CAP * 8, st>>>(n, k, ids, row0, flags, mode, *scratch, out,
+                                                                               push ? *push : BatchPush());
     count_launch(3);
     return cudaGetLastError();
+}
+
+cudaError_t preload_batch_kernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, sample_order_kernel<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, sample_order_kernel<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, union_threshold_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, refine_select_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, rescore_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, refine_sort_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, wait_flags_kernel);
+    return e;
 }
 
 }  // namespace svsb

@@ -599,4 +599,16 @@ cudaError_t launch_coarse_gemm(cudaStream_t st, int device, int mode, const void
     return cudaGetLastError();
 }
 
+// Load the coarse kernels onto the current device now (see preload_peer_kernels).
+cudaError_t preload_coarse_kernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, coarse_gemm_kernel<0, 1>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, coarse_gemm_kernel<1, 1>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, coarse_gemm_kernel<0, 2>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, coarse_gemm_kernel<1, 2>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, queries_to_f16_kernel);
+    return e;
+}
+
 }  // namespace svsb

@@ -95,6 +95,15 @@ __device__ __forceinline__ u64 warp_min_u64(u64 v) {
     for (int o = 16; o > 0; o >>= 1) { u64 t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
     return v;
 }
+// system-scope publication of data other GPUs read over NVLink peer memory (and its acquire side)
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fma4(float4& acc, const float4& a, const float4& b) {
     acc.x = fmaf(a.x, b.x, acc.x); acc.y = fmaf(a.y, b.y, acc.y);
     acc.z = fmaf(a.z, b.z, acc.z); acc.w = fmaf(a.w, b.w, acc.w);

@@ -157,6 +157,7 @@ static void free_slabs(svsb_engine* e) {
     e->slabs.clear(); e->slab_bytes_rows = 0; e->slab_ids_cap = 0;
 }
 
+static void bxchg_release(svsb_engine* e);
 static void xchg_release(svsb_engine* e) {
     Xchg* x = e->xchg.get();
     if (!x) return;
@@ -196,6 +197,7 @@ extern "C" void svsb_destroy(svsb_t* e) {
     if (e->mq_ws) e->mq_ws->release();
     for (auto& w : e->shard_ws) if (w) w->release();
     xchg_release(e);
+    bxchg_release(e);
     if (e->side_st) { cudaSetDevice(e->devs[0]); cudaStreamDestroy(e->side_st); }
     if (e->submit_st) { cudaSetDevice(e->devs[0]); cudaStreamDestroy(e->submit_st); }
     for (auto ev : e->kev) cudaEventDestroy(ev);
@@ -1761,13 +1763,216 @@ extern "C" int svsb_batch_global_records(svsb_t* e, void* stream, const float* d
     const Shard& s = g->shards[0];
     CU(cudaSetDevice(w->dev));
     const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
-    CU(launch_union_threshold(st, d_tops_all, world, b, sample_rank, w->eps, w->thr));
+    CU(launch_union_threshold(st, d_tops_all, (int64_t)b * SAMPLE_TOPX, world, b, sample_rank, w->eps, w->thr));
     CU(launch_coarse_gemm(st, w->dev, 0, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.n_tiles, 1,
                           w->thr, w->cand, w->cand_cnt, P.cand_cap, nullptr, 0));
     const int64_t rec = 2 * (int64_t)rec_cap + 1;
     RefineOut o{nullptr, reinterpret_cast<u64*>(d_records), d_records + rec_cap, rec, reinterpret_cast<int32_t*>(d_records + 2 * (int64_t)rec_cap), 2 * rec, rec_cap};
     CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, d_Q, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->thr, w->flags,
                      o, w->stats, &w->rs, REFINE_PARTIAL | REFINE_DEFER));
+    return SVSB_OK;
+}
+
+// ---- the same batch protocol with BOTH exchanges fused into the kernels over NVLink peer memory (no collective) -------
+// svsb_batch_peer = svsb_batch_sample_tops + all-gather + svsb_batch_global_records + all-gather + verifying merge, except
+// that the two all-gathers do not exist: the order-statistic kernel stores this rank's sample maxima straight into every
+// rank's batch window and the sort kernel of the refine does the same with the candidate records (BatchPush: peer
+// stores, a last-block ticket, a system-scope release of the batch's sequence number); the consumers -- the union
+// threshold kernel, the merge -- run behind a one-CTA kernel that acquires the `world` flags of its OWN window.  At 8
+// GPUs the two NCCL all-gathers were 75-85 us of a 380 us batch (profiles/r02_c3_phases_n8.txt).
+// Slot reuse: everything of a batch is on one stream per rank, so a rank can only push batch j+1's maxima after its own
+// merge of batch j has seen every peer's records of batch j, which those peers pushed after reading all maxima of
+// batch j: two slots are one more than the protocol needs.
+static void bxchg_release(svsb_engine* e) {
+    BXchg* x = e->bxchg.get();
+    if (!x) return;
+    cudaSetDevice(e->devs[0]);
+    cudaDeviceSynchronize();
+    for (void* p : x->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (x->block) cudaFree(x->block);
+    if (x->done) cudaFree(x->done);
+    if (x->status) cudaFree(x->status);
+    (void)cudaGetLastError();
+    e->bxchg.reset();
+}
+
+extern "C" int svsb_bxchg_create(svsb_t* e, int32_t world, int32_t rank, int32_t rec_cap, void* handle_out) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    if (e->devs.size() != 1) return fail(SVSB_E_INVALID, "svsb_bxchg_create: a sharded engine owns exactly one device");
+    if (world < 1 || world > XCHG_MAX_RANKS || rank < 0 || rank >= world) return fail(SVSB_E_INVALID, "svsb_bxchg_create: bad world / rank (<= 16 ranks)");
+    if (rec_cap < 1 || rec_cap > 1024) return fail(SVSB_E_INVALID, "svsb_bxchg_create: 1 <= rec_cap <= 1024");
+    bxchg_release(e);
+    e->bxchg.reset(new BXchg());
+    BXchg* x = e->bxchg.get();
+    x->world = world; x->rank = rank; x->rec_cap = rec_cap;
+    x->flags_bytes = ((size_t)2 * BXchg::SLOTS * world * 8 + 255) & ~(size_t)255;
+    x->tops_bytes = (size_t)BXchg::SLOTS * world * x->tops_region() * 4;
+    x->bytes = x->flags_bytes + x->tops_bytes + (size_t)BXchg::SLOTS * world * x->rec_region() * 8;
+    CU(cudaSetDevice(e->devs[0]));
+    CU(preload_batch_kernels());             // lazy module loading synchronises the context at a kernel's first launch --
+    CU(preload_coarse_kernels());            // while a wait kernel of another engine of this process may be spinning
+    CU(preload_merge_kernels());
+    CU(cudaMalloc(&x->block, x->bytes));
+    CU(cudaMemset(x->block, 0, x->flags_bytes));
+    CU(cudaMalloc(&x->done, 64)); CU(cudaMemset(x->done, 0, 64));
+    CU(cudaMalloc(&x->status, 64)); CU(cudaMemset(x->status, 0, 64));
+    CU(cudaDeviceSynchronize());
+    if (const char* v = getenv("SVSB_XCHG_TIMEOUT_MS")) { const long long ms = atoll(v); if (ms > 0) x->timeout_ns = (unsigned long long)ms * 1000000ull; }
+    x->peer_block.assign(world, nullptr);
+    x->peer_block[rank] = x->block;
+    if (handle_out) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, x->block));
+        memcpy(handle_out, &h, 64);
+    }
+    x->connected = world == 1;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_bxchg_connect(svsb_t* e, const void* handles) {
+    if (!e || !e->bxchg) return fail(SVSB_E_STATE, "svsb_bxchg_connect: svsb_bxchg_create first");
+    if (!handles) return fail(SVSB_E_INVALID, "svsb_bxchg_connect: NULL handles");
+    BXchg* x = e->bxchg.get();
+    CU(cudaSetDevice(e->devs[0]));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * 64, 64);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->ipc_opened.push_back(p);
+        x->peer_block[r] = static_cast<unsigned char*>(p);
+    }
+    x->connected = true;
+    return SVSB_OK;
+}
+
+extern "C" int svsb_bxchg_connect_local(svsb_t* e, svsb_t* const* engines) {
+    if (!e || !e->bxchg) return fail(SVSB_E_STATE, "svsb_bxchg_connect_local: svsb_bxchg_create first");
+    if (!engines) return fail(SVSB_E_INVALID, "svsb_bxchg_connect_local: NULL engines");
+    BXchg* x = e->bxchg.get();
+    CU(cudaSetDevice(e->devs[0]));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        svsb_engine* o = engines[r];
+        if (!o || !o->bxchg || o->bxchg->world != x->world || o->bxchg->rank != r || o->bxchg->rec_cap != x->rec_cap)
+            return fail(SVSB_E_INVALID, "svsb_bxchg_connect_local: peer engine has no matching batch window");
+        if (o->devs[0] != e->devs[0]) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, e->devs[0], o->devs[0]));
+            if (!can) return fail(SVSB_E_CUDA, "svsb_bxchg_connect_local: no peer access between the devices");
+            cudaError_t pe = cudaDeviceEnablePeerAccess(o->devs[0], 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CU(pe);
+            (void)cudaGetLastError();
+        }
+        x->peer_block[r] = o->bxchg->block;
+    }
+    x->connected = true;
+    return SVSB_OK;
+}
+
+// Stop pushing into the peers' windows (they may be freed next); the own window stays until svsb_destroy / the next create.
+extern "C" int svsb_bxchg_disconnect(svsb_t* e) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    BXchg* x = e->bxchg.get();
+    if (!x) return SVSB_OK;
+    CU(cudaSetDevice(e->devs[0]));
+    CU(cudaDeviceSynchronize());
+    for (void* p : x->ipc_opened) cudaIpcCloseMemHandle(p);
+    x->ipc_opened.clear();
+    for (int r = 0; r < x->world; ++r) if (r != x->rank) x->peer_block[r] = nullptr;
+    x->connected = x->world == 1;
+    return SVSB_OK;
+}
+
+// Size every buffer svsb_batch_peer uses for (b, k) now: allocations are implicit synchronisation points, and several
+// shard engines of ONE process (tests with virtual ranks) must not hit one while another engine's wait kernel spins.
+extern "C" int svsb_batch_peer_prepare(svsb_t* e, int32_t b, int32_t k) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (b < 1 || b > COARSE_MAX_BATCH) return fail(SVSB_E_INVALID, "svsb_batch_peer_prepare: 1 <= b <= 2048");
+    BatchPlan P;
+    if (!batch_plan_global(e, g.get(), k, P)) return fail(SVSB_E_STATE, "svsb_batch_peer_prepare: this shard / k is not eligible (svsb_batch_global_probe)");
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = nullptr;
+    int rc = batch_ws_get(e, w);
+    if (rc != SVSB_OK) return rc;
+    if ((rc = ensure_m16(g.get(), P, w->st)) != SVSB_OK) return rc;
+    const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+    if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
+    CU(cudaSetDevice(w->dev));
+    CU(cudaDeviceSynchronize());
+    return SVSB_OK;
+}
+
+extern "C" int svsb_batch_peer(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, float max_row_norm, int32_t sample_rank,
+                               int32_t rec_cap, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    BXchg* x = e->bxchg.get();
+    if (!x || !x->connected) return fail(SVSB_E_STATE, "svsb_batch_peer: svsb_bxchg_create + svsb_bxchg_connect first");
+    auto g = pin(e);
+    if (!g) return fail(SVSB_E_NOT_LOADED, "no matrix resident");
+    if (b < 1 || b > COARSE_MAX_BATCH || !d_Q || !d_out_scores || !d_out_ids || !d_out_counts)
+        return fail(SVSB_E_INVALID, "svsb_batch_peer: 1 <= b <= 2048, non-NULL buffers");
+    if (sample_rank < 1 || sample_rank > SAMPLE_TOPX) return fail(SVSB_E_INVALID, "svsb_batch_peer: 1 <= sample_rank <= 32");
+    if (rec_cap < 1 || rec_cap > k || rec_cap > x->rec_cap) return fail(SVSB_E_INVALID, "svsb_batch_peer: rec_cap must be <= k and <= the window's");
+    if (rec_cap < k && (int64_t)x->world * rec_cap > K_FAST_MAX) return fail(SVSB_E_INVALID, "svsb_batch_peer: truncated records need world * rec_cap <= 2048");
+    BatchPlan P;
+    if (!batch_plan_global(e, g.get(), k, P)) return fail(SVSB_E_STATE, "svsb_batch_peer: this shard / k is not eligible (svsb_batch_global_probe)");
+    if (!(max_row_norm >= P.max_row_norm) || !(max_row_norm <= 8.1f)) return fail(SVSB_E_INVALID, "svsb_batch_peer: max_row_norm below this shard's own, or unsafe for fp16 operands");
+    {
+        const double lam = (double)P.kk * std::min(1.0, (double)P.sample_rows / (double)P.n);
+        if ((double)sample_rank < std::ceil(lam + 6.0 * std::sqrt(lam) + 4.0) && sample_rank < SAMPLE_TOPX && env_int("SVSB_BATCH_GLOBAL_ANY_RANK", 0) == 0)
+            return fail(SVSB_E_INVALID, "svsb_batch_peer: sample_rank below this shard's own bound");
+    }
+    P.max_row_norm = max_row_norm;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    BatchWs* w = nullptr;
+    int rc = batch_ws_get(e, w);
+    if (rc != SVSB_OK) return rc;
+    if ((rc = ensure_m16(g.get(), P, st)) != SVSB_OK) return rc;
+    const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
+    if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
+    const Shard& s = g->shards[0];
+    CU(cudaSetDevice(w->dev));
+    const unsigned long long seq = ++x->seq;
+    const int slot = (int)(seq % BXchg::SLOTS);
+    BatchPush pa, pb;
+    pa.world = pb.world = x->world; pa.seq = pb.seq = seq; pa.done = x->done; pb.done = x->done + 1;
+    for (int p = 0; p < x->world; ++p) {
+        pa.dst[p] = x->tops(x->peer_block[p], slot, x->rank); pa.flag[p] = x->flag(x->peer_block[p], 0, slot, x->rank);
+        pb.dst[p] = x->recs(x->peer_block[p], slot, x->rank); pb.flag[p] = x->flag(x->peer_block[p], 1, slot, x->rank);
+    }
+    const int64_t rec = 2 * (int64_t)rec_cap + 1;
+    // 1. this rank's sample maxima -> every rank's window
+    CU(launch_queries_to_f16(st, d_Q, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags));
+    CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, st));
+    CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
+                          nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
+    CU(launch_sample_top(st, w->sample, P.sample_rows, b, nullptr, &pa));
+    // 2. all ranks' maxima are here -> ONE threshold per query; filter; exact re-score; records -> every rank's window
+    CU(launch_wait_flags(st, x->flag(x->block, 0, slot, 0), x->world, seq, x->timeout_ns, x->status));
+    CU(launch_union_threshold(st, x->tops(x->block, slot, 0), x->tops_region(), x->world, b, sample_rank, w->eps, w->thr));
+    CU(launch_coarse_gemm(st, w->dev, 0, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.n_tiles, 1,
+                          w->thr, w->cand, w->cand_cnt, P.cand_cap, nullptr, 0));
+    RefineOut o{nullptr, nullptr, nullptr, rec, nullptr, 2 * rec, rec_cap};
+    CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, d_Q, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->thr, w->flags,
+                     o, w->stats, &w->rs, REFINE_PARTIAL | REFINE_DEFER, &pb));
+    // 3. all ranks' records are here -> verifying merge
+    CU(launch_wait_flags(st, x->flag(x->block, 1, slot, 0), x->world, seq, x->timeout_ns, x->status));
+    const int64_t* r0 = x->recs(x->block, slot, 0);
+    u64* sk = nullptr; int64_t* sp = nullptr;
+    if ((int64_t)x->world * rec_cap > K_FAST_MAX) {
+        if (e->shard_ws.empty() || !e->shard_ws[0]) { e->shard_ws.resize(std::max<size_t>(1, e->shard_ws.size())); e->shard_ws[0].reset(new DevWs()); e->shard_ws[0]->dev = e->devs[0]; }
+        if ((rc = e->shard_ws[0]->ensure_merge_scratch((int64_t)b * x->world * rec_cap)) != SVSB_OK) return rc;
+        sk = e->shard_ws[0]->mscr_keys; sp = e->shard_ws[0]->mscr_ids;
+    }
+    const int64_t kk_global = k;       // the caller passes min(k, global rows) as k when the matrix is smaller (ShardedRetriever clips n)
+    CU(launch_merge_ex(st, reinterpret_cast<const u64*>(r0), r0 + rec_cap, reinterpret_cast<const int32_t*>(r0 + 2 * (int64_t)rec_cap),
+                       x->world, rec_cap, k, b, x->rec_region(), rec, x->rec_region() * 2, rec * 2, sk, sp,
+                       d_out_scores, d_out_ids, d_out_counts, (int)kk_global, x->status));
     return SVSB_OK;
 }
 

@@ -311,6 +311,28 @@ struct MqWs {
     }
 };
 
+// Batch window of the one-process-per-GPU deployment (svsb_bxchg_*, svsb_batch_peer): per slot and source rank a region
+// for the rank's sample maxima and one for its candidate records, written by the peers' kernels over NVLink peer memory.
+//   [flags: 2 phases x slots x world u64, padded to 256 B][tops: slots x world x B_MAX x 32 f32][records: slots x world x B_MAX x (2 rec_cap + 1) i64]
+struct BXchg {
+    static constexpr int SLOTS = 2, B_MAX = COARSE_MAX_BATCH;
+    int world = 0, rank = 0, rec_cap = 0;
+    unsigned char* block = nullptr;
+    size_t flags_bytes = 0, tops_bytes = 0, bytes = 0;
+    std::vector<unsigned char*> peer_block;
+    std::vector<void*> ipc_opened;
+    bool connected = false;
+    unsigned long long seq = 0;
+    unsigned long long timeout_ns = 30ull * 1000000000ull;
+    unsigned int* done = nullptr;            // two last-block tickets (sample maxima, records)
+    int* status = nullptr;                   // device word: 1 = a wait timed out
+    int64_t tops_region() const { return (int64_t)B_MAX * SAMPLE_TOPX; }                       // floats per (slot, source)
+    int64_t rec_region() const { return (int64_t)B_MAX * (2 * (int64_t)rec_cap + 1); }         // words per (slot, source)
+    u64* flag(unsigned char* blk, int phase, int slot, int src) const { return reinterpret_cast<u64*>(blk) + ((int64_t)phase * SLOTS + slot) * world + src; }
+    float* tops(unsigned char* blk, int slot, int src) const { return reinterpret_cast<float*>(blk + flags_bytes) + ((int64_t)slot * world + src) * tops_region(); }
+    int64_t* recs(unsigned char* blk, int slot, int src) const { return reinterpret_cast<int64_t*>(blk + flags_bytes + tops_bytes) + ((int64_t)slot * world + src) * rec_region(); }
+};
+
 // Peer exchange of the one-process-per-GPU deployment (kernels.cuh "peer exchange"): this rank's gather window,
 // the peers' windows opened over CUDA IPC (or plain pointers inside one process), and a synchronous query context.
 struct Xchg {
@@ -391,6 +413,7 @@ struct svsb_engine {
     cudaStream_t side_st = nullptr;                      // selection kernels of the pipelined sharded path
     std::vector<char> sel_pending;                       // per slot: a selection is (or was) in flight on side_st
     std::unique_ptr<Xchg> xchg;
+    std::unique_ptr<BXchg> bxchg;
     // several devices in ONE process (svsb_create with n_dev > 1, multi.cu): one shard engine per device, driven by one
     // worker thread each, candidate records pushed into device 0's gather window by the selection kernels
     struct Multi* multi = nullptr;

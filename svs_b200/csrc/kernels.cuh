@@ -86,6 +86,7 @@ cudaError_t launch_fullsort_topk(cudaStream_t st, const float* scores, int64_t n
 // gmax from a score vector alone (svsb_topk_scores: selection without the GEMV).
 cudaError_t launch_groupmax(cudaStream_t st, int device, const float* scores, int64_t n, u64* gmax, int group_shift);
 
+constexpr int MERGE_WINDOW_TIMED_OUT = -2;          // out_count of a merge whose peers' records did not arrive
 // Merge n_lists candidate lists (keys carry global rows; ids are the payload) into the top-k.
 // scratch: u64[next_pow2(n_lists * stride)] + int64[same] when n_lists * stride > K_FAST_MAX (else unused).
 cudaError_t launch_merge(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts,
@@ -99,7 +100,8 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
                             int64_t count_list_stride, int64_t count_batch_stride,
                             u64* scratch_keys, int64_t* scratch_ids,
                             float* out_scores, int64_t* out_ids, int32_t* out_count,
-                            int verify_k = -1);   // >= 0: count words are [count, ver] pairs, see MergeLayout (select.cu)
+                            int verify_k = -1,    // >= 0: count words are [count, ver] pairs, see MergeLayout (select.cu)
+                            const int* abort_flag = nullptr);   // device word; non-zero: every out_count = MERGE_WINDOW_TIMED_OUT
 
 // Any k: merge n_lists lists, each SORTED descending with unique keys (list l at keys / ids [l * stride ..), counts[l] valid).
 cudaError_t launch_merge_sorted_big(cudaStream_t st, const u64* keys, const int64_t* ids, const int32_t* counts, int n_lists,
@@ -120,6 +122,9 @@ struct PeerPush {
 // the context at a kernel's first launch -- while a merge kernel of the same process may be spinning on a flag).
 cudaError_t preload_gemv_kernels();
 cudaError_t preload_peer_kernels();
+cudaError_t preload_batch_kernels();     // batch.cu
+cudaError_t preload_coarse_kernels();    // coarse.cu
+cudaError_t preload_merge_kernels();     // select.cu
 // d_q[0..ld) = host_q_mapped[0..ld) (pinned host memory, read by a kernel: no copy-engine operation).  ld % 4 == 0.
 cudaError_t launch_stage_query(cudaStream_t st, const float* host_q_mapped, float* d_q, int ld);
 // Record with count 0 (this rank owns no rows): same publication protocol, one small CTA.
@@ -128,7 +133,6 @@ cudaError_t launch_push_empty(cudaStream_t st, const PeerPush& push);
 // (coherent loads: the data was written by remote GPUs) into the top-k.  scratch as launch_merge (world*cap > 2048).
 // A flag that does not arrive within timeout_ns (a peer died or left the SPMD call sequence) ends the kernel with
 // *out_count = MERGE_WINDOW_TIMED_OUT instead of hanging the GPU.
-constexpr int MERGE_WINDOW_TIMED_OUT = -2;
 cudaError_t launch_merge_window(cudaStream_t st, const u64* slot_base, const u64* flags, unsigned long long seq,
                                 int world, int cap, int k, unsigned long long timeout_ns, u64* scratch_keys, int64_t* scratch_ids,
                                 float* out_scores, int64_t* out_ids, int32_t* out_count,
@@ -193,16 +197,34 @@ struct RefineScratch { uint32_t* rows; u64* keys; int32_t* cnt; int32_t* ver; };
 constexpr int REFINE_PARTIAL = 1;     // sharded path, global threshold: < kk local candidates is normal; count word = [count, ver]
 constexpr int REFINE_DEFER = 2;       // a flagged query gets count -1 in its record (no host read of the flags in between)
 // scratch == nullptr (and mode == 0): the one-kernel variant (also SVSB_REFINE_FUSED=1).
+// Batched peer exchange (svsb_batch_peer): the kernel that PRODUCES a rank's contribution -- its sample maxima, then its
+// candidate records -- stores it straight into every rank's batch window over NVLink peer memory (dst[p], own window
+// included); the last CTA to finish (a device-scope ticket, `done`) fences at system scope and release-stores the batch's
+// sequence number into every rank's flag word.  Consumers run behind launch_wait_flags on their own window.
+struct BatchPush {
+    int world = 0;
+    unsigned long long seq = 0;
+    void* dst[XCHG_MAX_RANKS];          // this rank's region of rank p's window (slot applied)
+    u64* flag[XCHG_MAX_RANKS];          // rank p's flag word for (phase, slot, this rank)
+    unsigned int* done = nullptr;       // zero on entry, zero again on exit
+};
 cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, const int64_t* ids, int64_t row0,
                           const float* Q, int b, int ldq, int k, const u64* cand, const int32_t* cand_cnt, int cand_cap,
                           const float* eps, const float* thr, int32_t* flags, RefineOut out, int32_t* stats,
-                          const RefineScratch* scratch = nullptr, int mode = 0);
+                          const RefineScratch* scratch = nullptr, int mode = 0,
+                          const BatchPush* push = nullptr);   // push: records go to dst[p] + q * out.stride ([keys(out.cap) | ids(out.cap) | count, ver])
+// One small CTA: wait until flags[0..world) >= seq (ld.acquire.sys); *status |= 1 if a flag does not arrive within
+// timeout_ns.  Kernels enqueued behind it on the stream may read what the peers stored before publishing.
+cudaError_t launch_wait_flags(cudaStream_t st, const u64* flags, int world, unsigned long long seq, unsigned long long timeout_ns, int* status);
 // Sharded path with a GLOBAL filter threshold: every rank extracts the SAMPLE_TOPX largest values of its own sample
 // (top[q][0..SAMPLE_TOPX), descending), the lists are exchanged, and thr[q] = (rank-th largest of the union) - 2 eps[q]
 // on every rank (rank <= SAMPLE_TOPX; tops = [world][b][SAMPLE_TOPX]).
 constexpr int SAMPLE_TOPX = 32;
-cudaError_t launch_sample_top(cudaStream_t st, const void* sample, int64_t sample_rows, int b, float* top);
-cudaError_t launch_union_threshold(cudaStream_t st, const float* tops, int world, int b, int rank, const float* eps, float* thr);
+cudaError_t launch_sample_top(cudaStream_t st, const void* sample, int64_t sample_rows, int b, float* top,
+                              const BatchPush* push = nullptr);   // push: the lists go to dst[p][q][0..32) instead of top
+// list_stride: floats between rank l's and rank l+1's lists (b * SAMPLE_TOPX for a packed all-gather result)
+cudaError_t launch_union_threshold(cudaStream_t st, const float* tops, int64_t list_stride, int world, int b, int rank, const float* eps,
+                                   float* thr);
 constexpr int REFINE_FLAG_THRESHOLD_HIGH = 16;
 
 // ---- pairwise top pairs (pairs.cu): global candidate list on top of the coarse pass's pairwise mode --------

@@ -132,14 +132,6 @@ __device__ u64 block_kth_largest(const u64* keys, int64_t count, int kk, SelectS
 // after the CTA barrier thread p stores the count, fences at system scope (cumulative over the barrier) and
 // release-stores the sequence number into rank p's flag.  The consumer acquires the flag before reading.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
-    u64 v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void peer_publish(const PeerPush& push, int count) {
     __syncthreads();
     const int p = threadIdx.x;
@@ -551,6 +543,7 @@ struct MergeLayout {
     // count: the rank had more entries than the record holds, cap < k): fine as long as the list's last shipped entry
     // does not make the global top k -- then nothing behind it can; otherwise -1 as well.
     int verify_k;
+    const int* abort_flag;       // optional device word: non-zero = the records never arrived (peer exchange timed out)
 };
 constexpr int32_t RECORD_TRUNCATED = 1 << 30;
 
@@ -624,6 +617,7 @@ merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids
     out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
     uint32_t* cnt = sm.hist;                                  // per-list counts and offsets (list order is kept);
     uint32_t* off = sm.hist + 1024;                           // n_lists <= 1023 (launcher)
+    if (L.abort_flag && *L.abort_flag) { if (tid == 0) out_count[b] = MERGE_WINDOW_TIMED_OUT; return; }
     if (L.verify_k >= 0 && !merge_records_verified(sm, counts, L)) { if (tid == 0) out_count[b] = -1; return; }
     const uint32_t trunc_mask = L.verify_k >= 0 ? (uint32_t)sm.bcast32[2] : 0u;
     __shared__ int trunc_bad;
@@ -661,6 +655,84 @@ merge_lists_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids
     if (tid == 0) out_count[b] = kk;
 }
 
+// The same merge for SMALL records (n_lists <= 32, n_lists * cap <= 1024: batched records of 2..16 ranks): 256 threads and
+// 17 KB of shared memory, so eight CTAs share an SM instead of two -- a 1024-query batch is one wave, not four.
+constexpr int MERGE_SMALL_THREADS = 256;
+constexpr int MERGE_SMALL_SPAN = 1024;
+__global__ void __launch_bounds__(MERGE_SMALL_THREADS)
+merge_lists_small_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
+                         MergeLayout L, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                         int32_t* __restrict__ out_count)
+{
+    __shared__ u64 sk[MERGE_SMALL_SPAN];
+    __shared__ int64_t sp[MERGE_SMALL_SPAN];
+    __shared__ uint32_t cnt[32], off[33];
+    __shared__ int s_bad, s_ver, s_unsorted;
+    __shared__ uint32_t s_trunc;
+    const int tid = threadIdx.x, b = blockIdx.x;
+    keys += (int64_t)b * L.batch_stride; ids += (int64_t)b * L.batch_stride;
+    counts += (int64_t)b * L.count_batch_stride;
+    out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
+    if (L.abort_flag && *L.abort_flag) { if (tid == 0) out_count[b] = MERGE_WINDOW_TIMED_OUT; return; }
+    if (tid == 0) { s_bad = 0; s_ver = 0; s_unsorted = 0; s_trunc = 0; }
+    __syncthreads();
+    if (tid < L.n_lists) {
+        const int32_t* cw = counts + (int64_t)tid * L.count_list_stride;
+        int32_t c = cw[0];
+        if (L.verify_k >= 0) {
+            if (c < 0) atomicOr(&s_bad, 1);
+            else { atomicAdd(&s_ver, max(0, cw[1])); if (c & RECORD_TRUNCATED) atomicOr(&s_trunc, 1u << tid); }
+            c &= ~RECORD_TRUNCATED;
+        }
+        cnt[tid] = (uint32_t)max(0, min(c, L.cap));
+    }
+    __syncthreads();
+    if (L.verify_k >= 0 && (s_bad || s_ver < L.verify_k)) { if (tid == 0) out_count[b] = -1; return; }
+    if (tid == 0) { uint32_t o = 0; for (int l = 0; l < L.n_lists; ++l) { off[l] = o; o += cnt[l]; } off[L.n_lists] = o; }
+    __syncthreads();
+    const int span = L.n_lists * L.cap;
+    for (int i = tid; i < span; i += MERGE_SMALL_THREADS) {
+        const int l = i / L.cap, p = i - l * L.cap;
+        if ((uint32_t)p < cnt[l]) {
+            sk[off[l] + p] = keys[(int64_t)l * L.list_stride + p];
+            sp[off[l] + p] = ids[(int64_t)l * L.list_stride + p];
+        }
+    }
+    __syncthreads();
+    const int total = (int)off[L.n_lists];
+    const int kk = min(L.k, total);
+    const uint32_t trunc = s_trunc;
+    for (int i = tid; i < total; i += MERGE_SMALL_THREADS) {
+        int l = 0;
+        while (l + 1 < L.n_lists && (uint32_t)i >= off[l + 1]) ++l;
+        if ((uint32_t)i > off[l] && sk[i] >= sk[i - 1]) s_unsorted = 1;
+    }
+    __syncthreads();
+    const bool sorted = s_unsorted == 0;
+    __syncthreads();
+    for (int i = tid; i < total; i += MERGE_SMALL_THREADS) {
+        int l = 0;
+        while (l + 1 < L.n_lists && (uint32_t)i >= off[l + 1]) ++l;
+        const u64 key = sk[i];
+        int rank = 0;
+        if (sorted) {                                         // position in its own list + binary searches in the others
+            rank = i - (int)off[l];
+            for (int m = 0; m < L.n_lists; ++m) {
+                if (m == l) continue;
+                int lo = (int)off[m], hi = lo + (int)cnt[m];
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] > key) lo = mid + 1; else hi = mid; }
+                rank += lo - (int)off[m];
+            }
+        } else {                                              // a list out of order (stateless callers only): count
+            for (int j = 0; j < total; ++j) rank += sk[j] > key ? 1 : 0;
+        }
+        if (rank < kk) { out_scores[rank] = key_score(key); out_ids[rank] = sp[i]; }
+        if (((trunc >> l) & 1u) && i == (int)(off[l] + cnt[l]) - 1 && rank < L.k) s_bad = 1;
+    }
+    __syncthreads();
+    if (tid == 0) out_count[b] = s_bad ? -1 : kk;
+}
+
 // Generic merge for n_lists * cap > SORT_CAP: compact valid entries into scratch, select, sort.
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 merge_lists_big_kernel(const u64* __restrict__ keys, const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
@@ -675,6 +747,7 @@ merge_lists_big_kernel(const u64* __restrict__ keys, const int64_t* __restrict__
     counts += (int64_t)b * L.count_batch_stride;
     out_scores += (int64_t)b * L.k; out_ids += (int64_t)b * L.k;
     sk += (int64_t)b * span; sp += (int64_t)b * span;
+    if (L.abort_flag && *L.abort_flag) { if (tid == 0) out_count[b] = MERGE_WINDOW_TIMED_OUT; return; }
     if (L.verify_k >= 0 && (!merge_records_verified(sm, counts, L) || sm.bcast32[2] != 0)) { if (tid == 0) out_count[b] = -1; return; }
     if (tid == 0) sm.counter = 0;
     __syncthreads();
@@ -713,7 +786,7 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
                             int n_lists, int cap, int k, int batch, int64_t list_stride, int64_t batch_stride,
                             int64_t count_list_stride, int64_t count_batch_stride,
                             u64* scratch_keys, int64_t* scratch_ids,
-                            float* out_scores, int64_t* out_ids, int32_t* out_count, int verify_k)
+                            float* out_scores, int64_t* out_ids, int32_t* out_count, int verify_k, const int* abort_flag)
 {
     if (n_lists < 1 || n_lists > 1023 || cap < 1 || k < 1 || k > K_FAST_MAX || batch < 1) return cudaErrorInvalidValue;
     static bool attr_set[64][2] = {{false}};
@@ -726,7 +799,13 @@ cudaError_t launch_merge_ex(cudaStream_t st, const u64* keys, const int64_t* ids
         if (e != cudaSuccess) return e;
         attr_set[dev][big] = true;
     }
-    MergeLayout L{n_lists, cap, k, list_stride, batch_stride, count_list_stride, count_batch_stride, verify_k};
+    MergeLayout L{n_lists, cap, k, list_stride, batch_stride, count_list_stride, count_batch_stride, verify_k, abort_flag};
+    static const bool small_off = [] { const char* v = getenv("SVSB_MERGE_SMALL"); return v && atoi(v) == 0; }();
+    if (!small_off && batch >= 8 && n_lists <= 32 && (int64_t)n_lists * cap <= MERGE_SMALL_SPAN) {
+        merge_lists_small_kernel<<<batch, MERGE_SMALL_THREADS, 0, st>>>(keys, ids, counts, L, out_scores, out_ids, out_count);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (big) {
         if (!scratch_keys || !scratch_ids) return cudaErrorInvalidValue;
         merge_lists_big_kernel<<<batch, SEL_THREADS, sizeof(SelectSmem), st>>>(keys, ids, counts, L, scratch_keys, scratch_ids,
@@ -914,6 +993,15 @@ cudaError_t preload_peer_kernels()
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, stage_query_kernel);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectKeysSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(merge_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem));
+    return e;
+}
+
+cudaError_t preload_merge_kernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, merge_lists_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, merge_lists_big_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, merge_lists_small_kernel);
     return e;
 }
 

@@ -141,6 +141,34 @@ class CudaShardBackend:
                                                                n_lists, batch, rec_cap, k, verify_k, C.c_void_p(out_scores.data_ptr()),
                                                                C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_counts.data_ptr())))
 
+    # -- the batch protocol with both exchanges fused into the kernels over peer memory (svsb_bxchg_*, svsb_batch_peer) ----
+    BATCH_WINDOW_CAP = 128          # entries per record the batch window is sized for
+
+    def batch_exchange_handle(self, world: int, rank: int, rec_cap: int = BATCH_WINDOW_CAP) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.svsb_bxchg_create(self.engine._h, world, rank, rec_cap, buf))
+        return buf.raw
+
+    def batch_exchange_connect(self, handles: List[bytes]) -> None:
+        self._check(self._lib.svsb_bxchg_connect(self.engine._h, C.c_char_p(b"".join(handles))))
+
+    def batch_exchange_connect_local(self, backends: List["CudaShardBackend"]) -> None:
+        arr = (C.c_void_p * len(backends))(*[b.engine._h for b in backends])
+        self._check(self._lib.svsb_bxchg_connect_local(self.engine._h, arr))
+
+    def batch_exchange_disconnect(self) -> None:
+        self._check(self._lib.svsb_bxchg_disconnect(self.engine._h))
+
+    def batch_peer_prepare(self, b: int, k: int) -> None:
+        self._check(self._lib.svsb_batch_peer_prepare(self.engine._h, b, k))
+
+    def batch_peer(self, queries, k: int, max_row_norm: float, sample_rank: int, rec_cap: int, out_scores, out_ids, out_counts) -> None:
+        """One whole batch (<= 2048 device queries) on the current stream, no collective: see include/svsb200.h."""
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_batch_peer(self.engine._h, C.c_void_p(st), C.c_void_p(queries.data_ptr()), queries.shape[0], k,
+                                              C.c_float(max_row_norm), sample_rank, rec_cap, C.c_void_p(out_scores.data_ptr()),
+                                              C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_counts.data_ptr())))
+
     # -- peer exchange (fused selection + exchange over NVLink peer memory) -------------------------
     def exchange_handle(self, world: int, rank: int, k_max: int = 2048) -> bytes:
         """Allocate this rank's gather window; returns its CUDA IPC handle (64 bytes) for the other ranks."""
@@ -229,6 +257,7 @@ class ShardedRetriever:
         # the fused peer exchange needs a backend that owns device windows; injected CPU backends use the collective
         self.exchange = exchange if hasattr(self.backend, "exchange_handle") and world <= 16 else "collective"
         self._peer_ready = False
+        self._batch_peer_ready = False
         self.n = 0
         self.d = 0
         self.row0 = 0
@@ -271,6 +300,17 @@ class ShardedRetriever:
         if self.world > 1:
             self.dist.barrier(group=self.group)                    # every window is open before the first push
         self._peer_ready = True
+
+    def _ensure_batch_peer(self) -> None:
+        """One-time batch-window exchange (the batched counterpart of _ensure_peer)."""
+        if self._batch_peer_ready:
+            return
+        handle = self.backend.batch_exchange_handle(self.world, self.rank)
+        handles: List[Optional[bytes]] = [None] * self.world
+        self.dist.all_gather_object(handles, handle, group=self.group)
+        self.backend.batch_exchange_connect(handles)
+        self.dist.barrier(group=self.group)                        # every window is open before the first push
+        self._batch_peer_ready = True
 
     # -- queries ---------------------------------------------------------------------------------
     def set_queries(self, Q: np.ndarray) -> None:
@@ -376,6 +416,14 @@ class ShardedRetriever:
             return o_s, o_i, o_c
         sample_rank, max_row_norm, cap = plan
         self.last_fallbacks = 0
+        if self.exchange == "peer" and hasattr(self.backend, "batch_peer") and cap <= self.backend.BATCH_WINDOW_CAP:
+            # both exchanges fused into the kernels over NVLink peer memory: no collective call at all
+            self._ensure_batch_peer()
+            for c0 in range(0, b, 2048):
+                bc = min(2048, b - c0)
+                self.backend.batch_peer(dq[c0:c0 + bc], k, max_row_norm, sample_rank, cap, o_s[c0:c0 + bc], o_i[c0:c0 + bc], o_c[c0:c0 + bc])
+            self._last_counts = o_c
+            return o_s, o_i, o_c
         tkey = ("tops", b)
         if tkey not in self._bufs:
             self._bufs[tkey] = (self.backend.new_tops(min(b, 2048)), self.backend.new_tops(self.world * min(b, 2048)))
@@ -413,6 +461,8 @@ class ShardedRetriever:
         o_s, o_i, o_c = self._batch(self.backend.device_queries(Q), k)
         cnt = o_c.cpu().numpy()                                     # synchronises the stream
         s, i = o_s.cpu().numpy(), o_i.cpu().numpy()
+        if (cnt == -2).any():
+            raise RuntimeError("sharded batch: a peer's part of the batch did not arrive (SVSB_XCHG_TIMEOUT_MS)")
         redo = np.nonzero(cnt < 0)[0]                               # the coarse pass could not vouch for these (same on every rank)
         self.last_fallbacks += len(redo)
         for j in redo:
@@ -471,10 +521,12 @@ class ShardedRetriever:
 
     def close(self) -> None:
         """Collective when the peer exchange is up: unmap the peers' windows everywhere before any rank frees its own."""
-        if self._peer_ready:
-            if hasattr(self.backend, "exchange_disconnect"):
+        if self._peer_ready or self._batch_peer_ready:
+            if self._peer_ready and hasattr(self.backend, "exchange_disconnect"):
                 self.backend.exchange_disconnect()
+            if self._batch_peer_ready:
+                self.backend.batch_exchange_disconnect()
             if self.world > 1:
                 self.dist.barrier(group=self.group)
-            self._peer_ready = False
+            self._peer_ready = self._batch_peer_ready = False
         self.backend.close()

@@ -197,6 +197,65 @@ def test_global_threshold_batch_records_equal_the_single_query_records(world, n,
             b.close()
 
 
+@pytest.mark.parametrize("world,n,d,k", [(2, 24_001, 256, 50), (4, 60_000, 128, 100)])
+def test_batch_peer_exchange_virtual_ranks_equal_the_collective_form(world, n, d, k):
+    """svsb_batch_peer: the whole batch with BOTH exchanges fused into the kernels (sample maxima and candidate records
+    stored straight into every rank's batch window, consumers behind flag waits) -- `world` shard engines of this process,
+    one stream each, stand in for the ranks.  Every rank must hold the answer of the collective form (stacked
+    all-gathers), bit for bit; several batches in a row exercise the two window slots."""
+    torch = pytest.importorskip("torch")
+    from svs_b200.sharded import CudaShardBackend, partition
+    batch = 260
+    m = oracle.synth_matrix_uniform(n, d, 18)
+    ids = np.cumsum(np.random.default_rng(4).integers(1, 4, size=n)).astype(np.int64)
+    backs = []
+    for r in range(world):
+        b = CudaShardBackend(0)
+        row0, cnt = partition(n, world, r)
+        b.set_shard(row0)
+        b.load_rows(np.ascontiguousarray(m[row0:row0 + cnt]), np.ascontiguousarray(ids[row0:row0 + cnt]))
+        backs.append(b)
+    try:
+        probes = [b.batch_global_probe(k) for b in backs]
+        assert all(p[0] for p in probes)
+        f = max(min(1.0, p[1] / p[2]) for p in probes)
+        lam = k * f
+        rank = int(np.ceil(lam + 6.0 * np.sqrt(lam) + 4.0))
+        norm = max(p[3] for p in probes)
+        share = k / world
+        cap = min(k, int(np.ceil(share + 6.0 * np.sqrt(share) + 4.0)))
+        for r, b in enumerate(backs):
+            b.batch_exchange_handle(world, r, 128)
+        for b in backs:
+            b.batch_exchange_connect_local(backs)
+            b.batch_peer_prepare(batch, k)
+        streams = [torch.cuda.Stream() for _ in range(world)]
+        outs = [b.new_outputs(batch, k) for b in backs]
+        for rep in range(5):
+            qs = oracle.synth_queries(batch, d, 40 + rep)
+            ref_s, ref_i, ref_c, dq, _ = _global_batch(backs, world, n, qs, k, cap=cap)
+            torch.cuda.synchronize()
+            for r, b in enumerate(backs):                      # every rank's whole batch is enqueued before any is awaited
+                with torch.cuda.stream(streams[r]):
+                    b.batch_peer(dq, k, norm, rank, cap, *outs[r])
+            torch.cuda.synchronize()
+            for r in range(world):
+                o_s, o_i, o_c = (t.cpu().numpy() for t in outs[r])
+                assert np.array_equal(o_c, ref_c), (rep, r, np.nonzero(o_c != ref_c)[0][:8], o_c[:8])
+                ok = ref_c == k
+                assert ok.mean() > 0.9
+                assert np.array_equal(o_s[ok].view(np.uint32), ref_s[ok].view(np.uint32)) and np.array_equal(o_i[ok], ref_i[ok])
+            for j in range(0, batch, 61):
+                if ref_c[j] == k:
+                    got = list(zip(ref_s[j, :k].tolist(), ref_i[j, :k].tolist()))
+                    oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+    finally:
+        for b in backs:
+            b.batch_exchange_disconnect()
+        for b in backs:
+            b.close()
+
+
 def test_global_threshold_batch_refuses_what_it_cannot_verify():
     """Rows stored in an order correlated with the queries (every shard's strided sample then over-represents the top) and
     a sample_rank far too small: the thresholds come out too high, the ranks' verification counts do not add up to k,
@@ -242,7 +301,8 @@ def test_merge_records_rank_merge_and_unsorted_fallback():
     b = CudaShardBackend(0)
     b.load_rows(np.ones((4, 4), np.float32), np.arange(4, dtype=np.int64))      # the merge only needs an engine
     try:
-        for world, batch, k, shuffle in ((3, 2, 50, False), (3, 2, 50, True), (8, 5, 100, False), (16, 1, 128, False), (2, 3, 1, True)):
+        for world, batch, k, shuffle in ((3, 2, 50, False), (3, 2, 50, True), (8, 5, 100, False), (16, 1, 128, False), (2, 3, 1, True),
+                                         (8, 9, 100, False), (3, 12, 50, True), (2, 8, 1, False)):   # batch >= 8: the small-record kernel
             rec = np.zeros((world, batch, 2 * k + 1), dtype=np.int64)
             want = []
             for q in range(batch):
