@@ -731,6 +731,7 @@ def leg_batch_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
     clocks = sampler.stop() if rank == 0 else None
     fallbacks = sr.last_fallbacks + sr.last_batch_unanswered()    # queries of the last timed batch the coarse pass did not answer
     global_plan = sr._global_plan(k)
+    batch_peer = bool(global_plan) and sr._batch_peer_ready
     for _ in range(2):
         sr.retrieve_many_arrays(queries, k)
     dist.barrier(); torch.cuda.synchronize()
@@ -758,10 +759,15 @@ def leg_batch_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
         "dtype": "f32 results (f16 tensor-core coarse pass + exact f32 re-score)", "data": "synthetic",
         "config": config_of(name),
         "run": {"queries_per_step": BATCH, "per_gpu_f16_shadow_gb": local_rows * d * 2 / 1e9,
-                "parallelism": (f"row-sharded over {world} GPUs; per batch: one all-gather of {BATCH} x 32 sample maxima (ONE filter threshold per "
-                                f"query for all ranks, order statistic {global_plan[0]} of the union sample), one all-gather of {BATCH} k-candidate "
-                                "records per rank, one verifying merge launch; no host synchronisation in between" if global_plan else
-                                f"row-sharded over {world} GPUs, per-rank thresholds, one NCCL all-gather of {BATCH} k-candidate records per rank per batch + merge kernel")},
+                "parallelism": (
+                    (f"row-sharded over {world} GPUs, no collective: ONE filter threshold per query for all ranks (order statistic {global_plan[0]} of "
+                     f"the union of the ranks' samples), every rank's sample maxima and its <= {global_plan[2]} exact candidates per query stored "
+                     "into every rank's batch window over NVLink peer memory by the kernels that produce them, consumers behind flag waits, "
+                     "one verifying merge launch; no host synchronisation" if batch_peer else
+                     f"row-sharded over {world} GPUs; per batch: one all-gather of {BATCH} x 32 sample maxima (ONE filter threshold per query for "
+                     f"all ranks, order statistic {global_plan[0]} of the union sample), one all-gather of {BATCH} records of <= {global_plan[2]} "
+                     "candidates per rank, one verifying merge launch; no host synchronisation in between") if global_plan else
+                    f"row-sharded over {world} GPUs, per-rank thresholds, one NCCL all-gather of {BATCH} k-candidate records per rank per batch + merge kernel")},
         "ms_per_query": total_ms / nq,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
                      "traffic": None, "kernel": "whole batch step per GPU (coarse passes + refine + exchange + merge), rank-max time",
