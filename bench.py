@@ -732,14 +732,21 @@ def leg_batch_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
     fallbacks = sr.last_fallbacks + sr.last_batch_unanswered()    # queries of the last timed batch the coarse pass did not answer
     global_plan = sr._global_plan(k)
     batch_peer = bool(global_plan) and sr._batch_peer_ready
+    # e2e: host queries in (a page-locked tensor, DMA'd as is -- as the one-GPU leg passes page-locked arrays to
+    # svsb_query_batch), host results out (page-locked buffers), every batch; pageable NumPy arrays give the same answer
+    hq = torch.from_numpy(queries).pin_memory()
     for _ in range(2):
-        sr.retrieve_many_arrays(queries, k)
+        sr.retrieve_many_pinned(hq, k)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        out = sr.retrieve_many_arrays(queries, k)                 # host (b, d) array in, host (b, k) arrays out
+        out = sr.retrieve_many_pinned(hq, k)                      # host (b, d) in, host (b, k) arrays out
     torch.cuda.synchronize(); dist.barrier()
     (e2e_s,) = sp.max_over_ranks(time.perf_counter() - t0)
+    out = tuple(a.copy() for a in out)
+    ref = sr.retrieve_many_arrays(queries, k)
+    if not (np.array_equal(out[0].view(np.uint32), ref[0].view(np.uint32)) and np.array_equal(out[1], ref[1]) and np.array_equal(out[2], ref[2])):
+        raise AssertionError(f"{name}: page-locked and pageable batch calls disagree")
     pq = [0, 1, BATCH // 2, BATCH - 1][:PARITY_QUERIES]
     got = [[(float(s), int(i)) for s, i in zip(out[0][j, :out[2][j]], out[1][j, :out[2][j]])] for j in pq]
     parity = parity_sharded(dist, rank, world, sr, k, queries[pq], got)

@@ -189,39 +189,25 @@ __global__ void __launch_bounds__(256)
 union_threshold_kernel(const float* __restrict__ tops, int64_t list_stride, int world, int b, int rank, const float* __restrict__ eps,
                        float* __restrict__ thr)
 {
-    // Every rank's list arrives sorted descending, so an entry's rank in the union is its position in its own list plus,
-    // per other list, the number of entries ahead of it (binary search) -- ties broken by (list, position), which makes
-    // the ranks a permutation of 0 .. n-1; the entry of rank `rank - 1` carries the rank-th largest value.
-    __shared__ uint32_t vals[8][XCHG_MAX_RANKS * SAMPLE_TOPX];
+    // One warp per query; lane p holds entry p of every rank's list (ordered 32-bit keys).  The rank-th largest of the
+    // union is built bit by bit from the top: x grows by a bit whenever at least `rank` values are still >= x -- one
+    // ballot per list and bit, no shared memory, no dependent loads.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * 8 + warp;
     if (q >= b) return;
-    const int n = world * SAMPLE_TOPX;
-    uint32_t* v = vals[warp];
-    for (int l = 0; l < world; ++l)                              // lane = position in list l (SAMPLE_TOPX == 32)
-        v[l * SAMPLE_TOPX + lane] = f32_to_ordered(tops[(size_t)l * list_stride + (size_t)q * SAMPLE_TOPX + lane]);
-    __syncwarp();
-    uint32_t ans = 0; bool have = false;
-    for (int l = 0; l < world; ++l) {
-        const uint32_t mine = v[l * SAMPLE_TOPX + lane];
-        int r = lane;
-        for (int m = 0; m < world; ++m) {
-            if (m == l) continue;
-            const uint32_t* L = v + m * SAMPLE_TOPX;
-            int lo = 0, hi = SAMPLE_TOPX;                        // entries of list m ahead of mine: greater, or equal and m < l
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                const uint32_t o = L[mid];
-                if (o > mine || (o == mine && m < l)) lo = mid + 1; else hi = mid;
-            }
-            r += lo;
-        }
-        if (r == rank - 1) { ans = mine; have = true; }
+    uint32_t v[XCHG_MAX_RANKS];
+#pragma unroll
+    for (int l = 0; l < XCHG_MAX_RANKS; ++l)
+        v[l] = l < world ? f32_to_ordered(tops[(size_t)l * list_stride + (size_t)q * SAMPLE_TOPX + lane]) : 0u;
+    uint32_t x = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t t = x | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int l = 0; l < XCHG_MAX_RANKS; ++l) c += __popc(__ballot_sync(0xffffffffu, l < world && v[l] >= t));
+        if (c >= rank) x = t;
     }
-    const uint32_t who = __ballot_sync(0xffffffffu, have);
-    ans = __shfl_sync(0xffffffffu, ans, who ? __ffs(who) - 1 : 0);
-    if (lane == 0) thr[q] = ordered_to_f32(ans) - 2.0f * eps[q];
-    (void)n;
+    if (lane == 0) thr[q] = ordered_to_f32(x) - 2.0f * eps[q];
 }
 
 cudaError_t launch_union_threshold(cudaStream_t st, const float* tops, int64_t list_stride, int world, int b, int rank, const float* eps,
@@ -587,6 +573,197 @@ refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t ro
     batch_publish(push);
 }
 
+// ---------------------------------------------------------------------------------------------
+// refine, lean and fused (the default): select -> exact re-score -> sort -> emit / push in ONE kernel, one CTA of 256
+// threads per query with ~25-30 KB of shared memory, so seven CTAs share an SM and the latency-bound phases of some
+// overlap the HBM-bound re-score of the others -- the split's three launches (and the dependent global round trips at
+// the head of each) cost 25 us of a 1024-query batch at a 125 k-row shard (profiles/r02_c3_virtual_n8.md).
+// Shared memory for keys[cap_s] / rows[cap_s] is sized by the host from k (a query with more survivors: flag 8).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RS_THREADS)
+refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __restrict__ ids, int64_t row0,
+                   const float* __restrict__ Q, int ldq, int k, const u64* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+                   int cand_cap, const float* __restrict__ eps, const float* __restrict__ thr, int32_t* __restrict__ flags, int mode,
+                   int cap_s, RefineOut out, int32_t* __restrict__ stats, const __grid_constant__ BatchPush push)
+{
+    extern __shared__ __align__(16) unsigned char rl_smem_raw[];
+    __shared__ uint32_t cached[RS_CACHE];
+    __shared__ uint32_t hist[RF_BINS];
+    __shared__ uint32_t scratch[72];
+    __shared__ uint32_t small[RF_SMALL];
+    __shared__ u64 sel_sorted[RS_THREADS];
+    __shared__ u64 sel_bcast;
+    __shared__ uint32_t counter, vcount, lcount;
+    float4* sq = reinterpret_cast<float4*>(rl_smem_raw);
+    u64* skeys = reinterpret_cast<u64*>(rl_smem_raw + (size_t)d4 * 16);
+    uint32_t* srows = reinterpret_cast<uint32_t*>(skeys + cap_s);
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RS_THREADS / 32;
+    const int kk = (int)min((int64_t)k, n);
+    const bool partial = (mode & REFINE_PARTIAL) != 0;
+    const int flag_in = flags[q];                                   // independent loads first: one round trip
+    const int total = cand_cnt[q];
+    const float eps_q = eps[q];
+    const float thr_q = thr ? thr[q] : 0.f;
+    int32_t* out_count = push.world ? nullptr : out.counts + (int64_t)q * out.count_stride;
+    int flag_out = flag_in;
+    if (flag_in == 0 && (total > cand_cap || (!partial && total < kk))) flag_out = total > cand_cap ? 2 : 4;
+    if (tid == 0) { counter = 0; vcount = 0; lcount = 0; if (stats) stats[q] = 0; }
+    const u64* cq = cand + (size_t)q * cand_cap;
+    int C = 0, ver = 0;
+    if (flag_out == 0) {
+        for (int c = tid; c < d4; c += RS_THREADS) sq[c] = reinterpret_cast<const float4*>(Q + (size_t)q * ldq)[c];
+        const int lim = min(total, RS_CACHE);
+        for (int i0 = tid; i0 < lim; i0 += RS_THREADS * 4) {
+            u64 kv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * RS_THREADS; kv[u] = i < lim ? cq[i] : 0ull; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * RS_THREADS; if (i < lim) cached[i] = (uint32_t)(kv[u] >> 32); }
+        }
+        __syncthreads();
+        auto score_o = [&](int64_t i) { return i < RS_CACHE ? cached[i] : (uint32_t)(cq[i] >> 32); };
+        float cutoff = __int_as_float(0xff800000);                  // -inf: keep every candidate (partial, total < kk)
+        if (total >= kk) {
+            uint32_t tau_o = 0;
+            bool have = false;
+            if (kk <= RS_THREADS / 2) {                             // thread maxima + exact refilter (see sample_order_kernel)
+                uint32_t m = 0;
+                for (int i = tid; i < total; i += RS_THREADS) m = max(m, score_o(i));
+                const uint32_t tau0 = (uint32_t)(block_select_unique<u64>(((u64)m << 32) | (u64)(RS_THREADS - 1 - tid), kk, sel_sorted, &sel_bcast) >> 32);
+                for (int i = tid; i < total; i += RS_THREADS) {
+                    const uint32_t o = score_o(i);
+                    if (o >= tau0) { const uint32_t p = atomicAdd(&lcount, 1u); if (p < (uint32_t)RS_LIST) hist[p] = o; }
+                }
+                __syncthreads();
+                const int c = (int)lcount;
+                if (c <= RS_LIST) {
+                    for (int i = tid; i < c; i += RS_THREADS) {
+                        const uint32_t mine = hist[i];
+                        uint32_t gt = 0, ge = 0;
+                        for (int j = 0; j < c; ++j) { const uint32_t o = hist[j]; gt += o > mine ? 1u : 0u; ge += o >= mine ? 1u : 0u; }
+                        if (gt < (uint32_t)kk && ge >= (uint32_t)kk) scratch[7] = mine;   // equal values write the same word
+                    }
+                    __syncthreads();
+                    tau_o = scratch[7];
+                    have = true;
+                }
+                __syncthreads();
+            }
+            if (!have) tau_o = block_kth_largest_o32(score_o, total, kk, hist, scratch, small);
+            cutoff = ordered_to_f32(tau_o) - 2.0f * eps_q;
+            // the list holds exactly the rows with coarse >= thr and at least kk of them, so tau_o IS the kk-th largest coarse
+            // score of all (local) rows; rows with coarse in [cutoff, thr) would be missing from the list
+            if (!partial && thr && !(cutoff >= thr_q)) flag_out = REFINE_FLAG_THRESHOLD_HIGH;
+        }
+        if (flag_out == 0) {
+            const float vthr = partial ? __fadd_ru(thr_q, __fmul_ru(2.0f, eps_q)) : 0.f;
+            for (int i0 = 0; i0 < total; i0 += RS_THREADS) {
+                const int i = i0 + tid;
+                const float s = i < total ? ordered_to_f32(score_o(i)) : 0.f;
+                if (i < total && s >= cutoff) {
+                    const uint32_t p = atomicAdd(&counter, 1u);
+                    if (p < (uint32_t)cap_s) srows[p] = key_row(cq[i]);
+                }
+                if (partial) {
+                    const uint32_t v = __ballot_sync(0xffffffffu, i < total && s >= vthr);
+                    if (lane == 0 && v) atomicAdd(&vcount, (uint32_t)__popc(v));
+                }
+            }
+            __syncthreads();
+            C = (int)counter; ver = (int)vcount;
+            if (C > cap_s) flag_out = 8;
+        }
+    }
+    if (flag_out != 0) {                                            // the exact path answers this query
+        if (tid == 0) {
+            if (flag_out != flag_in) flags[q] = flag_out;
+            const int32_t c0 = (mode & REFINE_DEFER) ? -1 : 0;
+            if (out_count) { out_count[0] = c0; if (partial) out_count[1] = 0; }
+            for (int p = 0; p < push.world; ++p) {
+                int32_t* cw = reinterpret_cast<int32_t*>(static_cast<u64*>(push.dst[p]) + (int64_t)q * out.stride + 2 * out.cap);
+                cw[0] = c0; cw[1] = 0;
+            }
+        }
+        batch_publish(push);
+        return;
+    }
+    if (tid == 0 && stats) stats[q] = C;
+
+    // exact fp32 re-score, one warp per survivor, two survivors per warp iteration (summation order == gemv_tma_kernel)
+    const float4* M4 = reinterpret_cast<const float4*>(M);
+    for (int i = warp; i < C; i += 2 * nwarps) {
+        const int i2 = i + nwarps;
+        const bool two = i2 < C;
+        const uint32_t rowa = srows[i], rowb = srows[two ? i2 : i];
+        const float4* pa = M4 + (int64_t)rowa * d4;                  // candidate keys carry LOCAL rows
+        const float4* pb = M4 + (int64_t)rowb * d4;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        int c = lane;
+        for (; c + 96 < d4; c += 128) {
+            const float4 m0 = ldg_stream(pa + c), m1 = ldg_stream(pa + c + 32), m2 = ldg_stream(pa + c + 64), m3 = ldg_stream(pa + c + 96);
+            const float4 n0 = ldg_stream(pb + c), n1 = ldg_stream(pb + c + 32), n2 = ldg_stream(pb + c + 64), n3 = ldg_stream(pb + c + 96);
+            const float4 q0 = sq[c], q1 = sq[c + 32], q2 = sq[c + 64], q3 = sq[c + 96];
+            fma4(a0, m0, q0); fma4(a1, m1, q1); fma4(a0, m2, q2); fma4(a1, m3, q3);
+            fma4(b0, n0, q0); fma4(b1, n1, q1); fma4(b0, n2, q2); fma4(b1, n3, q3);
+        }
+        for (; c + 32 < d4; c += 64) {
+            const float4 m0 = ldg_stream(pa + c), m1 = ldg_stream(pa + c + 32);
+            const float4 n0 = ldg_stream(pb + c), n1 = ldg_stream(pb + c + 32);
+            const float4 q0 = sq[c], q1 = sq[c + 32];
+            fma4(a0, m0, q0); fma4(a1, m1, q1);
+            fma4(b0, n0, q0); fma4(b1, n1, q1);
+        }
+        if (c < d4) {
+            const float4 m0 = ldg_stream(pa + c), n0 = ldg_stream(pb + c);
+            const float4 q0 = sq[c];
+            fma4(a0, m0, q0); fma4(b0, n0, q0);
+        }
+        const float sa = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
+        const float sb = warp_sum(((b0.x + b1.x) + (b0.y + b1.y)) + ((b0.z + b1.z) + (b0.w + b1.w)));
+        if (lane == 0) { skeys[i] = make_key(sa, rowa); if (two) skeys[i2] = make_key(sb, rowb); }
+    }
+    __syncthreads();
+
+    const u64* sorted;
+    if (C <= RANK_SORT_MAX) {                                       // sel_sorted doubles as the rank sort's destination
+        block_rank_sort_desc(skeys, sel_sorted, C);
+        sorted = sel_sorted;
+    } else {
+        int np2 = 1; while (np2 < C) np2 <<= 1;                     // np2 <= cap_s (a power of two)
+        for (int i = C + tid; i < np2; i += RS_THREADS) skeys[i] = 0ull;
+        __syncthreads();
+        block_bitonic_desc<false>(skeys, nullptr, np2);
+        sorted = skeys;
+    }
+    const int full = min(kk, C);
+    const int cnt = (out.cap > 0 && partial) ? min(full, out.cap) : full;
+    for (int i = tid; i < cnt; i += RS_THREADS) {
+        const u64 key = sorted[i];
+        const uint32_t row = key_row(key);
+        const int64_t grow = row0 + (int64_t)row;                    // global row (row0 = first row of this shard)
+        const u64 gkey = (key & 0xffffffff00000000ull) | (u64)(uint32_t)(~(uint32_t)grow);
+        const int64_t id = ids ? ids[row] : grow;
+        if (push.world == 0) {
+            if (out.scores) out.scores[(int64_t)q * out.stride + i] = key_score(key);
+            if (out.keys) out.keys[(int64_t)q * out.stride + i] = gkey;
+            out.ids[(int64_t)q * out.stride + i] = id;
+        }
+        for (int p = 0; p < push.world; ++p) {                       // the record, straight into every rank's window
+            u64* r = static_cast<u64*>(push.dst[p]) + (int64_t)q * out.stride;
+            r[i] = gkey; r[out.cap + i] = (u64)id;
+        }
+    }
+    if (tid == 0) {
+        const int32_t c0 = cnt | (cnt < full ? REFINE_COUNT_TRUNCATED : 0);
+        if (out_count) { out_count[0] = c0; if (partial) out_count[1] = ver; }
+        for (int p = 0; p < push.world; ++p) {
+            int32_t* cw = reinterpret_cast<int32_t*>(static_cast<u64*>(push.dst[p]) + (int64_t)q * out.stride + 2 * out.cap);
+            cw[0] = c0; cw[1] = ver;
+        }
+    }
+    batch_publish(push);
+}
+
 __global__ void __launch_bounds__(32)
 wait_flags_kernel(const u64* flags, int world, u64 seq, u64 timeout_ns, int* status)
 {
@@ -627,17 +804,40 @@ cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, co
     if (k < 1 || (ld & 3) || ldq < ld) return cudaErrorInvalidValue;
     const int64_t kk = k < n ? k : n;
     if (kk > REFINE_SURVIVOR_CAP) return cudaErrorInvalidValue;
-    static const bool fused_env = [] { const char* v = getenv("SVSB_REFINE_FUSED"); return v && atoi(v) != 0; }();
-    const bool fused = (fused_env || !scratch || !scratch->rows) && mode == 0 && !push;
-    if (!fused && (!scratch || !scratch->rows || !scratch->keys || !scratch->cnt || !scratch->ver)) return cudaErrorInvalidValue;
+    // SVSB_REFINE = lean (default) | split | fused ; SVSB_REFINE_FUSED=1 is the old spelling of "fused"
+    static const int variant = [] {
+        const char* v = getenv("SVSB_REFINE");
+        const char* f = getenv("SVSB_REFINE_FUSED");
+        if (f && atoi(f) != 0) return 2;
+        if (v && !strcmp(v, "split")) return 1;
+        if (v && !strcmp(v, "fused")) return 2;
+        return 0;
+    }();
+    // survivors the lean kernel holds in shared memory: a power of two >= 2.5 kk (tau~ - 2 eps keeps kk plus a margin band).
+    // Beyond 1024 (kk > 409) its CTAs get so fat that two share an SM; the split form -- re-score grid-wide from global
+    // lists -- is then the faster one (1M x 3072, k = 1000, 256 queries: 2.16 ms against 2.92 ms).
+    int cap_s = 512;
+    while (cap_s < 4096 && cap_s < (int)((5 * kk + 1) / 2)) cap_s <<= 1;
+    const bool have_scratch = scratch && scratch->rows && scratch->keys && scratch->cnt && scratch->ver;
+    const bool fused = variant == 2 && mode == 0 && !push;
+    const bool split = have_scratch && (variant == 1 || (variant == 0 && cap_s > 1024));
     if ((mode & REFINE_PARTIAL) && !thr) return cudaErrorInvalidValue;
     static bool attr_set[64] = {false};
     int dev = 0; cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(refine_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
+    }
+    if (!fused && !split) {
+        const size_t smem = (size_t)ld * 4 + (size_t)cap_s * 12;
+        if (smem > 180 * 1024) return cudaErrorInvalidValue;
+        refine_lean_kernel<<<b, RS_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, thr, flags, mode,
+                                                        cap_s, out, stats, push ? *push : BatchPush());
+        count_launch();
+        return cudaGetLastError();
     }
     if (fused) {
         const size_t smem = ((sizeof(RefineSmem) + 15) & ~(size_t)15) + (size_t)ld * 4;
@@ -648,8 +848,8 @@ cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, co
     }
     if ((size_t)ld * 4 > 200 * 1024) return cudaErrorInvalidValue;
     refine_select_kernel<<<b, RS_THREADS, 0, st>>>(n, k, cand, cand_cnt, cand_cap, eps, thr, flags, mode, *scratch, stats);
-    static const int split = [] { const char* v = getenv("SVSB_RESCORE_SPLIT"); const int x = v ? atoi(v) : 0; return x >= 1 && x <= 64 ? x : 4; }();
-    rescore_kernel<<<dim3(b, split), RS_THREADS, (size_t)ld * 4, st>>>(M, ld / 4, Q, ldq, *scratch);
+    static const int rs_split = [] { const char* v = getenv("SVSB_RESCORE_SPLIT"); const int x = v ? atoi(v) : 0; return x >= 1 && x <= 64 ? x : 4; }();
+    rescore_kernel<<<dim3(b, rs_split), RS_THREADS, (size_t)ld * 4, st>>>(M, ld / 4, Q, ldq, *scratch);
     refine_sort_kernel<<<b, RS_THREADS, (size_t)REFINE_SURVIVOR_CAP * 8, st>>>(n, k, ids, row0, flags, mode, *scratch, out,
                                                                                push ? *push : BatchPush());
     count_launch(3);

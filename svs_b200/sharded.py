@@ -470,6 +470,44 @@ class ShardedRetriever:
             cnt[j] = len(sj); s[j, :len(sj)] = sj; i[j, :len(ij)] = ij
         return s, i, cnt
 
+    def retrieve_many_pinned(self, queries, n: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """retrieve_many_arrays without pageable staging: `queries` is a PINNED torch tensor (b, d) float32 (torch
+        `pin_memory()`), DMA'd to the device as is; the results come back into page-locked buffers owned by this object and
+        are returned as NumPy views of them -- valid until the next call.  Same answers as retrieve_many_arrays."""
+        t = self.backend.torch
+        if not (isinstance(queries, t.Tensor) and queries.is_pinned() and queries.dtype == t.float32 and queries.dim() == 2
+                and queries.is_contiguous()):
+            raise ValueError("retrieve_many_pinned: a contiguous pinned float32 torch tensor (b, d) is required")
+        if queries.shape[1] != self.d or self.n == 0:
+            raise ValueError(f"shapes ({self.n},{self.d if self.n else 0}) and {tuple(queries.shape)} not aligned")
+        b = queries.shape[0]
+        if n <= 0 or b == 0:
+            return (np.zeros((b, 0), np.float32), np.zeros((b, 0), np.int64), np.zeros(b, np.int32))
+        if n > 2048 and self.n > 2048:
+            raise NotImplementedError("n > 2048 is not supported by the sharded path")
+        k = min(int(n), 2048, self.n)
+        ld = (self.d + 3) & ~3
+        dq = queries.to(self.backend.device, non_blocking=True)
+        if ld != self.d:
+            dq = t.nn.functional.pad(dq, (0, ld - self.d))
+        o_s, o_i, o_c = self._batch(dq, k)
+        key = ("pinned_out", b, k)
+        if key not in self._bufs:
+            self._bufs[key] = (t.empty((b, k), dtype=t.float32).pin_memory(), t.empty((b, k), dtype=t.int64).pin_memory(),
+                               t.empty((b,), dtype=t.int32).pin_memory())
+        h_s, h_i, h_c = self._bufs[key]
+        h_s.copy_(o_s, non_blocking=True); h_i.copy_(o_i, non_blocking=True); h_c.copy_(o_c, non_blocking=True)
+        t.cuda.current_stream(self.backend.device).synchronize()
+        s, i, cnt = h_s.numpy(), h_i.numpy(), h_c.numpy()
+        if (cnt == -2).any():
+            raise RuntimeError("sharded batch: a peer's part of the batch did not arrive (SVSB_XCHG_TIMEOUT_MS)")
+        redo = np.nonzero(cnt < 0)[0]
+        self.last_fallbacks += len(redo)
+        for j in redo:
+            sj, ij = self.retrieve_arrays(queries[j].numpy(), k)
+            cnt[j] = len(sj); s[j, :len(sj)] = sj; i[j, :len(ij)] = ij
+        return s, i, cnt
+
     def retrieve_many(self, query_vecs: np.ndarray, n: int) -> List[List[Tuple[float, int]]]:
         """superheavy() for every row of query_vecs on every rank: host queries in, host lists out."""
         s, i, cnt = self.retrieve_many_arrays(query_vecs, n)

@@ -514,6 +514,12 @@ def test_world_size_one_process_group_runs_the_real_collective(exchange):
         assert sr.last_fallbacks == 0
         for j in (0, 5, 10):
             assert many[j] == sr.retrieve(qs[j], 100)
+        # page-locked tensor in, page-locked buffers out: the same bits as the pageable form
+        ps, pi, pc = sr.retrieve_many_pinned(torch.from_numpy(qs).pin_memory(), 100)
+        as_, ai, ac = sr.retrieve_many_arrays(qs, 100)
+        assert np.array_equal(ps.view(np.uint32), as_.view(np.uint32)) and np.array_equal(pi, ai) and np.array_equal(pc, ac)
+        with pytest.raises(ValueError):
+            sr.retrieve_many_pinned(torch.from_numpy(qs), 100)  # not pinned
         sr.close()
     finally:
         dist.destroy_process_group()
