@@ -283,7 +283,12 @@ int svsb_bxchg_connect_local(svsb_t* e, svsb_t* const* engines);
 int svsb_bxchg_disconnect(svsb_t* e);
 int svsb_batch_peer_prepare(svsb_t* e, int32_t b, int32_t k);
 int svsb_batch_peer(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, float max_row_norm, int32_t sample_rank,
-                    int32_t rec_cap, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts);
+                    int32_t rec_cap, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts, int32_t flags);
+/* flags bit 0 = pipelined: the batch's verifying merge (the only step that waits for the peers' records) is enqueued
+ * behind the FIRST phase of the next svsb_batch_peer call on this engine, or by svsb_batch_peer_flush -- the peers get
+ * that long to deliver, which hides the ranks' skew in a stream of batches.  The outputs are complete after whichever
+ * enqueues the merge. */
+int svsb_batch_peer_flush(svsb_t* e, void* stream);
 /* ---- peer exchange: the exchange step fused into the kernels, over NVLink / NVSwitch peer memory ----------
  * Replaces "all-gather the records over NCCL, then merge" for single queries: every rank owns a GATHER WINDOW in its
  * HBM (slots x world records + one flag word per record); the selection kernel's epilogue stores its record into the

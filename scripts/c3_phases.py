@@ -69,7 +69,8 @@ torch.cuda.synchronize(); dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(iters):
-    sr.run_batch(k)
+    sr.run_batch(k, defer=True)
+sr.flush_batches()
 e1.record(); torch.cuda.synchronize()
 loop = torch.tensor([e0.elapsed_time(e1) / iters * 1e3], device="cuda"); dist.all_reduce(loop, op=dist.ReduceOp.MAX)
 unanswered = sr.last_batch_unanswered()

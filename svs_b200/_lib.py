@@ -96,7 +96,8 @@ SIGNATURES = {
     "svsb_bxchg_disconnect": (C.c_int, [C.c_void_p]),
     "svsb_batch_peer_prepare": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "svsb_batch_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32,
-                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "svsb_batch_peer_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
     "svsb_enqueue_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "svsb_enqueue_merge_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1906,8 +1906,38 @@ extern "C" int svsb_batch_peer_prepare(svsb_t* e, int32_t b, int32_t k) {
     return SVSB_OK;
 }
 
+// wait for every rank's records of the deferred batch, then the verifying merge
+static int bxchg_enqueue_merge(svsb_engine* e, cudaStream_t st, const BXchg::Deferred& d) {
+    BXchg* x = e->bxchg.get();
+    CU(launch_wait_flags(st, x->flag(x->block, 1, d.slot, 0), x->world, d.seq, x->timeout_ns, x->status));
+    const int64_t rec = 2 * (int64_t)d.rec_cap + 1;
+    const int64_t* r0 = x->recs(x->block, d.slot, 0);
+    u64* sk = nullptr; int64_t* sp = nullptr;
+    if ((int64_t)x->world * d.rec_cap > K_FAST_MAX) {
+        if (e->shard_ws.empty() || !e->shard_ws[0]) { e->shard_ws.resize(std::max<size_t>(1, e->shard_ws.size())); e->shard_ws[0].reset(new DevWs()); e->shard_ws[0]->dev = e->devs[0]; }
+        int rc = e->shard_ws[0]->ensure_merge_scratch((int64_t)d.b * x->world * d.rec_cap);
+        if (rc != SVSB_OK) return rc;
+        sk = e->shard_ws[0]->mscr_keys; sp = e->shard_ws[0]->mscr_ids;
+    }
+    CU(launch_merge_ex(st, reinterpret_cast<const u64*>(r0), r0 + d.rec_cap, reinterpret_cast<const int32_t*>(r0 + 2 * (int64_t)d.rec_cap),
+                       x->world, d.rec_cap, d.k, d.b, x->rec_region(), rec, x->rec_region() * 2, rec * 2, sk, sp,
+                       d.out_scores, d.out_ids, d.out_counts, d.k, x->status));
+    return SVSB_OK;
+}
+
+extern "C" int svsb_batch_peer_flush(svsb_t* e, void* stream) {
+    if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
+    BXchg* x = e->bxchg.get();
+    if (!x || !x->deferred.pending) return SVSB_OK;
+    CU(cudaSetDevice(e->devs[0]));
+    std::lock_guard<std::mutex> lk(e->batch_mu);
+    int rc = bxchg_enqueue_merge(e, (cudaStream_t)stream, x->deferred);
+    x->deferred.pending = false;
+    return rc;
+}
+
 extern "C" int svsb_batch_peer(svsb_t* e, void* stream, const float* d_Q, int32_t b, int32_t k, float max_row_norm, int32_t sample_rank,
-                               int32_t rec_cap, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts) {
+                               int32_t rec_cap, float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_counts, int32_t flags) {
     if (!e) return fail(SVSB_E_INVALID, "engine is NULL");
     BXchg* x = e->bxchg.get();
     if (!x || !x->connected) return fail(SVSB_E_STATE, "svsb_batch_peer: svsb_bxchg_create + svsb_bxchg_connect first");
@@ -1952,6 +1982,11 @@ extern "C" int svsb_batch_peer(svsb_t* e, void* stream, const float* d_Q, int32_
     CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
                           nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
     CU(launch_sample_top(st, w->sample, P.sample_rows, b, nullptr, &pa));
+    if (x->deferred.pending) {                 // the previous batch's merge: its peers had this phase's time to deliver
+        rc = bxchg_enqueue_merge(e, st, x->deferred);
+        x->deferred.pending = false;
+        if (rc != SVSB_OK) return rc;
+    }
     // 2. all ranks' maxima are here -> ONE threshold per query; filter; exact re-score; records -> every rank's window
     CU(launch_wait_flags(st, x->flag(x->block, 0, slot, 0), x->world, seq, x->timeout_ns, x->status));
     CU(launch_union_threshold(st, x->tops(x->block, slot, 0), x->tops_region(), x->world, b, sample_rank, w->eps, w->thr));
@@ -1960,20 +1995,12 @@ extern "C" int svsb_batch_peer(svsb_t* e, void* stream, const float* d_Q, int32_
     RefineOut o{nullptr, nullptr, nullptr, rec, nullptr, 2 * rec, rec_cap};
     CU(launch_refine(st, s.M, P.n, P.ld, s.ids, s.row0, d_Q, b, P.ld, P.k, w->cand, w->cand_cnt, P.cand_cap, w->eps, w->thr, w->flags,
                      o, w->stats, &w->rs, REFINE_PARTIAL | REFINE_DEFER, &pb));
-    // 3. all ranks' records are here -> verifying merge
-    CU(launch_wait_flags(st, x->flag(x->block, 1, slot, 0), x->world, seq, x->timeout_ns, x->status));
-    const int64_t* r0 = x->recs(x->block, slot, 0);
-    u64* sk = nullptr; int64_t* sp = nullptr;
-    if ((int64_t)x->world * rec_cap > K_FAST_MAX) {
-        if (e->shard_ws.empty() || !e->shard_ws[0]) { e->shard_ws.resize(std::max<size_t>(1, e->shard_ws.size())); e->shard_ws[0].reset(new DevWs()); e->shard_ws[0]->dev = e->devs[0]; }
-        if ((rc = e->shard_ws[0]->ensure_merge_scratch((int64_t)b * x->world * rec_cap)) != SVSB_OK) return rc;
-        sk = e->shard_ws[0]->mscr_keys; sp = e->shard_ws[0]->mscr_ids;
-    }
-    const int64_t kk_global = k;       // the caller passes min(k, global rows) as k when the matrix is smaller (ShardedRetriever clips n)
-    CU(launch_merge_ex(st, reinterpret_cast<const u64*>(r0), r0 + rec_cap, reinterpret_cast<const int32_t*>(r0 + 2 * (int64_t)rec_cap),
-                       x->world, rec_cap, k, b, x->rec_region(), rec, x->rec_region() * 2, rec * 2, sk, sp,
-                       d_out_scores, d_out_ids, d_out_counts, (int)kk_global, x->status));
-    return SVSB_OK;
+    // 3. all ranks' records are here -> verifying merge (now, or behind the first phase of the next batch)
+    BXchg::Deferred d;
+    d.pending = true; d.slot = slot; d.rec_cap = rec_cap; d.k = k; d.b = b; d.seq = seq;
+    d.out_scores = d_out_scores; d.out_ids = d_out_ids; d.out_counts = d_out_counts;
+    if (flags & 1) { x->deferred = d; return SVSB_OK; }
+    return bxchg_enqueue_merge(e, st, d);
 }
 
 // ---- peer exchange: the fused selection + exchange step and the waiting merge (kernels.cuh, select.cu) -------------

@@ -326,6 +326,13 @@ struct BXchg {
     unsigned long long timeout_ns = 30ull * 1000000000ull;
     unsigned int* done = nullptr;            // two last-block tickets (sample maxima, records)
     int* status = nullptr;                   // device word: 1 = a wait timed out
+    // svsb_batch_peer with flag bit 0: the verifying merge of batch j is enqueued behind the FIRST phase of batch j+1 (or by
+    // svsb_batch_peer_flush), so the peers have that long to deliver their records before this rank's stream waits for them
+    struct Deferred {
+        bool pending = false;
+        int slot = 0, rec_cap = 0, k = 0, b = 0; unsigned long long seq = 0;
+        float* out_scores = nullptr; int64_t* out_ids = nullptr; int32_t* out_counts = nullptr;
+    } deferred;
     int64_t tops_region() const { return (int64_t)B_MAX * SAMPLE_TOPX; }                       // floats per (slot, source)
     int64_t rec_region() const { return (int64_t)B_MAX * (2 * (int64_t)rec_cap + 1); }         // words per (slot, source)
     u64* flag(unsigned char* blk, int phase, int slot, int src) const { return reinterpret_cast<u64*>(blk) + ((int64_t)phase * SLOTS + slot) * world + src; }

@@ -162,12 +162,18 @@ class CudaShardBackend:
     def batch_peer_prepare(self, b: int, k: int) -> None:
         self._check(self._lib.svsb_batch_peer_prepare(self.engine._h, b, k))
 
-    def batch_peer(self, queries, k: int, max_row_norm: float, sample_rank: int, rec_cap: int, out_scores, out_ids, out_counts) -> None:
-        """One whole batch (<= 2048 device queries) on the current stream, no collective: see include/svsb200.h."""
+    def batch_peer(self, queries, k: int, max_row_norm: float, sample_rank: int, rec_cap: int, out_scores, out_ids, out_counts,
+                   defer_merge: bool = False) -> None:
+        """One whole batch (<= 2048 device queries) on the current stream, no collective: see include/svsb200.h.
+        defer_merge: the verifying merge is enqueued by the next batch_peer call (behind its first phase) or batch_peer_flush."""
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.svsb_batch_peer(self.engine._h, C.c_void_p(st), C.c_void_p(queries.data_ptr()), queries.shape[0], k,
                                               C.c_float(max_row_norm), sample_rank, rec_cap, C.c_void_p(out_scores.data_ptr()),
-                                              C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_counts.data_ptr())))
+                                              C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_counts.data_ptr()), 1 if defer_merge else 0))
+
+    def batch_peer_flush(self) -> None:
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.svsb_batch_peer_flush(self.engine._h, C.c_void_p(st)))
 
     # -- peer exchange (fused selection + exchange over NVLink peer memory) -------------------------
     def exchange_handle(self, world: int, rank: int, k_max: int = 2048) -> bytes:
@@ -394,7 +400,7 @@ class ShardedRetriever:
             self._plans[key] = plan
         return self._plans[key]
 
-    def _batch(self, dq, k: int):
+    def _batch(self, dq, k: int, defer: bool = False):
         """b device queries -> (scores (b, k), ids (b, k), counts (b,)) device tensors, identical on every rank:
         per-rank batched candidate records, ONE all-gather of b records per rank, ONE merge launch (a CTA per query).
         With a global plan the ranks first agree on one filter threshold per query (a b x 32-float all-gather), each
@@ -419,9 +425,12 @@ class ShardedRetriever:
         if self.exchange == "peer" and hasattr(self.backend, "batch_peer") and cap <= self.backend.BATCH_WINDOW_CAP:
             # both exchanges fused into the kernels over NVLink peer memory: no collective call at all
             self._ensure_batch_peer()
-            for c0 in range(0, b, 2048):
+            for c0 in range(0, b, 2048):                           # chunks pipeline: merge of chunk c behind the first phase of c+1
                 bc = min(2048, b - c0)
-                self.backend.batch_peer(dq[c0:c0 + bc], k, max_row_norm, sample_rank, cap, o_s[c0:c0 + bc], o_i[c0:c0 + bc], o_c[c0:c0 + bc])
+                self.backend.batch_peer(dq[c0:c0 + bc], k, max_row_norm, sample_rank, cap, o_s[c0:c0 + bc], o_i[c0:c0 + bc], o_c[c0:c0 + bc],
+                                        defer_merge=True)
+            if not defer:
+                self.backend.batch_peer_flush()
             self._last_counts = o_c
             return o_s, o_i, o_c
         tkey = ("tops", b)
@@ -440,12 +449,18 @@ class ShardedRetriever:
 
     def last_batch_unanswered(self) -> int:
         """Queries of the last global-threshold batch that came out with count -1 (synchronises); 0 otherwise."""
+        self.flush_batches()
         return 0 if self._last_counts is None else int((self._last_counts < 0).sum().item())
 
-    def run_batch(self, k: int) -> None:
-        """One batch of ALL uploaded queries, device-resident end to end (bench path)."""
+    def run_batch(self, k: int, defer: bool = False) -> None:
+        """One batch of ALL uploaded queries, device-resident end to end (bench path).  defer: in a stream of batches the
+        batch's verifying merge goes behind the next batch's first phase (flush_batches() ends the stream)."""
         assert self._queries is not None, "set_queries first"
-        self._batch(self._queries, k)
+        self._batch(self._queries, k, defer=defer)
+
+    def flush_batches(self) -> None:
+        if self._batch_peer_ready:
+            self.backend.batch_peer_flush()
 
     def retrieve_many_arrays(self, query_vecs: np.ndarray, n: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """superheavy() for every row of query_vecs on every rank, as arrays: host queries in; host

@@ -237,7 +237,11 @@ def test_batch_peer_exchange_virtual_ranks_equal_the_collective_form(world, n, d
             torch.cuda.synchronize()
             for r, b in enumerate(backs):                      # every rank's whole batch is enqueued before any is awaited
                 with torch.cuda.stream(streams[r]):
-                    b.batch_peer(dq, k, norm, rank, cap, *outs[r])
+                    b.batch_peer(dq, k, norm, rank, cap, *outs[r], defer_merge=(rep % 2 == 1))
+            if rep % 2 == 1:                                   # pipelined form: the merges are enqueued by the flush
+                for r, b in enumerate(backs):
+                    with torch.cuda.stream(streams[r]):
+                        b.batch_peer_flush()
             torch.cuda.synchronize()
             for r in range(world):
                 o_s, o_i, o_c = (t.cpu().numpy() for t in outs[r])
@@ -249,6 +253,29 @@ def test_batch_peer_exchange_virtual_ranks_equal_the_collective_form(world, n, d
                 if ref_c[j] == k:
                     got = list(zip(ref_s[j, :k].tolist(), ref_i[j, :k].tolist()))
                     oracle.compare_retrieval(got, oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+        # a stream of three pipelined batches: the merge of each is enqueued behind the first phase of the next
+        refs, dqs = [], []
+        for rep in range(3):
+            qs = oracle.synth_queries(batch, d, 60 + rep)
+            ref_s, ref_i, ref_c, dq, _ = _global_batch(backs, world, n, qs, k, cap=cap)
+            refs.append((ref_s, ref_i, ref_c)); dqs.append(dq.clone())
+        torch.cuda.synchronize()
+        outs3 = [[b.new_outputs(batch, k) for _ in range(3)] for b in backs]
+        for rep in range(3):
+            for r, b in enumerate(backs):
+                with torch.cuda.stream(streams[r]):
+                    b.batch_peer(dqs[rep], k, norm, rank, cap, *outs3[r][rep], defer_merge=True)
+        for r, b in enumerate(backs):
+            with torch.cuda.stream(streams[r]):
+                b.batch_peer_flush()
+        torch.cuda.synchronize()
+        for rep in range(3):
+            ref_s, ref_i, ref_c = refs[rep]
+            ok = ref_c == k
+            for r in range(world):
+                o_s, o_i, o_c = (t.cpu().numpy() for t in outs3[r][rep])
+                assert np.array_equal(o_c, ref_c), (rep, r)
+                assert np.array_equal(o_s[ok].view(np.uint32), ref_s[ok].view(np.uint32)) and np.array_equal(o_i[ok], ref_i[ok])
     finally:
         for b in backs:
             b.batch_exchange_disconnect()
