@@ -578,13 +578,14 @@ refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t ro
 // threads per query with ~25-30 KB of shared memory, so seven CTAs share an SM and the latency-bound phases of some
 // overlap the HBM-bound re-score of the others -- the split's three launches (and the dependent global round trips at
 // the head of each) cost 25 us of a 1024-query batch at a 125 k-row shard (profiles/r02_c3_virtual_n8.md).
-// Shared memory for keys[cap_s] / rows[cap_s] is sized by the host from k (a query with more survivors: flag 8).
+// Shared memory for keys[cap_s] / rows[cap_s] is sized by the host from k; a query with more survivors keeps the rest in
+// global lists (RefineScratch) and sorts there -- slower, exact all the same; more than REFINE_SURVIVOR_CAP: flag 8.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RS_THREADS)
 refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __restrict__ ids, int64_t row0,
                    const float* __restrict__ Q, int ldq, int k, const u64* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
                    int cand_cap, const float* __restrict__ eps, const float* __restrict__ thr, int32_t* __restrict__ flags, int mode,
-                   int cap_s, RefineOut out, int32_t* __restrict__ stats, const __grid_constant__ BatchPush push)
+                   int cap_s, RefineScratch spill, RefineOut out, int32_t* __restrict__ stats, const __grid_constant__ BatchPush push)
 {
     extern __shared__ __align__(16) unsigned char rl_smem_raw[];
     __shared__ uint32_t cached[RS_CACHE];
@@ -609,6 +610,10 @@ refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t
     if (flag_in == 0 && (total > cand_cap || (!partial && total < kk))) flag_out = total > cand_cap ? 2 : 4;
     if (tid == 0) { counter = 0; vcount = 0; lcount = 0; if (stats) stats[q] = 0; }
     const u64* cq = cand + (size_t)q * cand_cap;
+    // survivors beyond cap_s (a score distribution packed more tightly than the host's sizing rule assumes) spill to global lists
+    uint32_t* grows = spill.rows ? spill.rows + (size_t)q * REFINE_SURVIVOR_CAP : nullptr;
+    u64* gkeys = spill.keys ? spill.keys + (size_t)q * REFINE_SURVIVOR_CAP : nullptr;
+    const int cap_all = grows && gkeys ? REFINE_SURVIVOR_CAP : cap_s;
     int C = 0, ver = 0;
     if (flag_out == 0) {
         for (int c = tid; c < d4; c += RS_THREADS) sq[c] = reinterpret_cast<const float4*>(Q + (size_t)q * ldq)[c];
@@ -663,6 +668,7 @@ refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t
                 if (i < total && s >= cutoff) {
                     const uint32_t p = atomicAdd(&counter, 1u);
                     if (p < (uint32_t)cap_s) srows[p] = key_row(cq[i]);
+                    else if (p < (uint32_t)cap_all) grows[p] = key_row(cq[i]);
                 }
                 if (partial) {
                     const uint32_t v = __ballot_sync(0xffffffffu, i < total && s >= vthr);
@@ -671,7 +677,7 @@ refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t
             }
             __syncthreads();
             C = (int)counter; ver = (int)vcount;
-            if (C > cap_s) flag_out = 8;
+            if (C > cap_all) flag_out = 8;
         }
     }
     if (flag_out != 0) {                                            // the exact path answers this query
@@ -694,7 +700,8 @@ refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t
     for (int i = warp; i < C; i += 2 * nwarps) {
         const int i2 = i + nwarps;
         const bool two = i2 < C;
-        const uint32_t rowa = srows[i], rowb = srows[two ? i2 : i];
+        const int ib = two ? i2 : i;
+        const uint32_t rowa = i < cap_s ? srows[i] : grows[i], rowb = ib < cap_s ? srows[ib] : grows[ib];
         const float4* pa = M4 + (int64_t)rowa * d4;                  // candidate keys carry LOCAL rows
         const float4* pb = M4 + (int64_t)rowb * d4;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
@@ -720,7 +727,11 @@ refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t
         }
         const float sa = warp_sum(((a0.x + a1.x) + (a0.y + a1.y)) + ((a0.z + a1.z) + (a0.w + a1.w)));
         const float sb = warp_sum(((b0.x + b1.x) + (b0.y + b1.y)) + ((b0.z + b1.z) + (b0.w + b1.w)));
-        if (lane == 0) { skeys[i] = make_key(sa, rowa); if (two) skeys[i2] = make_key(sb, rowb); }
+        if (lane == 0) {
+            const u64 ka = make_key(sa, rowa), kb = make_key(sb, rowb);
+            if (i < cap_s) skeys[i] = ka; else gkeys[i] = ka;
+            if (two) { if (i2 < cap_s) skeys[i2] = kb; else gkeys[i2] = kb; }
+        }
     }
     __syncthreads();
 
@@ -728,12 +739,18 @@ refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t
     if (C <= RANK_SORT_MAX) {                                       // sel_sorted doubles as the rank sort's destination
         block_rank_sort_desc(skeys, sel_sorted, C);
         sorted = sel_sorted;
-    } else {
+    } else if (C <= cap_s) {
         int np2 = 1; while (np2 < C) np2 <<= 1;                     // np2 <= cap_s (a power of two)
         for (int i = C + tid; i < np2; i += RS_THREADS) skeys[i] = 0ull;
         __syncthreads();
         block_bitonic_desc<false>(skeys, nullptr, np2);
         sorted = skeys;
+    } else {                                                        // spilled: sort the whole list where it is, in global memory
+        int np2 = 1; while (np2 < C) np2 <<= 1;                     // <= REFINE_SURVIVOR_CAP
+        for (int i = tid; i < np2; i += RS_THREADS) { if (i < cap_s) gkeys[i] = skeys[i]; else if (i >= C) gkeys[i] = 0ull; }
+        __syncthreads();
+        block_bitonic_desc<false>(gkeys, nullptr, np2);
+        sorted = gkeys;
     }
     const int full = min(kk, C);
     const int cnt = (out.cap > 0 && partial) ? min(full, out.cap) : full;
@@ -813,10 +830,11 @@ cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, co
         if (v && !strcmp(v, "fused")) return 2;
         return 0;
     }();
-    // survivors the lean kernel holds in shared memory: a power of two >= 2.5 kk (tau~ - 2 eps keeps kk plus a margin band).
+    // survivors the lean kernel holds in shared memory: a power of two >= max(1024, 2.5 kk) (tau~ - 2 eps keeps kk plus a margin
+    // band whose population depends on how tightly the scores are packed; what does not fit spills to global lists).
     // Beyond 1024 (kk > 409) its CTAs get so fat that two share an SM; the split form -- re-score grid-wide from global
     // lists -- is then the faster one (1M x 3072, k = 1000, 256 queries: 2.16 ms against 2.92 ms).
-    int cap_s = 512;
+    int cap_s = 1024;
     while (cap_s < 4096 && cap_s < (int)((5 * kk + 1) / 2)) cap_s <<= 1;
     const bool have_scratch = scratch && scratch->rows && scratch->keys && scratch->cnt && scratch->ver;
     const bool fused = variant == 2 && mode == 0 && !push;
@@ -835,7 +853,8 @@ cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, co
         const size_t smem = (size_t)ld * 4 + (size_t)cap_s * 12;
         if (smem > 180 * 1024) return cudaErrorInvalidValue;
         refine_lean_kernel<<<b, RS_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, thr, flags, mode,
-                                                        cap_s, out, stats, push ? *push : BatchPush());
+                                                        cap_s, have_scratch ? *scratch : RefineScratch{nullptr, nullptr, nullptr, nullptr}, out, stats,
+                                                        push ? *push : BatchPush());
         count_launch();
         return cudaGetLastError();
     }

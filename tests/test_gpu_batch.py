@@ -94,6 +94,31 @@ def test_batch_with_massive_ties_falls_back_and_stays_exact(engine):
     _assert_same_as_single(engine, q, k, s, i, c)
 
 
+def test_batch_with_thousands_of_survivors_spills_and_stays_exact(engine):
+    """2 500 rows within a hair of each other at the top of every query's ranking: all of them lie inside the 2-eps band
+    under the k-th coarse score, so the refine kernel must re-score ~2 500 rows per query -- more than it holds in shared
+    memory (1024): the rest goes through its global lists.  No query may be handed to the fallback, and the bits must
+    equal the single-query path's."""
+    rng = np.random.default_rng(321)
+    n, d, k, b = 60_000, 128, 100, 24
+    m = _unit(rng, (n, d), "normal")
+    centre = _unit(rng, (1, d), "normal")[0]
+    near = centre[None, :] + 2e-4 * rng.standard_normal((2500, d)).astype(np.float32)
+    near /= np.sqrt((near * near).sum(axis=1))[:, None]
+    where = rng.choice(n, size=2500, replace=False)
+    m[where] = near
+    ids = np.arange(10, n + 10, dtype=np.int64)
+    q = centre[None, :] + 0.05 * rng.standard_normal((b, d)).astype(np.float32)
+    q /= np.sqrt((q * q).sum(axis=1))[:, None]
+    q = q.astype(np.float32)
+    engine.load(m, ids)
+    s, i, c = engine.query_batch(q, k)
+    cand, resc, flags = engine.batch_stats(b)
+    assert (flags == 0).all(), flags
+    assert resc.min() > 1024 and resc.max() <= 4096, (resc.min(), resc.max())
+    _assert_same_as_single(engine, q, k, s, i, c)
+
+
 def test_statistical_thresholds_fail_verification_on_sorted_rows_and_stay_exact(engine):
     """Rows stored in descending similarity to the queries' common direction: the strided row sample then holds the
     overall top rows, the sample's order statistic lands ABOVE the true cut-off, the refine kernel's verification
