@@ -472,7 +472,7 @@ cudaError_t launch_rows_to_f16(cudaStream_t st, int device, const float* M, int6
 __global__ void __launch_bounds__(256)
 queries_to_f16_kernel(const float* __restrict__ Q, int b, int b_pad, int d, int ldq, __half* __restrict__ Q16, int ld16,
                       float scale, float eps_coef, float max_row_norm, float* __restrict__ eps, float* __restrict__ thr,
-                      int32_t* __restrict__ flags)
+                      int32_t* __restrict__ flags, int32_t* __restrict__ cand_cnt)
 {
     const int lane = threadIdx.x & 31;
     const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -491,16 +491,17 @@ queries_to_f16_kernel(const float* __restrict__ Q, int b, int b_pad, int d, int 
         eps[q] = eps_coef * nrm * max_row_norm + 1e-8f;
         thr[q] = __int_as_float(0x7f800000);                     // +inf until the sample pass sets it (padding keeps it)
         flags[q] = (q < b && bad) ? 1 : 0;
+        if (cand_cnt) cand_cnt[q] = 0;                           // the filter pass counts from zero (saves a memset node per batch)
     }
 }
 
 cudaError_t launch_queries_to_f16(cudaStream_t st, const float* Q, int b, int b_pad, int d, int ldq, void* Q16, int ld16,
-                                  float eps_coef, float max_row_norm, float* eps, float* thr, int32_t* flags)
+                                  float eps_coef, float max_row_norm, float* eps, float* thr, int32_t* flags, int32_t* cand_cnt)
 {
     if (b_pad <= 0) return cudaSuccess;
     const int blocks = (b_pad * 32 + 255) / 256;
     queries_to_f16_kernel<<<blocks, 256, 0, st>>>(Q, b, b_pad, d, ldq, reinterpret_cast<__half*>(Q16), ld16,
-                                                  COARSE_OPERAND_SCALE, eps_coef, max_row_norm, eps, thr, flags);
+                                                  COARSE_OPERAND_SCALE, eps_coef, max_row_norm, eps, thr, flags, cand_cnt);
     count_launch();
     return cudaGetLastError();
 }

@@ -873,8 +873,7 @@ static int batch_enqueue(BatchWs* w, const Generation* g, const BatchPlan& P, co
     const Shard& s = g->shards[0];
     const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
     CU(cudaSetDevice(w->dev));
-    CU(launch_queries_to_f16(st, dQ, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags));
-    CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, st));
+    CU(launch_queries_to_f16(st, dQ, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags, w->cand_cnt));
     CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
                           nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
     CU(launch_sample_threshold(st, w->sample, P.sample_rows, b, P.sample_rank, w->eps, w->thr));
@@ -1729,8 +1728,7 @@ extern "C" int svsb_batch_sample_tops(svsb_t* e, void* stream, const float* d_Q,
     const int b_pad = (b + COARSE_TILE_QUERIES - 1) / COARSE_TILE_QUERIES * COARSE_TILE_QUERIES;
     if ((rc = batch_ws_ensure(w, P, b_pad)) != SVSB_OK) return rc;
     CU(cudaSetDevice(w->dev));
-    CU(launch_queries_to_f16(st, d_Q, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags));
-    CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, st));
+    CU(launch_queries_to_f16(st, d_Q, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags, w->cand_cnt));
     CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
                           nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
     CU(launch_sample_top(st, w->sample, P.sample_rows, b, d_tops));
@@ -1977,8 +1975,7 @@ extern "C" int svsb_batch_peer(svsb_t* e, void* stream, const float* d_Q, int32_
     }
     const int64_t rec = 2 * (int64_t)rec_cap + 1;
     // 1. this rank's sample maxima -> every rank's window
-    CU(launch_queries_to_f16(st, d_Q, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags));
-    CU(cudaMemsetAsync(w->cand_cnt, 0, (size_t)b_pad * 4, st));
+    CU(launch_queries_to_f16(st, d_Q, b, b_pad, P.d, P.ld, w->dQ16, P.ld16, P.eps_coef, P.max_row_norm, w->eps, w->thr, w->flags, w->cand_cnt));
     CU(launch_coarse_gemm(st, w->dev, 1, g->M16, P.n, w->dQ16, b_pad, P.ld16, P.s_tiles, P.tile_stride,
                           nullptr, nullptr, nullptr, 0, w->sample, P.sample_rows));
     CU(launch_sample_top(st, w->sample, P.sample_rows, b, nullptr, &pa));

@@ -160,7 +160,8 @@ cudaError_t launch_rows_to_f16(cudaStream_t st, int device, const float* M, int6
 // Q16 (b_pad rows, rows >= b zero) from fp32 queries Q[b][ldq]; eps[q] = eps_coef * ||q|| * max_row_norm + 1e-8,
 // thr[q] = +inf, flags[q] = 1 for queries the coarse path must not handle (non-finite / huge norm).
 cudaError_t launch_queries_to_f16(cudaStream_t st, const float* Q, int b, int b_pad, int d, int ldq, void* Q16, int ld16,
-                                  float eps_coef, float max_row_norm, float* eps, float* thr, int32_t* flags);
+                                  float eps_coef, float max_row_norm, float* eps, float* thr, int32_t* flags,
+                                  int32_t* cand_cnt = nullptr);   // optional: cand_cnt[0..b_pad) = 0
 // mode 0: filter -- every (row, query) whose coarse score >= thr[query] is appended to cand[query][..cand_cap)
 //         (key = ordered coarse score << 32 | ~row), cand_cnt[query] counts ALL survivors (may exceed cand_cap).
 // mode 1: sample -- coarse scores of row tiles 0, tile_stride, 2*tile_stride, ... (n_tiles of them), rounded DOWN to
