@@ -2,7 +2,7 @@
 (rank 0's view and the max over ranks).  Phases of the global-threshold path (svs_b200/sharded.py _batch):
 sample maxima | all-gather (b x 32 floats) | union threshold + filter pass + exact refine | all-gather (records) | verifying merge.
 
-    python -m torch.distributed.run --nproc-per-node N scripts/c3_phases.py [rows] [dims] [k] [batch] [iters]
+    python -m torch.distributed.run --nproc-per-node N scripts/c3_phases.py [rows] [dims] [k] [batch] [iters] [peer|collective]
 """
 import os
 import sys
@@ -23,7 +23,8 @@ iters = int(sys.argv[5]) if len(sys.argv) > 5 else 30
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-sr = ShardedRetriever(rank, world, local)
+exchange = sys.argv[6] if len(sys.argv) > 6 else "peer"
+sr = ShardedRetriever(rank, world, local, exchange=exchange)
 sr.load_synthetic(n, d, seed=0, id0=1, id_step=1)
 rng = np.random.default_rng(2)
 q = rng.standard_normal((b, d)).astype(np.float32)
@@ -38,7 +39,9 @@ dq = sr._queries
 rec, gath, (o_s, o_i, o_c) = sr._bufs[("batch", k, b)]
 names = ["sample maxima", "all-gather tops", "threshold+filter+refine", "all-gather records", "merge"]
 acc = np.zeros(len(names))
-if plan is not None:
+if plan is not None and sr._batch_peer_ready:
+    names, acc = [], np.zeros(0)      # fused exchange: no phase boundaries on the host side
+elif plan is not None:
     tops, tops_all = sr._bufs[("tops", b)]
     for it in range(iters):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
@@ -67,17 +70,21 @@ mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
 # back-to-back batches (what bench.py times)
 torch.cuda.synchronize(); dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
 e0.record()
+t_host0 = time.perf_counter()
 for _ in range(iters):
     sr.run_batch(k, defer=True)
 sr.flush_batches()
+t_host = (time.perf_counter() - t_host0) / iters * 1e6          # host time to ENQUEUE a batch (nothing synchronises)
 e1.record(); torch.cuda.synchronize()
 loop = torch.tensor([e0.elapsed_time(e1) / iters * 1e3], device="cuda"); dist.all_reduce(loop, op=dist.ReduceOp.MAX)
 unanswered = sr.last_batch_unanswered()
 if rank == 0:
-    print(f"rows={n} d={d} k={k} b={b} world={world} plan={plan}")
+    print(f"rows={n} d={d} k={k} b={b} world={world} plan={plan} exchange={'fused peer' if sr._batch_peer_ready else exchange}")
     for nm, a, m in zip(names, acc, mx.tolist()):
         print(f"  {nm:28s} rank0 {a:8.1f} us   max over ranks {m:8.1f} us")
+    print(f"  host enqueue time per batch (rank 0): {t_host:.1f} us")
     print(f"  sum of phases (rank 0) {acc.sum():.1f} us; back-to-back loop {loop.item():.1f} us per batch = {b / loop.item() * 1e6:.0f} queries/s; unanswered {unanswered}")
 sr.close()
 dist.destroy_process_group()

@@ -16,6 +16,14 @@ CMDV="python scripts/c3_virtual_ranks.py 1000000 768 100 1024 8 1"
 timeout 300 $CMDV > gpurun_out/plain_virtual.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c3_virtual_n8.csv $CMDV > gpurun_out/ncu_list_virtual.log 2>&1
 echo "ncu list virtual rc=$?"
+{
+for n in 125000 1000000; do
+  timeout 120 python scripts/c3_breakdown.py $n 768 100 1024 40
+  SVSB_REFINE=split timeout 120 python scripts/c3_breakdown.py $n 768 100 1024 40
+  SVSB_REFINE=fused SVSB_SAMPLE_GENERIC=1 timeout 120 python scripts/c3_breakdown.py $n 768 100 1024 40
+done
+timeout 200 python scripts/c3_virtual_ranks.py
+} > gpurun_out/r2f_c3_breakdown.txt 2>&1
 python - <<'PY'
 import json
 try:

@@ -98,7 +98,8 @@ if __name__ == "__main__":
             ("prof_select.ncu-rep", "selection kernel (select_topk_kernel), workload c2, k = 100", None, None),
             ("prof_coarse.ncu-rep", "batched coarse contraction (coarse_gemm_kernel<1> sample pass, <0> filter pass), workload c3",
              "c3", "coarse_gemm_kernel<0"),
-            ("prof_refine.ncu-rep", "batched path: sample_threshold_kernel and refine_kernel, workload c3", None, None),
+            ("prof_refine.ncu-rep", "batched path: sample_order_kernel (order statistic of the sample) and refine_lean_kernel (select + exact "
+             "re-score + sort, one CTA per query), workload c3", None, None),
             ("prof_mq.ncu-rep", "small exact batches (scripts/mq_profile.py): gemv_tma_mq_kernel (4 and 8 queries per pass) and the batched "
              "selection (one CTA per query), 1M x 1536, k = 100", "c2_mq", "gemv_tma_mq"),
             ("prof_peer.ncu-rep", "peer exchange at world size 1 (scripts/peer_profile.py): select_topk_kernel with the fused push, "
@@ -112,6 +113,8 @@ if __name__ == "__main__":
         launches(f"{rtag}_launches")
     if os.path.exists(os.path.join(OUT, "launches_c3.csv")):
         launches(f"{rtag}_launches_c3", os.path.join(OUT, "launches_c3.csv"))
+    if os.path.exists(os.path.join(OUT, "launches_c3_virtual_n8.csv")):   # scripts/c3_virtual_ranks.py: one rank's batch of an 8-rank run
+        launches(f"{rtag}_launches_c3_virtual_n8", os.path.join(OUT, "launches_c3_virtual_n8.csv"))
     tf = os.path.join(PROF, f"{rtag}_traffic.json")
     old = json.load(open(tf)) if os.path.exists(tf) else {}
     old.update(out)
