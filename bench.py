@@ -365,13 +365,19 @@ def parity_sharded(dist, rank, world, sr, k: int, queries: np.ndarray, got_lists
 # ---------------------------------------------------------------------------------------------------
 def e2e_pipelined(eng, queries: np.ndarray, k: int, steps: int, in_flight: int = 3):
     """The e2e metric with `in_flight` queries pending (Engine.submit / Pending.result): host query in, host result out for
-    every query.  Two passes of steps x QUERIES_PER_STEP queries each, the better one reported (a host-side hiccup -- another
-    tenant's burst on the box, a page fault storm -- once cost a pass 20 %; scripts/e2e_repeat.py: eight passes within
-    1.3 % otherwise); both are listed.  Returns (queries/s, the first len(queries) results, [queries/s of every pass])."""
+    every query.  The warm-up keeps `in_flight` queries pending too, so that every query context (stream, workspace,
+    pinned staging: created on first use) exists before the clock starts -- warming up one query at a time left the
+    second and third context's allocations inside the timed pass (4 % at C2, 20 % at C5).  Two passes of
+    steps x QUERIES_PER_STEP queries, the better one reported, both listed.
+    Returns (queries/s, the first len(queries) results, [queries/s of every pass])."""
     import gc
     first = []
-    for i in range(8):
-        eng.submit(queries[i], k).result()
+    warm = [eng.submit(queries[i], k) for i in range(in_flight)]
+    for i in range(in_flight, 4 * in_flight):
+        warm.pop(0).result()
+        warm.append(eng.submit(queries[i % len(queries)], k))
+    for p in warm:
+        p.result()
     nq = steps * QUERIES_PER_STEP
     rates = []
     for _pass in range(2):
@@ -652,8 +658,11 @@ def leg_sharded(sp: Spmd, name: str, steps: int, warmup: int) -> dict:
     # the same with 3 queries in flight (svsb_query_peer_submit / _wait): every query still goes in from host memory and
     # comes back to host memory inside the timed region
     piped = []
-    for i in range(4):
-        sr.wait(sr.submit(queries[i], k))
+    warm = [sr.submit(queries[i], k) for i in range(3)]           # warm up with all three tickets in flight
+    for i in range(3, 9):
+        sr.wait(warm.pop(0)); warm.append(sr.submit(queries[i], k))
+    for p in warm:
+        sr.wait(p)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     pend = []
