@@ -425,7 +425,7 @@ def incremental_probe(eng, n: int, d: int, k: int) -> dict:
         raise AssertionError("incremental delete: a tombstoned row was returned")
     phys, live = eng.generation_rows()
     out.update({"rows_physical": phys, "rows_live": live,
-                "note": "first add re-allocates the matrix with head-room (one device-to-device copy); later adds append in place"})
+                "note": "a loaded shard carries 0.4 % head-room, so adds append in place; a shard that fills up is re-allocated with 12.5 % head-room (one device-to-device copy)"})
     return out
 
 

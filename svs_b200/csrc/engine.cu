@@ -232,9 +232,12 @@ int alloc_generation(svsb_engine* e, int64_t n, int d, std::shared_ptr<Generatio
         CU(cudaSetDevice(s.dev));
         s.buf.reset(new ShardBuf());
         s.buf->dev = s.dev;
-        CU(cudaMalloc(&s.buf->M, (size_t)s.n * g->ld * 4));
-        CU(cudaMalloc(&s.buf->ids, (size_t)s.n * 8));
-        s.buf->cap_rows = s.n;
+        // a little head-room (0.4 %, at least 1024 rows): the first incremental appends (svsb_apply_mutations) then go in
+        // place instead of paying for a re-allocation and a device-to-device copy of the whole shard
+        const int64_t cap = s.n + std::max<int64_t>(1024, s.n / 256);
+        CU(cudaMalloc(&s.buf->M, (size_t)cap * g->ld * 4));
+        CU(cudaMalloc(&s.buf->ids, (size_t)cap * 8));
+        s.buf->cap_rows = cap;
         s.M = s.buf->M; s.ids = s.buf->ids;
     }
     out = g;
