@@ -581,7 +581,8 @@ refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t ro
 // Shared memory for keys[cap_s] / rows[cap_s] is sized by the host from k; a query with more survivors keeps the rest in
 // global lists (RefineScratch) and sorts there -- slower, exact all the same; more than REFINE_SURVIVOR_CAP: flag 8.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RS_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB)
 refine_lean_kernel(const float* __restrict__ M, int64_t n, int d4, const int64_t* __restrict__ ids, int64_t row0,
                    const float* __restrict__ Q, int ldq, int k, const u64* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
                    int cand_cap, const float* __restrict__ eps, const float* __restrict__ thr, int32_t* __restrict__ flags, int mode,
@@ -845,16 +846,27 @@ cudaError_t launch_refine(cudaStream_t st, const float* M, int64_t n, int ld, co
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(refine_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(refine_lean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(refine_lean_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+        // the CTAs are small: ask for the largest shared-memory carve-out so that registers, not the default split, bound residency
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(refine_lean_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(refine_lean_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
     if (!fused && !split) {
         const size_t smem = (size_t)ld * 4 + (size_t)cap_s * 12;
         if (smem > 180 * 1024) return cudaErrorInvalidValue;
-        refine_lean_kernel<<<b, RS_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, thr, flags, mode,
-                                                        cap_s, have_scratch ? *scratch : RefineScratch{nullptr, nullptr, nullptr, nullptr}, out, stats,
-                                                        push ? *push : BatchPush());
+        // five resident CTAs per SM (48 registers) when the query and the lists leave room, else three (72 registers)
+        static const int minb_env = [] { const char* v = getenv("SVSB_REFINE_MINB"); return v ? atoi(v) : 0; }();
+        const bool five = minb_env ? minb_env >= 5 : smem <= 20 * 1024;
+        const RefineScratch sp = have_scratch ? *scratch : RefineScratch{nullptr, nullptr, nullptr, nullptr};
+        if (five)
+            refine_lean_kernel<5><<<b, RS_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, thr, flags, mode,
+                                                               cap_s, sp, out, stats, push ? *push : BatchPush());
+        else
+            refine_lean_kernel<3><<<b, RS_THREADS, smem, st>>>(M, n, ld / 4, ids, row0, Q, ldq, k, cand, cand_cnt, cand_cap, eps, thr, flags, mode,
+                                                               cap_s, sp, out, stats, push ? *push : BatchPush());
         count_launch();
         return cudaGetLastError();
     }
@@ -884,6 +896,8 @@ cudaError_t preload_batch_kernels()
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, refine_select_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, rescore_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, refine_sort_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, refine_lean_kernel<3>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, refine_lean_kernel<5>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, wait_flags_kernel);
     return e;
 }
