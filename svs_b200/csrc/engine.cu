@@ -827,7 +827,8 @@ static int batch_ws_ensure(BatchWs* w, const BatchPlan& P, int b_pad) {
     CU(cudaSetDevice(w->dev));
     const int64_t need_sample = std::max(P.sample_rows, P.sample_alloc_rows);
     if (b_pad > w->cap_b || P.ld > w->cap_ld || P.k > w->cap_k || need_sample > w->cap_sample || P.cand_cap != w->cand_cap) {
-        CU(cudaStreamSynchronize(w->st));
+        // the sharded entry points run this workspace's kernels on the CALLER's stream: wait for the device, not for w->st only
+        CU(cudaDeviceSynchronize());
         const int nb = std::max(b_pad, w->cap_b), nld = std::max(P.ld, w->cap_ld), nk = std::max(P.k, w->cap_k);
         const int64_t ns = std::max(need_sample, w->cap_sample);
         w->release_device();
@@ -1883,6 +1884,7 @@ extern "C" int svsb_bxchg_disconnect(svsb_t* e) {
     x->ipc_opened.clear();
     for (int r = 0; r < x->world; ++r) if (r != x->rank) x->peer_block[r] = nullptr;
     x->connected = x->world == 1;
+    x->deferred.pending = false;             // a merge nobody flushed dies with the connection
     return SVSB_OK;
 }
 

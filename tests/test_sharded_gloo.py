@@ -314,6 +314,7 @@ def _global_batch_worker(rank, world, port, n, d, k, spoil, ret):
         sr.load_global(m, ids)
         plan = sr._global_plan(k)
         assert plan is not None and 1 <= plan[0] <= 32 and 1 <= plan[2] <= k, plan
+        assert sr._global_plan(400) is None      # the agreed order statistic would exceed the 32 exchanged maxima: per-rank thresholds
         qs = oracle.synth_queries(21, d, 32, "normal")
         qs[3] = m[9]
         many = sr.retrieve_many(qs, k)
@@ -327,6 +328,34 @@ def _global_batch_worker(rank, world, port, n, d, k, spoil, ret):
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def _ineligible_worker(rank, world, port, n, d, k, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = oracle.synth_matrix_normal(n, d, 41)
+        ids = np.arange(1, n + 1, dtype=np.int64)
+        sr = ShardedRetriever(rank, world, backend=NumpyGlobalBatchBackend())
+        sr.load_global(m, ids)
+        # the last rank's shard is too small to take part (its probe says so): EVERY rank must fall back to per-rank thresholds
+        assert sr._global_plan(k) is None
+        qs = oracle.synth_queries(5, d, 42, "normal")
+        many = sr.retrieve_many(qs, k)
+        for j in range(len(qs)):
+            oracle.compare_retrieval(many[j], oracle.superheavy(m, ids, qs[j], k), oracle.scores_of(m, qs[j]), ids)
+        ret[rank] = many
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_threshold_plan_falls_back_on_every_rank_when_one_rank_cannot_take_part():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ineligible_worker, args=(3, _free_port(), 1489, 24, 10, ret), nprocs=3, join=True)   # shards of 497, 497, 495 rows: the last samples 31 < 32
+    assert len(ret) == 3 and ret[1] == ret[0] and ret[2] == ret[0]
 
 
 @pytest.mark.parametrize("world,n,k,spoil", [(2, 3001, 10, False), (3, 4000, 25, False), (2, 2500, 10, True)])
