@@ -36,7 +36,7 @@ for _ in range(30):
 torch.cuda.synchronize(); dist.barrier()
 be = sr.backend
 dq = sr._queries
-rec, gath, (o_s, o_i, o_c) = sr._bufs[("batch", k, b)]
+rec, gath, (o_s, o_i, o_c) = sr._bufs[("batch", k, b, k if plan is None else plan[2])]
 names = ["sample maxima", "all-gather tops", "threshold+filter+refine", "all-gather records", "merge"]
 acc = np.zeros(len(names))
 if plan is not None and sr._batch_peer_ready:

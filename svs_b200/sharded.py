@@ -409,7 +409,7 @@ class ShardedRetriever:
         b = dq.shape[0]
         plan = self._global_plan(k)
         cap = k if plan is None else plan[2]
-        key = ("batch", k, b)
+        key = ("batch", k, b, cap)                                  # cap changes with the plan (a reload can switch it on or off)
         if key not in self._bufs:
             self._bufs[key] = (self.backend.new_records(b, cap), self.backend.new_records(self.world * b, cap),
                                self.backend.new_outputs(b, k))
