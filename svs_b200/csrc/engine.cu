@@ -1783,8 +1783,9 @@ extern "C" int svsb_batch_global_records(svsb_t* e, void* stream, const float* d
 // threshold kernel, the merge -- run behind a one-CTA kernel that acquires the `world` flags of its OWN window.  At 8
 // GPUs the two NCCL all-gathers were 75-85 us of a 380 us batch (profiles/r02_c3_phases_n8.txt).
 // Slot reuse: everything of a batch is on one stream per rank, so a rank can only push batch j+1's maxima after its own
-// merge of batch j has seen every peer's records of batch j, which those peers pushed after reading all maxima of
-// batch j: two slots are one more than the protocol needs.
+// merge of batch j (immediate form) or j-1 (pipelined form, flags bit 0) has seen every peer's records of that batch, which
+// those peers pushed after reading all its maxima: the immediate form would do with one slot, the pipelined form needs the two
+// it has (tests/test_batch_window_protocol.py checks the interleavings).
 static void bxchg_release(svsb_engine* e) {
     BXchg* x = e->bxchg.get();
     if (!x) return;
