@@ -574,10 +574,12 @@ refine_sort_kernel(int64_t n, int k, const int64_t* __restrict__ ids, int64_t ro
 }
 
 // ---------------------------------------------------------------------------------------------
-// refine, lean and fused (the default): select -> exact re-score -> sort -> emit / push in ONE kernel, one CTA of 256
-// threads per query with ~25-30 KB of shared memory, so seven CTAs share an SM and the latency-bound phases of some
-// overlap the HBM-bound re-score of the others -- the split's three launches (and the dependent global round trips at
-// the head of each) cost 25 us of a 1024-query batch at a 125 k-row shard (profiles/r02_c3_virtual_n8.md).
+// refine, lean and fused (the default for k <= 409): select -> exact re-score -> sort -> emit / push in ONE kernel, one CTA
+// of 256 threads per query with 21 KB static + 12-15 KB dynamic shared memory; MINB = 5 (48 registers) puts five CTAs on
+// an SM when the query and the lists are small, MINB = 3 otherwise, so that the latency-bound phases of some overlap the
+// HBM-bound re-score of the others.  At a 125 k-row shard it replaces the split's three launches (15 + 60 + 11 us, each
+// with dependent global round trips at its head) by one of 74-86 us (profiles/r02_launches_c3_virtual_n8.md); on one GPU
+// with the bench's data it is no faster than round 1's kernel.
 // Shared memory for keys[cap_s] / rows[cap_s] is sized by the host from k; a query with more survivors keeps the rest in
 // global lists (RefineScratch) and sorts there -- slower, exact all the same; more than REFINE_SURVIVOR_CAP: flag 8.
 // ---------------------------------------------------------------------------------------------
